@@ -1,0 +1,81 @@
+"""pytest configuration: markers, sys.path for the oracle and the product package, golden loader."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'speech-translation-joint-embedding-passing_b200')
+for p in (ROOT, PKG, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
+GOLDEN_CASES = ['st_tiny_ragged', 'st_tiny_aligned', 'st_small']
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason='no CUDA device')
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
+
+
+class Golden:
+    """One tests/golden/*.npz fixture written by oracle/make_golden.py (outputs of the real reference)."""
+
+    def __init__(self, name):
+        self.name = name
+        self.z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+
+    def group(self, prefix, as_torch=True):
+        out = {}
+        for k in self.z.files:
+            if k.startswith(prefix + '/'):
+                v = self.z[k]
+                out[k[len(prefix) + 1:]] = torch.from_numpy(np.array(v)) if as_torch else v
+        return out
+
+    def __getitem__(self, k):
+        return torch.from_numpy(np.array(self.z[k]))
+
+    @property
+    def cfg(self):
+        from oracle.st_oracle import STConfig
+        c = {k: int(v) for k, v in self.group('cfg', as_torch=False).items()}
+        return STConfig(enc_vocab_size=c['V'], dec_vocab_size=c['V'], enc_embedding_size=c['E'],
+                        dec_embedding_size=c['E'], max_seq_len_src=c['S'], max_seq_len_tgt=c['L'],
+                        num_heads=c['heads'], dim_model=c['dim_model'], dim_feedforward=c['FF'],
+                        enc_layers=c['layers'], dec_layers=c['layers'], acous_dim=c['F'],
+                        acous_hidden_size=c['H'])
+
+    def params(self, requires_grad=False, dtype=torch.float32):
+        p = {k: v.to(dtype).clone() for k, v in self.group('param').items()}
+        if requires_grad:
+            for v in p.values():
+                v.requires_grad_(True)
+        return p
+
+    def inputs(self):
+        i = self.group('in')
+        i['acous_lens'] = [int(v) for v in i['acous_lens']]
+        return i
+
+
+@pytest.fixture(params=GOLDEN_CASES)
+def golden(request):
+    return Golden(request.param)
+
+
+def rel_err(a, b):
+    a = a.double().flatten()
+    b = b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
