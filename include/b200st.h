@@ -1,0 +1,183 @@
+/*
+ * b200st.h — C ABI of libb200st.so: hand-written sm_100a kernels for the joint speech-translation
+ * hot path (forward + backward of acoustic encoder -> embedding passing -> translation decoder -> loss).
+ *
+ * The reference (EdieLu/speech-translation-joint-embedding-passing) has no FFI of its own: every kernel
+ * it launches is a PyTorch library call made from Python nn.Modules.  Each entry
+ * point below therefore names the reference *call site* (file:line under the reference root) whose
+ * library kernel(s) it replaces.  The Python host layer (speech-translation-joint-embedding-passing_b200/)
+ * keeps the reference's module signatures and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain C, raw device pointers, int64 sizes/strides in ELEMENTS, no torch types;
+ *   - `dtype`: B200ST_F32 (0) or B200ST_BF16 (1) = storage type of activation tensors; parameters
+ *     named `const float*` are always fp32 (the nn.Parameter storage itself); all accumulation is fp32;
+ *   - every call is asynchronous on `stream` (a cudaStream_t), allocates nothing, never syncs;
+ *   - return 0 on success, non-zero on error with a message in b200st_last_error() (thread-local).
+ */
+#ifndef B200ST_H_
+#define B200ST_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ST_F32 0
+#define B200ST_BF16 1
+
+typedef void* b200st_stream_t; /* cudaStream_t */
+
+int b200st_version(void);
+const char* b200st_last_error(void);
+/* Number of kernels launched by this library in the calling process since load (bench gpu_launches). */
+int64_t b200st_launch_count(void);
+
+/* ---- dense contraction -------------------------------------------------------------------------
+ * C[b] = relu?( alpha * op(A[b]) * op(B[b]) + bias ) + R[b]        b = 0..batch-1
+ * op(A) is M x K: trans_a=0 -> A stored [M,K] (lda), trans_a=1 -> A stored [K,M].
+ * op(B) is K x N: trans_b=0 -> B stored [K,N] (ldb), trans_b=1 -> B stored [N,K] (an nn.Linear weight).
+ * R (same dtype/shape as C, may alias C, may be NULL), bias fp32[N] or NULL.
+ * Replaces every nn.Linear / matmul / bmm on the path: layers.py:131-134,158-160,192-194,238-249,
+ * Seq2seq.py:124-131,180,195,207,253, Dec.py:96-98,432-436, attention.py:192-193, and the LSTM input
+ * projections inside torch.nn.LSTM (Enc.py:50-66, Dec.py:104-118). */
+int b200st_gemm(int dtype_ab, int dtype_c, int trans_a, int trans_b,
+                int64_t M, int64_t N, int64_t K, float alpha,
+                const void* A, int64_t lda, int64_t stride_a,
+                const void* B, int64_t ldb, int64_t stride_b,
+                void* C, int64_t ldc, int64_t stride_c,
+                const void* R, int64_t ldr, int64_t stride_r,
+                const float* bias, int relu, int64_t batch, b200st_stream_t stream);
+
+/* ---- LayerNorm (layers.py:139,153,240,245; TFEnc.py:61,89; TFDec.py:58,127) -------------------- */
+int b200st_layernorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y,
+                         float* mean, float* rstd, int64_t rows, int64_t cols, float eps,
+                         b200st_stream_t stream);
+/* dgamma/dbeta are ACCUMULATED into (caller zero-fills or passes the running .grad buffer). */
+int b200st_layernorm_bwd(int dtype, const void* dy, const void* x, const float* gamma,
+                         const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                         int64_t rows, int64_t cols, b200st_stream_t stream);
+
+/* ---- multi-head scaled-dot-product attention core (layers.py:162-170,213-229) -------------------
+ * q,k,v are the projection outputs viewed as [B, L, H, d] with row strides ldq/ldk/ldv (elements);
+ * mask uint8 [B, 1|Lq, Lk] (nonzero = keep; masked scores are SET to -1e9, layers.py:224), addressed
+ * mask[b*mask_sb + i*mask_sq + j]; NULL = no mask.  o: [B, Lq, H*d] (ldo); p: [B,H,Lq,Lk] softmax
+ * probabilities (the `attn` the reference returns).  Scores use (q / temperature) . k. */
+int b200st_mha_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                   const void* v, int64_t ldv, const uint8_t* mask, int64_t mask_sb, int64_t mask_sq,
+                   void* o, int64_t ldo, void* p, int64_t B, int64_t H, int64_t Lq, int64_t Lk,
+                   int64_t d, float temperature, b200st_stream_t stream);
+/* ds: workspace [B,H,Lq,Lk] (same dtype as p); dq/dk/dv written (not accumulated). */
+int b200st_mha_bwd(int dtype, const void* dout, int64_t ldo, const void* q, int64_t ldq,
+                   const void* k, int64_t ldk, const void* v, int64_t ldv, const void* p, void* ds,
+                   void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                   int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d, float temperature,
+                   b200st_stream_t stream);
+
+/* ---- LSTM cell pointwise (one step of torch.nn.LSTM, Dec.py:393-419) ----------------------------
+ * gates [B,4H] = pre-activations (x W_ih^T + h W_hh^T + b_ih + b_hh), PyTorch order i,f,g,o.
+ * acts [B,4H] fp32 = post-activation gates, c/c_prev fp32 [B,H] (c_prev NULL = zeros),
+ * h [B,H] dtype; if residual != NULL, out_res = h + residual (Dec.py:417-418). */
+int b200st_lstm_cell_fwd(int dtype, const void* gates, const float* c_prev, void* h, float* c,
+                         float* acts, const void* residual, void* out_res, int64_t B, int64_t H,
+                         b200st_stream_t stream);
+/* dh = dh_a + dh_b + dh_c (NULLs skipped); dc_next NULL = zeros; c_prev NULL = zeros. */
+int b200st_lstm_cell_bwd(int dtype, const void* dh_a, const void* dh_b, const void* dh_c,
+                         const float* dc_next, const float* acts, const float* c_prev, const float* c,
+                         void* dgates, float* dc_prev, int64_t B, int64_t H, b200st_stream_t stream);
+
+/* ---- bidirectional packed-sequence LSTM recurrence (torch.nn.LSTM(bidirectional) on a
+ * PackedSequence, Enc.py:150-157,172-177,189-194,206-211), one persistent thread-block-cluster kernel.
+ * xproj [2][T][B][4H] dtype: per direction, time-major input projections INCLUDING both biases.
+ * w_hh_f / w_hh_r: [4H,H] fp32 (weight_hh_l0 / weight_hh_l0_reverse).  lens int32[B]: valid frames.
+ * out: h written at  out[(t/pair)*out_ld_t + b*out_ld_b + (t%pair)*2H + dir*H + u]  (zeros for t>=len):
+ *      pair=2 folds the pyramid frame-pair concat (Enc.py:166-167) into the store.
+ * hs   [2][T+1][B][H] dtype: forward dir stores h_t at [0][t+1] ([0][0] = 0); reverse at [1][t] ([1][T] = 0).
+ * acts [2][T][B][4H] fp32, cs [2][T][B][H] fp32: saved for backward (NULL to skip, inference). */
+int b200st_blstm_fwd(int dtype, const void* xproj, const float* w_hh_f, const float* w_hh_r,
+                     const int32_t* lens, void* out, int64_t out_ld_t, int64_t out_ld_b, int pair,
+                     void* hs, float* acts, float* cs, int64_t T, int64_t B, int64_t H,
+                     b200st_stream_t stream);
+/* dout in the same layout as out; dgates [2][T][B][4H] dtype written (zeros for t>=len). */
+int b200st_blstm_bwd(int dtype, const void* dout, int64_t out_ld_t, int64_t out_ld_b, int pair,
+                     const float* acts, const float* cs, const float* w_hh_f, const float* w_hh_r,
+                     const int32_t* lens, void* dgates, int64_t T, int64_t B, int64_t H,
+                     b200st_stream_t stream);
+
+/* ---- LAS bilinear attention step (attention.py:190-193,250-273; Dec.py:423-425) ------------------
+ * score[b,j] = q[b] . wk[b,j]; j >= klens[b] -> -1e12; softmax; ctx[b] = sum_j p[b,j] vals[b,j]. */
+int b200st_las_attn_fwd(int dtype, const void* q, const void* wk, const void* vals,
+                        const int32_t* klens, void* ctx, float* probs, int64_t B, int64_t Tk,
+                        int64_t D, int64_t Dv, b200st_stream_t stream);
+/* dscore [B,Tk] fp32 out; dq [B,D] dtype out.  (d wk / d vals are batched GEMMs over saved stacks.) */
+int b200st_las_attn_bwd(int dtype, const void* dctx, const void* wk, const void* vals,
+                        const float* probs, float* dscore, void* dq, int64_t B, int64_t Tk,
+                        int64_t D, int64_t Dv, b200st_stream_t stream);
+/* argmax over the last dim (Dec.py:331 topk(1), Seq2seq.py:255 topk(1)); first index wins ties. */
+int b200st_argmax_rows(int dtype, const void* x, int64_t ld, int64_t rows, int64_t cols,
+                       int64_t* idx, int64_t idx_stride, b200st_stream_t stream);
+/* Dec.decode lengths rule (Dec.py:334-340) kept on device: if sym in {EOS,PAD} and lengths[b] > step
+ * then lengths[b] = step + 1. */
+int b200st_las_update_lengths(const int64_t* sym, int64_t sym_stride, int32_t* lengths, int step,
+                              int64_t B, b200st_stream_t stream);
+
+/* ---- embeddings and the embedding-passing mix (Seq2seq.py:183-211; Dec.py:166,223) ---------------- */
+int b200st_embedding_fwd(int dtype, const int64_t* ids, const float* table, void* out, int64_t ld_out,
+                         int64_t n, int64_t dim, int64_t vocab, b200st_stream_t stream);
+/* dtable[ids[i]] += dout[i] for ids[i] != padding_idx (nn.Embedding(padding_idx=PAD), Seq2seq.py:106). */
+int b200st_embedding_bwd(int dtype, const int64_t* ids, const void* dout, int64_t ld_dout,
+                         float* dtable, int64_t n, int64_t dim, int64_t vocab, int64_t padding_idx,
+                         b200st_stream_t stream);
+/* cat[i] = [ table[ids[i]] , dyn[i] ]  (Seq2seq.py:188-191) written in `dtype`, row width E + D. */
+int b200st_mix_gather_concat(int dtype, const int64_t* ids, const float* table, const void* dyn,
+                             int64_t ld_dyn, void* cat, int64_t n, int64_t E, int64_t D, int64_t vocab,
+                             b200st_stream_t stream);
+
+/* ---- softmax / loss over the vocabulary (Seq2seq.py:254-255; Dec.py:436; loss.py:130-132) --------- */
+int b200st_log_softmax_fwd(int dtype, const void* x, void* y, int64_t rows, int64_t cols,
+                           int64_t* argmax, b200st_stream_t stream);
+int b200st_log_softmax_bwd(int dtype, const void* dy, const void* y, void* dx, int64_t rows,
+                           int64_t cols, b200st_stream_t stream);
+/* loss_sum += sum_{mask} -logp[r, target[r]];  ld = row stride of logp. */
+int b200st_masked_nll_fwd(int dtype, const void* logp, int64_t ld, const int64_t* target,
+                          const uint8_t* mask, float* loss_sum, int64_t rows, int64_t cols,
+                          b200st_stream_t stream);
+/* dlogp (dense [rows, cols], ld) = 0 except dlogp[r, target[r]] = -gscale[0] where mask. */
+int b200st_masked_nll_bwd(int dtype, const float* gscale, const int64_t* target, const uint8_t* mask,
+                          void* dlogp, int64_t ld, int64_t rows, int64_t cols, b200st_stream_t stream);
+/* Fused softmax + masked NLL + gradient (K17): one read of logits, one write of dlogits.
+ * loss_sum += sum_mask (lse - logit[target]); dlogits = (softmax - onehot) * mask * scale[0];
+ * eps = label smoothing (0 for parity with the reference, which has none).  dlogits may alias logits. */
+int b200st_softmax_nll_fused(int dtype, const void* logits, int64_t ld, const int64_t* target,
+                             const uint8_t* mask, const float* scale, float eps, float* loss_sum,
+                             void* dlogits, int64_t ld_d, int64_t rows, int64_t cols,
+                             b200st_stream_t stream);
+
+/* ---- small glue kernels ------------------------------------------------------------------------ */
+int b200st_add(int dtype, const void* a, const void* b, void* out, int64_t n, b200st_stream_t stream);
+/* out[b,l,:] = x[b,l,:] + pe[l,:]  (TFEnc.py:82-83, TFDec.py:85-86) */
+int b200st_add_posenc(int dtype, const void* x, const float* pe, void* out, int64_t B, int64_t L,
+                      int64_t D, b200st_stream_t stream);
+/* in [A,Bd,C] -> out [Bd,A,C] */
+int b200st_transpose01(int dtype_in, int dtype_out, const void* in, void* out, int64_t A, int64_t Bd,
+                       int64_t C, b200st_stream_t stream);
+int b200st_cast(int dtype_in, int dtype_out, const void* in, void* out, int64_t n,
+                b200st_stream_t stream);
+/* out[c] (+)= sum_r x[r, c] */
+int b200st_colsum(int dtype, const void* x, int64_t ld, float* out, int64_t rows, int64_t cols,
+                  int accumulate, b200st_stream_t stream);
+int b200st_relu_bwd(int dtype, const void* dy, const void* y, void* dx, int64_t n,
+                    b200st_stream_t stream);
+/* mask[b, i, j] = (ids[b, j] != pad) && (!causal || j <= i), uint8 [B, Lq, L]; Lq = causal ? L : 1
+ * (Seq2seq.py:204-205 / layers.py:269-289). */
+int b200st_token_mask(const int64_t* ids, uint8_t* mask, int64_t B, int64_t L, int64_t pad, int causal,
+                      b200st_stream_t stream);
+/* mask[b, 0, j] = j < lengths[b]   (Seq2seq.py:494-497) */
+int b200st_length_mask(const int32_t* lengths, uint8_t* mask, int64_t B, int64_t L,
+                       b200st_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ST_H_ */

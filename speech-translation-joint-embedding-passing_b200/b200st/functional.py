@@ -1,0 +1,530 @@
+"""Autograd functions that orchestrate the b200st kernels (forward and hand-written backward).
+
+Everything numerical happens inside libb200st.so; this file only sequences launches, owns the saved
+buffers and tells autograd which gradient belongs to which input.  Citations are to the reference files
+whose PyTorch library calls each function replaces.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch.autograd import Function
+
+from .kernels import K
+from . import runtime as rt
+
+PAD, UNK, BOS, EOS, SPC = 0, 1, 2, 3, 4   # utils/config.py:7
+
+
+def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Gradients arrive from autograd with arbitrary strides; kernels want dense rows."""
+    return None if t is None else (t if t.is_contiguous() else t.contiguous())
+
+
+# ------------------------------------------------------------------------------------------------
+# Linear (+bias, +ReLU, +residual): nn.Linear call sites, layers.py:131-134,158-160,192-195,238-252
+# ------------------------------------------------------------------------------------------------
+class _Linear(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu, residual):
+        assert not (relu and residual is not None)
+        k = weight.size(1)
+        x2 = x.reshape(-1, k)
+        w = rt.operand(weight)
+        r2 = None if residual is None else residual.reshape(-1, weight.size(0))
+        y = K().gemm(x2, w, trans_b=True, bias=bias, relu=relu, residual=r2)
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x2, weight, y if relu else None)
+        return y.view(*x.shape[:-1], weight.size(0))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, y = ctx.saved_tensors
+        n = weight.size(0)
+        dy2 = _c(dy).reshape(-1, n)
+        dz = K().relu_bwd(dy2, y) if ctx.relu else dy2
+        w = rt.operand(weight)
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = K().gemm(dz, w).view(*dy.shape[:-1], weight.size(1))
+        if ctx.needs_input_grad[1]:
+            dw = K().gemm(dz, x2, trans_a=True, out_dtype=torch.float32)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = K().colsum(dz)
+        if ctx.has_res and ctx.needs_input_grad[4]:
+            dres = dy
+        return dx, dw, db, None, dres
+
+
+def linear(x, weight, bias=None, relu=False, residual=None):
+    return _Linear.apply(x, weight, bias, relu, residual)
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm: layers.py:139,153,240,245; TFEnc.py:61,89; TFDec.py:58,127
+# ------------------------------------------------------------------------------------------------
+class _LayerNorm(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        xc = _c(x)
+        y, mean, rstd = K().layernorm_fwd(xc, weight, bias, eps)
+        ctx.save_for_backward(xc, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dgamma = torch.zeros_like(weight)
+        dbeta = torch.zeros_like(weight)
+        dx = K().layernorm_bwd(_c(dy), x, weight, mean, rstd, dgamma, dbeta)
+        return dx, dgamma, dbeta, None
+
+
+def layer_norm(x, weight, bias, eps):
+    return _LayerNorm.apply(x, weight, bias, eps)
+
+
+# ------------------------------------------------------------------------------------------------
+# Scaled-dot-product attention core: layers.py:162-170,213-229
+# ------------------------------------------------------------------------------------------------
+class _MHACore(Function):
+    @staticmethod
+    def forward(ctx, q, k, v, mask, n_head, temperature):
+        o, p = K().mha_fwd(q, k, v, mask, n_head, temperature)
+        ctx.n_head, ctx.temperature = n_head, temperature
+        ctx.save_for_backward(q, k, v, p)
+        ctx.mark_non_differentiable(p)
+        return o, p
+
+    @staticmethod
+    def backward(ctx, do, _dp):
+        q, k, v, p = ctx.saved_tensors
+        dq, dk, dv = K().mha_bwd(_c(do), q, k, v, p, ctx.n_head, ctx.temperature)
+        return dq, dk, dv, None, None, None
+
+
+def mha_core(q, k, v, mask, n_head, temperature):
+    """q [B,Lq,H*d], k/v [B,Lk,H*d] (dense last dim), mask uint8/bool [B,1|Lq,Lk] or None."""
+    return _MHACore.apply(q, k, v, mask, n_head, temperature)
+
+
+# ------------------------------------------------------------------------------------------------
+# Embedding lookups: Seq2seq.py:188,207; Dec.py:166,223
+# ------------------------------------------------------------------------------------------------
+class _Embedding(Function):
+    @staticmethod
+    def forward(ctx, ids, table, padding_idx):
+        ids = _c(ids)
+        out = K().embedding_fwd(ids, table, rt.compute_dtype())
+        ctx.padding_idx = padding_idx
+        ctx.save_for_backward(ids, table)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ids, table = ctx.saved_tensors
+        dtable = torch.zeros_like(table)
+        K().embedding_bwd(ids.reshape(-1), _c(dout).reshape(-1, table.size(1)), dtable, ctx.padding_idx)
+        return None, dtable, None
+
+
+def embedding(ids, table, padding_idx=PAD):
+    return _Embedding.apply(ids, table, padding_idx)
+
+
+class _AddPosEnc(Function):
+    @staticmethod
+    def forward(ctx, x, pe):
+        return K().add_posenc(_c(x), pe)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, None
+
+
+def add_posenc(x, pe):
+    """x + time_signal[:, :L] (TFEnc.py:82-83, TFDec.py:85-86); pe: fp32 [max_len, D] on the device."""
+    return _AddPosEnc.apply(x, pe)
+
+
+# ------------------------------------------------------------------------------------------------
+# The embedding-passing mix: Seq2seq._get_src_emb, Seq2seq.py:183-199
+#   emb_src = enc_emb_proj(cat(E_static[src], e_dyn)),  Linear(E + D -> D, no bias)
+# ------------------------------------------------------------------------------------------------
+class _Mix(Function):
+    @staticmethod
+    def forward(ctx, ids, table, dyn, weight):
+        b, s = ids.shape
+        ids = _c(ids)
+        dyn2 = _c(dyn).reshape(b * s, -1)
+        cat = K().mix_gather_concat(ids.reshape(-1), table, dyn2)
+        out = K().gemm(cat, rt.operand(weight), trans_b=True)
+        ctx.save_for_backward(ids, table, cat, weight)
+        return out.view(b, s, weight.size(0))
+
+    @staticmethod
+    def backward(ctx, dy):
+        ids, table, cat, weight = ctx.saved_tensors
+        e = table.size(1)
+        d_out = weight.size(0)
+        dy2 = _c(dy).reshape(-1, d_out)
+        w = rt.operand(weight)
+        dtable = ddyn = dw = None
+        if ctx.needs_input_grad[1]:
+            dstatic = K().gemm(dy2, w[:, :e])                     # [n, E]
+            dtable = torch.zeros_like(table)
+            K().embedding_bwd(ids.reshape(-1), dstatic, dtable, PAD)   # padding_idx=PAD, Seq2seq.py:106-107
+        if ctx.needs_input_grad[2]:
+            ddyn = K().gemm(dy2, w[:, e:]).view(ids.size(0), ids.size(1), -1)
+        if ctx.needs_input_grad[3]:
+            dw = K().gemm(dy2, cat, trans_a=True, out_dtype=torch.float32)
+        return None, dtable, ddyn, dw
+
+
+def mix(ids, table, dyn, weight):
+    return _Mix.apply(ids, table, dyn, weight)
+
+
+# ------------------------------------------------------------------------------------------------
+# log-softmax (+arg-max) and the masked NLL: Seq2seq.py:254-255; loss.py:116-132
+# ------------------------------------------------------------------------------------------------
+class _LogSoftmax(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x2 = _c(x).reshape(-1, x.size(-1))
+        y, am = K().log_softmax_fwd(x2, want_argmax=True)
+        ctx.save_for_backward(y)
+        am = am.view(*x.shape[:-1], 1)
+        ctx.mark_non_differentiable(am)
+        return y.view(x.shape), am
+
+    @staticmethod
+    def backward(ctx, dy, _dam):
+        (y,) = ctx.saved_tensors
+        dx = K().log_softmax_bwd(_c(dy).reshape(y.shape), y)
+        return dx.view(dy.shape)
+
+
+def log_softmax_argmax(x):
+    """Returns (log_softmax(x, -1), argmax(x, -1, keepdim=True)) in one pass over the vocabulary."""
+    return _LogSoftmax.apply(x)
+
+
+class _MaskedNLL(Function):
+    @staticmethod
+    def forward(ctx, logp, target, mask):
+        lp = logp if (logp.dim() == 2 and logp.stride(1) == 1) else _c(logp)
+        mask = None if mask is None else _c(mask)
+        target = _c(target)
+        loss = K().masked_nll_fwd(lp, target, mask)
+        ctx.save_for_backward(target, mask)
+        ctx.shape, ctx.dtype = tuple(logp.shape), logp.dtype
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        target, mask = ctx.saved_tensors
+        g32 = _c(g).reshape(1).to(torch.float32)
+        d = K().masked_nll_bwd(g32, target, mask, ctx.shape[0], ctx.shape[1], ctx.dtype)
+        return d, None, None
+
+
+def masked_nll_sum(logp, target, mask):
+    """sum over rows with mask!=0 of -logp[r, target[r]] (loss.py:130-132).  Scalar fp32."""
+    return _MaskedNLL.apply(logp, target, mask)
+
+
+class _FusedSoftmaxNLL(Function):
+    """K17: softmax + masked NLL + gradient in one pass; gradient is formed in forward."""
+
+    @staticmethod
+    def forward(ctx, logits, target, mask, scale, eps):
+        x2 = logits.reshape(-1, logits.size(-1))
+        loss, d = K().softmax_nll_fused(x2, _c(target).reshape(-1), None if mask is None else _c(mask).reshape(-1),
+                                        scale, eps)
+        ctx.save_for_backward(d)
+        ctx.shape = logits.shape
+        return (loss * scale).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        # g is 1 in the training step; anything else is a (rare) scalar rescale of the stored gradient
+        dl = d.view(ctx.shape)
+        if g.numel() == 1:
+            dl = dl * g.to(dl.dtype)
+        return dl, None, None, None, None
+
+
+def fused_softmax_nll(logits, target, mask, scale, eps=0.0):
+    """mean-style loss `scale * sum_mask(lse - logit[target])` with dlogits produced in the same kernel.
+    `scale` is a 1-element fp32 device tensor (e.g. 1 / #non-PAD)."""
+    return _FusedSoftmaxNLL.apply(logits, target, mask, scale, eps)
+
+
+# ------------------------------------------------------------------------------------------------
+# One bidirectional packed LSTM layer of the pyramidal encoder: Enc.py:150-167 (x4)
+# ------------------------------------------------------------------------------------------------
+class _BLSTMLayer(Function):
+    @staticmethod
+    def forward(ctx, x, lens, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, pair,
+                batch_first_out):
+        # x: [T, B, I] time-major, compute dtype; lens int32 [B] valid frames at this layer.
+        k = K()
+        T, B, I = x.shape
+        H = w_hh_f.size(1)
+        x2 = x.reshape(T * B, I)
+        xproj = torch.empty((2, T, B, 4 * H), dtype=x.dtype, device=x.device)
+        k.gemm(x2, rt.operand(w_ih_f), trans_b=True, bias=k.add(b_ih_f, b_hh_f), out=xproj[0].view(T * B, 4 * H))
+        k.gemm(x2, rt.operand(w_ih_r), trans_b=True, bias=k.add(b_ih_r, b_hh_r), out=xproj[1].view(T * B, 4 * H))
+        if batch_first_out:
+            assert pair == 1
+            out = torch.empty((B, T, 2 * H), dtype=x.dtype, device=x.device)
+            ld_t, ld_b = 2 * H, T * 2 * H
+        else:
+            assert T % pair == 0
+            out = torch.empty((T // pair, B, pair * 2 * H), dtype=x.dtype, device=x.device)
+            ld_t, ld_b = B * pair * 2 * H, pair * 2 * H
+        need_grad = any(ctx.needs_input_grad)
+        hs, acts, cs = k.blstm_fwd(xproj, w_hh_f, w_hh_r, lens, out, ld_t, ld_b, pair, save=need_grad)
+        ctx.geom = (T, B, I, H, pair, ld_t, ld_b)
+        ctx.save_for_backward(x2, lens, hs, acts, cs, w_ih_f, w_hh_f, w_ih_r, w_hh_r)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        k = K()
+        x2, lens, hs, acts, cs, w_ih_f, w_hh_f, w_ih_r, w_hh_r = ctx.saved_tensors
+        T, B, I, H, pair, ld_t, ld_b = ctx.geom
+        dg = k.blstm_bwd(_c(dout), ld_t, ld_b, pair, acts, cs, w_hh_f, w_hh_r, lens, x2.dtype)
+        dgf, dgr = dg[0].view(T * B, 4 * H), dg[1].view(T * B, 4 * H)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = k.gemm(dgf, rt.operand(w_ih_f))
+            k.gemm(dgr, rt.operand(w_ih_r), residual=dx, out=dx)
+            dx = dx.view(T, B, I)
+        f32 = torch.float32
+        dw_ih_f = k.gemm(dgf, x2, trans_a=True, out_dtype=f32)
+        dw_ih_r = k.gemm(dgr, x2, trans_a=True, out_dtype=f32)
+        dw_hh_f = k.gemm(dgf, hs[0, :T].reshape(T * B, H), trans_a=True, out_dtype=f32)
+        dw_hh_r = k.gemm(dgr, hs[1, 1:].reshape(T * B, H), trans_a=True, out_dtype=f32)
+        db_f = k.colsum(dgf)
+        db_r = k.colsum(dgr)
+        return dx, None, dw_ih_f, dw_hh_f, db_f, db_f, dw_ih_r, dw_hh_r, db_r, db_r, None, None
+
+
+def blstm_layer(x_tm, lens, weights_f, weights_r, pair, batch_first_out=False):
+    """weights_*: (w_ih, w_hh, b_ih, b_hh) nn.Parameters of one direction of torch.nn.LSTM."""
+    return _BLSTMLayer.apply(x_tm, lens, *weights_f, *weights_r, pair, batch_first_out)
+
+
+# ------------------------------------------------------------------------------------------------
+# LAS attention-LSTM decoder loop: Dec.forward / forward_step / decode, Dec.py:130-233,320-438
+# ------------------------------------------------------------------------------------------------
+class _LASDecoder(Function):
+    """One autograd node for the whole S-step loop; backward is hand-written BPTT.
+
+    inputs : enc [B,Tk,2H] (keys = values), klens int32[B] | None, ids_tf int64[B,S+1] | None (teacher
+             forcing tokens; None = free running from BOS), emb_table, w_att, w_ffn, w_out, b_out,
+             then (w_ih, w_hh, b_ih, b_hh) for each of the `n_layers` uni-LSTMs.
+    outputs: embs [B,S,D] (the dynamic embedding = pre-softmax `cell_value`, Dec.py:433),
+             logps [B,S,V] | empty, symbols int64 [B,S], lengths int32 [B].
+    """
+
+    @staticmethod
+    def forward(ctx, enc, klens, ids_tf, n_steps, need_logps, emb_table, w_att, w_ffn, w_out, b_out,
+                *lstm_params):
+        k = K()
+        dt = enc.dtype
+        dev = enc.device
+        enc = _c(enc)
+        B, Tk, H2 = enc.shape
+        S = n_steps
+        E = emb_table.size(1)
+        D = w_ffn.size(0)
+        V = w_out.size(0)
+        n_layers = len(lstm_params) // 4
+        lp = [lstm_params[4 * i:4 * i + 4] for i in range(n_layers)]
+        wih = [rt.operand(p[0]) for p in lp]
+        whh = [rt.operand(p[1]) for p in lp]
+        bias = [k.add(p[2], p[3]) for p in lp]
+        wf = rt.operand(w_ffn)
+        wo = rt.operand(w_out)
+        # step-invariant bilinear key projection, hoisted out of the loop (attention.py:192)
+        wk = k.gemm(enc.view(B * Tk, H2), rt.operand(w_att), trans_b=True).view(B, Tk, D)
+
+        z = lambda *s, dtype=dt: torch.zeros(s, dtype=dtype, device=dev)
+        e = lambda *s, dtype=dt: torch.empty(s, dtype=dtype, device=dev)
+        CV = z(S + 1, B, D)                                   # CV[s+1] = cell_value of step s; CV[0] = 0
+        Hst = [z(S + 1, B, D) for _ in range(n_layers)]
+        Cst = [z(S + 1, B, D, dtype=torch.float32) for _ in range(n_layers)]
+        ACT = [e(S, B, 4 * D, dtype=torch.float32) for _ in range(n_layers)]
+        RES = [e(S, B, D) if 0 < i < n_layers - 1 else None for i in range(n_layers)]   # Dec.py:417-418
+        CTX = e(S, B, H2)
+        PROBS = e(S, B, Tk, dtype=torch.float32)
+        EMB = e(S, B, E)
+        LOGITS = e(S, B, V)
+        SYM = e(S, B, dtype=torch.int64)
+        lengths = torch.full((B,), S + 1, dtype=torch.int32, device=dev)       # Dec.py:163
+        if ids_tf is None:
+            IDS = e(S + 1, B, dtype=torch.int64)
+            IDS[0].fill_(BOS)                                                  # Dec.py:158-160,199
+            ids_in = IDS[:S]
+            sym_dst = IDS[1:]
+        else:
+            ids_in = ids_tf.t()[:S].contiguous()
+            sym_dst = SYM
+        G = e(B, 4 * D)
+        for s in range(S):
+            k.embedding_fwd(ids_in[s], emb_table, dt, out=EMB[s])
+            x = EMB[s]
+            for i in range(n_layers):
+                # gates = x W_ih^T + b_ih + b_hh + h W_hh^T   (torch.nn.LSTM step, Dec.py:393-415)
+                if i == 0:      # x = cat(emb, prev cell_value) (Dec.py:383) without materialising the concat
+                    k.gemm(x, wih[0][:, :E], trans_b=True, bias=bias[0], out=G)
+                    if s > 0:
+                        k.gemm(CV[s], wih[0][:, E:], trans_b=True, residual=G, out=G)
+                else:
+                    k.gemm(x, wih[i], trans_b=True, bias=bias[i], out=G)
+                if s > 0:
+                    k.gemm(Hst[i][s], whh[i], trans_b=True, residual=G, out=G)
+                res_in = x if RES[i] is not None else None
+                _, _, _, out_res = k.lstm_cell_fwd(G, Cst[i][s], residual=res_in, h_out=Hst[i][s + 1],
+                                                   c_out=Cst[i][s + 1], acts_out=ACT[i][s],
+                                                   res_out=RES[i][s] if RES[i] is not None else None)
+                x = out_res if out_res is not None else Hst[i][s + 1]
+            dec_out = x
+            k.las_attn_fwd(dec_out, wk, enc, klens, ctx_out=CTX[s], probs_out=PROBS[s])
+            # cell_value = acous_ffn(cat(context, dec_out)) (Dec.py:431-433), again without the concat
+            k.gemm(CTX[s], wf[:, :H2], trans_b=True, out=CV[s + 1])
+            k.gemm(dec_out, wf[:, H2:], trans_b=True, residual=CV[s + 1], out=CV[s + 1])
+            k.gemm(CV[s + 1], wo, trans_b=True, bias=b_out, out=LOGITS[s])       # Dec.py:434
+            k.argmax_rows(LOGITS[s], sym_dst[s])                                 # Dec.py:331
+            k.las_update_lengths(sym_dst[s], lengths, s)                         # Dec.py:334-340
+        if ids_tf is None:
+            SYM = IDS[1:]
+        embs = k.transpose01(CV[1:])                                             # [B,S,D]
+        if need_logps:
+            logp_tm, _ = k.log_softmax_fwd(LOGITS.view(S * B, V))
+            logps = k.transpose01(logp_tm.view(S, B, V))
+        else:
+            logp_tm = None
+            logps = torch.empty(0, dtype=dt, device=dev)
+        symbols = SYM.t().contiguous()
+        ctx.geom = (B, Tk, H2, S, E, D, V, n_layers)
+        ctx.need_logps = need_logps
+        ctx.has_klens = klens is not None
+        ctx.n_fixed = 10
+        saved = [enc, klens, ids_in.contiguous(), wk, CV, CTX, PROBS, EMB, logp_tm, emb_table, w_att,
+                 w_ffn, w_out]
+        saved += Hst + Cst + ACT + [r for r in RES if r is not None]
+        saved += list(lstm_params)
+        ctx.res_layers = [i for i in range(n_layers) if RES[i] is not None]
+        ctx.save_for_backward(*saved)
+        ctx.mark_non_differentiable(symbols, lengths)
+        return embs, logps, symbols, lengths
+
+    @staticmethod
+    def backward(ctx, d_embs, d_logps, _ds, _dl):
+        k = K()
+        B, Tk, H2, S, E, D, V, n_layers = ctx.geom
+        sv = list(ctx.saved_tensors)
+        (enc, klens, ids_in, wk, CV, CTX, PROBS, EMB, logp_tm, emb_table, w_att, w_ffn, w_out) = sv[:13]
+        p = 13
+        Hst = sv[p:p + n_layers]; p += n_layers
+        Cst = sv[p:p + n_layers]; p += n_layers
+        ACT = sv[p:p + n_layers]; p += n_layers
+        RES = [None] * n_layers
+        for i in ctx.res_layers:
+            RES[i] = sv[p]; p += 1
+        lstm_params = sv[p:]
+        lp = [lstm_params[4 * i:4 * i + 4] for i in range(n_layers)]
+        dt, dev, f32 = enc.dtype, enc.device, torch.float32
+        wih = [rt.operand(q[0]) for q in lp]
+        whh = [rt.operand(q[1]) for q in lp]
+        wf = rt.operand(w_ffn)
+        e = lambda *s, dtype=dt: torch.empty(s, dtype=dtype, device=dev)
+
+        # DCV[s] accumulates the total gradient w.r.t. cell_value of step s
+        if d_embs is not None:
+            DCV = k.transpose01(_c(d_embs))                                      # [S,B,D]
+        else:
+            DCV = torch.zeros((S, B, D), dtype=dt, device=dev)
+        dw_out = db_out = None
+        if ctx.need_logps and d_logps is not None and d_logps.numel() > 0:
+            dlogits = k.log_softmax_bwd(k.transpose01(_c(d_logps)).view(S * B, V), logp_tm)
+            k.gemm(dlogits, rt.operand(w_out), residual=DCV.view(S * B, D), out=DCV.view(S * B, D))
+            dw_out = k.gemm(dlogits, CV[1:].reshape(S * B, D), trans_a=True, out_dtype=f32)
+            db_out = k.colsum(dlogits)
+
+        DG = [e(S, B, 4 * D) for _ in range(n_layers)]
+        DCTX = e(S, B, H2)
+        DSC = e(S, B, Tk, dtype=f32)
+        DEMB = e(S, B, E)
+        dh_next: List[Optional[torch.Tensor]] = [None] * n_layers
+        dc_next: List[Optional[torch.Tensor]] = [None] * n_layers
+        for s in reversed(range(S)):
+            dcv = DCV[s]
+            # cell_value = ctx Wf[:, :2H]^T + dec_out Wf[:, 2H:]^T
+            k.gemm(dcv, wf[:, :H2], out=DCTX[s])
+            d_out = k.gemm(dcv, wf[:, H2:])                                      # [B,D]
+            _, dq_att = k.las_attn_bwd(DCTX[s], wk, enc, PROBS[s], dscore_out=DSC[s])
+            # dec_out = y_{n-1};  y_i = h_i (+ y_{i-1} on residual layers, Dec.py:417-418)
+            dy_parts = [d_out, dq_att]
+            for i in reversed(range(n_layers)):
+                _, dc_next[i] = k.lstm_cell_bwd(dy_parts + [dh_next[i]], dc_next[i], ACT[i][s], Cst[i][s],
+                                                Cst[i][s + 1], dt, dgates_out=DG[i][s])
+                dgi = DG[i][s]
+                if s > 0:
+                    dh_next[i] = k.gemm(dgi, whh[i])
+                if i > 0:
+                    if RES[i] is not None:      # the skip connection carries dy_i straight to y_{i-1}
+                        skip = dy_parts[0] if len(dy_parts) == 1 else k.add(dy_parts[0], dy_parts[1])
+                        dy_parts = [k.gemm(dgi, wih[i], residual=skip)]
+                    else:
+                        dy_parts = [k.gemm(dgi, wih[i])]
+                else:
+                    k.gemm(dgi, wih[0][:, :E], out=DEMB[s])
+                    if s > 0:
+                        k.gemm(dgi, wih[0][:, E:], residual=DCV[s - 1], out=DCV[s - 1])
+
+        SB = S * B
+        grads_lstm = []
+        for i in range(n_layers):
+            dg2 = DG[i].view(SB, 4 * D)
+            if i == 0:
+                dw_ih = torch.empty_like(lp[0][0])
+                k.gemm(dg2, EMB.view(SB, E), trans_a=True, out=dw_ih[:, :E])
+                k.gemm(dg2, CV[:S].reshape(SB, D), trans_a=True, out=dw_ih[:, E:])
+            else:
+                below = RES[i - 1] if RES[i - 1] is not None else Hst[i - 1][1:]
+                dw_ih = k.gemm(dg2, below.reshape(SB, D), trans_a=True, out_dtype=f32)
+            dw_hh = k.gemm(dg2, Hst[i][:S].reshape(SB, D), trans_a=True, out_dtype=f32)
+            db = k.colsum(dg2)
+            grads_lstm += [dw_ih, dw_hh, db, db]
+        dec_out_stack = RES[n_layers - 1] if RES[n_layers - 1] is not None else Hst[n_layers - 1][1:]
+        dcv2 = DCV.view(SB, D)
+        dw_ffn = torch.empty_like(w_ffn)
+        k.gemm(dcv2, CTX.view(SB, H2), trans_a=True, out=dw_ffn[:, :H2])
+        k.gemm(dcv2, dec_out_stack.reshape(SB, D), trans_a=True, out=dw_ffn[:, H2:])
+        d_table = torch.zeros_like(emb_table)
+        k.embedding_bwd(ids_in.reshape(-1), DEMB.view(SB, E), d_table, PAD)      # Dec.py:80-81 padding_idx
+        # keys / values: d wk[b] = dscore[:, b]^T dec_out[:, b];  d vals[b] = probs[:, b]^T dctx[:, b]
+        dsc = k.cast(DSC, dt).permute(1, 0, 2)                                   # [B][S,Tk]
+        prb = k.cast(PROBS, dt).permute(1, 0, 2)
+        d_wk = k.gemm(dsc, dec_out_stack.permute(1, 0, 2), trans_a=True)         # [B,Tk,D]
+        d_enc = k.gemm(prb, DCTX.permute(1, 0, 2), trans_a=True)                 # [B,Tk,2H]
+        k.gemm(d_wk.view(B * Tk, D), rt.operand(w_att), residual=d_enc.view(B * Tk, H2),
+               out=d_enc.view(B * Tk, H2))
+        dw_att = k.gemm(d_wk.view(B * Tk, D), enc.view(B * Tk, H2), trans_a=True, out_dtype=f32)
+        return (d_enc, None, None, None, None, d_table, dw_att, dw_ffn, dw_out, db_out, *grads_lstm)
+
+
+def las_decoder(enc, klens, ids_tf, n_steps, need_logps, emb_table, w_att, w_ffn, w_out, b_out,
+                lstm_params):
+    flat = [t for layer in lstm_params for t in layer]
+    return _LASDecoder.apply(enc, klens, ids_tf, n_steps, need_logps, emb_table, w_att, w_ffn, w_out,
+                             b_out, *flat)

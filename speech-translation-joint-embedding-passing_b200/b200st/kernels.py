@@ -1,0 +1,446 @@
+"""Tensor-level wrappers over the C ABI (include/b200st.h).
+
+`CudaKernels` is the only implementation shipped: every method launches hand-written sm_100a kernels from
+libb200st.so on the current CUDA stream.  PyTorch is used for device memory (torch.empty) and the stream
+handle only.  Tests may install a different object with the same methods via `set_backend()` to exercise
+the host-side orchestration on a machine without a GPU; nothing in the product does.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import lib as _lib
+
+F32, BF16 = 0, 1
+
+
+def _dt(t_or_dtype) -> int:
+    d = t_or_dtype.dtype if torch.is_tensor(t_or_dtype) else t_or_dtype
+    if d == torch.float32:
+        return F32
+    if d == torch.bfloat16:
+        return BF16
+    raise TypeError(f'b200st kernels take float32 or bfloat16 activations, got {d}')
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """2-D tensor whose last dim is dense; returned as-is (row stride may exceed the width)."""
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.size(1) == 1), (t.shape, t.stride())
+    return t
+
+
+class CudaKernels:
+    name = 'cuda'
+
+    def __init__(self):
+        self.lib = _lib.load()
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    @staticmethod
+    def _stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    @staticmethod
+    def _need_cuda(*ts):
+        for t in ts:
+            if t is not None and not t.is_cuda:
+                raise RuntimeError('b200st kernels are CUDA-only (sm_100a); got a CPU tensor. '
+                                   'There is no CPU fallback.')
+
+    def launch_count(self) -> int:
+        return int(self.lib.b200st_launch_count())
+
+    # -- GEMM -------------------------------------------------------------------------------------
+    def gemm(self, a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=None,
+             relu=False, residual=None, alpha=1.0):
+        """out = relu?(alpha * op(a) @ op(b) + bias) + residual.  a, b: 2-D (row-strided) or 3-D batched
+        (batch stride arbitrary).  op(a) is [M,K], op(b) is [K,N]."""
+        self._need_cuda(a, b, out, bias, residual)
+        batched = a.dim() == 3
+        if batched:
+            assert b.dim() == 3 and a.size(0) == b.size(0)
+            nb = a.size(0)
+            a2, b2 = a[0], b[0]
+            sa, sb = a.stride(0), b.stride(0)
+        else:
+            nb, a2, b2, sa, sb = 1, a, b, 0, 0
+        _rows(a2), _rows(b2)
+        M, K = (a2.size(1), a2.size(0)) if trans_a else (a2.size(0), a2.size(1))
+        Kb, N = (b2.size(1), b2.size(0)) if trans_b else (b2.size(0), b2.size(1))
+        assert K == Kb, f'gemm inner dims differ: {K} vs {Kb}'
+        assert a.dtype == b.dtype
+        if out is None:
+            od = out_dtype or (residual.dtype if residual is not None else a.dtype)
+            out = torch.empty((nb, M, N) if batched else (M, N), dtype=od, device=a.device)
+        o2 = out[0] if batched else out
+        _rows(o2)
+        assert o2.size(0) == M and o2.size(1) == N, (o2.shape, M, N)
+        so = out.stride(0) if batched else 0
+        if residual is not None:
+            r2 = residual[0] if batched else residual
+            _rows(r2)
+            assert residual.dtype == out.dtype and r2.shape == o2.shape
+            ldr, sr = r2.stride(0), (residual.stride(0) if batched else 0)
+        else:
+            ldr, sr = 0, 0
+        if bias is not None:
+            assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+        _lib.check(self.lib.b200st_gemm(
+            _dt(a), _dt(out), int(trans_a), int(trans_b), M, N, K, float(alpha),
+            _p(a), a2.stride(0), sa, _p(b), b2.stride(0), sb, _p(out), o2.stride(0), so,
+            _p(residual), ldr, sr, _p(bias), int(relu), nb, self._stream()), 'gemm')
+        return out
+
+    # -- LayerNorm --------------------------------------------------------------------------------
+    def layernorm_fwd(self, x, gamma, beta, eps, save_stats=True):
+        self._need_cuda(x, gamma, beta)
+        assert x.is_contiguous()
+        rows, cols = x.numel() // x.size(-1), x.size(-1)
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+        _lib.check(self.lib.b200st_layernorm_fwd(_dt(x), _p(x), _p(gamma), _p(beta), _p(y), _p(mean),
+                                                 _p(rstd), rows, cols, float(eps), self._stream()),
+                   'layernorm_fwd')
+        return y, mean, rstd
+
+    def layernorm_bwd(self, dy, x, gamma, mean, rstd, dgamma, dbeta):
+        assert dy.is_contiguous() and x.is_contiguous()
+        rows, cols = x.numel() // x.size(-1), x.size(-1)
+        dx = torch.empty_like(x)
+        _lib.check(self.lib.b200st_layernorm_bwd(_dt(x), _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd),
+                                                 _p(dx), _p(dgamma), _p(dbeta), rows, cols,
+                                                 self._stream()), 'layernorm_bwd')
+        return dx
+
+    # -- multi-head attention core ----------------------------------------------------------------
+    @staticmethod
+    def _bld(t):
+        """[B, L, HD] view with dense last dim and stride(0) == L * stride(1)."""
+        assert t.dim() == 3 and t.stride(2) == 1 and (t.size(0) == 1 or t.stride(0) == t.size(1) * t.stride(1)), \
+            (t.shape, t.stride())
+        return t.stride(1)
+
+    def mha_fwd(self, q, k, v, mask, n_head, temperature, want_probs=True):
+        self._need_cuda(q, k, v, mask)
+        B, Lq, HD = q.shape
+        Lk = k.size(1)
+        d = HD // n_head
+        o = torch.empty((B, Lq, HD), dtype=q.dtype, device=q.device)
+        p = torch.empty((B, n_head, Lq, Lk), dtype=q.dtype, device=q.device) if want_probs else None
+        if mask is not None:
+            assert mask.dtype in (torch.uint8, torch.bool) and mask.dim() == 3 and mask.stride(2) == 1
+            assert mask.size(0) == B and mask.size(2) == Lk and mask.size(1) in (1, Lq)
+            msb, msq = mask.stride(0), (mask.stride(1) if mask.size(1) == Lq and Lq > 1 else 0)
+            if mask.size(1) == 1:
+                msq = 0
+        else:
+            msb = msq = 0
+        _lib.check(self.lib.b200st_mha_fwd(_dt(q), _p(q), self._bld(q), _p(k), self._bld(k), _p(v),
+                                           self._bld(v), _p(mask), msb, msq, _p(o), HD, _p(p), B,
+                                           n_head, Lq, Lk, d, float(temperature), self._stream()),
+                   'mha_fwd')
+        return o, p
+
+    def mha_bwd(self, dout, q, k, v, p, n_head, temperature):
+        B, Lq, HD = q.shape
+        Lk = k.size(1)
+        d = HD // n_head
+        assert dout.is_contiguous()
+        ds = torch.empty_like(p)
+        dq = torch.empty((B, Lq, HD), dtype=q.dtype, device=q.device)
+        dk = torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device)
+        dv = torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device)
+        _lib.check(self.lib.b200st_mha_bwd(_dt(q), _p(dout), HD, _p(q), self._bld(q), _p(k),
+                                           self._bld(k), _p(v), self._bld(v), _p(p), _p(ds), _p(dq), HD,
+                                           _p(dk), HD, _p(dv), HD, B, n_head, Lq, Lk, d,
+                                           float(temperature), self._stream()), 'mha_bwd')
+        return dq, dk, dv
+
+    # -- LSTM -------------------------------------------------------------------------------------
+    def lstm_cell_fwd(self, gates, c_prev, residual=None, save_acts=True, h_out=None, c_out=None,
+                      acts_out=None, res_out=None):
+        self._need_cuda(gates, c_prev, residual)
+        B, H4 = gates.shape
+        H = H4 // 4
+        assert gates.is_contiguous()
+        h = h_out if h_out is not None else torch.empty((B, H), dtype=gates.dtype, device=gates.device)
+        c = c_out if c_out is not None else torch.empty((B, H), dtype=torch.float32, device=gates.device)
+        assert h.is_contiguous() and c.is_contiguous()
+        acts = acts_out if acts_out is not None else (
+            torch.empty((B, H4), dtype=torch.float32, device=gates.device) if save_acts else None)
+        out_res = None
+        if residual is not None:
+            out_res = res_out if res_out is not None else torch.empty_like(h)
+            assert residual.is_contiguous() and out_res.is_contiguous()
+        _lib.check(self.lib.b200st_lstm_cell_fwd(_dt(gates), _p(gates), _p(c_prev), _p(h), _p(c),
+                                                 _p(acts), _p(residual), _p(out_res), B, H,
+                                                 self._stream()), 'lstm_cell_fwd')
+        return h, c, acts, out_res
+
+    def lstm_cell_bwd(self, dhs: Sequence[Optional[torch.Tensor]], dc_next, acts, c_prev, c, dtype,
+                      dgates_out=None):
+        dhs = [d for d in dhs if d is not None]
+        assert 1 <= len(dhs) <= 3 and all(d.is_contiguous() for d in dhs)
+        dhs = dhs + [None] * (3 - len(dhs))
+        B, H = c.shape
+        dgates = dgates_out if dgates_out is not None else torch.empty((B, 4 * H), dtype=dtype, device=c.device)
+        assert dgates.is_contiguous()
+        dc_prev = torch.empty((B, H), dtype=torch.float32, device=c.device)
+        _lib.check(self.lib.b200st_lstm_cell_bwd(_dt(dtype), _p(dhs[0]), _p(dhs[1]), _p(dhs[2]),
+                                                 _p(dc_next), _p(acts), _p(c_prev), _p(c), _p(dgates),
+                                                 _p(dc_prev), B, H, self._stream()), 'lstm_cell_bwd')
+        return dgates, dc_prev
+
+    def blstm_fwd(self, xproj, w_hh_f, w_hh_r, lens, out, out_ld_t, out_ld_b, pair, save=True):
+        self._need_cuda(xproj, w_hh_f, w_hh_r, lens, out)
+        _, T, B, H4 = xproj.shape
+        H = H4 // 4
+        assert xproj.is_contiguous() and w_hh_f.is_contiguous() and w_hh_r.is_contiguous()
+        assert lens.dtype == torch.int32 and out.dtype == xproj.dtype
+        dev = xproj.device
+        hs = torch.empty((2, T + 1, B, H), dtype=xproj.dtype, device=dev) if save else None
+        acts = torch.empty((2, T, B, H4), dtype=torch.float32, device=dev) if save else None
+        cs = torch.empty((2, T, B, H), dtype=torch.float32, device=dev) if save else None
+        _lib.check(self.lib.b200st_blstm_fwd(_dt(xproj), _p(xproj), _p(w_hh_f), _p(w_hh_r), _p(lens),
+                                             _p(out), out_ld_t, out_ld_b, pair, _p(hs), _p(acts),
+                                             _p(cs), T, B, H, self._stream()), 'blstm_fwd')
+        return hs, acts, cs
+
+    def blstm_bwd(self, dout, out_ld_t, out_ld_b, pair, acts, cs, w_hh_f, w_hh_r, lens, dtype):
+        _, T, B, H = cs.shape
+        assert dout.is_contiguous()
+        dgates = torch.empty((2, T, B, 4 * H), dtype=dtype, device=cs.device)
+        _lib.check(self.lib.b200st_blstm_bwd(_dt(dtype), _p(dout), out_ld_t, out_ld_b, pair, _p(acts),
+                                             _p(cs), _p(w_hh_f), _p(w_hh_r), _p(lens), _p(dgates), T, B,
+                                             H, self._stream()), 'blstm_bwd')
+        return dgates
+
+    # -- LAS attention / decode helpers -------------------------------------------------------------
+    def las_attn_fwd(self, q, wk, vals, klens, ctx_out=None, probs_out=None):
+        self._need_cuda(q, wk, vals, klens)
+        B, Tk, D = wk.shape
+        Dv = vals.size(2)
+        assert q.is_contiguous() and wk.is_contiguous() and vals.is_contiguous()
+        ctx = ctx_out if ctx_out is not None else torch.empty((B, Dv), dtype=q.dtype, device=q.device)
+        probs = probs_out if probs_out is not None else torch.empty((B, Tk), dtype=torch.float32, device=q.device)
+        assert ctx.is_contiguous() and probs.is_contiguous()
+        _lib.check(self.lib.b200st_las_attn_fwd(_dt(q), _p(q), _p(wk), _p(vals), _p(klens), _p(ctx),
+                                                _p(probs), B, Tk, D, Dv, self._stream()),
+                   'las_attn_fwd')
+        return ctx, probs
+
+    def las_attn_bwd(self, dctx, wk, vals, probs, dscore_out=None):
+        B, Tk, D = wk.shape
+        Dv = vals.size(2)
+        assert dctx.is_contiguous() and probs.is_contiguous()
+        dscore = dscore_out if dscore_out is not None else torch.empty((B, Tk), dtype=torch.float32, device=wk.device)
+        assert dscore.is_contiguous()
+        dq = torch.empty((B, D), dtype=wk.dtype, device=wk.device)
+        _lib.check(self.lib.b200st_las_attn_bwd(_dt(wk), _p(dctx), _p(wk), _p(vals), _p(probs),
+                                                _p(dscore), _p(dq), B, Tk, D, Dv, self._stream()),
+                   'las_attn_bwd')
+        return dscore, dq
+
+    def argmax_rows(self, x, idx_out):
+        """x [rows, cols] (row-strided); idx_out: int64 1-D view (any stride) of length rows."""
+        self._need_cuda(x, idx_out)
+        _rows(x)
+        assert idx_out.dtype == torch.int64 and idx_out.dim() == 1 and idx_out.numel() == x.size(0)
+        _lib.check(self.lib.b200st_argmax_rows(_dt(x), _p(x), x.stride(0), x.size(0), x.size(1),
+                                               _p(idx_out), idx_out.stride(0) if idx_out.numel() > 1 else 1,
+                                               self._stream()), 'argmax_rows')
+        return idx_out
+
+    def las_update_lengths(self, sym, lengths, step):
+        assert sym.dtype == torch.int64 and sym.dim() == 1 and lengths.dtype == torch.int32
+        _lib.check(self.lib.b200st_las_update_lengths(_p(sym), sym.stride(0) if sym.numel() > 1 else 1,
+                                                      _p(lengths), int(step), sym.numel(),
+                                                      self._stream()), 'las_update_lengths')
+
+    # -- embeddings / mix ---------------------------------------------------------------------------
+    def embedding_fwd(self, ids, table, dtype, out=None):
+        self._need_cuda(ids, table, out)
+        assert ids.dtype == torch.int64 and ids.is_contiguous() and table.is_contiguous()
+        n, dim = ids.numel(), table.size(1)
+        if out is None:
+            out = torch.empty(tuple(ids.shape) + (dim,), dtype=dtype, device=table.device)
+            ld = dim
+        else:
+            assert out.dim() == 2 and out.stride(1) == 1 and out.size(0) == n
+            ld = out.stride(0)
+        _lib.check(self.lib.b200st_embedding_fwd(_dt(out), _p(ids), _p(table), _p(out), ld, n, dim,
+                                                 table.size(0), self._stream()), 'embedding_fwd')
+        return out
+
+    def embedding_bwd(self, ids, dout, dtable, padding_idx):
+        """dtable (fp32, pre-zeroed or running) += scatter of dout rows; dout 2-D row-strided."""
+        assert ids.is_contiguous() and dtable.dtype == torch.float32 and dtable.is_contiguous()
+        _rows(dout)
+        n, dim = ids.numel(), dtable.size(1)
+        assert dout.size(0) == n and dout.size(1) == dim
+        _lib.check(self.lib.b200st_embedding_bwd(_dt(dout), _p(ids), _p(dout), dout.stride(0),
+                                                 _p(dtable), n, dim, dtable.size(0),
+                                                 -1 if padding_idx is None else int(padding_idx),
+                                                 self._stream()), 'embedding_bwd')
+        return dtable
+
+    def mix_gather_concat(self, ids, table, dyn):
+        """cat[i] = [table[ids[i]], dyn[i]];  ids [n], dyn [n, D] row-strided -> [n, E + D]."""
+        self._need_cuda(ids, table, dyn)
+        _rows(dyn)
+        n, E, D = ids.numel(), table.size(1), dyn.size(1)
+        cat = torch.empty((n, E + D), dtype=dyn.dtype, device=dyn.device)
+        _lib.check(self.lib.b200st_mix_gather_concat(_dt(dyn), _p(ids), _p(table), _p(dyn),
+                                                     dyn.stride(0), _p(cat), n, E, D, table.size(0),
+                                                     self._stream()), 'mix_gather_concat')
+        return cat
+
+    # -- softmax / loss -----------------------------------------------------------------------------
+    def log_softmax_fwd(self, x, want_argmax=False):
+        self._need_cuda(x)
+        assert x.dim() == 2 and x.is_contiguous()
+        y = torch.empty_like(x)
+        am = torch.empty(x.size(0), dtype=torch.int64, device=x.device) if want_argmax else None
+        _lib.check(self.lib.b200st_log_softmax_fwd(_dt(x), _p(x), _p(y), x.size(0), x.size(1), _p(am),
+                                                   self._stream()), 'log_softmax_fwd')
+        return y, am
+
+    def log_softmax_bwd(self, dy, y):
+        assert dy.is_contiguous() and y.is_contiguous() and dy.dim() == 2
+        dx = torch.empty_like(y)
+        _lib.check(self.lib.b200st_log_softmax_bwd(_dt(y), _p(dy), _p(y), _p(dx), y.size(0), y.size(1),
+                                                   self._stream()), 'log_softmax_bwd')
+        return dx
+
+    def masked_nll_fwd(self, logp, target, mask):
+        self._need_cuda(logp, target, mask)
+        _rows(logp)
+        assert target.dtype == torch.int64 and target.is_contiguous()
+        if mask is not None:
+            assert mask.dtype in (torch.uint8, torch.bool) and mask.is_contiguous()
+        loss = torch.zeros(1, dtype=torch.float32, device=logp.device)
+        _lib.check(self.lib.b200st_masked_nll_fwd(_dt(logp), _p(logp), logp.stride(0), _p(target),
+                                                  _p(mask), _p(loss), logp.size(0), logp.size(1),
+                                                  self._stream()), 'masked_nll_fwd')
+        return loss
+
+    def masked_nll_bwd(self, gscale, target, mask, rows, cols, dtype):
+        assert gscale.dtype == torch.float32
+        d = torch.empty((rows, cols), dtype=dtype, device=target.device)
+        _lib.check(self.lib.b200st_masked_nll_bwd(_dt(dtype), _p(gscale), _p(target), _p(mask), _p(d),
+                                                  cols, rows, cols, self._stream()), 'masked_nll_bwd')
+        return d
+
+    def softmax_nll_fused(self, logits, target, mask, scale, eps=0.0, inplace=False):
+        """Returns (loss_sum[1], dlogits) with dlogits = (softmax - onehot) * mask * scale[0]."""
+        self._need_cuda(logits, target, mask, scale)
+        _rows(logits)
+        assert scale.dtype == torch.float32 and target.is_contiguous()
+        loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
+        d = logits if inplace else torch.empty((logits.size(0), logits.size(1)), dtype=logits.dtype,
+                                               device=logits.device)
+        _lib.check(self.lib.b200st_softmax_nll_fused(_dt(logits), _p(logits), logits.stride(0),
+                                                     _p(target), _p(mask), _p(scale), float(eps),
+                                                     _p(loss), _p(d), d.stride(0), logits.size(0),
+                                                     logits.size(1), self._stream()),
+                   'softmax_nll_fused')
+        return loss, d
+
+    # -- glue ---------------------------------------------------------------------------------------
+    def add(self, a, b, out=None):
+        self._need_cuda(a, b)
+        assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape and a.dtype == b.dtype
+        out = torch.empty_like(a) if out is None else out
+        _lib.check(self.lib.b200st_add(_dt(a), _p(a), _p(b), _p(out), a.numel(), self._stream()), 'add')
+        return out
+
+    def add_posenc(self, x, pe):
+        """x [B, L, D] + pe[:L] (fp32 table [>=L, D])."""
+        self._need_cuda(x, pe)
+        B, L, D = x.shape
+        assert x.is_contiguous() and pe.is_contiguous() and pe.size(0) >= L and pe.size(1) == D
+        out = torch.empty_like(x)
+        _lib.check(self.lib.b200st_add_posenc(_dt(x), _p(x), _p(pe), _p(out), B, L, D, self._stream()),
+                   'add_posenc')
+        return out
+
+    def transpose01(self, x, out_dtype=None):
+        self._need_cuda(x)
+        assert x.dim() == 3 and x.is_contiguous()
+        A, Bd, C = x.shape
+        out = torch.empty((Bd, A, C), dtype=out_dtype or x.dtype, device=x.device)
+        _lib.check(self.lib.b200st_transpose01(_dt(x), _dt(out), _p(x), _p(out), A, Bd, C,
+                                               self._stream()), 'transpose01')
+        return out
+
+    def cast(self, x, dtype):
+        self._need_cuda(x)
+        if x.dtype == dtype:
+            return x
+        assert x.is_contiguous()
+        out = torch.empty(x.shape, dtype=dtype, device=x.device)
+        _lib.check(self.lib.b200st_cast(_dt(x), _dt(out), _p(x), _p(out), x.numel(), self._stream()),
+                   'cast')
+        return out
+
+    def colsum(self, x, out=None, accumulate=False):
+        self._need_cuda(x)
+        _rows(x)
+        if out is None:
+            out = torch.empty(x.size(1), dtype=torch.float32, device=x.device)
+            accumulate = False
+        _lib.check(self.lib.b200st_colsum(_dt(x), _p(x), x.stride(0), _p(out), x.size(0), x.size(1),
+                                          int(accumulate), self._stream()), 'colsum')
+        return out
+
+    def relu_bwd(self, dy, y):
+        assert dy.is_contiguous() and y.is_contiguous()
+        dx = torch.empty_like(dy)
+        _lib.check(self.lib.b200st_relu_bwd(_dt(dy), _p(dy), _p(y), _p(dx), dy.numel(), self._stream()),
+                   'relu_bwd')
+        return dx
+
+    def token_mask(self, ids, pad, causal):
+        self._need_cuda(ids)
+        assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.dim() == 2
+        B, L = ids.shape
+        mask = torch.empty((B, L if causal else 1, L), dtype=torch.uint8, device=ids.device)
+        _lib.check(self.lib.b200st_token_mask(_p(ids), _p(mask), B, L, int(pad), int(causal),
+                                              self._stream()), 'token_mask')
+        return mask
+
+    def length_mask(self, lengths, L):
+        self._need_cuda(lengths)
+        assert lengths.dtype == torch.int32 and lengths.is_contiguous()
+        B = lengths.numel()
+        mask = torch.empty((B, 1, L), dtype=torch.uint8, device=lengths.device)
+        _lib.check(self.lib.b200st_length_mask(_p(lengths), _p(mask), B, L, self._stream()),
+                   'length_mask')
+        return mask
+
+
+_backend = None
+
+
+def K():
+    """The kernel backend.  Created on first use; raises if libb200st.so was not built."""
+    global _backend
+    if _backend is None:
+        _backend = CudaKernels()
+    return _backend
+
+
+def set_backend(obj):
+    """TEST HOOK ONLY: install an object implementing the CudaKernels methods (see tests/fake_kernels.py)."""
+    global _backend
+    old = _backend
+    _backend = obj
+    return old

@@ -1,0 +1,48 @@
+"""Process-wide numerical mode and cached low-precision operands.
+
+Compute dtype: 'fp32' (exact CUDA-core GEMMs; the 1e-4 parity mode) or 'bf16' (tcgen05 tensor-core GEMMs,
+fp32 accumulation; the 2e-2 mode the benchmark runs).  nn.Parameters always stay fp32 and keep their
+reference names; in bf16 mode kernels read a bf16 shadow copy that is refreshed whenever the parameter's
+version counter changes (optimizer step, load_state_dict), so no re-packed weight ever escapes state_dict.
+"""
+from __future__ import annotations
+
+import os
+import weakref
+
+import torch
+
+_DTYPES = {'fp32': torch.float32, 'float32': torch.float32, 'bf16': torch.bfloat16,
+           'bfloat16': torch.bfloat16}
+_compute_dtype = _DTYPES[os.environ.get('B200ST_DTYPE', 'fp32').lower()]
+_cache = {}
+
+
+def set_compute_dtype(d):
+    global _compute_dtype
+    _compute_dtype = _DTYPES[d.lower()] if isinstance(d, str) else d
+    _cache.clear()
+
+
+def compute_dtype() -> torch.dtype:
+    return _compute_dtype
+
+
+def operand(param: torch.Tensor) -> torch.Tensor:
+    """The tensor a GEMM should read for `param` in the current compute dtype."""
+    p = param.detach()
+    if p.dtype == _compute_dtype:
+        return p
+    key = id(param)
+    hit = _cache.get(key)
+    ver = param._version
+    if hit is not None and hit[0]() is param and hit[1] == ver and hit[2] == p.data_ptr():
+        return hit[3]
+    from .kernels import K
+    shadow = K().cast(p.contiguous(), _compute_dtype)
+    _cache[key] = (weakref.ref(param), ver, p.data_ptr(), shadow)
+    return shadow
+
+
+def clear_cache():
+    _cache.clear()

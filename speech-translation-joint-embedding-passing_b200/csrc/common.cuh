@@ -1,0 +1,74 @@
+// Shared helpers for libb200st (sm_100a).  Host-side error plumbing + device-side dtype/reduction utils.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200st.h"
+
+namespace b200st {
+
+int set_error(const char* fmt, ...);       // formats into the thread-local error slot, returns -1
+void count_launch(int n = 1);
+
+#define B200ST_LAUNCH_CHECK(name)                                                        \
+  do {                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) return b200st::set_error("%s: %s", name, cudaGetErrorString(e__)); \
+    b200st::count_launch();                                                              \
+  } while (0)
+
+#define B200ST_CUDA(call)                                                                \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) return b200st::set_error("%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define B200ST_DISPATCH(dtype, T, ...)                                                   \
+  do {                                                                                   \
+    if ((dtype) == B200ST_F32) { using T = float; __VA_ARGS__; }                         \
+    else if ((dtype) == B200ST_BF16) { using T = __nv_bfloat16; __VA_ARGS__; }           \
+    else return b200st::set_error("unsupported dtype %d", (int)(dtype));                 \
+  } while (0)
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Block-wide reductions through a 32-float shared scratch; every thread gets the result.
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? scratch[lane] : 0.f;
+  return warp_sum(r);
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? scratch[lane] : -INFINITY;
+  return warp_max(r);
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace b200st

@@ -1,0 +1,285 @@
+// Embedding gather/scatter, the embedding-passing concat (mix prologue), masks and small glue kernels.
+// All of these are pure data movement: vectorisable, coalesced along the feature dimension, grid sized
+// from the element count.
+#include "common.cuh"
+
+namespace b200st {
+
+template <typename T>
+__global__ void embedding_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table,
+                                     T* __restrict__ out, int64_t ld_out, int64_t n, int dim,
+                                     int64_t vocab) {
+  const int64_t i = blockIdx.x;
+  int64_t id = ids[i];
+  if (id < 0 || id >= vocab) id = 0;   // out-of-range ids read the PAD row instead of faulting
+  const float* src = table + id * dim;
+  T* dst = out + i * ld_out;
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) dst[c] = from_f<T>(src[c]);
+}
+
+template <typename T>
+__global__ void embedding_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ dout,
+                                     int64_t ld_dout, float* __restrict__ dtable, int64_t n, int dim,
+                                     int64_t vocab, int64_t padding_idx) {
+  const int64_t i = blockIdx.x;
+  const int64_t id = ids[i];
+  if (id == padding_idx || id < 0 || id >= vocab) return;
+  const T* src = dout + i * ld_dout;
+  float* dst = dtable + id * dim;
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) atomicAdd(&dst[c], to_f(src[c]));
+}
+
+template <typename T>
+__global__ void mix_gather_concat_kernel(const int64_t* __restrict__ ids,
+                                         const float* __restrict__ table, const T* __restrict__ dyn,
+                                         int64_t ld_dyn, T* __restrict__ cat, int E, int D,
+                                         int64_t vocab) {
+  const int64_t i = blockIdx.x;
+  int64_t id = ids[i];
+  if (id < 0 || id >= vocab) id = 0;
+  const float* src = table + id * E;
+  const T* dr = dyn + i * ld_dyn;
+  T* dst = cat + i * (int64_t)(E + D);
+  for (int c = threadIdx.x; c < E + D; c += blockDim.x)
+    dst[c] = (c < E) ? from_f<T>(src[c]) : dr[c - E];
+}
+
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
+                           int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = from_f<T>(to_f(a[i]) + to_f(b[i]));
+}
+
+template <typename T>
+__global__ void add_posenc_kernel(const T* __restrict__ x, const float* __restrict__ pe,
+                                  T* __restrict__ out, int64_t n, int64_t LD, int D) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = from_f<T>(to_f(x[i]) + pe[i % LD]);
+}
+
+template <typename TI, typename TO>
+__global__ void transpose01_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t A,
+                                   int64_t Bd, int64_t C) {
+  // one CTA per (a, b) row of C contiguous elements
+  const int64_t a = blockIdx.x / Bd, b = blockIdx.x % Bd;
+  const TI* src = in + (a * Bd + b) * C;
+  TO* dst = out + (b * A + a) * C;
+  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) dst[c] = from_f<TO>(to_f(src[c]));
+}
+
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = from_f<TO>(to_f(in[i]));
+}
+
+// Column sums: grid.x covers column tiles of 32, grid.y splits the rows; warp lanes run along columns.
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, float* __restrict__ out,
+                              int64_t rows, int64_t cols, int64_t rows_per_block) {
+  __shared__ float part[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float s = 0.f;
+  if (c < cols)
+    for (int64_t r = r0 + w; r < r1; r += 8) s += to_f(x[r * ld + c]);
+  part[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][lane];
+    atomicAdd(&out[c], t);
+  }
+}
+
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx,
+                                int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = to_f(y[i]) > 0.f ? dy[i] : from_f<T>(0.f);
+}
+
+__global__ void token_mask_kernel(const int64_t* __restrict__ ids, uint8_t* __restrict__ mask, int64_t B,
+                                  int64_t L, int64_t pad, int causal) {
+  const int64_t Lq = causal ? L : 1;
+  const int64_t n = B * Lq * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i % L, q = (i / L) % Lq, b = i / (L * Lq);
+    mask[i] = (ids[b * L + j] != pad) && (!causal || j <= q);
+  }
+}
+
+__global__ void length_mask_kernel(const int32_t* __restrict__ lengths, uint8_t* __restrict__ mask,
+                                   int64_t B, int64_t L) {
+  const int64_t n = B * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    mask[i] = (i % L) < lengths[i / L];
+}
+
+static unsigned flat_grid(int64_t n, int block) {
+  int64_t g = ceil_div(n, block);
+  if (g > 148 * 16) g = 148 * 16;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
+}  // namespace b200st
+
+using namespace b200st;
+
+extern "C" {
+
+int b200st_embedding_fwd(int dtype, const int64_t* ids, const float* table, void* out, int64_t ld_out,
+                         int64_t n, int64_t dim, int64_t vocab, b200st_stream_t stream) {
+  if (n <= 0) return 0;
+  B200ST_DISPATCH(dtype, T, {
+    embedding_fwd_kernel<T><<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(ids, table, (T*)out, ld_out,
+                                                                           n, (int)dim, vocab);
+  });
+  B200ST_LAUNCH_CHECK("embedding_fwd");
+  return 0;
+}
+
+int b200st_embedding_bwd(int dtype, const int64_t* ids, const void* dout, int64_t ld_dout,
+                         float* dtable, int64_t n, int64_t dim, int64_t vocab, int64_t padding_idx,
+                         b200st_stream_t stream) {
+  if (n <= 0) return 0;
+  B200ST_DISPATCH(dtype, T, {
+    embedding_bwd_kernel<T><<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(
+        ids, (const T*)dout, ld_dout, dtable, n, (int)dim, vocab, padding_idx);
+  });
+  B200ST_LAUNCH_CHECK("embedding_bwd");
+  return 0;
+}
+
+int b200st_mix_gather_concat(int dtype, const int64_t* ids, const float* table, const void* dyn,
+                             int64_t ld_dyn, void* cat, int64_t n, int64_t E, int64_t D, int64_t vocab,
+                             b200st_stream_t stream) {
+  if (n <= 0) return 0;
+  B200ST_DISPATCH(dtype, T, {
+    mix_gather_concat_kernel<T><<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(
+        ids, table, (const T*)dyn, ld_dyn, (T*)cat, (int)E, (int)D, vocab);
+  });
+  B200ST_LAUNCH_CHECK("mix_gather_concat");
+  return 0;
+}
+
+int b200st_add(int dtype, const void* a, const void* b, void* out, int64_t n, b200st_stream_t stream) {
+  if (n <= 0) return 0;
+  B200ST_DISPATCH(dtype, T, {
+    add_kernel<T><<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b,
+                                                                       (T*)out, n);
+  });
+  B200ST_LAUNCH_CHECK("add");
+  return 0;
+}
+
+int b200st_add_posenc(int dtype, const void* x, const float* pe, void* out, int64_t B, int64_t L,
+                      int64_t D, b200st_stream_t stream) {
+  const int64_t n = B * L * D;
+  if (n <= 0) return 0;
+  B200ST_DISPATCH(dtype, T, {
+    add_posenc_kernel<T><<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, pe, (T*)out,
+                                                                              n, L * D, (int)D);
+  });
+  B200ST_LAUNCH_CHECK("add_posenc");
+  return 0;
+}
+
+int b200st_transpose01(int dtype_in, int dtype_out, const void* in, void* out, int64_t A, int64_t Bd,
+                       int64_t C, b200st_stream_t stream) {
+  if (A * Bd * C <= 0) return 0;
+  const unsigned grid = (unsigned)(A * Bd);
+  const int block = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype_in == B200ST_F32 && dtype_out == B200ST_F32)
+    transpose01_kernel<float, float><<<grid, block, 0, st>>>((const float*)in, (float*)out, A, Bd, C);
+  else if (dtype_in == B200ST_F32 && dtype_out == B200ST_BF16)
+    transpose01_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>((const float*)in, (__nv_bfloat16*)out, A, Bd, C);
+  else if (dtype_in == B200ST_BF16 && dtype_out == B200ST_BF16)
+    transpose01_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, A, Bd, C);
+  else if (dtype_in == B200ST_BF16 && dtype_out == B200ST_F32)
+    transpose01_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, (float*)out, A, Bd, C);
+  else
+    return set_error("transpose01: bad dtypes");
+  B200ST_LAUNCH_CHECK("transpose01");
+  return 0;
+}
+
+int b200st_cast(int dtype_in, int dtype_out, const void* in, void* out, int64_t n,
+                b200st_stream_t stream) {
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = flat_grid(n, 256);
+  if (dtype_in == B200ST_F32 && dtype_out == B200ST_BF16)
+    cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)in, (__nv_bfloat16*)out, n);
+  else if (dtype_in == B200ST_BF16 && dtype_out == B200ST_F32)
+    cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (float*)out, n);
+  else if (dtype_in == B200ST_F32 && dtype_out == B200ST_F32)
+    cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, n);
+  else if (dtype_in == B200ST_BF16 && dtype_out == B200ST_BF16)
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, n);
+  else
+    return set_error("cast: bad dtypes");
+  B200ST_LAUNCH_CHECK("cast");
+  return 0;
+}
+
+int b200st_colsum(int dtype, const void* x, int64_t ld, float* out, int64_t rows, int64_t cols,
+                  int accumulate, b200st_stream_t stream) {
+  if (cols <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) B200ST_CUDA(cudaMemsetAsync(out, 0, cols * sizeof(float), st));
+  if (rows <= 0) return 0;
+  const int64_t col_tiles = ceil_div(cols, 32);
+  int64_t row_blocks = ceil_div(148 * 4, col_tiles);
+  if (row_blocks > ceil_div(rows, 64)) row_blocks = ceil_div(rows, 64);
+  if (row_blocks < 1) row_blocks = 1;
+  const int64_t rpb = ceil_div(rows, row_blocks);
+  dim3 grid((unsigned)col_tiles, (unsigned)ceil_div(rows, rpb));
+  B200ST_DISPATCH(dtype, T, {
+    colsum_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ld, out, rows, cols, rpb);
+  });
+  B200ST_LAUNCH_CHECK("colsum");
+  return 0;
+}
+
+int b200st_relu_bwd(int dtype, const void* dy, const void* y, void* dx, int64_t n,
+                    b200st_stream_t stream) {
+  if (n <= 0) return 0;
+  B200ST_DISPATCH(dtype, T, {
+    relu_bwd_kernel<T><<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)y,
+                                                                            (T*)dx, n);
+  });
+  B200ST_LAUNCH_CHECK("relu_bwd");
+  return 0;
+}
+
+int b200st_token_mask(const int64_t* ids, uint8_t* mask, int64_t B, int64_t L, int64_t pad, int causal,
+                      b200st_stream_t stream) {
+  const int64_t n = B * (causal ? L : 1) * L;
+  if (n <= 0) return 0;
+  token_mask_kernel<<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(ids, mask, B, L, pad, causal);
+  B200ST_LAUNCH_CHECK("token_mask");
+  return 0;
+}
+
+int b200st_length_mask(const int32_t* lengths, uint8_t* mask, int64_t B, int64_t L,
+                       b200st_stream_t stream) {
+  if (B * L <= 0) return 0;
+  length_mask_kernel<<<flat_grid(B * L, 256), 256, 0, (cudaStream_t)stream>>>(lengths, mask, B, L);
+  B200ST_LAUNCH_CHECK("length_mask");
+  return 0;
+}
+
+}  // extern "C"

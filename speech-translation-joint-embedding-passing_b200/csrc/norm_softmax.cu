@@ -1,0 +1,338 @@
+// HBM-bound row kernels: LayerNorm fwd/bwd, log-softmax fwd/bwd (+argmax), masked NLL, and the fused
+// softmax + NLL + gradient kernel (K17).  One row is owned by one warp (LayerNorm, D <= a few K) or one
+// CTA with the row staged in shared memory (vocabulary rows), so HBM sees each element once per pass.
+#include "common.cuh"
+
+namespace b200st {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: y = (x - mean) * rstd * gamma + beta, biased variance, two-pass statistics in fp32.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, T* __restrict__ y,
+                                     float* __restrict__ mean, float* __restrict__ rstd, int64_t rows,
+                                     int cols, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * cols;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += to_f(xr[c]);
+  const float mu = warp_sum(s) / cols;
+  float v = 0.f;
+  for (int c = lane; c < cols; c += 32) { const float d = to_f(xr[c]) - mu; v += d * d; }
+  const float rs = rsqrtf(warp_sum(v) / cols + eps);
+  T* yr = y + row * cols;
+  for (int c = lane; c < cols; c += 32)
+    yr[c] = from_f<T>((to_f(xr[c]) - mu) * rs * gamma[c] + beta[c]);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += dy * xhat; dbeta += dy.
+// Each CTA walks a strip of rows; column partials live in shared memory and are flushed once.
+template <typename T>
+__global__ void layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd, T* __restrict__ dx,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                     int64_t rows, int cols, int rows_per_block) {
+  extern __shared__ float sm[];   // [2][cols]
+  float* sg = sm;
+  float* sb = sm + cols;
+  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  for (int64_t row = r0 + w; row < r0 + rows_per_block && row < rows; row += nw) {
+    const T* dyr = dy + row * cols;
+    const T* xr = x + row * cols;
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float g = to_f(dyr[c]) * gamma[c];
+      const float xh = (to_f(xr[c]) - mu) * rs;
+      s1 += g;
+      s2 += g * xh;
+    }
+    s1 = warp_sum(s1) / cols;
+    s2 = warp_sum(s2) / cols;
+    T* dxr = dx + row * cols;
+    for (int c = lane; c < cols; c += 32) {
+      const float d = to_f(dyr[c]);
+      const float xh = (to_f(xr[c]) - mu) * rs;
+      dxr[c] = from_f<T>(rs * (d * gamma[c] - s1 - xh * s2));
+      atomicAdd(&sg[c], d * xh);
+      atomicAdd(&sb[c], d);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    atomicAdd(&dgamma[c], sg[c]);
+    atomicAdd(&dbeta[c], sb[c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Vocabulary rows.  The row is staged once in shared memory as fp32.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void log_softmax_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int cols,
+                                       int64_t* __restrict__ argmax) {
+  extern __shared__ float row[];
+  __shared__ float scratch[32];
+  __shared__ int s_idx[32];
+  const int64_t r = blockIdx.x;
+  const T* xr = x + r * cols;
+  float mx = -INFINITY;
+  int mi = 0x7fffffff;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float v = to_f(xr[c]);
+    row[c] = v;
+    if (v > mx) { mx = v; mi = c; }
+  }
+  // arg-max with first-index tie break
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (ov > mx || (ov == mx && oi < mi)) { mx = ov; mi = oi; }
+  }
+  if (lane == 0) { scratch[w] = mx; s_idx[w] = mi; }
+  __syncthreads();
+  if (w == 0) {
+    float v = lane < nw ? scratch[lane] : -INFINITY;
+    int i = lane < nw ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+      if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+    if (lane == 0) { scratch[0] = v; s_idx[0] = i; }
+  }
+  __syncthreads();
+  mx = scratch[0];
+  if (argmax && threadIdx.x == 0) argmax[r] = s_idx[0];
+  float s = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) s += expf(row[c] - mx);
+  s = block_sum(s, scratch);
+  const float lse = mx + logf(s);
+  T* yr = y + r * cols;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) yr[c] = from_f<T>(row[c] - lse);
+}
+
+// dx = dy - exp(y) * sum(dy)
+template <typename T>
+__global__ void log_softmax_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y,
+                                       T* __restrict__ dx, int cols) {
+  extern __shared__ float row[];
+  __shared__ float scratch[32];
+  const int64_t r = blockIdx.x;
+  const T* dyr = dy + r * cols;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float v = to_f(dyr[c]);
+    row[c] = v;
+    s += v;
+  }
+  s = block_sum(s, scratch);
+  const T* yr = y + r * cols;
+  T* dxr = dx + r * cols;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x)
+    dxr[c] = from_f<T>(row[c] - expf(to_f(yr[c])) * s);
+}
+
+template <typename T>
+__global__ void masked_nll_fwd_kernel(const T* __restrict__ logp, int64_t ld,
+                                      const int64_t* __restrict__ target,
+                                      const uint8_t* __restrict__ mask, float* loss_sum, int64_t rows,
+                                      int64_t cols) {
+  __shared__ float scratch[32];
+  float s = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    if (mask && !mask[r]) continue;
+    const int64_t t = target[r];
+    if (t >= 0 && t < cols) s -= to_f(logp[r * ld + t]);
+  }
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, s);
+}
+
+template <typename T>
+__global__ void masked_nll_bwd_kernel(const float* __restrict__ gscale,
+                                      const int64_t* __restrict__ target,
+                                      const uint8_t* __restrict__ mask, T* __restrict__ dlogp,
+                                      int64_t ld, int64_t cols) {
+  const int64_t r = blockIdx.x;
+  const bool keep = !mask || mask[r];
+  const int64_t t = target[r];
+  const float g = -gscale[0];
+  T* dr = dlogp + r * ld;
+  for (int64_t c = threadIdx.x; c < cols; c += blockDim.x)
+    dr[c] = from_f<T>((keep && c == t) ? g : 0.f);
+}
+
+// K17: loss_sum += mask * (lse - (1-eps) * x[t] - eps/V * sum(x));  dx = mask * scale * (softmax - q),
+// q = (1-eps) * onehot + eps/V.  eps = 0 reproduces log_softmax + NLLLoss (loss.py:130-132).
+template <typename T>
+__global__ void softmax_nll_fused_kernel(const T* __restrict__ x, int64_t ld,
+                                         const int64_t* __restrict__ target,
+                                         const uint8_t* __restrict__ mask,
+                                         const float* __restrict__ scale, float eps, float* loss_sum,
+                                         T* dx, int64_t ld_d, int cols) {
+  extern __shared__ float row[];
+  __shared__ float scratch[32];
+  const int64_t r = blockIdx.x;
+  const bool keep = !mask || mask[r];
+  T* dr = dx + r * ld_d;
+  if (!keep) {   // masked rows contribute nothing; never read the logits
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) dr[c] = from_f<T>(0.f);
+    return;
+  }
+  const T* xr = x + r * ld;
+  float mx = -INFINITY, sx = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float v = to_f(xr[c]);
+    row[c] = v;
+    mx = fmaxf(mx, v);
+    sx += v;
+  }
+  mx = block_max(mx, scratch);
+  float s = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) s += expf(row[c] - mx);
+  s = block_sum(s, scratch);
+  const float lse = mx + logf(s);
+  const int64_t t = target[r];
+  const float u = eps / cols;
+  if (eps != 0.f) sx = block_sum(sx, scratch);
+  if (threadIdx.x == 0) {
+    float l = lse - (1.f - eps) * row[t];
+    if (eps != 0.f) l -= u * sx;
+    atomicAdd(loss_sum, l);
+  }
+  const float sc = scale[0];
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float p = expf(row[c] - lse);
+    const float q = (c == t ? 1.f - eps : 0.f) + u;
+    dr[c] = from_f<T>(sc * (p - q));
+  }
+}
+
+static int set_row_smem(const void* fn, size_t bytes, const char* name) {
+  if (bytes > 200 * 1024) return set_error("%s: row of %zu bytes does not fit shared memory", name, bytes);
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return set_error("%s: %s", name, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+}  // namespace b200st
+
+using namespace b200st;
+
+extern "C" {
+
+int b200st_layernorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y,
+                         float* mean, float* rstd, int64_t rows, int64_t cols, float eps,
+                         b200st_stream_t stream) {
+  if (rows <= 0) return 0;
+  const int wpb = 4;
+  B200ST_DISPATCH(dtype, T, {
+    layernorm_fwd_kernel<T><<<(unsigned)ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        (const T*)x, gamma, beta, (T*)y, mean, rstd, rows, (int)cols, eps);
+  });
+  B200ST_LAUNCH_CHECK("layernorm_fwd");
+  return 0;
+}
+
+int b200st_layernorm_bwd(int dtype, const void* dy, const void* x, const float* gamma,
+                         const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                         int64_t rows, int64_t cols, b200st_stream_t stream) {
+  if (rows <= 0) return 0;
+  const size_t smem = 2 * cols * sizeof(float);
+  if (smem > 48 * 1024) return set_error("layernorm_bwd: cols %lld too large", (long long)cols);
+  // ~2 CTAs per SM worth of row strips keeps the final atomics few while filling the chip.
+  int rpb = (int)ceil_div(rows, 296);
+  if (rpb < 4) rpb = 4;
+  B200ST_DISPATCH(dtype, T, {
+    layernorm_bwd_kernel<T><<<(unsigned)ceil_div(rows, rpb), 128, smem, (cudaStream_t)stream>>>(
+        (const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta, rows, (int)cols, rpb);
+  });
+  B200ST_LAUNCH_CHECK("layernorm_bwd");
+  return 0;
+}
+
+int b200st_log_softmax_fwd(int dtype, const void* x, void* y, int64_t rows, int64_t cols,
+                           int64_t* argmax, b200st_stream_t stream) {
+  if (rows <= 0) return 0;
+  const size_t smem = cols * sizeof(float);
+  B200ST_DISPATCH(dtype, T, {
+    if (set_row_smem((const void*)log_softmax_fwd_kernel<T>, smem, "log_softmax_fwd")) return -1;
+    log_softmax_fwd_kernel<T><<<(unsigned)rows, 256, smem, (cudaStream_t)stream>>>(
+        (const T*)x, (T*)y, (int)cols, argmax);
+  });
+  B200ST_LAUNCH_CHECK("log_softmax_fwd");
+  return 0;
+}
+
+int b200st_log_softmax_bwd(int dtype, const void* dy, const void* y, void* dx, int64_t rows,
+                           int64_t cols, b200st_stream_t stream) {
+  if (rows <= 0) return 0;
+  const size_t smem = cols * sizeof(float);
+  B200ST_DISPATCH(dtype, T, {
+    if (set_row_smem((const void*)log_softmax_bwd_kernel<T>, smem, "log_softmax_bwd")) return -1;
+    log_softmax_bwd_kernel<T><<<(unsigned)rows, 256, smem, (cudaStream_t)stream>>>(
+        (const T*)dy, (const T*)y, (T*)dx, (int)cols);
+  });
+  B200ST_LAUNCH_CHECK("log_softmax_bwd");
+  return 0;
+}
+
+int b200st_masked_nll_fwd(int dtype, const void* logp, int64_t ld, const int64_t* target,
+                          const uint8_t* mask, float* loss_sum, int64_t rows, int64_t cols,
+                          b200st_stream_t stream) {
+  if (rows <= 0) return 0;
+  unsigned grid = (unsigned)ceil_div(rows, 256);
+  if (grid > 296) grid = 296;
+  B200ST_DISPATCH(dtype, T, {
+    masked_nll_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)logp, ld, target, mask,
+                                                                     loss_sum, rows, cols);
+  });
+  B200ST_LAUNCH_CHECK("masked_nll_fwd");
+  return 0;
+}
+
+int b200st_masked_nll_bwd(int dtype, const float* gscale, const int64_t* target, const uint8_t* mask,
+                          void* dlogp, int64_t ld, int64_t rows, int64_t cols, b200st_stream_t stream) {
+  if (rows <= 0) return 0;
+  B200ST_DISPATCH(dtype, T, {
+    masked_nll_bwd_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(gscale, target, mask,
+                                                                               (T*)dlogp, ld, cols);
+  });
+  B200ST_LAUNCH_CHECK("masked_nll_bwd");
+  return 0;
+}
+
+int b200st_softmax_nll_fused(int dtype, const void* logits, int64_t ld, const int64_t* target,
+                             const uint8_t* mask, const float* scale, float eps, float* loss_sum,
+                             void* dlogits, int64_t ld_d, int64_t rows, int64_t cols,
+                             b200st_stream_t stream) {
+  if (rows <= 0) return 0;
+  const size_t smem = cols * sizeof(float);
+  B200ST_DISPATCH(dtype, T, {
+    if (set_row_smem((const void*)softmax_nll_fused_kernel<T>, smem, "softmax_nll_fused")) return -1;
+    softmax_nll_fused_kernel<T><<<(unsigned)rows, 256, smem, (cudaStream_t)stream>>>(
+        (const T*)logits, ld, target, mask, scale, eps, loss_sum, (T*)dlogits, ld_d, (int)cols);
+  });
+  B200ST_LAUNCH_CHECK("softmax_nll_fused");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,410 @@
+"""Joint speech-translation model (acoustic LAS -> embedding passing -> Transformer enc/dec) on b200st kernels.
+
+Drop-in mirror of the reference's models/Seq2seq.py (class Seq2seq): identical constructor signature,
+`forward_train / forward_eval / forward_translate / forward_translate_refen` signatures and returned
+dict keys, identical parameter (state_dict) names.  All arithmetic runs in hand-written sm_100a kernels
+(libb200st.so); PyTorch only owns memory and autograd bookkeeping.
+
+Differences that do not change results: masks and the LAS `lengths` are built and kept on
+the device (no per-call CPU mask construction + H2D copy, no D2H sync inside the step), the sinusoid table
+is uploaded once, and the mix `enc_emb_proj(cat(static, dynamic))` consumes the gathered static rows and
+the dynamic embedding without a separate concat + copy.
+"""
+import os
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from b200st import functional as BF
+from b200st import runtime as rt
+from b200st.kernels import K
+from utils.config import PAD, EOS, BOS, UNK
+from utils.misc import check_device
+
+from .Las import LAS
+from .TFDec import Decoder
+from .TFEnc import Encoder
+
+warnings.filterwarnings("ignore")
+
+
+class Seq2seq(nn.Module):
+
+    def __init__(self, enc_vocab_size, dec_vocab_size, share_embedder, enc_embedding_size=200,
+                 dec_embedding_size=200, load_embedding_src=None, load_embedding_tgt=None,
+                 max_seq_len_src=32, max_seq_len_tgt=300, num_heads=8, dim_model=512,
+                 dim_feedforward=1024, enc_layers=6, dec_layers=6, embedding_dropout=0.0, dropout=0.2,
+                 act=False, enc_word2id=None, enc_id2word=None, dec_word2id=None, dec_id2word=None,
+                 transformer_type='standard', enc_emb_proj=False, dec_emb_proj=False, acous_dim=40,
+                 acous_hidden_size=256, mode='ASR', load_mode='ASR'):
+        super().__init__()
+        # Seq2seq.py:64-66 loads a hard-coded relative .npy (average dynamic embedding, used by MT /
+        # ST_BASE modes only).  Same path; a missing file falls back to zeros instead of crashing.
+        self.EMB_DYN_AVE_PATH = 'models/base/ted-asr-v001/eval_ted_train_STATS/2020_09_02_04_10_44/dyn_emb_ave.npy'
+        if os.path.exists(self.EMB_DYN_AVE_PATH):
+            self.EMB_DYN_AVE = torch.from_numpy(np.load(self.EMB_DYN_AVE_PATH))
+        else:
+            self.EMB_DYN_AVE = torch.zeros(dim_model)
+        if load_embedding_src or load_embedding_tgt:
+            raise NotImplementedError('pre-trained embedding files are host I/O outside the hot path; '
+                                      'load them into enc_embedder/dec_embedder.weight after construction')
+        self.enc_vocab_size, self.dec_vocab_size = enc_vocab_size, dec_vocab_size
+        self.enc_embedding_size, self.dec_embedding_size = enc_embedding_size, dec_embedding_size
+        self.load_embedding_src, self.load_embedding_tgt = load_embedding_src, load_embedding_tgt
+        self.max_seq_len_src, self.max_seq_len_tgt = max_seq_len_src, max_seq_len_tgt
+        self.num_heads, self.dim_model, self.dim_feedforward = num_heads, dim_model, dim_feedforward
+        self.enc_layers, self.dec_layers = enc_layers, dec_layers
+        self.embedding_dropout = nn.Dropout(embedding_dropout)
+        self.dropout = nn.Dropout(dropout)
+        self.act = act
+        self.enc_word2id, self.enc_id2word = enc_word2id, enc_id2word
+        self.dec_word2id, self.dec_id2word = dec_word2id, dec_id2word
+        self.transformer_type = transformer_type
+        self.mode, self.load_mode = mode, load_mode
+
+        # ---- embedders (Seq2seq.py:98-131)
+        self.enc_embedder = nn.Embedding(enc_vocab_size, enc_embedding_size, sparse=False, padding_idx=PAD)
+        self.dec_embedder = nn.Embedding(dec_vocab_size, dec_embedding_size, sparse=False, padding_idx=PAD)
+        if share_embedder:
+            assert enc_vocab_size == dec_vocab_size
+            self.enc_embedder = self.dec_embedder
+        self.enc_emb_proj_flag = True
+        self.enc_emb_proj = nn.Linear(enc_embedding_size + dim_model, dim_model, bias=False)
+        self.dec_emb_proj_flag = False
+        if (dec_embedding_size != dim_model) or (dec_emb_proj is True):
+            self.dec_emb_proj_flag = True
+            self.dec_emb_proj = nn.Linear(dec_embedding_size, dim_model, bias=False)
+        else:
+            self.dec_emb_proj = dec_emb_proj
+
+        # ---- sub-models (Seq2seq.py:133-180)
+        self.acous_dim, self.acous_hidden_size = acous_dim, acous_hidden_size
+        enc_params = (dim_model, dim_feedforward, num_heads, enc_layers, act, dropout, transformer_type)
+        dec_params = (dim_model, dim_feedforward, num_heads, dec_layers, act, dropout, transformer_type)
+        comb_mode = '-'.join([mode, load_mode])
+        if 'ASR' in comb_mode or 'ST' in comb_mode:
+            self.las = LAS(enc_vocab_size, embedding_size=enc_embedding_size, acous_dim=acous_dim,
+                           acous_hidden_size=acous_hidden_size, acous_att_mode='bilinear',
+                           hidden_size_dec=dim_model, hidden_size_shared=dim_model, num_unilstm_dec=3,
+                           acous_norm=True, spec_aug=True, batch_norm=False, enc_mode='pyramid',
+                           embedding_dropout=embedding_dropout, dropout=dropout, residual=True,
+                           batch_first=True, max_seq_len=max_seq_len_src, embedder=None,
+                           word2id=enc_word2id, id2word=enc_id2word, hard_att=False)
+        if 'AE' in comb_mode:
+            self.out_src = self.las.decoder.acous_out
+        if 'ST' in comb_mode or 'MT' in comb_mode:
+            self.enc_src = Encoder(*enc_params)
+            self.dec_tgt = Decoder(*dec_params)
+            self.out_tgt = nn.Linear(dim_model, dec_vocab_size, bias=False)
+
+    # ------------------------------------------------------------------------------------------
+    # building blocks (same names as the reference's private helpers)
+    # ------------------------------------------------------------------------------------------
+    def _check_dropout(self):
+        if self.training and self.embedding_dropout.p > 0:
+            raise NotImplementedError('embedding_dropout > 0 is not implemented by the b200st kernels yet')
+
+    def _get_src_emb(self, src, emb_src_dyn, device):
+        """The mix (Seq2seq.py:183-199).  Returns (src_mask, emb_src, src_mask_input) like the reference;
+        both masks are uint8 device tensors."""
+        self._check_dropout()
+        src = src.contiguous()
+        src_mask_input = K().token_mask(src, PAD, causal=False)           # [B,1,S]
+        src_mask = K().token_mask(src, PAD, causal=True)                  # [B,S,S]
+        emb_src = BF.mix(src, self.enc_embedder.weight, emb_src_dyn, self.enc_emb_proj.weight)
+        return src_mask, emb_src, src_mask_input
+
+    def _get_tgt_emb(self, tgt, device):
+        """Seq2seq.py:202-211: pad & causal mask [B,L,L] + (projected) target embeddings."""
+        self._check_dropout()
+        tgt = tgt.contiguous()
+        tgt_mask = K().token_mask(tgt, PAD, causal=True)
+        emb_tgt = BF.embedding(tgt, self.dec_embedder.weight, PAD)
+        if self.dec_emb_proj_flag:
+            emb_tgt = BF.linear(emb_tgt, self.dec_emb_proj.weight)
+        return tgt_mask, emb_tgt
+
+    def _pre_proc_src(self, src, device):
+        return src[:, 1:]                                                  # Seq2seq.py:214-219
+
+    def _encoder_acous(self, acous_feats, acous_lens, device, use_gpu, tgt=None, is_training=False,
+                       teacher_forcing_ratio=0.0, lm_mode='null', lm_model=None, need_logps=True):
+        """Returns (emb_src_dyn, logps_src, preds_src, lengths) with lengths an int32 DEVICE tensor."""
+        if lm_mode != 'null':
+            raise NotImplementedError("LM fusion is out of scope; use lm_mode='null'")
+        return self.las.forward_device(acous_feats, acous_lens=acous_lens, tgt=tgt,
+                                       is_training=is_training,
+                                       teacher_forcing_ratio=teacher_forcing_ratio,
+                                       need_logps=need_logps)
+
+    def _encoder_en(self, emb_src, src_mask=None):
+        enc_outputs, *_ = self.enc_src(emb_src, src_mask=src_mask)
+        return enc_outputs
+
+    def _decoder_de(self, emb_tgt, enc_outputs, tgt_mask=None, src_mask=None, beam_width=1):
+        """Seq2seq.py:249-257: decoder stack, vocabulary projection, log-softmax and top-k (top-1 fused)."""
+        dec_outputs_tgt, *_ = self.dec_tgt(emb_tgt, enc_outputs, tgt_mask=tgt_mask, src_mask=src_mask)
+        logits_tgt = BF.linear(dec_outputs_tgt, self.out_tgt.weight)
+        logps_tgt, preds_top1 = BF.log_softmax_argmax(logits_tgt)
+        if beam_width == 1:
+            preds_tgt = preds_top1
+            scores_tgt = None
+        else:
+            scores_tgt, preds_tgt = logps_tgt.data.float().topk(beam_width)
+        return dec_outputs_tgt, logits_tgt, logps_tgt, preds_tgt, scores_tgt
+
+    def _length_mask(self, lengths, max_len):
+        """src_mask_input from the LAS lengths (Seq2seq.py:494-497), on the device."""
+        return K().length_mask(lengths, max_len)
+
+    def _dyn_ave(self, batch, length, device):
+        ave = self.EMB_DYN_AVE.to(device=device, dtype=rt.compute_dtype())
+        return ave.repeat(batch, length, 1)
+
+    # ------------------------------------------------------------------------------------------
+    # training forward (Seq2seq.py:396-509)
+    # ------------------------------------------------------------------------------------------
+    def forward_train(self, src, tgt=None, acous_feats=None, acous_lens=None, mode='ST', use_gpu=True,
+                      lm_mode='null', lm_model=None):
+        out_dict = {}
+        device = check_device(use_gpu)
+        mode = mode.upper()
+        assert src is not None
+        if 'ST' in mode or 'ASR' in mode:
+            assert acous_feats is not None
+        if 'ST' in mode or 'MT' in mode:
+            assert tgt is not None
+
+        if 'ASR' in mode:       # teacher-forced LAS with SpecAug (Seq2seq.py:422-436)
+            emb_src, logps_src, preds_src, lengths = self._encoder_acous(
+                acous_feats, acous_lens, device, use_gpu, tgt=src, is_training=True,
+                teacher_forcing_ratio=1.0, lm_mode=lm_mode, lm_model=lm_model)
+            out_dict['emb_asr'] = emb_src
+            out_dict['preds_asr'] = preds_src
+            out_dict['logps_asr'] = logps_src
+            out_dict['lengths_asr'] = lengths
+
+        if 'MT' in mode:        # Seq2seq.py:438-466
+            tgt_mask, emb_tgt = self._get_tgt_emb(tgt, device)
+            src_trim = self._pre_proc_src(src, device)
+            dyn = self._dyn_ave(src_trim.size(0), src_trim.size(1), src.device)
+            src_mask, emb_src, src_mask_input = self._get_src_emb(src_trim, dyn, device)
+            enc_outputs = self._encoder_en(emb_src, src_mask=src_mask_input)
+            _, _, logps_tgt, preds_tgt, _ = self._decoder_de(emb_tgt, enc_outputs, tgt_mask=tgt_mask,
+                                                             src_mask=src_mask_input)
+            out_dict['emb_mt'] = emb_src
+            out_dict['preds_mt'] = preds_tgt
+            out_dict['logps_mt'] = logps_tgt
+
+        if 'ST' in mode:        # Seq2seq.py:468-507
+            tgt_mask, emb_tgt = self._get_tgt_emb(tgt, device)
+            if 'ASR' in mode:
+                emb_src_dyn = out_dict['emb_asr']
+                lengths = out_dict['lengths_asr']
+            else:               # free running, no SpecAug (Seq2seq.py:484-487); logps are not needed
+                emb_src_dyn, _, _, lengths = self._encoder_acous(
+                    acous_feats, acous_lens, device, use_gpu, is_training=False,
+                    teacher_forcing_ratio=0.0, lm_mode=lm_mode, lm_model=lm_model, need_logps=False)
+            src_trim = self._pre_proc_src(src, device)
+            _, emb_src, _ = self._get_src_emb(src_trim, emb_src_dyn, device)
+            src_mask_input = self._length_mask(self._as_device_lengths(lengths, emb_src.device),
+                                               emb_src.size(1))
+            enc_outputs = self._encoder_en(emb_src, src_mask=src_mask_input)
+            _, _, logps_tgt, preds_tgt, _ = self._decoder_de(emb_tgt, enc_outputs, tgt_mask=tgt_mask,
+                                                             src_mask=src_mask_input)
+            out_dict['emb_st'] = emb_src
+            out_dict['preds_st'] = preds_tgt
+            out_dict['logps_st'] = logps_tgt
+
+        if 'lengths_asr' in out_dict and torch.is_tensor(out_dict['lengths_asr']):
+            out_dict['lengths_asr'] = out_dict['lengths_asr'].cpu().numpy().astype(np.int64)
+        return out_dict
+
+    @staticmethod
+    def _as_device_lengths(lengths, device):
+        if torch.is_tensor(lengths):
+            return lengths.to(device=device, dtype=torch.int32)
+        return torch.as_tensor(np.asarray(lengths), dtype=torch.int32).to(device)
+
+    # ------------------------------------------------------------------------------------------
+    # greedy evaluation (Seq2seq.py:260-304, 512-638)
+    # ------------------------------------------------------------------------------------------
+    def _greedy_decode(self, enc_outputs, src_mask_input, batch, length_out, device):
+        """The shared free-running loop of forward_eval (no KV cache: the reference re-runs the decoder on
+        the whole prefix each step; kept so that token ids are identical)."""
+        dt = rt.compute_dtype()
+        eos_mask = torch.zeros(batch, dtype=torch.bool, device=device)
+        logps = torch.full((batch, length_out, self.dec_vocab_size),
+                           float(torch.tensor(1.0 / self.dec_vocab_size).log()), dtype=dt, device=device)
+        preds = torch.full((batch, 1), BOS, dtype=torch.int64, device=device)
+        for i in range(1, self.max_seq_len_tgt):
+            tgt_mask, emb_tgt = self._get_tgt_emb(preds, device)
+            _, _, logp_tgt, pred_tgt, _ = self._decoder_de(emb_tgt, enc_outputs, tgt_mask=tgt_mask,
+                                                           src_mask=src_mask_input)
+            eos_mask = eos_mask | (pred_tgt[:, i - 1].squeeze(1) == EOS)            # Seq2seq.py:284-285
+            logps[:, i, :] = logp_tgt[:, i - 1, :]
+            preds = torch.cat((preds, pred_tgt[:, i - 1]), dim=1)
+            if int(eos_mask.sum()) == batch:                                         # Seq2seq.py:297-302
+                if length_out != preds.size(1):
+                    pad = torch.full((batch, length_out - preds.size(1)), PAD, dtype=torch.int64,
+                                     device=device)
+                    preds = torch.cat((preds, pad), dim=1)
+                break
+        return preds, logps
+
+    def forward_eval(self, src=None, acous_feats=None, acous_lens=None, mode='ST', use_gpu=True,
+                     lm_mode='null', lm_model=None):
+        out_dict = {}
+        device = check_device(use_gpu)
+        mode = mode.upper()
+        if 'ST' in mode or 'ASR' in mode:
+            assert acous_feats is not None
+            batch = acous_feats.size(0)
+            device = acous_feats.device
+        if 'MT' in mode or 'AE' in mode:
+            assert src is not None
+            batch = src.size(0)
+            device = src.device
+        with torch.no_grad():
+            if 'ASR' in mode:
+                emb_src, logps_src, preds_src, lengths = self._encoder_acous(
+                    acous_feats, acous_lens, device, use_gpu, is_training=False,
+                    teacher_forcing_ratio=0.0, lm_mode=lm_mode, lm_model=lm_model)
+                out_dict['emb_asr'] = emb_src
+                out_dict['preds_asr'] = preds_src
+                out_dict['logps_asr'] = logps_src
+                out_dict['lengths_asr'] = lengths
+            if 'MT' in mode:
+                src_trim = self._pre_proc_src(src, device)
+                dyn = self._dyn_ave(src_trim.size(0), src_trim.size(1), device)
+                _, emb_src, src_mask_input = self._get_src_emb(src_trim, dyn, device)
+                enc_outputs = self._encoder_en(emb_src, src_mask=src_mask_input)
+                preds_tgt, logps_tgt = self._greedy_decode(enc_outputs, src_mask_input, batch,
+                                                           self.max_seq_len_tgt, device)
+                out_dict['emb_mt'] = emb_src
+                out_dict['preds_mt'] = preds_tgt
+                out_dict['logps_mt'] = logps_tgt
+            if 'ST' in mode:
+                if 'ASR' in mode:
+                    preds_src, emb_src_dyn, lengths = (out_dict['preds_asr'], out_dict['emb_asr'],
+                                                       out_dict['lengths_asr'])
+                else:
+                    emb_src_dyn, _, preds_src, lengths = self._encoder_acous(
+                        acous_feats, acous_lens, device, use_gpu, is_training=False,
+                        teacher_forcing_ratio=0.0, lm_mode=lm_mode, lm_model=lm_model, need_logps=False)
+                _, emb_src, _ = self._get_src_emb(preds_src.squeeze(2), emb_src_dyn, device)
+                src_mask_input = self._length_mask(self._as_device_lengths(lengths, device), emb_src.size(1))
+                enc_outputs = self._encoder_en(emb_src, src_mask=src_mask_input)
+                preds_tgt, logps_tgt = self._greedy_decode(enc_outputs, src_mask_input, batch,
+                                                           self.max_seq_len_tgt, device)
+                out_dict['emb_st'] = emb_src
+                out_dict['preds_st'] = preds_tgt
+                out_dict['logps_st'] = logps_tgt
+        if 'lengths_asr' in out_dict and torch.is_tensor(out_dict['lengths_asr']):
+            out_dict['lengths_asr'] = out_dict['lengths_asr'].cpu().numpy().astype(np.int64)
+        return out_dict
+
+    # ------------------------------------------------------------------------------------------
+    # beam-search inference (Seq2seq.py:307-393, 641-903)
+    # ------------------------------------------------------------------------------------------
+    def _beam_search(self, enc_outputs, src_mask_input, batch, beam_width, penalty_factor, max_seq_len,
+                     device):
+        """_prep_translate + the step loop + _step_translate (Seq2seq.py:307-393,720-739), including the
+        final `reshape(batch, -1)[:, :max_seq_len]` slice quirk (Seq2seq.py:738)."""
+        k = beam_width
+        S = enc_outputs.size(1)
+        eos_mask = torch.zeros(batch * k, dtype=torch.bool, device=device)
+        len_map = torch.ones(batch * k, device=device)
+        enc_exp = enc_outputs.repeat(1, k, 1).view(-1, S, self.dim_model)
+        preds_exp = torch.full((batch * k, 1), BOS, dtype=torch.int64, device=device)
+        scores_exp = torch.zeros(batch * k, device=device)
+        mask_exp = src_mask_input.repeat(1, k, 1).view(-1, 1, S).contiguous()
+        for i in range(1, max_seq_len):
+            tgt_mask, emb_tgt = self._get_tgt_emb(preds_exp, device)
+            _, _, logp_all, pred_all, score_all = self._decoder_de(emb_tgt, enc_exp, tgt_mask=tgt_mask,
+                                                                   src_mask=mask_exp, beam_width=k)
+            if k == 1:
+                score_all = logp_all.data.float().gather(2, pred_all)
+            pred = pred_all[:, i - 1]
+            score = score_all[:, i - 1]
+            if i == 1:
+                scores_exp = scores_exp + score.reshape(batch, -1)[:, :k].contiguous().view(-1)
+                pred_select = pred.reshape(batch, -1)[:, :k].contiguous().view(-1)
+                preds_exp = torch.cat((preds_exp, pred_select.unsqueeze(-1)), dim=1)
+            else:
+                eos_exp = eos_mask.reshape(-1, 1).repeat(1, k)
+                eos_exp[:, 0] = False
+                score_temp = scores_exp.reshape(-1, 1) + score.masked_fill(
+                    eos_mask.reshape(-1, 1), 0).masked_fill(eos_exp, -1e9)
+                score_temp = score_temp / (len_map.reshape(-1, 1) ** penalty_factor)
+                score_select, pos = score_temp.reshape(batch, -1).topk(k)
+                scores_exp = score_select.view(-1) * (len_map.reshape(-1, 1) ** penalty_factor).view(-1)
+                pos = (pos.float() + torch.arange(0, batch * k * k, k * k, device=device).float()
+                       .reshape(batch, 1)).long()
+                r_idxs, c_idxs = pos // k, pos % k
+                pred_select = pred[r_idxs, c_idxs].view(-1)
+                preds_exp[:, :i] = preds_exp[r_idxs.view(-1), :i]
+                preds_exp = torch.cat((preds_exp, pred_select.unsqueeze(-1)), dim=1)
+            eos_mask = (pred_select == EOS) | eos_mask
+            len_map = len_map + torch.ones(batch * k, device=device).masked_fill(eos_mask, 0)
+            if int(eos_mask.sum()) == eos_mask.size(0):
+                break
+        return preds_exp.reshape(batch, -1)[:, :max_seq_len].contiguous()
+
+    def _translate(self, acous_feats, acous_lens, src, beam_width, penalty_factor, use_gpu, max_seq_len,
+                   mode, lm_mode, lm_model, ref_en):
+        device = check_device(use_gpu)
+        with torch.no_grad():
+            if mode == 'ASR':
+                if ref_en:
+                    _, _, preds_src, _ = self._encoder_acous(acous_feats, acous_lens, device, use_gpu,
+                                                             tgt=src, is_training=False,
+                                                             teacher_forcing_ratio=1.0)
+                else:
+                    _, _, preds_src, _ = self._encoder_acous(acous_feats, acous_lens, device, use_gpu,
+                                                             is_training=False, teacher_forcing_ratio=0.0)
+                return preds_src
+            if mode == 'MT':
+                batch, device = src.size(0), src.device
+                src_trim = self._pre_proc_src(src, device)
+                dyn = self._dyn_ave(src_trim.size(0), src_trim.size(1), device)
+                _, emb_src, src_mask_input = self._get_src_emb(src_trim, dyn, device)
+            elif mode in ('ST', 'ST_BASE'):
+                batch, device = acous_feats.size(0), acous_feats.device
+                if ref_en:
+                    emb_src_dyn, _, preds_src, lengths = self._encoder_acous(
+                        acous_feats, acous_lens, device, use_gpu, tgt=src, is_training=False,
+                        teacher_forcing_ratio=1.0, need_logps=False)
+                    ids = self._pre_proc_src(src, device)
+                else:
+                    emb_src_dyn, _, preds_src, lengths = self._encoder_acous(
+                        acous_feats, acous_lens, device, use_gpu, is_training=False,
+                        teacher_forcing_ratio=0.0, need_logps=False)
+                    ids = preds_src.squeeze(2)
+                if mode == 'ST_BASE':
+                    emb_src_dyn = self._dyn_ave(ids.size(0), ids.size(1), device)
+                _, emb_src, _ = self._get_src_emb(ids, emb_src_dyn, device)
+                src_mask_input = self._length_mask(self._as_device_lengths(lengths, device), emb_src.size(1))
+            else:
+                raise ValueError(f'unknown mode {mode}')
+            enc_outputs = self._encoder_en(emb_src, src_mask=src_mask_input)
+            return self._beam_search(enc_outputs, src_mask_input, batch, beam_width, penalty_factor,
+                                     max_seq_len, device)
+
+    def forward_translate(self, acous_feats=None, acous_lens=None, src=None, beam_width=1,
+                          penalty_factor=1, use_gpu=True, max_seq_len=900, mode='ST', lm_mode='null',
+                          lm_model=None):
+        return self._translate(acous_feats, acous_lens, src, beam_width, penalty_factor, use_gpu,
+                               max_seq_len, mode, lm_mode, lm_model, ref_en=False)
+
+    def forward_translate_refen(self, acous_feats=None, acous_lens=None, src=None, beam_width=1,
+                                penalty_factor=1, use_gpu=True, max_seq_len=900, mode='ST',
+                                lm_mode='null', lm_model=None):
+        return self._translate(acous_feats, acous_lens, src, beam_width, penalty_factor, use_gpu,
+                               max_seq_len, mode, lm_mode, lm_model, ref_en=True)
+
+    def check_var(self, var_name, var_val_set=None):
+        if not hasattr(self, var_name):
+            setattr(self, var_name, var_val_set if var_val_set is not None else None)

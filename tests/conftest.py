@@ -76,6 +76,6 @@ def golden(request):
 
 
 def rel_err(a, b):
-    a = a.double().flatten()
-    b = b.double().flatten()
+    a = a.detach().double().flatten()
+    b = b.detach().double().flatten()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))

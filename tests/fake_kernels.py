@@ -1,0 +1,320 @@
+"""TEST INFRASTRUCTURE ONLY — a pure-PyTorch stand-in for `b200st.kernels.CudaKernels`.
+
+Two uses, both in tests/:
+  * CPU (`-m "not gpu"`): lets the host-side orchestration (autograd functions, hand-written BPTT of the
+    LAS decoder and BLSTM layers, mask plumbing, module mirror) be checked against the oracle on a
+    machine without a GPU;
+  * GPU (`-m gpu`): an independent per-kernel reference — every CUDA kernel is compared with the method of
+    the same name here, run with torch ops on the same device.
+It is never imported by the product package; `b200st.kernels.set_backend` is the only hook.
+Each method restates the contract documented in include/b200st.h.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+class FakeKernels:
+    name = 'fake-torch'
+
+    def __init__(self):
+        self.launches = 0
+
+    def launch_count(self):
+        return self.launches
+
+    # -- GEMM -------------------------------------------------------------------------------------
+    def gemm(self, a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=None,
+             relu=False, residual=None, alpha=1.0):
+        self.launches += 1
+        A = a.float().transpose(-1, -2) if trans_a else a.float()
+        Bm = b.float().transpose(-1, -2) if trans_b else b.float()
+        y = alpha * torch.matmul(A, Bm)
+        if bias is not None:
+            y = y + bias
+        if relu:
+            y = torch.relu(y)
+        if residual is not None:
+            y = y + residual.float()
+        if out is None:
+            od = out_dtype or (residual.dtype if residual is not None else a.dtype)
+            return y.to(od)
+        out.copy_(y.to(out.dtype))
+        return out
+
+    # -- LayerNorm --------------------------------------------------------------------------------
+    def layernorm_fwd(self, x, gamma, beta, eps, save_stats=True):
+        xf = x.float()
+        mean = xf.mean(-1)
+        var = xf.var(-1, unbiased=False)
+        rstd = torch.rsqrt(var + eps)
+        y = (xf - mean[..., None]) * rstd[..., None] * gamma + beta
+        return y.to(x.dtype), mean.reshape(-1), rstd.reshape(-1)
+
+    def layernorm_bwd(self, dy, x, gamma, mean, rstd, dgamma, dbeta):
+        cols = x.size(-1)
+        xf, dyf = x.float().reshape(-1, cols), dy.float().reshape(-1, cols)
+        xh = (xf - mean[:, None]) * rstd[:, None]
+        g = dyf * gamma
+        dx = rstd[:, None] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+        dgamma += (dyf * xh).sum(0)
+        dbeta += dyf.sum(0)
+        return dx.to(x.dtype).view(x.shape)
+
+    # -- attention --------------------------------------------------------------------------------
+    def mha_fwd(self, q, k, v, mask, n_head, temperature, want_probs=True):
+        B, Lq, HD = q.shape
+        Lk = k.size(1)
+        d = HD // n_head
+        qf = (q.float() / temperature).view(B, Lq, n_head, d).transpose(1, 2)
+        kf = k.float().reshape(B, Lk, n_head, d).transpose(1, 2)
+        vf = v.float().reshape(B, Lk, n_head, d).transpose(1, 2)
+        s = torch.matmul(qf, kf.transpose(2, 3))
+        if mask is not None:
+            s = s.masked_fill(mask.unsqueeze(1) == 0, -1e9)
+        p = torch.softmax(s, dim=-1)
+        o = torch.matmul(p, vf).transpose(1, 2).reshape(B, Lq, HD)
+        return o.to(q.dtype), (p.to(q.dtype) if want_probs else None)
+
+    def mha_bwd(self, dout, q, k, v, p, n_head, temperature):
+        B, Lq, HD = q.shape
+        Lk = k.size(1)
+        d = HD // n_head
+        do = dout.float().view(B, Lq, n_head, d).transpose(1, 2)
+        qf = (q.float() / temperature).reshape(B, Lq, n_head, d).transpose(1, 2)
+        kf = k.float().reshape(B, Lk, n_head, d).transpose(1, 2)
+        vf = v.float().reshape(B, Lk, n_head, d).transpose(1, 2)
+        pf = p.float()
+        dp = torch.matmul(do, vf.transpose(2, 3))
+        ds = pf * (dp - (dp * pf).sum(-1, keepdim=True))
+        dq = torch.matmul(ds, kf) / temperature
+        dk = torch.matmul(ds.transpose(2, 3), qf)
+        dv = torch.matmul(pf.transpose(2, 3), do)
+        back = lambda t, L: t.transpose(1, 2).reshape(B, L, HD).to(q.dtype)
+        return back(dq, Lq), back(dk, Lk), back(dv, Lk)
+
+    # -- LSTM cell --------------------------------------------------------------------------------
+    def lstm_cell_fwd(self, gates, c_prev, residual=None, save_acts=True, h_out=None, c_out=None,
+                      acts_out=None, res_out=None):
+        i, f, g, o = gates.float().chunk(4, dim=-1)
+        i, f, g, o = torch.sigmoid(i), torch.sigmoid(f), torch.tanh(g), torch.sigmoid(o)
+        cp = 0 if c_prev is None else c_prev
+        c = f * cp + i * g
+        h = (o * torch.tanh(c))
+        acts = torch.cat([i, f, g, o], -1)
+        hq = h.to(gates.dtype)
+        if h_out is not None:
+            h_out.copy_(hq); hq = h_out
+        if c_out is not None:
+            c_out.copy_(c); c = c_out
+        if acts_out is not None:
+            acts_out.copy_(acts); acts = acts_out
+        out_res = None
+        if residual is not None:
+            out_res = (h + residual.float()).to(gates.dtype)
+            if res_out is not None:
+                res_out.copy_(out_res); out_res = res_out
+        return hq, c, acts, out_res
+
+    def lstm_cell_bwd(self, dhs, dc_next, acts, c_prev, c, dtype, dgates_out=None):
+        dh = sum(d.float() for d in dhs if d is not None)
+        i, f, g, o = acts.chunk(4, dim=-1)
+        tc = torch.tanh(c)
+        cp = 0 if c_prev is None else c_prev
+        dc = (0 if dc_next is None else dc_next) + dh * o * (1 - tc * tc)
+        dg = torch.cat([dc * g * i * (1 - i), dc * cp * f * (1 - f), dc * i * (1 - g * g),
+                        dh * tc * o * (1 - o)], -1).to(dtype)
+        if dgates_out is not None:
+            dgates_out.copy_(dg); dg = dgates_out
+        return dg, dc * f
+
+    # -- persistent BLSTM recurrence ----------------------------------------------------------------
+    @staticmethod
+    def _out_index(out, t, pair, H, d, out_ld_t, out_ld_b, B):
+        """Flat element offsets of out[(t/pair)*ld_t + b*ld_b + (t%pair)*2H + d*H + u] for all b,u."""
+        b = torch.arange(B, device=out.device)[:, None]
+        u = torch.arange(H, device=out.device)[None, :]
+        return (t // pair) * out_ld_t + b * out_ld_b + (t % pair) * 2 * H + d * H + u
+
+    def blstm_fwd(self, xproj, w_hh_f, w_hh_r, lens, out, out_ld_t, out_ld_b, pair, save=True):
+        _, T, B, H4 = xproj.shape
+        H = H4 // 4
+        dev = xproj.device
+        hs = torch.zeros((2, T + 1, B, H), dtype=xproj.dtype, device=dev)
+        acts = torch.zeros((2, T, B, H4), dtype=torch.float32, device=dev)
+        cs = torch.zeros((2, T, B, H), dtype=torch.float32, device=dev)
+        flat = out.view(-1)
+        ln = lens.to(dev).long()
+        for d, w in ((0, w_hh_f), (1, w_hh_r)):
+            h = torch.zeros(B, H, device=dev)
+            c = torch.zeros(B, H, device=dev)
+            for s in range(T):
+                t = T - 1 - s if d else s
+                gates = xproj[d, t].float() + h @ w.t()
+                i, f, g, o = gates.chunk(4, -1)
+                i, f, g, o = torch.sigmoid(i), torch.sigmoid(f), torch.tanh(g), torch.sigmoid(o)
+                valid = (t < ln)[:, None]
+                c_new = torch.where(valid, f * c + i * g, c)
+                h_new = torch.where(valid, o * torch.tanh(c_new), h)
+                h, c = h_new, c_new
+                acts[d, t] = torch.cat([i, f, g, o], -1)
+                cs[d, t] = c
+                ho = torch.where(valid, h, torch.zeros_like(h)).to(xproj.dtype)
+                flat[self._out_index(out, t, pair, H, d, out_ld_t, out_ld_b, B).view(-1)] = ho.view(-1)
+                hs[d, t if d else t + 1] = ho
+        if not save:
+            return None, None, None
+        return hs, acts, cs
+
+    def blstm_bwd(self, dout, out_ld_t, out_ld_b, pair, acts, cs, w_hh_f, w_hh_r, lens, dtype):
+        _, T, B, H = cs.shape
+        dev = cs.device
+        dg_all = torch.zeros((2, T, B, 4 * H), dtype=dtype, device=dev)
+        flat = dout.reshape(-1)
+        ln = lens.to(dev).long()
+        for d, w in ((0, w_hh_f), (1, w_hh_r)):
+            dhrec = torch.zeros(B, H, device=dev)
+            dcrec = torch.zeros(B, H, device=dev)
+            for s in range(T):
+                t = s if d else T - 1 - s
+                valid = (t < ln)[:, None]
+                i, f, g, o = acts[d, t].chunk(4, -1)
+                c_t = cs[d, t]
+                tp = t + 1 if d else t - 1
+                c_prev = cs[d, tp] if 0 <= tp < T else torch.zeros_like(c_t)
+                do = flat[self._out_index(dout, t, pair, H, d, out_ld_t, out_ld_b, B).view(-1)].view(B, H).float()
+                dh = do + dhrec
+                tc = torch.tanh(c_t)
+                dc = dcrec + dh * o * (1 - tc * tc)
+                dg = torch.cat([dc * g * i * (1 - i), dc * c_prev * f * (1 - f), dc * i * (1 - g * g),
+                                dh * tc * o * (1 - o)], -1)
+                dg = torch.where(valid, dg, torch.zeros_like(dg))
+                dcrec = torch.where(valid, dc * f, torch.zeros_like(dc))
+                dg_all[d, t] = dg.to(dtype)
+                dhrec = dg @ w
+        return dg_all
+
+    # -- LAS attention / decode helpers -------------------------------------------------------------
+    def las_attn_fwd(self, q, wk, vals, klens, ctx_out=None, probs_out=None):
+        B, Tk, D = wk.shape
+        s = torch.bmm(q.float().unsqueeze(1), wk.float().transpose(1, 2)).squeeze(1)
+        if klens is not None:
+            m = torch.arange(Tk, device=q.device)[None, :] >= klens.long()[:, None]
+            s = s.masked_fill(m, -1e12)
+        p = torch.softmax(s, dim=1)
+        c = torch.bmm(p.unsqueeze(1), vals.float()).squeeze(1).to(q.dtype)
+        if ctx_out is not None:
+            ctx_out.copy_(c); c = ctx_out
+        if probs_out is not None:
+            probs_out.copy_(p); p = probs_out
+        return c, p
+
+    def las_attn_bwd(self, dctx, wk, vals, probs, dscore_out=None):
+        dp = torch.bmm(dctx.float().unsqueeze(1), vals.float().transpose(1, 2)).squeeze(1)
+        ds = probs * (dp - (dp * probs).sum(1, keepdim=True))
+        dq = torch.bmm(ds.unsqueeze(1), wk.float()).squeeze(1).to(wk.dtype)
+        if dscore_out is not None:
+            dscore_out.copy_(ds); ds = dscore_out
+        return ds, dq
+
+    def argmax_rows(self, x, idx_out):
+        idx_out.copy_(x.float().argmax(dim=1))
+        return idx_out
+
+    def las_update_lengths(self, sym, lengths, step):
+        ended = ((sym == 3) | (sym == 0)) & (lengths > step)
+        lengths[ended] = step + 1
+
+    # -- embeddings / mix ---------------------------------------------------------------------------
+    def embedding_fwd(self, ids, table, dtype, out=None):
+        e = table[ids].to(dtype)
+        if out is None:
+            return e
+        out.copy_(e.view(out.shape))
+        return out
+
+    def embedding_bwd(self, ids, dout, dtable, padding_idx):
+        keep = ids != (padding_idx if padding_idx is not None else -1)
+        dtable.index_add_(0, ids[keep], dout.float()[keep])
+        return dtable
+
+    def mix_gather_concat(self, ids, table, dyn):
+        return torch.cat([table[ids].to(dyn.dtype), dyn], dim=1)
+
+    # -- softmax / loss -----------------------------------------------------------------------------
+    def log_softmax_fwd(self, x, want_argmax=False):
+        y = torch.log_softmax(x.float(), dim=1).to(x.dtype)
+        return y, (x.float().argmax(1) if want_argmax else None)
+
+    def log_softmax_bwd(self, dy, y):
+        dyf = dy.float()
+        return (dyf - torch.exp(y.float()) * dyf.sum(1, keepdim=True)).to(y.dtype)
+
+    def masked_nll_fwd(self, logp, target, mask):
+        per = -logp.float().gather(1, target[:, None]).squeeze(1)
+        if mask is not None:
+            per = per * mask.to(per.dtype)
+        return per.sum().reshape(1)
+
+    def masked_nll_bwd(self, gscale, target, mask, rows, cols, dtype):
+        d = torch.zeros((rows, cols), dtype=torch.float32, device=target.device)
+        v = -gscale.expand(rows).clone()
+        if mask is not None:
+            v = v * mask.to(v.dtype)
+        d.scatter_(1, target[:, None], v[:, None])
+        return d.to(dtype)
+
+    def softmax_nll_fused(self, logits, target, mask, scale, eps=0.0, inplace=False):
+        x = logits.float()
+        V = x.size(1)
+        lse = torch.logsumexp(x, dim=1)
+        q = torch.full_like(x, eps / V)
+        q.scatter_add_(1, target[:, None], torch.full_like(x[:, :1], 1 - eps))
+        per = lse - (q * x).sum(1)
+        m = torch.ones_like(per) if mask is None else mask.to(per.dtype)
+        loss = (per * m).sum().reshape(1)
+        d = ((torch.softmax(x, 1) - q) * m[:, None] * scale).to(logits.dtype)
+        if inplace:
+            logits.copy_(d); d = logits
+        return loss, d
+
+    # -- glue ---------------------------------------------------------------------------------------
+    def add(self, a, b, out=None):
+        y = (a.float() + b.float()).to(a.dtype)
+        if out is None:
+            return y
+        out.copy_(y)
+        return out
+
+    def add_posenc(self, x, pe):
+        return (x.float() + pe[:x.size(1)]).to(x.dtype)
+
+    def transpose01(self, x, out_dtype=None):
+        return x.transpose(0, 1).contiguous().to(out_dtype or x.dtype)
+
+    def cast(self, x, dtype):
+        return x.to(dtype)
+
+    def colsum(self, x, out=None, accumulate=False):
+        s = x.float().sum(0)
+        if out is None:
+            return s
+        if accumulate:
+            out += s
+        else:
+            out.copy_(s)
+        return out
+
+    def relu_bwd(self, dy, y):
+        return torch.where(y.float() > 0, dy, torch.zeros_like(dy))
+
+    def token_mask(self, ids, pad, causal):
+        B, L = ids.shape
+        m = (ids != pad).unsqueeze(1)
+        if causal:
+            m = m & torch.tril(torch.ones(L, L, dtype=torch.bool, device=ids.device)).unsqueeze(0)
+        return m.to(torch.uint8).contiguous()
+
+    def length_mask(self, lengths, L):
+        return (torch.arange(L, device=lengths.device)[None, :] < lengths.long()[:, None]).unsqueeze(1).to(torch.uint8)

@@ -1,0 +1,267 @@
+"""Per-kernel parity on the GPU: every C-ABI entry point (through b200st.kernels.CudaKernels) against the
+independent torch restatement in tests/fake_kernels.py, on the same device and inputs.
+
+fp32 tolerance 1e-5 relative L2 (different summation order only); bf16 tolerance 2e-2 (contract)."""
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ks():
+    from b200st.kernels import CudaKernels
+    from fake_kernels import FakeKernels
+    return CudaKernels(), FakeKernels()
+
+
+def rnd(*shape, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator(device='cpu').manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to('cuda').to(dtype)
+
+
+TOL = {torch.float32: 2e-5, torch.bfloat16: 2e-2}
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('ta,tb', [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize('M,N,K', [(1, 1, 1), (37, 29, 13), (64, 64, 64), (200, 130, 70), (513, 1024, 300),
+                                   (3200, 512, 512), (16384, 1024, 80)])
+def test_gemm(ks, dtype, ta, tb, M, N, K):
+    c, f = ks
+    a = rnd(K, M, dtype=dtype) if ta else rnd(M, K, dtype=dtype)
+    b = rnd(N, K, dtype=dtype, seed=1) if tb else rnd(K, N, dtype=dtype, seed=1)
+    bias = rnd(N, seed=2)
+    res = rnd(M, N, dtype=dtype, seed=3)
+    y = c.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, residual=res, alpha=0.5)
+    yr = f.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, residual=res, alpha=0.5)
+    assert rel_err(y, yr) < TOL[dtype]
+    y = c.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, relu=True)
+    yr = f.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, relu=True)
+    assert rel_err(y, yr) < TOL[dtype]
+
+
+def test_gemm_strided_views_and_batched(ks):
+    c, f = ks
+    w = rnd(96, 50)
+    x = rnd(33, 20)
+    # column-sliced weight (ldb > K), output into a column slice (ldc > N), in-place accumulate
+    out = torch.zeros(33, 128, device='cuda')
+    c.gemm(x, w[:, 30:], trans_b=True, out=out[:, 16:112])
+    c.gemm(x, w[:, 10:30], trans_b=True, residual=out[:, 16:112], out=out[:, 16:112])
+    ref = x @ w[:, 30:].t() + x @ w[:, 10:30].t()
+    assert rel_err(out[:, 16:112], ref) < 2e-5 and float(out[:, :16].abs().sum()) == 0
+    # batched with permuted (strided) operands, transposed A: [B][S,T]^T @ [B][S,D]
+    a = rnd(7, 5, 11).permute(1, 0, 2)
+    b = rnd(7, 5, 13, seed=4).permute(1, 0, 2)
+    y = c.gemm(a, b, trans_a=True)
+    assert rel_err(y, torch.matmul(a.transpose(1, 2), b)) < 2e-5
+    # bf16 operands, fp32 output (weight gradients)
+    a16, b16 = rnd(300, 40, dtype=torch.bfloat16), rnd(300, 24, dtype=torch.bfloat16, seed=5)
+    y = c.gemm(a16, b16, trans_a=True, out_dtype=torch.float32)
+    assert y.dtype == torch.float32 and rel_err(y, a16.float().t() @ b16.float()) < 1e-5
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('rows,cols', [(1, 8), (50, 32), (3200, 512), (77, 1000)])
+def test_layernorm(ks, dtype, rows, cols):
+    c, f = ks
+    x = rnd(rows, cols, dtype=dtype, scale=2.0) + 0.5
+    g, b = rnd(cols, seed=1) + 1, rnd(cols, seed=2)
+    y, mean, rstd = c.layernorm_fwd(x, g, b, 1e-6)
+    yr, meanr, rstdr = f.layernorm_fwd(x, g, b, 1e-6)
+    assert rel_err(y, yr) < TOL[dtype] and rel_err(mean, meanr) < 1e-5 and rel_err(rstd, rstdr) < 1e-5
+    dy = rnd(rows, cols, dtype=dtype, seed=3)
+    dg, db = torch.zeros(cols, device='cuda'), torch.zeros(cols, device='cuda')
+    dgr, dbr = torch.zeros(cols, device='cuda'), torch.zeros(cols, device='cuda')
+    dx = c.layernorm_bwd(dy, x, g, mean, rstd, dg, db)
+    dxr = f.layernorm_bwd(dy, x, g, meanr, rstdr, dgr, dbr)
+    assert rel_err(dx, dxr) < TOL[dtype] and rel_err(dg, dgr) < 1e-4 and rel_err(db, dbr) < 1e-4
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('B,H,Lq,Lk,d,mask_kind', [(2, 4, 7, 7, 8, 'causal'), (3, 8, 50, 31, 64, 'key'),
+                                                   (64, 8, 50, 50, 64, 'causal'), (2, 8, 9, 12, 6, None),
+                                                   (2, 2, 5, 150, 64, 'key')])
+def test_mha(ks, dtype, B, H, Lq, Lk, d, mask_kind):
+    c, f = ks
+    qkv = rnd(B, max(Lq, Lk), 3 * H * d, dtype=dtype)            # packed buffer: exercises row strides
+    q, k, v = qkv[:, :Lq, :H * d], qkv[:, :Lk, H * d:2 * H * d], qkv[:, :Lk, 2 * H * d:]
+    if Lq != Lk:
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    mask = None
+    if mask_kind == 'key':
+        lens = torch.randint(1, Lk + 1, (B,), device='cuda')
+        mask = (torch.arange(Lk, device='cuda')[None, :] < lens[:, None]).unsqueeze(1).to(torch.uint8)
+    elif mask_kind == 'causal':
+        ids = torch.randint(0, 3, (B, Lk), device='cuda'); ids[:, 0] = 2
+        mask = f.token_mask(ids, 0, True)
+    temp = d ** 0.5
+    o, p = c.mha_fwd(q, k, v, mask, H, temp)
+    orf, pr = f.mha_fwd(q, k, v, mask, H, temp)
+    assert rel_err(o, orf) < TOL[dtype] and rel_err(p, pr) < TOL[dtype]
+    do = rnd(B, Lq, H * d, dtype=dtype, seed=9)
+    dq, dk, dv = c.mha_bwd(do, q, k, v, pr, H, temp)
+    dqr, dkr, dvr = f.mha_bwd(do, q, k, v, pr, H, temp)
+    for a, b in ((dq, dqr), (dk, dkr), (dv, dvr)):
+        assert rel_err(a, b) < TOL[dtype]
+
+
+def test_mha_fully_masked_row_is_uniform(ks):
+    """-1e9 fill is finite: a row with every key masked softmaxes to uniform (layers.py:224)."""
+    c, f = ks
+    q, k, v = rnd(1, 3, 16), rnd(1, 5, 16, seed=1), rnd(1, 5, 16, seed=2)
+    mask = torch.zeros(1, 1, 5, dtype=torch.uint8, device='cuda')
+    o, p = c.mha_fwd(q, k, v, mask, 2, 2.0)
+    assert torch.allclose(p, torch.full_like(p, 0.2), atol=1e-6)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_lstm_cell(ks, dtype):
+    c, f = ks
+    B, H = 5, 24
+    gates, cp, res = rnd(B, 4 * H, dtype=dtype), rnd(B, H, seed=1), rnd(B, H, dtype=dtype, seed=2)
+    h, cc, acts, outr = c.lstm_cell_fwd(gates, cp, residual=res)
+    hr, ccr, actsr, outrr = f.lstm_cell_fwd(gates, cp, residual=res)
+    for a, b in ((h, hr), (cc, ccr), (acts, actsr), (outr, outrr)):
+        assert rel_err(a, b) < TOL[dtype]
+    h0, c0, _, _ = c.lstm_cell_fwd(gates, None)
+    hr0, cr0, _, _ = f.lstm_cell_fwd(gates, None)
+    assert rel_err(h0, hr0) < TOL[dtype]
+    dhs = [rnd(B, H, dtype=dtype, seed=3), None, rnd(B, H, dtype=dtype, seed=4)]
+    dcn = rnd(B, H, seed=5)
+    dg, dcp = c.lstm_cell_bwd(dhs, dcn, actsr, cp, ccr, dtype)
+    dgr, dcpr = f.lstm_cell_bwd(dhs, dcn, actsr, cp, ccr, dtype)
+    assert rel_err(dg, dgr) < TOL[dtype] and rel_err(dcp, dcpr) < 1e-5
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('T,B,H,pair', [(8, 3, 16, 2), (24, 5, 24, 2), (6, 11, 16, 1), (40, 9, 32, 2),
+                                        (16, 8, 256, 2)])
+def test_blstm_recurrence(ks, dtype, T, B, H, pair):
+    c, f = ks
+    xproj = rnd(2, T, B, 4 * H, dtype=dtype)
+    wf, wr = rnd(4 * H, H, seed=1, scale=H ** -0.5), rnd(4 * H, H, seed=2, scale=H ** -0.5)
+    lens = torch.randint(1, T + 1, (B,), device='cuda', dtype=torch.int32)
+    lens[0] = T
+    if pair == 2:
+        shape, ld_t, ld_b = (T // 2, B, 4 * H), B * 4 * H, 4 * H
+    else:
+        shape, ld_t, ld_b = (B, T, 2 * H), 2 * H, T * 2 * H
+    out = torch.full(shape, 7.0, dtype=dtype, device='cuda')
+    outr = torch.full(shape, 7.0, dtype=dtype, device='cuda')
+    hs, acts, cs = c.blstm_fwd(xproj, wf, wr, lens, out, ld_t, ld_b, pair)
+    hsr, actsr, csr = f.blstm_fwd(xproj, wf, wr, lens, outr, ld_t, ld_b, pair)
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    assert rel_err(out, outr) < tol
+    assert rel_err(hs, hsr) < tol
+    valid = (torch.arange(T, device='cuda')[:, None] < lens[None, :]).float()[None, :, :, None]
+    assert rel_err(acts * valid, actsr * valid) < tol and rel_err(cs * valid, csr * valid) < tol
+    dout = rnd(*shape, dtype=dtype, seed=7)
+    dg = c.blstm_bwd(dout, ld_t, ld_b, pair, actsr, csr, wf, wr, lens, dtype)
+    dgr = f.blstm_bwd(dout, ld_t, ld_b, pair, actsr, csr, wf, wr, lens, dtype)
+    assert rel_err(dg, dgr) < tol
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_las_attention(ks, dtype):
+    c, f = ks
+    B, Tk, D, Dv = 6, 13, 32, 48
+    q, wk, vals = rnd(B, D, dtype=dtype), rnd(B, Tk, D, dtype=dtype, seed=1), rnd(B, Tk, Dv, dtype=dtype, seed=2)
+    klens = torch.tensor([13, 1, 5, 7, 13, 2], dtype=torch.int32, device='cuda')
+    cx, p = c.las_attn_fwd(q, wk, vals, klens)
+    cxr, pr = f.las_attn_fwd(q, wk, vals, klens)
+    assert rel_err(cx, cxr) < TOL[dtype] and rel_err(p, pr) < TOL[dtype]
+    assert float(p[1, 1:].abs().sum()) == 0.0
+    dctx = rnd(B, Dv, dtype=dtype, seed=3)
+    ds, dq = c.las_attn_bwd(dctx, wk, vals, pr)
+    dsr, dqr = f.las_attn_bwd(dctx, wk, vals, pr)
+    assert rel_err(ds, dsr) < TOL[dtype] and rel_err(dq, dqr) < TOL[dtype]
+
+
+def test_argmax_and_lengths(ks):
+    c, f = ks
+    x = rnd(9, 1000)
+    x[3, 17] = 50.0; x[3, 400] = 50.0            # tie: first index wins
+    idx = torch.empty(4, 9, dtype=torch.int64, device='cuda')
+    c.argmax_rows(x, idx[2])
+    assert torch.equal(idx[2], x.argmax(1)) and int(idx[2, 3]) == 17
+    col = torch.empty(9, 3, dtype=torch.int64, device='cuda')
+    c.argmax_rows(x, col[:, 1])
+    assert torch.equal(col[:, 1], x.argmax(1))
+    sym = torch.tensor([3, 5, 0, 9, 3], device='cuda')
+    lengths = torch.tensor([7, 7, 7, 7, 2], dtype=torch.int32, device='cuda')
+    c.las_update_lengths(sym, lengths, 3)
+    assert lengths.tolist() == [4, 7, 4, 7, 2]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_embedding_and_mix(ks, dtype):
+    c, f = ks
+    V, E, D, n = 50, 12, 20, 37
+    table = rnd(V, E)
+    ids = torch.randint(0, V, (n,), device='cuda'); ids[:5] = 0
+    assert rel_err(c.embedding_fwd(ids, table, dtype), f.embedding_fwd(ids, table, dtype)) < 1e-6 + TOL[dtype]
+    buf = torch.zeros(n, 40, dtype=dtype, device='cuda')
+    c.embedding_fwd(ids, table, dtype, out=buf[:, 4:4 + E])
+    assert rel_err(buf[:, 4:4 + E], table[ids].to(dtype)) < 1e-6 and float(buf[:, :4].abs().sum()) == 0
+    dout = rnd(n, E, dtype=dtype, seed=1)
+    dt1, dt2 = torch.zeros(V, E, device='cuda'), torch.zeros(V, E, device='cuda')
+    c.embedding_bwd(ids, dout, dt1, 0)
+    f.embedding_bwd(ids, dout, dt2, 0)
+    assert rel_err(dt1, dt2) < 1e-5 and float(dt1[0].abs().sum()) == 0.0
+    dyn = rnd(n, D, dtype=dtype, seed=2)
+    assert rel_err(c.mix_gather_concat(ids, table, dyn), f.mix_gather_concat(ids, table, dyn)) < 1e-6 + TOL[dtype]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('rows,cols', [(5, 41), (64, 10000), (3, 33000)])
+def test_softmax_family(ks, dtype, rows, cols):
+    c, f = ks
+    x = rnd(rows, cols, dtype=dtype, scale=3.0)
+    y, am = c.log_softmax_fwd(x, want_argmax=True)
+    yr, amr = f.log_softmax_fwd(x, want_argmax=True)
+    assert rel_err(y, yr) < TOL[dtype]
+    if dtype == torch.float32:
+        assert torch.equal(am, amr)
+    dy = rnd(rows, cols, dtype=dtype, seed=1)
+    assert rel_err(c.log_softmax_bwd(dy, yr), f.log_softmax_bwd(dy, yr)) < TOL[dtype]
+    tgt = torch.randint(0, cols, (rows,), device='cuda')
+    mask = (torch.arange(rows, device='cuda') % 3 != 1).to(torch.uint8)
+    l, lr = c.masked_nll_fwd(yr, tgt, mask), f.masked_nll_fwd(yr, tgt, mask)
+    assert rel_err(l, lr) < 1e-5
+    g = torch.tensor([0.25], device='cuda')
+    assert rel_err(c.masked_nll_bwd(g, tgt, mask, rows, cols, dtype), f.masked_nll_bwd(g, tgt, mask, rows, cols, dtype)) < 1e-6
+    for eps in (0.0, 0.1):
+        ls, d = c.softmax_nll_fused(x, tgt, mask, g, eps)
+        lsr, dr = f.softmax_nll_fused(x, tgt, mask, g, eps)
+        assert rel_err(ls, lsr) < 1e-5 and rel_err(d, dr) < TOL[dtype]
+    # fused == log_softmax + nll  (eps = 0)
+    ls, _ = c.softmax_nll_fused(x, tgt, mask, g, 0.0)
+    assert rel_err(ls, lr) < 1e-3 if dtype == torch.bfloat16 else rel_err(ls, lr) < 1e-5
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_glue(ks, dtype):
+    c, f = ks
+    a, b = rnd(7, 33, dtype=dtype), rnd(7, 33, dtype=dtype, seed=1)
+    assert rel_err(c.add(a, b), f.add(a, b)) < 1e-6 + TOL[dtype] * 0.5
+    x, pe = rnd(3, 9, 16, dtype=dtype), rnd(500, 16, seed=2)
+    assert rel_err(c.add_posenc(x, pe), f.add_posenc(x, pe)) < 1e-6 + TOL[dtype] * 0.5
+    t = rnd(5, 7, 11, dtype=dtype)
+    assert torch.equal(c.transpose01(t), f.transpose01(t))
+    assert torch.equal(c.transpose01(t.float(), out_dtype=dtype), f.transpose01(t.float(), out_dtype=dtype))
+    assert torch.equal(c.cast(t.float(), dtype), t.float().to(dtype))
+    big = rnd(5000, 130, dtype=dtype)
+    assert rel_err(c.colsum(big), f.colsum(big)) < 1e-4
+    acc = torch.ones(130, device='cuda')
+    c.colsum(big, out=acc, accumulate=True)
+    assert rel_err(acc, f.colsum(big) + 1) < 1e-4
+    assert torch.equal(c.relu_bwd(a, b), f.relu_bwd(a, b))
+    ids = torch.randint(0, 4, (6, 9), device='cuda')
+    assert torch.equal(c.token_mask(ids, 0, True), f.token_mask(ids, 0, True))
+    assert torch.equal(c.token_mask(ids, 0, False), f.token_mask(ids, 0, False))
+    ln = torch.tensor([1, 9, 4], dtype=torch.int32, device='cuda')
+    assert torch.equal(c.length_mask(ln, 9), f.length_mask(ln, 9))
