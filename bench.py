@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Benchmark of the joint speech-translation training hot path (BASELINE.json metric: joint-ST train utt/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+
+One "step" = Seq2seq.forward_train(mode='ST') + masked NLL (trainer_st.py:268-288) + backward (+ gradient
+mean-all-reduce when N > 1), on BASELINE.json configs[2]: synthetic 80-dim fbank, 1000 frames (padded to
+1008 by the reference's rule), per-GPU batch 64, V=10k, d=512, 8 heads, 6+6 layers, E=200, H=256,
+max_seq_len_src=32, target length 50.  Weak scaling: per-GPU batch is fixed, N=8 is the global-batch-512
+config.  Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for what each key means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'speech-translation-joint-embedding-passing_b200')
+for p in (ROOT, PKG, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = 'joint_st_train_utt_per_s'
+UNIT = 'utt/s'
+
+
+def st_config():
+    from oracle.st_oracle import STConfig
+    return STConfig(enc_vocab_size=10000, dec_vocab_size=10000, enc_embedding_size=200,
+                    dec_embedding_size=200, max_seq_len_src=32, max_seq_len_tgt=50, num_heads=8,
+                    dim_model=512, dim_feedforward=1024, enc_layers=6, dec_layers=6, acous_dim=80,
+                    acous_hidden_size=256)
+
+
+def workload(args):
+    return {'workload': 'BASELINE.json configs[2]: joint ST embedding passing, pyramidal BLSTM enc -> dynamic+'
+                        'static embedding mix -> TFEnc/TFDec 6+6, fwd+bwd',
+            'per_gpu_batch': args.batch, 'global_batch': args.batch * args.gpus, 'frames': args.frames,
+            'frames_padded': args.frames + 8 - args.frames % 8, 'acous_dim': 80, 'vocab': 10000,
+            'dim_model': 512, 'heads': 8, 'layers': '6+6', 'max_seq_len_src': 32, 'tgt_len': 50,
+            'step': 'forward_train(ST) + masked NLL + backward' + (' + grad all-reduce' if args.gpus > 1 else ''),
+            'parallelism': f'dp{args.gpus}', 'dropout': 0.0}
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work: forward FLOPs per batch, de-duplicated key projection
+# ------------------------------------------------------------------------------------------------
+def algorithmic_flops(B, T_pad, F=80, H=256, D=512, FF=1024, V=10000, E=200, S=31, L=50, n_enc=6, n_dec=6):
+    blstm = 0
+    for layer in range(4):
+        t = T_pad // (2 ** layer)
+        i = F if layer == 0 else 4 * H
+        blstm += 2 * B * t * (i + H) * 4 * H * 2
+    tk = T_pad // 8
+    las_step = 2 * B * ((E + 2 * D) * 4 * D + 2 * (2 * D) * 4 * D + 2 * tk * D + (2 * H + D) * D + D * V)
+    las = S * las_step + 2 * B * tk * 2 * H * D          # key projection once
+    mix = 2 * B * S * (E + D) * D
+
+    def mha(lq, lk):
+        return 2 * B * D * D * (2 * lq + 2 * lk) + 4 * B * lq * lk * D
+    ffn = lambda l: 4 * B * l * D * FF
+    tfenc = n_enc * (mha(S, S) + ffn(S))
+    tfdec = n_dec * (mha(L, L) + mha(L, S) + ffn(L)) + 2 * B * L * E * D
+    out = 2 * B * L * D * V
+    fwd = blstm + las + mix + tfenc + tfdec + out
+    return {'fwd': fwd, 'fwd_bwd': 3 * fwd, 'blstm_recurrent_fwd': sum(
+        2 * B * (T_pad // 2 ** l) * H * 4 * H * 2 for l in range(4))}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# per-kernel-family timing with CUDA events on the launching stream
+# ------------------------------------------------------------------------------------------------
+class KernelTimer:
+    """Wraps methods of the kernel backend; records a CUDA event pair around each call of the chosen
+    families.  Events are recorded on the current stream = the stream the kernels are launched on."""
+
+    def __init__(self, backend, names):
+        self.backend, self.names = backend, list(names)
+        self.records = {n: [] for n in names}
+        self.meta = {n: [] for n in names}
+        self._orig = {}
+
+    def __enter__(self):
+        for n in self.names:
+            orig = getattr(self.backend, n)
+            self._orig[n] = orig
+
+            def wrapped(*a, __orig=orig, __n=n, **kw):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = __orig(*a, **kw)
+                e1.record()
+                self.records[__n].append((e0, e1))
+                if __n == 'gemm':
+                    x, y = a[0], a[1]
+                    ta, tb = kw.get('trans_a', False), kw.get('trans_b', False)
+                    x2 = x[0] if x.dim() == 3 else x
+                    y2 = y[0] if y.dim() == 3 else y
+                    m, k = (x2.size(1), x2.size(0)) if ta else (x2.size(0), x2.size(1))
+                    n_ = y2.size(0) if tb else y2.size(1)
+                    self.meta[__n].append(2 * m * n_ * k * (x.size(0) if x.dim() == 3 else 1))
+                elif __n in ('blstm_fwd',):
+                    _, T, B, H4 = a[0].shape
+                    self.meta[__n].append(2 * 2 * T * B * (H4 // 4) * H4)
+                elif __n in ('blstm_bwd',):
+                    _, T, B, H = a[5].shape
+                    self.meta[__n].append(2 * 2 * T * B * H * 4 * H)
+                return r
+            setattr(self.backend, n, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        for n, orig in self._orig.items():
+            try:
+                delattr(self.backend, n)          # restore the class method
+            except AttributeError:
+                setattr(self.backend, n, orig)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for n, evs in self.records.items():
+            ms = [a.elapsed_time(b) for a, b in evs]
+            out[n] = {'calls': len(ms), 'ms': sum(ms), 'flops': float(sum(self.meta[n])) if self.meta[n] else None}
+        return out
+
+
+ALL_FAMILIES = ['gemm', 'layernorm_fwd', 'layernorm_bwd', 'mha_fwd', 'mha_bwd', 'lstm_cell_fwd', 'lstm_cell_bwd',
+                'blstm_fwd', 'blstm_bwd', 'las_attn_fwd', 'las_attn_bwd', 'argmax_rows', 'las_update_lengths',
+                'embedding_fwd', 'embedding_bwd', 'mix_gather_concat', 'log_softmax_fwd', 'log_softmax_bwd',
+                'masked_nll_fwd', 'masked_nll_bwd', 'add', 'add_posenc', 'transpose01', 'cast', 'colsum',
+                'relu_bwd', 'token_mask', 'length_mask']
+
+
+# ------------------------------------------------------------------------------------------------
+# the CPU arm: the reference's algorithm (oracle port, plain PyTorch fp32) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step(P, cfg, data):
+    from oracle import st_oracle as O
+    for v in P.values():
+        v.grad = None
+    loss, _ = O.train_step_st(P, cfg, data['src'], data['tgt'], data['acous_feats'], data['acous_lens'])
+    loss.backward()
+    return float(loss.detach())
+
+
+def cpu_baseline(args, budget_s=25.0, steps=1, warmup=0):
+    """Times `steps` oracle steps on a bounded sample of the workload (same shapes, smaller batch)."""
+    from oracle import st_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = st_config()
+    P = {k: v.requires_grad_(True) for k, v in O.init_params(cfg, seed=333).items()}
+    probe = O.synthetic_batch(cfg, 1, args.frames, seed=1)
+    t0 = time.perf_counter(); cpu_step(P, cfg, probe); t1 = time.perf_counter() - t0   # also warms threads
+    per_utt = t1
+    total_steps = steps + warmup
+    b = int(max(1, min(args.batch, budget_s / max(per_utt, 1e-3) / max(total_steps, 1))))
+    b = min(b, 8) if total_steps == 1 else b
+    data = O.synthetic_batch(cfg, b, args.frames, seed=333)
+    for _ in range(warmup):
+        cpu_step(P, cfg, data)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(P, cfg, data)
+    dt = (time.perf_counter() - t0) / steps
+    return {'value': b / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'configs[2] shapes ({args.frames} frames, V=10k, 6+6 layers), batch {b} of {args.batch}, '
+                      f'{steps} timed step(s) of fwd+bwd, fp32, torch.set_num_threads({cores}); the reference is '
+                      f'pure Python/PyTorch and cannot travel to the GPU box, so its algorithm is timed through '
+                      f'oracle/st_oracle.py (same torch primitives at the same call sites)',
+            'ms_per_step': dt * 1e3, 'batch': b}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args, budget_s=150.0, steps=max(1, args.steps), warmup=max(0, args.warmup))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': cb['ms_per_step'],
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': workload(args), 'cpu_baseline': {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# the GPU arm
+# ------------------------------------------------------------------------------------------------
+def build_model(cfg, device):
+    from models.Seq2seq import Seq2seq
+    torch.manual_seed(333)
+    m = Seq2seq(cfg.enc_vocab_size, cfg.dec_vocab_size, share_embedder=False,
+                enc_embedding_size=cfg.enc_embedding_size, dec_embedding_size=cfg.dec_embedding_size,
+                max_seq_len_src=cfg.max_seq_len_src, max_seq_len_tgt=cfg.max_seq_len_tgt,
+                num_heads=cfg.num_heads, dim_model=cfg.dim_model, dim_feedforward=cfg.dim_feedforward,
+                enc_layers=cfg.enc_layers, dec_layers=cfg.dec_layers, embedding_dropout=0.0, dropout=0.0,
+                acous_dim=cfg.acous_dim, acous_hidden_size=cfg.acous_hidden_size, mode='ST', load_mode='null')
+    for mod in m.modules():
+        if type(mod).__name__ == 'ScaledDotProductAttention':
+            mod.dropout.p = 0.0
+    return m.to(device).train()
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from oracle import st_oracle as O
+    from b200st import runtime
+    from b200st.dp import GradAllReducer
+    from b200st.kernels import K
+    from trainer.trainer_st import Trainer_ST
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)'
+    runtime.set_compute_dtype(args.dtype)
+    cfg = st_config()
+    model = build_model(cfg, device)
+    reducer = GradAllReducer(model) if world > 1 else None
+    trainer = Trainer_ST(use_gpu=True, batch_size=args.batch, minibatch_partition=1, reducer=reducer)
+
+    host = O.synthetic_batch(cfg, args.batch, args.frames, seed=333 + rank)
+    pin = lambda t: t.pin_memory()
+    batch_items = {'srcid': [pin(host['src'])], 'tgtid': [pin(host['tgt'])],
+                   'acous_feat': [pin(host['acous_feats'])], 'acouslen': host['acous_lens'],
+                   'srclen': [cfg.max_seq_len_src] * args.batch, 'tgtlen': [cfg.max_seq_len_tgt] * args.batch}
+    h2d = sum(batch_items[k][0].numel() * batch_items[k][0].element_size() for k in ('srcid', 'tgtid', 'acous_feat'))
+    dev_items = dict(batch_items)
+    for k in ('srcid', 'tgtid', 'acous_feat'):
+        dev_items[k] = [batch_items[k][0].to(device)]
+
+    def step(items):
+        out = trainer._train_batch(model, items)
+        model.zero_grad(set_to_none=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(items, steps, sync_loss):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            step(items)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms / steps
+
+    for _ in range(max(args.warmup, 3)):
+        step(dev_items)
+    # ---- profiling pass (untimed): every kernel family, to find the dominant one
+    with KernelTimer(K(), ALL_FAMILIES) as kt:
+        step(dev_items)
+    fam = kt.summary()
+    dominant = max(('blstm_fwd', 'blstm_bwd', 'gemm'), key=lambda n: fam[n]['ms'])
+    roof_names = ['blstm_fwd', 'blstm_bwd'] if dominant.startswith('blstm') else [dominant]
+    live = sum(fam[n]['calls'] for n in roof_names) <= 64
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = K().launch_count()
+    if live:
+        with KernelTimer(K(), roof_names) as rt_timer:
+            ms_dev = timed(dev_items, args.steps, False)
+        roof = rt_timer.summary()
+    else:
+        ms_dev = timed(dev_items, args.steps, False)
+        roof = {n: fam[n] for n in roof_names}
+    launches = K().launch_count() - n0
+    # ---- timed region 2: end to end through Trainer_ST._train_batch with HOST (pinned) buffers
+    ms_e2e = timed(batch_items, args.steps, True)
+    clocks = sampler.stop()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+        peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
+        r_calls = sum(roof[n]['calls'] for n in roof_names)
+        r_ms = sum(roof[n]['ms'] for n in roof_names)
+        r_flops = sum(roof[n]['flops'] or 0 for n in roof_names)
+        achieved = r_flops / max(r_ms, 1e-9) / 1e9          # TFLOP/s
+        t_pad = args.frames + 8 - args.frames % 8
+        alg = algorithmic_flops(args.batch, t_pad)
+        total_units = args.batch * world
+        line = {
+            'metric': METRIC, 'value': total_units / (ms_dev / 1e3), 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16' if args.dtype == 'bf16' else 'f32', 'data': 'synthetic',
+            'config': dict(workload(args), l2='per-step working set (saved activations > 1 GB) exceeds the 126 MB L2; no flush needed',
+                           step_share_ms={k: round(v['ms'], 3) for k, v in fam.items() if v['ms'] > 0.01},
+                           algorithmic_tflop_per_step=alg['fwd_bwd'] / 1e12,
+                           whole_step_tflops=alg['fwd_bwd'] / 1e12 / (ms_dev / 1e3)),
+            'e2e': {'value': total_units / (ms_e2e / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'roofline': {'kernel': '+'.join(roof_names), 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
+                         'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                         'launches': r_calls, 'avg_launch_ms': r_ms / max(r_calls, 1),
+                         'timed': 'live CUDA events in the timed region' if live else 'profiling pass',
+                         'note': 'recurrent-GEMM FLOPs 2*2dirs*T*B*H*4H per launch; this kernel is bound by the '
+                                 'serial time-step chain (latency), not by tensor throughput'},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline(args)
+            line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--dtype', default=os.environ.get('B200ST_BENCH_DTYPE', 'bf16'), choices=['bf16', 'fp32'])
+    ap.add_argument('--batch', type=int, default=64)
+    ap.add_argument('--frames', type=int, default=1000)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -50,6 +50,11 @@ int b200st_gemm(int dtype_ab, int dtype_c, int trans_a, int trans_b,
                 const void* R, int64_t ldr, int64_t stride_r,
                 const float* bias, int relu, int64_t batch, b200st_stream_t stream);
 
+/* GEMM kernel selection: 0 = auto (bf16 operands that TMA can address -> tcgen05 tensor-core kernel, everything
+ * else -> exact CUDA-core kernel), 1 = CUDA cores only, 2 = tensor cores required (error if not eligible).
+ * Returns the previous mode.  Used by tests to compare the two kernels; the product leaves it at 0. */
+int b200st_set_gemm_backend(int mode);
+
 /* ---- LayerNorm (layers.py:139,153,240,245; TFEnc.py:61,89; TFDec.py:58,127) -------------------- */
 int b200st_layernorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y,
                          float* mean, float* rstd, int64_t rows, int64_t cols, float eps,
@@ -99,6 +104,9 @@ int b200st_blstm_fwd(int dtype, const void* xproj, const float* w_hh_f, const fl
                      const int32_t* lens, void* out, int64_t out_ld_t, int64_t out_ld_b, int pair,
                      void* hs, float* acts, float* cs, int64_t T, int64_t B, int64_t H,
                      b200st_stream_t stream);
+/* Recurrence kernel selection: 0 = auto (bf16 activations with H = 256 -> tcgen05 kernel), 1 = CUDA cores only.
+ * Returns the previous mode (test hook). */
+int b200st_set_blstm_backend(int mode);
 /* dout in the same layout as out; dgates [2][T][B][4H] dtype written (zeros for t>=len). */
 int b200st_blstm_bwd(int dtype, const void* dout, int64_t out_ld_t, int64_t out_ld_b, int pair,
                      const float* acts, const float* cs, const float* w_hh_f, const float* w_hh_r,

@@ -1,0 +1,88 @@
+"""Data-parallel gradient exchange: bucketed NCCL all-reduce launched from autograd hooks so that it
+overlaps with the rest of backward (the BLSTM backward is the long tail that hides the other buckets).
+
+The reference has no multi-GPU path; its batch-splitting mechanism is serial gradient accumulation over
+`minibatch_partition` slices (trainer_base.py:83-85, trainer_st.py:225-290), each slice's loss normalised
+by its own #non-PAD tokens and divided by n_minibatch.  N ranks x per-rank normalisation + MEAN all-reduce
+is arithmetically the same thing, so `batch_size=N*b, minibatch_partition=N` on the reference is the
+oracle for N ranks of batch b here.  No token-count all-reduce is needed.
+
+Parameters that never receive a gradient (template layers enc_src.enc.*, dec_tgt.dec.*, and
+las.decoder.acous_out.* in ST-only mode) simply never fire their hook; buckets flush what is ready at
+`finish()`, so nothing waits on them.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradAllReducer:
+    def __init__(self, module: torch.nn.Module, bucket_bytes: int = 32 << 20,
+                 process_group: Optional[dist.ProcessGroup] = None):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.bucket_bytes = bucket_bytes
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self._pending: List[torch.Tensor] = []      # grads ready but not yet sent
+        self._pending_bytes = 0
+        self._inflight = []                          # (work, flat, [grads])
+        self._hooks = []
+        self._stream = None
+        if self.world > 1:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    # -- hook path --------------------------------------------------------------------------------
+    def _on_grad(self, p: torch.Tensor):
+        g = p.grad
+        if g is None:
+            return
+        self._pending.append(g)
+        self._pending_bytes += g.numel() * g.element_size()
+        if self._pending_bytes >= self.bucket_bytes:
+            self._flush()
+
+    def _flush(self):
+        if not self._pending:
+            return
+        grads, self._pending, self._pending_bytes = self._pending, [], 0
+        if grads[0].is_cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream()
+            # the bucket becomes ready on the compute stream; ship it from a side stream
+            self._stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._stream):
+                flat = torch._utils._flatten_dense_tensors(grads)
+                flat.div_(self.world)
+                work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            flat = torch._utils._flatten_dense_tensors(grads)
+            flat.div_(self.world)
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._inflight.append((work, flat, grads))
+
+    def finish(self):
+        """Call after backward(): sends the last partial bucket, waits, writes the means back."""
+        if self.world <= 1:
+            return
+        self._flush()
+        for work, flat, grads in self._inflight:
+            work.wait()
+            if flat.is_cuda:
+                with torch.cuda.stream(self._stream):
+                    for g, s in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                        g.copy_(s)
+            else:
+                for g, s in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                    g.copy_(s)
+        if self._stream is not None:
+            torch.cuda.current_stream().wait_stream(self._stream)
+        self._inflight = []
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

@@ -57,6 +57,14 @@ class CudaKernels:
     def launch_count(self) -> int:
         return int(self.lib.b200st_launch_count())
 
+    def set_gemm_backend(self, mode: int) -> int:
+        """0 auto, 1 CUDA cores only, 2 tensor cores required.  Returns the previous mode (test hook)."""
+        return int(self.lib.b200st_set_gemm_backend(int(mode)))
+
+    def set_blstm_backend(self, mode: int) -> int:
+        """0 auto (tcgen05 recurrence for bf16/H=256), 1 CUDA cores only.  Returns the previous mode."""
+        return int(self.lib.b200st_set_blstm_backend(int(mode)))
+
     # -- GEMM -------------------------------------------------------------------------------------
     def gemm(self, a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=None,
              relu=False, residual=None, alpha=1.0):

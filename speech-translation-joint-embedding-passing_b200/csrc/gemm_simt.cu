@@ -157,12 +157,39 @@ int gemm_simt(int dtype_ab, int dtype_c, int ta, int tb, int64_t M, int64_t N, i
 
 }  // namespace b200st
 
+namespace b200st {
+bool gemm_tc_eligible(int dtype_ab, int ta, int tb, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                      const void* B, int64_t ldb, int64_t batch);
+int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const void* A, int64_t lda,
+            const void* B, int64_t ldb, void* C, int64_t ldc, const void* R, int64_t ldr, const float* bias, int relu,
+            cudaStream_t st);
+static int g_gemm_backend = 0;   // 0 auto, 1 CUDA cores only, 2 tensor cores required
+}  // namespace b200st
+
+extern "C" int b200st_set_gemm_backend(int mode) {
+  const int old = b200st::g_gemm_backend;
+  if (mode >= 0 && mode <= 2) b200st::g_gemm_backend = mode;
+  return old;
+}
+
 extern "C" int b200st_gemm(int dtype_ab, int dtype_c, int trans_a, int trans_b, int64_t M, int64_t N,
                            int64_t K, float alpha, const void* A, int64_t lda, int64_t stride_a,
                            const void* B, int64_t ldb, int64_t stride_b, void* C, int64_t ldc,
                            int64_t stride_c, const void* R, int64_t ldr, int64_t stride_r,
                            const float* bias, int relu, int64_t batch, b200st_stream_t stream) {
-  return b200st::gemm_simt(dtype_ab, dtype_c, trans_a, trans_b, M, N, K, alpha, A, lda, stride_a, B,
-                           ldb, stride_b, C, ldc, stride_c, R, ldr, stride_r, bias, relu, batch,
-                           (cudaStream_t)stream);
+  using namespace b200st;
+  if (M <= 0 || N <= 0 || batch <= 0) return 0;
+  const bool ok = g_gemm_backend != 1 &&
+                  gemm_tc_eligible(dtype_ab, trans_a, trans_b, M, N, K, A, lda, B, ldb, batch);
+  // bf16 operands go to the tcgen05 kernel whenever TMA can address them; tiny problems (less work than one
+  // tile row of MMAs) and everything fp32 stay on the exact CUDA-core kernel.
+  if (ok && (g_gemm_backend == 2 || M * N * K >= (1ll << 16)))
+    return gemm_tc(dtype_c, trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, C, ldc, R, ldr, bias, relu,
+                   (cudaStream_t)stream);
+  if (g_gemm_backend == 2)
+    return set_error("gemm: tensor-core backend forced but operands are not TMA-addressable "
+                     "(need bf16, batch 1, 16-byte aligned bases and leading dims %% 8 == 0)");
+  return gemm_simt(dtype_ab, dtype_c, trans_a, trans_b, M, N, K, alpha, A, lda, stride_a, B,
+                   ldb, stride_b, C, ldc, stride_c, R, ldr, stride_r, bias, relu, batch,
+                   (cudaStream_t)stream);
 }

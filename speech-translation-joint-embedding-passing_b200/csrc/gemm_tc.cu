@@ -1,0 +1,363 @@
+// bf16 GEMM on the 5th-generation tensor cores (sm_100a): TMA -> shared memory (128B swizzle) ->
+// tcgen05.mma (accumulator in TMEM) -> tcgen05.ld epilogue with fused alpha / bias / ReLU / residual.
+//
+//   C[M,N] = relu?(alpha * op(A) op(B) + bias) + R        A,B bf16; C,R bf16 or fp32; fp32 accumulate
+//
+// One CTA computes one 128 x BN output tile (x one K split).  Warp roles (256 threads):
+//   warp 0  : TMA producer  — one elected lane issues cp.async.bulk.tensor loads into a 4-stage ring
+//   warp 1  : MMA issuer    — one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x 4 per stage and
+//                             releases the stage with tcgen05.commit
+//   warp 2  : TMEM allocator (BN fp32 columns)
+//   warps 4-7: epilogue     — each thread owns one accumulator row (TMEM lane), reads 32 columns at a time
+// All four transpose forms are served by the same kernel: an operand stored with K contiguous is staged
+// K-major (box 128 rows x 64 k), an operand stored with M/N contiguous is staged MN-major (boxes of
+// 64 k-rows x 64 mn) and the UMMA shared-memory / instruction descriptors carry the major-ness, so no
+// transposed copies of activations or weights are ever made.  Out-of-range rows/cols/k are zero-filled by TMA.
+// Split-K (grid.z) with fp32 atomics covers the weight-gradient shapes (small M x N, K = T*B).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace b200st {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 256;
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (spin > (1u << 22)) __trap();   // a lost arrival must fault, never hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (InstrDescriptor): c_format F32=1 [4,6), a/b format BF16=1 [7,10)/[10,13),
+// a_major [15], b_major [16] (1 = MN-major), N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN>
+struct TcSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = TC_STAGES * STAGE;
+  static constexpr int TOTAL = BAR_OFF + (2 * TC_STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+};
+
+template <int BN, bool A_MN, bool B_MN, typename TC, bool ATOMIC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               TC* __restrict__ C, int64_t ldc, const TC* R, int64_t ldr, const float* __restrict__ bias,
+               int relu, float alpha, int M, int N, int K, int kb_per_split) {
+  using S = TcSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* tmem_full = empty + TC_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int kb_total = (K + TC_BK - 1) / TC_BK;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(kb_total, kb_begin + kb_per_split);
+  const int n_iter = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* sa = smem + s * S::STAGE;
+        uint8_t* sb = sa + S::A_BYTES;
+        mbar_expect_tx(&full[s], S::STAGE);
+        const int k0 = (kb_begin + it) * TC_BK;
+        if (A_MN) {
+#pragma unroll
+          for (int c = 0; c < TC_BM / 64; ++c) tma_load_2d(sa + c * (TC_BK * 128), &tma_a, m0 + c * 64, k0, &full[s]);
+        } else {
+          tma_load_2d(sa, &tma_a, k0, m0, &full[s]);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (TC_BK * 128), &tma_b, n0 + c * 64, k0, &full[s]);
+        } else {
+          tma_load_2d(sb, &tma_b, k0, n0, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(TC_BM, BN, A_MN, B_MN);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * S::STAGE);
+        const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          // K-major: 16 k-elements = 32 B inside the 128 B swizzled row; SBO = 8 rows * 128 B.
+          // MN-major: 16 k-rows = 2048 B; LBO = next 64-wide mn chunk (BK*128 B), SBO = 8 k-rows * 128 B.
+          const uint64_t da = A_MN ? umma_desc(sa + k * 2048, TC_BK * 128, 1024) : umma_desc(sa + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? umma_desc(sb + k * 2048, TC_BK * 128, 1024) : umma_desc(sb + k * 32, 16, 1024);
+          tc_mma_f16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(&empty[s]);          // frees the smem stage once these MMAs have read it
+      }
+      tc_commit(tmem_full);            // accumulator complete
+    }
+  } else if (warp >= 4) {
+    const int wq = warp - 4;           // == warp % 4: the TMEM lane quarter this warp may access
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int row = m0 + wq * 32 + lane;
+    const bool row_ok = row < M;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, r);
+      if (!row_ok || n_iter <= 0) continue;
+      const int col0 = n0 + c0;
+      if (col0 >= N) continue;
+      TC* crow = C + (int64_t)row * ldc + col0;
+      const TC* rrow = R ? R + (int64_t)row * ldr + col0 : nullptr;
+      const int nvalid = min(32, N - col0);
+      if (ATOMIC) {
+        for (int j = 0; j < nvalid; ++j) atomicAdd(reinterpret_cast<float*>(crow) + j, alpha * __uint_as_float(r[j]));
+      } else {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = alpha * __uint_as_float(r[j]);
+          if (bias && j < nvalid) x += bias[col0 + j];
+          if (relu) x = fmaxf(x, 0.f);
+          v[j] = x;
+        }
+        const bool vec_ok = nvalid == 32 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) &&
+                            (!rrow || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
+        if (vec_ok) {
+          if constexpr (sizeof(TC) == 4) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (rrow) { const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rrow) + j); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(crow) + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (rrow) {
+                const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(rrow) + j);
+                const __nv_bfloat162* qq = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { const float2 f = __bfloat1622float2(qq[t]); v[j + 2 * t] += f.x; v[j + 2 * t + 1] += f.y; }
+              }
+              uint4 o;
+              __nv_bfloat162* oo = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) oo[t] = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(crow) + j) = o;
+            }
+          }
+        } else {
+          for (int j = 0; j < nvalid; ++j) {
+            float x = v[j];
+            if (rrow) x += to_f(rrow[j]);
+            crow[j] = from_f<TC>(x);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// Tensor map over a row-major bf16 matrix [rows, cols] (cols contiguous, leading dim ld), box = 64 cols x box_rows.
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error("gemm_tc: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+bool gemm_tc_eligible(int dtype_ab, int ta, int tb, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                      const void* B, int64_t ldb, int64_t batch) {
+  if (dtype_ab != B200ST_BF16 || batch != 1) return false;
+  if (M < 1 || N < 8 || K < 8) return false;
+  if (lda % 8 || ldb % 8) return false;                       // TMA: 16-byte global strides
+  if (((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return false;
+  if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return false;
+  return get_encode() != nullptr;
+}
+
+template <int BN, bool A_MN, bool B_MN, typename TC>
+static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const CUtensorMap& ma, const CUtensorMap& mb,
+                     void* C, int64_t ldc, const void* R, int64_t ldr, const float* bias, int relu, int splits,
+                     int kb_per_split, cudaStream_t st) {
+  using S = TcSmem<BN>;
+  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, TC_BM), (unsigned)splits);
+  if (splits > 1) {
+    if constexpr (sizeof(TC) == 4) {
+      auto kern = gemm_tc_kernel<BN, A_MN, B_MN, float, true>;
+      B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+      kern<<<grid, TC_THREADS, S::TOTAL, st>>>(ma, mb, (float*)C, ldc, nullptr, 0, nullptr, 0, alpha, (int)M, (int)N, (int)K, kb_per_split);
+    } else {
+      return set_error("gemm_tc: split-K needs an fp32 output");
+    }
+  } else {
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TC, false>;
+    B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    kern<<<grid, TC_THREADS, S::TOTAL, st>>>(ma, mb, (TC*)C, ldc, (const TC*)R, ldr, bias, relu, alpha, (int)M, (int)N, (int)K, kb_per_split);
+  }
+  B200ST_LAUNCH_CHECK("gemm_tc");
+  return 0;
+}
+
+int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const void* A, int64_t lda,
+            const void* B, int64_t ldb, void* C, int64_t ldc, const void* R, int64_t ldr, const float* bias, int relu,
+            cudaStream_t st) {
+  // op(A) is M x K: ta=0 -> stored [M,K] (K-major); ta=1 -> stored [K,M] (M-major).
+  // op(B) is K x N: tb=1 -> stored [N,K] (K-major); tb=0 -> stored [K,N] (N-major).
+  const bool a_mn = ta != 0, b_mn = tb == 0;
+  const int BN = (N <= 64) ? 64 : 128;
+  CUtensorMap ma, mb;
+  if (a_mn) { if (make_map(&ma, A, K, M, lda, TC_BK)) return -1; }
+  else      { if (make_map(&ma, A, M, K, lda, TC_BM)) return -1; }
+  if (b_mn) { if (make_map(&mb, B, K, N, ldb, TC_BK)) return -1; }
+  else      { if (make_map(&mb, B, N, K, ldb, BN)) return -1; }
+  // split-K when the output has few tiles and K is long (weight gradients): fp32 output, plain sum only.
+  const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
+  const int kb_total = (int)ceil_div(K, TC_BK);
+  int splits = 1;
+  if (dtype_c == B200ST_F32 && !bias && !relu && !R && tiles < 96 && kb_total >= 16) {
+    splits = (int)(296 / tiles);
+    if (splits > kb_total / 4) splits = kb_total / 4;
+    if (splits < 1) splits = 1;
+  }
+  int kb_per_split = (int)ceil_div(kb_total, splits);
+  splits = (int)ceil_div(kb_total, kb_per_split);
+  if (splits > 1) B200ST_CUDA(cudaMemset2DAsync(C, ldc * 4, 0, N * 4, M, st));
+#define TC_GO(BN_, AMN, BMN)                                                                               \
+  do {                                                                                                     \
+    if (dtype_c == B200ST_F32)                                                                             \
+      return launch_tc<BN_, AMN, BMN, float>(M, N, K, alpha, ma, mb, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
+    return launch_tc<BN_, AMN, BMN, __nv_bfloat16>(M, N, K, alpha, ma, mb, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
+  } while (0)
+#define TC_BNSEL(AMN, BMN) do { if (BN == 64) TC_GO(64, AMN, BMN); else TC_GO(128, AMN, BMN); } while (0)
+  if (!a_mn && !b_mn) TC_BNSEL(false, false);
+  if (!a_mn && b_mn) TC_BNSEL(false, true);
+  if (a_mn && !b_mn) TC_BNSEL(true, false);
+  TC_BNSEL(true, true);
+#undef TC_BNSEL
+#undef TC_GO
+}
+
+}  // namespace b200st

@@ -303,11 +303,26 @@ static int launch_cluster(K kernel, dim3 grid, int C, size_t smem, cudaStream_t 
   return 0;
 }
 
+bool blstm_tc_eligible(int dtype, int64_t H, int64_t out_ld_t, int64_t out_ld_b);
+int blstm_fwd_tc(const void* xproj, const float* w_hh_f, const float* w_hh_r, const int32_t* lens, void* out,
+                 int64_t out_ld_t, int64_t out_ld_b, int pair, void* hs, float* acts, float* cs, int64_t T_, int64_t B,
+                 cudaStream_t st);
+int blstm_bwd_tc(const void* dout, int64_t out_ld_t, int64_t out_ld_b, int pair, const float* acts, const float* cs,
+                 const float* w_hh_f, const float* w_hh_r, const int32_t* lens, void* dgates, int64_t T_, int64_t B,
+                 cudaStream_t st);
+static int g_blstm_backend = 0;   // 0 auto, 1 CUDA cores only
+
 }  // namespace b200st
 
 using namespace b200st;
 
 extern "C" {
+
+int b200st_set_blstm_backend(int mode) {
+  const int old = g_blstm_backend;
+  if (mode == 0 || mode == 1) g_blstm_backend = mode;
+  return old;
+}
 
 int b200st_lstm_cell_fwd(int dtype, const void* gates, const float* c_prev, void* h, float* c,
                          float* acts, const void* residual, void* out_res, int64_t B, int64_t H,
@@ -341,6 +356,15 @@ int b200st_blstm_fwd(int dtype, const void* xproj, const float* w_hh_f, const fl
   if (T_ <= 0 || B <= 0) return 0;
   if (H % 4 != 0) return set_error("blstm_fwd: hidden size %lld must be a multiple of 4", (long long)H);
   if (pair != 1 && pair != 2) return set_error("blstm_fwd: pair must be 1 or 2");
+  if (g_blstm_backend == 0 && blstm_tc_eligible(dtype, H, out_ld_t, out_ld_b)) {
+    if (hs) {
+      const size_t plane = (size_t)B * H * 2;
+      B200ST_CUDA(cudaMemsetAsync(hs, 0, plane, (cudaStream_t)stream));
+      B200ST_CUDA(cudaMemsetAsync((char*)hs + ((size_t)(T_ + 1) + T_) * plane, 0, plane, (cudaStream_t)stream));
+    }
+    return blstm_fwd_tc(xproj, w_hh_f, w_hh_r, lens, out, out_ld_t, out_ld_b, pair, hs, acts, cs, T_, B,
+                        (cudaStream_t)stream);
+  }
   constexpr int NB = 8;
   const int C = pick_cluster(H);
   const int UPC = (int)H / C, R = 4 * UPC;
@@ -367,6 +391,9 @@ int b200st_blstm_bwd(int dtype, const void* dout, int64_t out_ld_t, int64_t out_
                      b200st_stream_t stream) {
   if (T_ <= 0 || B <= 0) return 0;
   if (H % 4 != 0) return set_error("blstm_bwd: hidden size %lld must be a multiple of 4", (long long)H);
+  if (g_blstm_backend == 0 && blstm_tc_eligible(dtype, H, out_ld_t, out_ld_b))
+    return blstm_bwd_tc(dout, out_ld_t, out_ld_b, pair, acts, cs, w_hh_f, w_hh_r, lens, dgates, T_, B,
+                        (cudaStream_t)stream);
   constexpr int NB = 8;
   const int C = pick_cluster(H);
   const int UPC = (int)H / C;

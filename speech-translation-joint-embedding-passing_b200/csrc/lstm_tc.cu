@@ -1,0 +1,439 @@
+// Persistent bidirectional LSTM recurrence on the tcgen05 tensor cores (bf16 operands, fp32 accumulate/state).
+// Specialised for the reference's acoustic encoder: H = 256 hidden units per direction (Seq2seq.py:57).
+//
+// Layout of the work (forward):
+//   grid = (8, ceil(B/16), 2): one thread-block CLUSTER of 8 CTAs per (direction, group of 16 sequences).
+//   CTA `rank` owns hidden units [32*rank, 32*rank+32): the 128 matching rows of W_hh (4 gates x 32 units) are
+//   converted to bf16 once and stay resident in shared memory in the 128B-swizzled K-major layout UMMA reads.
+//   Every time step:  D[128 gate rows, 16 seqs] = W_slice[128,256] . h_{t-1}^T   (16 tcgen05.mma, K=16 each,
+//   accumulator in TMEM) -> tcgen05.ld -> + x-projection -> sigmoid/tanh -> cell update (state in registers)
+//   -> the CTA's 32x16 slice of h_t is written as bf16 straight into the *next-step B operand* of all 8 CTAs
+//   (16-byte st.shared::cluster stores into the swizzled layout) -> barrier.cluster.arrive; the matching
+//   barrier.cluster.wait sits right before the next step's MMA so global stores/prefetch overlap the barrier.
+//
+// Backward keeps W_hh^T[256 units, own 128 gate rows] resident instead: each CTA multiplies its own gate
+// gradients (no all-gather) into partial dh for all 256 units, and the partials are reduce-scattered to the
+// owning CTAs through distributed shared memory.
+#include "common.cuh"
+
+namespace b200st {
+
+constexpr int RT_H = 256;        // hidden units per direction
+constexpr int RT_C = 8;          // CTAs per cluster
+constexpr int RT_UPC = 32;       // units per CTA
+constexpr int RT_NB = 16;        // sequences per cluster (= UMMA N)
+constexpr int RT_THREADS = 128;
+
+__device__ __forceinline__ uint32_t rt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t rt_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t rt_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void rt_st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void rt_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void rt_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void rt_fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void rt_tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void rt_tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void rt_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rt_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void rt_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = rt_smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (spin > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void rt_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(rt_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void rt_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void rt_tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// K-major, 128B-swizzled operand descriptor: SBO = 8 rows * 128 B (see gemm_tc.cu / mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t rt_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+constexpr uint32_t RT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(RT_NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ float rt_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rt_sigmoid(float x) { return fmaf(rt_tanh(0.5f * x), 0.5f, 0.5f); }
+__device__ __forceinline__ uint32_t rt_pack(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+// byte offset of the 16-byte chunk holding k..k+7 (k % 8 == 0) of row `row` inside one [rows x 64 k] SW128 tile
+__device__ __forceinline__ uint32_t rt_swz(uint32_t row, uint32_t k_in_tile) {
+  return row * 128 + ((((k_in_tile >> 3) ^ (row & 7))) << 4);
+}
+
+// shared memory map (forward): W [4 kb][128 rows][128 B] 64 KB | hbuf [2][4 kb][16 rows][128 B] 16 KB |
+// actbuf float [4 gates][16 seqs][32 units] 8 KB | barrier + tmem slot
+constexpr int FWD_W_OFF = 0, FWD_H_OFF = 65536, FWD_ACT_OFF = FWD_H_OFF + 16384, FWD_BAR_OFF = FWD_ACT_OFF + 8192;
+constexpr int FWD_SMEM = FWD_BAR_OFF + 64 + 1024;
+
+__global__ void __cluster_dims__(RT_C, 1, 1) __launch_bounds__(RT_THREADS, 1)
+blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __restrict__ w_hh_f,
+                    const float* __restrict__ w_hh_r, const int32_t* __restrict__ lens,
+                    __nv_bfloat16* __restrict__ out, int64_t out_ld_t, int64_t out_ld_b, int pair,
+                    __nv_bfloat16* __restrict__ hs, float* __restrict__ acts, float* __restrict__ cs, int Tn, int B) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* Wsm = smem + FWD_W_OFF;
+  uint8_t* hbuf = smem + FWD_H_OFF;
+  float* actbuf = (float*)(smem + FWD_ACT_OFF);
+  uint64_t* mma_bar = (uint64_t*)(smem + FWD_BAR_OFF);
+  uint32_t* tmem_slot = (uint32_t*)(smem + FWD_BAR_OFF + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = rt_cluster_rank();
+  const int grp = blockIdx.y, dir = blockIdx.z;
+  const float* w = dir ? w_hh_r : w_hh_f;
+
+  // ---- resident weights: local row lr = gate*32 + ul  <->  W_hh row gate*256 + 32*rank + ul
+  for (int chunk = tid; chunk < 128 * 32; chunk += RT_THREADS) {
+    const int lr = chunk >> 5, kc = chunk & 31;
+    const int grow = (lr >> 5) * RT_H + rank * RT_UPC + (lr & 31);
+    const float4* src = reinterpret_cast<const float4*>(w + (size_t)grow * RT_H + kc * 8);
+    const float4 a = src[0], b = src[1];
+    uint4 v = make_uint4(rt_pack(a.x, a.y), rt_pack(a.z, a.w), rt_pack(b.x, b.y), rt_pack(b.z, b.w));
+    *reinterpret_cast<uint4*>(Wsm + (kc >> 3) * 16384 + rt_swz(lr, (kc & 7) * 8)) = v;
+  }
+  for (int i = tid; i < 16384 / 16; i += RT_THREADS) reinterpret_cast<uint4*>(hbuf)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    rt_mbar_init(mma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rt_smem_u32(tmem_slot)), "r"(32u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  rt_fence_async();
+  rt_tc_before();
+  __syncthreads();
+  rt_tc_after();
+  const uint32_t tmem_base = *tmem_slot;
+  rt_cluster_arrive();      // pairs with the wait of step 0: every CTA has zeroed its h buffers
+
+  // ---- per-thread roles
+  // (1) gate phase: thread owns gate row lr = tid (gate = warp, unit = lane) for all 16 sequences
+  const int grow_g = warp * RT_H + rank * RT_UPC + lane;
+  // (2) cell phase: thread owns sequence cb = tid / 8 and units 4*ug .. 4*ug+3, ug = tid % 8
+  const int cb = tid >> 3, ug = tid & 7;
+  const int b0 = grp * RT_NB;
+  const int bglob = b0 + cb;
+  const bool b_ok = bglob < B;
+  const int len_b = b_ok ? lens[bglob] : 0;
+  const int ubase = rank * RT_UPC + 4 * ug;
+  float c_st[4] = {0.f, 0.f, 0.f, 0.f}, h_st[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t hbuf_u32 = rt_smem_u32(hbuf);
+  // destination chunk (16 B = 8 units) of this thread pair inside one h buffer
+  const uint32_t k0 = rank * RT_UPC + 4 * (ug & ~1);
+  const uint32_t h_chunk_off = (k0 >> 6) * 2048 + rt_swz(cb, k0 & 63);
+
+  float x[16];
+  auto load_x = [&](int t) {
+    const __nv_bfloat16* xp = xproj + (((size_t)dir * Tn + t) * B) * (4 * RT_H) + grow_g;
+#pragma unroll
+    for (int b = 0; b < RT_NB; ++b) x[b] = (b0 + b < B) ? __bfloat162float(xp[(size_t)(b0 + b) * (4 * RT_H)]) : 0.f;
+  };
+  if (Tn > 0) load_x(dir ? Tn - 1 : 0);
+
+  int cur = 0;
+  uint32_t phase = 0;
+  for (int s = 0; s < Tn; ++s) {
+    const int t = dir ? (Tn - 1 - s) : s;
+    rt_cluster_wait();                       // h_{t-1} slices of all 8 CTAs have landed in hbuf[cur]
+    if (tid == 0) {
+      rt_fence_async();
+      rt_tc_after();
+      const uint32_t wa = rt_smem_u32(Wsm), hb = hbuf_u32 + cur * 8192;
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks)
+        rt_mma(tmem_base, rt_desc(wa + (ks >> 2) * 16384 + (ks & 3) * 32), rt_desc(hb + (ks >> 2) * 2048 + (ks & 3) * 32),
+               RT_IDESC, ks > 0 ? 1u : 0u);
+      rt_commit(mma_bar);
+    }
+    rt_mbar_wait(mma_bar, phase);
+    phase ^= 1;
+    rt_tc_after();
+    float g[16];
+    rt_tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16), g);
+    rt_tc_before();
+    // gate non-linearity: warp 2 holds the candidate gate (tanh), the others sigmoid (PyTorch order i,f,g,o)
+#pragma unroll
+    for (int b = 0; b < RT_NB; ++b) {
+      const float v = g[b] + x[b];
+      actbuf[(warp * RT_NB + b) * RT_UPC + lane] = (warp == 2) ? rt_tanh(v) : rt_sigmoid(v);
+    }
+    if (s + 1 < Tn) load_x(dir ? (Tn - 2 - s) : (s + 1));     // prefetch next step's x-projection
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // ---- cell update for (sequence cb, units ubase..ubase+3)
+    const bool valid = t < len_b;
+    const float4 gi = *reinterpret_cast<const float4*>(&actbuf[(0 * RT_NB + cb) * RT_UPC + 4 * ug]);
+    const float4 gf = *reinterpret_cast<const float4*>(&actbuf[(1 * RT_NB + cb) * RT_UPC + 4 * ug]);
+    const float4 gg = *reinterpret_cast<const float4*>(&actbuf[(2 * RT_NB + cb) * RT_UPC + 4 * ug]);
+    const float4 go = *reinterpret_cast<const float4*>(&actbuf[(3 * RT_NB + cb) * RT_UPC + 4 * ug]);
+    const float ai[4] = {gi.x, gi.y, gi.z, gi.w}, af[4] = {gf.x, gf.y, gf.z, gf.w};
+    const float ag[4] = {gg.x, gg.y, gg.z, gg.w}, ao[4] = {go.x, go.y, go.z, go.w};
+    float ho[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (valid) {
+        c_st[q] = fmaf(af[q], c_st[q], ai[q] * ag[q]);
+        h_st[q] = ao[q] * rt_tanh(c_st[q]);
+      }
+      ho[q] = valid ? h_st[q] : 0.f;
+    }
+    // ---- scatter this pair's 8 units of h_t into the next-step B operand of every CTA in the cluster
+    const uint32_t p0 = rt_pack(h_st[0], h_st[1]), p1 = rt_pack(h_st[2], h_st[3]);
+    const uint32_t q0 = __shfl_down_sync(0xffffffffu, p0, 1), q1 = __shfl_down_sync(0xffffffffu, p1, 1);
+    if ((ug & 1) == 0) {
+      const uint32_t dst = hbuf_u32 + (cur ^ 1) * 8192 + h_chunk_off;
+#pragma unroll
+      for (uint32_t r = 0; r < RT_C; ++r) rt_st_cluster_v4(rt_mapa(dst, r), p0, p1, q0, q1);
+    }
+    rt_fence_async();
+    rt_cluster_arrive();
+    // ---- global stores overlap the cluster barrier
+    if (b_ok) {
+      const size_t row = ((size_t)dir * Tn + t) * B + bglob;
+      if (acts) {
+        float* a = acts + row * (4 * RT_H) + ubase;
+        *reinterpret_cast<float4*>(a) = gi;
+        *reinterpret_cast<float4*>(a + RT_H) = gf;
+        *reinterpret_cast<float4*>(a + 2 * RT_H) = gg;
+        *reinterpret_cast<float4*>(a + 3 * RT_H) = go;
+      }
+      if (cs) *reinterpret_cast<float4*>(cs + row * RT_H + ubase) = make_float4(c_st[0], c_st[1], c_st[2], c_st[3]);
+      const uint2 hv = make_uint2(rt_pack(ho[0], ho[1]), rt_pack(ho[2], ho[3]));
+      *reinterpret_cast<uint2*>(out + (size_t)(t / pair) * out_ld_t + (size_t)bglob * out_ld_b +
+                                (size_t)(t % pair) * 2 * RT_H + dir * RT_H + ubase) = hv;
+      if (hs) *reinterpret_cast<uint2*>(hs + (((size_t)dir * (Tn + 1) + (dir ? t : t + 1)) * B + bglob) * RT_H + ubase) = hv;
+    }
+    cur ^= 1;
+  }
+  rt_cluster_wait();         // peers are done addressing this CTA's shared memory
+  rt_tc_before();
+  __syncthreads();
+  if (warp == 0) {
+    rt_tc_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
+  }
+}
+
+// shared memory map (backward): A = W_hh^T [2 m-tiles][2 kb][128 rows][128 B] 64 KB | B = own dG [2 kb][16][128 B] 4 KB |
+// red float [2][8 src][32 units][16 seqs] 32 KB | barrier + tmem slot
+constexpr int BWD_A_OFF = 0, BWD_B_OFF = 65536, BWD_RED_OFF = BWD_B_OFF + 4096, BWD_BAR_OFF = BWD_RED_OFF + 32768;
+constexpr int BWD_SMEM = BWD_BAR_OFF + 64 + 1024;
+
+__global__ void __cluster_dims__(RT_C, 1, 1) __launch_bounds__(RT_THREADS, 1)
+blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, int64_t out_ld_b, int pair,
+                    const float* __restrict__ acts, const float* __restrict__ cs, const float* __restrict__ w_hh_f,
+                    const float* __restrict__ w_hh_r, const int32_t* __restrict__ lens,
+                    __nv_bfloat16* __restrict__ dgates, int Tn, int B) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* Asm = smem + BWD_A_OFF;
+  uint8_t* Bsm = smem + BWD_B_OFF;
+  float* red = (float*)(smem + BWD_RED_OFF);
+  uint64_t* mma_bar = (uint64_t*)(smem + BWD_BAR_OFF);
+  uint32_t* tmem_slot = (uint32_t*)(smem + BWD_BAR_OFF + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = rt_cluster_rank();
+  const int grp = blockIdx.y, dir = blockIdx.z;
+  const float* w = dir ? w_hh_r : w_hh_f;
+
+  // ---- resident W_hh^T: A[mt][kb] row = unit % 128, k = own gate row kl = gate*32 + ul
+  for (int chunk = tid; chunk < 256 * 16; chunk += RT_THREADS) {
+    const int u = chunk & 255, klg = chunk >> 8;           // 8 consecutive kl per chunk; lanes run along u (coalesced)
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int kl = klg * 8 + i;
+      const int grow = (kl >> 5) * RT_H + rank * RT_UPC + (kl & 31);
+      v[i] = w[(size_t)grow * RT_H + u];
+    }
+    const uint4 pk = make_uint4(rt_pack(v[0], v[1]), rt_pack(v[2], v[3]), rt_pack(v[4], v[5]), rt_pack(v[6], v[7]));
+    *reinterpret_cast<uint4*>(Asm + ((u >> 7) * 2 + (klg >> 3)) * 16384 + rt_swz(u & 127, (klg & 7) * 8)) = pk;
+  }
+  for (int i = tid; i < (4096 + 32768) / 16; i += RT_THREADS) reinterpret_cast<uint4*>(Bsm)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    rt_mbar_init(mma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rt_smem_u32(tmem_slot)), "r"(32u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  rt_fence_async();
+  rt_tc_before();
+  __syncthreads();
+  rt_tc_after();
+  const uint32_t tmem_base = *tmem_slot;
+  rt_cluster_arrive();
+
+  // thread owns unit ul = lane of this CTA and sequences 4*warp .. 4*warp+3 in the pointwise phase
+  const int ul = lane, u = rank * RT_UPC + ul;
+  const int b0 = grp * RT_NB;
+  int len_b[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) len_b[q] = (b0 + 4 * warp + q < B) ? lens[b0 + 4 * warp + q] : 0;
+  float dcrec[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t red_u32 = rt_smem_u32(red);
+  const size_t G4 = 4 * RT_H;
+
+  int cur = 0;
+  uint32_t phase = 0;
+  for (int s = 0; s < Tn; ++s) {
+    const int t = dir ? s : (Tn - 1 - s);
+    const int tp = dir ? t + 1 : t - 1;
+    // ---- issue this step's loads before waiting on the cluster: they do not depend on the recurrence
+    float ai[4], af[4], ag[4], ao[4], ct[4], cp[4], dy[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int b = b0 + 4 * warp + q;
+      const bool valid = t < len_b[q];
+      if (valid) {
+        const size_t row = ((size_t)dir * Tn + t) * B + b;
+        const float* a = acts + row * G4 + u;
+        ai[q] = a[0]; af[q] = a[RT_H]; ag[q] = a[2 * RT_H]; ao[q] = a[3 * RT_H];
+        ct[q] = cs[row * RT_H + u];
+        cp[q] = (tp >= 0 && tp < Tn) ? cs[(((size_t)dir * Tn + tp) * B + b) * RT_H + u] : 0.f;
+        dy[q] = __bfloat162float(dout[(size_t)(t / pair) * out_ld_t + (size_t)b * out_ld_b + (size_t)(t % pair) * 2 * RT_H + dir * RT_H + u]);
+      } else {
+        ai[q] = af[q] = ag[q] = ao[q] = ct[q] = cp[q] = dy[q] = 0.f;
+      }
+    }
+    rt_cluster_wait();                       // partial dh of the previous step from all 8 CTAs is in red[cur]
+    float dg[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float dh = dy[q];
+#pragma unroll
+      for (int i = 0; i < RT_C; ++i) dh += red[((cur * RT_C + i) * RT_UPC + ul) * RT_NB + 4 * warp + q];
+      const bool valid = t < len_b[q];
+      const float tc = rt_tanh(ct[q]);
+      const float dc = dcrec[q] + dh * ao[q] * (1.f - tc * tc);
+      dg[0][q] = valid ? dc * ag[q] * ai[q] * (1.f - ai[q]) : 0.f;
+      dg[1][q] = valid ? dc * cp[q] * af[q] * (1.f - af[q]) : 0.f;
+      dg[2][q] = valid ? dc * ai[q] * (1.f - ag[q] * ag[q]) : 0.f;
+      dg[3][q] = valid ? dh * tc * ao[q] * (1.f - ao[q]) : 0.f;
+      dcrec[q] = valid ? dc * af[q] : 0.f;
+    }
+    // ---- own gate gradients -> B operand [16 seqs][128 k], k = gate*32 + ul (K-major, swizzled) and -> global
+#pragma unroll
+    for (int gte = 0; gte < 4; ++gte) {
+      const uint32_t kl = gte * 32 + ul;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t b = 4 * warp + q;
+        const __nv_bfloat16 v = __float2bfloat16_rn(dg[gte][q]);
+        *reinterpret_cast<__nv_bfloat16*>(Bsm + (kl >> 6) * 2048 + rt_swz(b, kl & 63) + (kl & 7) * 2) = v;
+        if (b0 + b < B) dgates[(((size_t)dir * Tn + t) * B + b0 + b) * G4 + gte * RT_H + u] = v;
+      }
+    }
+    rt_fence_async();
+    rt_tc_before();
+    __syncthreads();
+    if (tid == 0) {
+      rt_tc_after();
+      const uint32_t aa = rt_smem_u32(Asm), bb = rt_smem_u32(Bsm);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          rt_mma(tmem_base + mt * RT_NB, rt_desc(aa + (mt * 2 + (ks >> 2)) * 16384 + (ks & 3) * 32),
+                 rt_desc(bb + (ks >> 2) * 2048 + (ks & 3) * 32), RT_IDESC, ks > 0 ? 1u : 0u);
+      rt_commit(mma_bar);
+    }
+    rt_mbar_wait(mma_bar, phase);
+    phase ^= 1;
+    rt_tc_after();
+    // ---- partial dh_{t-1}[unit, seq] for all 256 units: send each 32-unit block to the CTA that owns it
+    const int nxt = cur ^ 1;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float p[16];
+      rt_tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + mt * RT_NB, p);
+      const uint32_t owner = mt * 4 + warp;                 // unit mt*128 + warp*32 + lane lives on CTA `owner`
+      const uint32_t dst = rt_mapa(red_u32 + (uint32_t)((((nxt * RT_C + rank) * RT_UPC + lane) * RT_NB) * 4), owner);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        rt_st_cluster_v4(dst + j * 16, __float_as_uint(p[4 * j]), __float_as_uint(p[4 * j + 1]),
+                         __float_as_uint(p[4 * j + 2]), __float_as_uint(p[4 * j + 3]));
+    }
+    rt_tc_before();
+    rt_cluster_arrive();
+    cur = nxt;
+  }
+  rt_cluster_wait();
+  rt_tc_before();
+  __syncthreads();
+  if (warp == 0) {
+    rt_tc_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
+  }
+}
+
+bool blstm_tc_eligible(int dtype, int64_t H, int64_t out_ld_t, int64_t out_ld_b) {
+  return dtype == B200ST_BF16 && H == RT_H && out_ld_t % 4 == 0 && out_ld_b % 4 == 0;
+}
+
+int blstm_fwd_tc(const void* xproj, const float* w_hh_f, const float* w_hh_r, const int32_t* lens, void* out,
+                 int64_t out_ld_t, int64_t out_ld_b, int pair, void* hs, float* acts, float* cs, int64_t T_, int64_t B,
+                 cudaStream_t st) {
+  B200ST_CUDA(cudaFuncSetAttribute((const void*)blstm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+  dim3 grid(RT_C, (unsigned)ceil_div(B, RT_NB), 2);
+  blstm_fwd_tc_kernel<<<grid, RT_THREADS, FWD_SMEM, st>>>((const __nv_bfloat16*)xproj, w_hh_f, w_hh_r, lens,
+                                                           (__nv_bfloat16*)out, out_ld_t, out_ld_b, pair,
+                                                           (__nv_bfloat16*)hs, acts, cs, (int)T_, (int)B);
+  B200ST_LAUNCH_CHECK("blstm_fwd_tc");
+  return 0;
+}
+
+int blstm_bwd_tc(const void* dout, int64_t out_ld_t, int64_t out_ld_b, int pair, const float* acts, const float* cs,
+                 const float* w_hh_f, const float* w_hh_r, const int32_t* lens, void* dgates, int64_t T_, int64_t B,
+                 cudaStream_t st) {
+  B200ST_CUDA(cudaFuncSetAttribute((const void*)blstm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+  dim3 grid(RT_C, (unsigned)ceil_div(B, RT_NB), 2);
+  blstm_bwd_tc_kernel<<<grid, RT_THREADS, BWD_SMEM, st>>>((const __nv_bfloat16*)dout, out_ld_t, out_ld_b, pair, acts, cs,
+                                                           w_hh_f, w_hh_r, lens, (__nv_bfloat16*)dgates, (int)T_, (int)B);
+  B200ST_LAUNCH_CHECK("blstm_bwd_tc");
+  return 0;
+}
+
+}  // namespace b200st

@@ -139,7 +139,7 @@ def test_lstm_cell(ks, dtype):
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('T,B,H,pair', [(8, 3, 16, 2), (24, 5, 24, 2), (6, 11, 16, 1), (40, 9, 32, 2),
-                                        (16, 8, 256, 2)])
+                                        (16, 8, 256, 2), (64, 40, 256, 2), (24, 16, 256, 1), (2, 1, 256, 2)])
 def test_blstm_recurrence(ks, dtype, T, B, H, pair):
     c, f = ks
     xproj = rnd(2, T, B, 4 * H, dtype=dtype)
@@ -240,7 +240,7 @@ def test_softmax_family(ks, dtype, rows, cols):
         assert rel_err(ls, lsr) < 1e-5 and rel_err(d, dr) < TOL[dtype]
     # fused == log_softmax + nll  (eps = 0)
     ls, _ = c.softmax_nll_fused(x, tgt, mask, g, 0.0)
-    assert rel_err(ls, lr) < 1e-3 if dtype == torch.bfloat16 else rel_err(ls, lr) < 1e-5
+    assert rel_err(ls, lr) < (1e-2 if dtype == torch.bfloat16 else 1e-5)
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
@@ -265,3 +265,48 @@ def test_glue(ks, dtype):
     assert torch.equal(c.token_mask(ids, 0, False), f.token_mask(ids, 0, False))
     ln = torch.tensor([1, 9, 4], dtype=torch.int32, device='cuda')
     assert torch.equal(c.length_mask(ln, 9), f.length_mask(ln, 9))
+
+
+@pytest.mark.parametrize('ta,tb', [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (100, 72, 80), (3200, 512, 512), (64, 2048, 712),
+                                   (64, 10000, 512), (1024, 80, 4096), (1024, 1024, 16384), (37, 24, 8)])
+def test_gemm_tensor_core(ks, ta, tb, M, N, K):
+    """tcgen05/TMA/TMEM kernel (forced) vs fp32 matmul of the same bf16 operands: K-major and MN-major
+    operand staging, M/N/K tails (TMA zero fill), bf16 and fp32 (split-K atomics) outputs."""
+    c, f = ks
+    a = rnd(K, M, dtype=torch.bfloat16) if ta else rnd(M, K, dtype=torch.bfloat16)
+    b = rnd(N, K, dtype=torch.bfloat16, seed=1) if tb else rnd(K, N, dtype=torch.bfloat16, seed=1)
+    if a.stride(0) % 8 or b.stride(0) % 8:
+        pytest.skip('leading dimension not TMA addressable: served by the CUDA-core kernel')
+    old = c.set_gemm_backend(2)
+    try:
+        y16 = c.gemm(a, b, trans_a=ta, trans_b=tb)
+        y32 = c.gemm(a, b, trans_a=ta, trans_b=tb, out_dtype=torch.float32)
+        bias, res = rnd(N, seed=2), rnd(M, N, dtype=torch.bfloat16, seed=3)
+        ye = c.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, residual=res, alpha=0.5)
+        yr = c.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, relu=True)
+    finally:
+        c.set_gemm_backend(old)
+    ref = (a.float().t() if ta else a.float()) @ (b.float().t() if tb else b.float())
+    assert rel_err(y32, ref) < 1e-4
+    assert rel_err(y16, ref) < 1e-2
+    assert rel_err(ye, 0.5 * ref + bias + res.float()) < 1e-2
+    assert rel_err(yr, torch.relu(ref + bias)) < 1e-2
+
+
+def test_gemm_tensor_core_views(ks):
+    c, f = ks
+    a, w = rnd(300, 712, dtype=torch.bfloat16), rnd(512, 712, dtype=torch.bfloat16, seed=1)
+    old = c.set_gemm_backend(2)
+    try:
+        y = c.gemm(a[:, 200:], w[:, 200:], trans_b=True)
+        out = torch.zeros(300, 1024, device='cuda', dtype=torch.bfloat16)
+        c.gemm(a, w, trans_b=True, out=out[:, 256:768])
+        c.gemm(a, w, trans_b=True, residual=out[:, 256:768], out=out[:, 256:768])
+        with pytest.raises(RuntimeError):
+            c.gemm(a[:, 3:], w[:, 3:], trans_b=True)        # misaligned base: not TMA addressable
+    finally:
+        c.set_gemm_backend(old)
+    assert rel_err(y, a[:, 200:].float() @ w[:, 200:].float().t()) < 1e-2
+    assert rel_err(out[:, 256:768], 2 * (a.float() @ w.float().t())) < 1e-2
+    assert float(out[:, :256].abs().sum()) == 0 and float(out[:, 768:].abs().sum()) == 0
