@@ -285,12 +285,12 @@ def run_b200(args):
     batch_items = {'srcid': [pin(host['src'])], 'tgtid': [pin(host['tgt'])],
                    'acous_feat': [pin(host['acous_feats'])], 'acouslen': host['acous_lens'],
                    'srclen': [cfg.max_seq_len_src] * args.batch, 'tgtlen': [cfg.max_seq_len_tgt] * args.batch}
-    h2d = sum(batch_items[k][0].numel() * batch_items[k][0].element_size() for k in ('srcid', 'tgtid', 'acous_feat'))
+    h2d = sum(batch_items[k][0].numel() * batch_items[k][0].element_size() for k in ('srcid', 'tgtid', 'acous_feat')) + 4 * args.batch
     dev_items = dict(batch_items)
     for k in ('srcid', 'tgtid', 'acous_feat'):
         dev_items[k] = [batch_items[k][0].to(device)]
 
-    def step(items):
+    def eager_step(items):
         out = trainer._train_batch(model, items)
         model.zero_grad(set_to_none=True)
         return out
@@ -300,12 +300,12 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(items, steps, sync_loss):
+    def timed(fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
         for _ in range(steps):
-            step(items)
+            fn()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -316,29 +316,44 @@ def run_b200(args):
         return ms / steps
 
     for _ in range(max(args.warmup, 3)):
-        step(dev_items)
-    # ---- profiling pass (untimed): every kernel family, to find the dominant one
+        eager_step(dev_items)
+    # ---- profiling pass (eager, untimed): every kernel family with CUDA events around each launch
+    n_before = K().launch_count()
     with KernelTimer(K(), ALL_FAMILIES) as kt:
-        step(dev_items)
+        eager_step(dev_items)
+    launches_per_step = K().launch_count() - n_before
     fam = kt.summary()
     dominant = max(('blstm_fwd', 'blstm_bwd', 'gemm'), key=lambda n: fam[n]['ms'])
     roof_names = ['blstm_fwd', 'blstm_bwd'] if dominant.startswith('blstm') else [dominant]
-    live = sum(fam[n]['calls'] for n in roof_names) <= 64
+    roof = {n: fam[n] for n in roof_names}
+    ms_eager = timed(lambda: eager_step(dev_items), args.steps)
 
-    # ---- timed region 1: inputs resident in HBM
+    # ---- the measured step: one CUDA graph of forward_train + loss + backward (+ all-reduce)
+    graphed = None
+    if not args.no_graph:
+        try:
+            from b200st.graph import GraphedTrainStep
+            graphed = GraphedTrainStep(model, trainer, dev_items)
+        except Exception as ex:            # e.g. a collective that cannot be captured: stay eager, say so
+            print(f'[bench] CUDA graph capture failed ({type(ex).__name__}: {ex}); timing the eager step', file=sys.stderr)
+            graphed = None
+            model.zero_grad(set_to_none=True)
     sampler = ClockSampler(local)
     sampler.start()
-    n0 = K().launch_count()
-    if live:
-        with KernelTimer(K(), roof_names) as rt_timer:
-            ms_dev = timed(dev_items, args.steps, False)
-        roof = rt_timer.summary()
+    if graphed is not None:
+        for _ in range(max(args.warmup, 3)):
+            graphed()
+        ms_dev = timed(lambda: graphed(), args.steps)                    # inputs resident in HBM
+
+        def e2e_step():
+            graphed.load(batch_items)                                    # H2D from pinned host memory
+            return float(graphed())                                      # D2H read of the loss
+        ms_e2e = timed(e2e_step, args.steps)
     else:
-        ms_dev = timed(dev_items, args.steps, False)
-        roof = {n: fam[n] for n in roof_names}
-    launches = K().launch_count() - n0
-    # ---- timed region 2: end to end through Trainer_ST._train_batch with HOST (pinned) buffers
-    ms_e2e = timed(batch_items, args.steps, True)
+        ms_dev = ms_eager
+        ms_e2e = timed(lambda: eager_step(batch_items), args.steps)
+    launches = launches_per_step * args.steps
+    live = False
     clocks = sampler.stop()
 
     if rank == 0:
@@ -367,12 +382,15 @@ def run_b200(args):
                            whole_step_tflops=alg['fwd_bwd'] / 1e12 / (ms_dev / 1e3)),
             'e2e': {'value': total_units / (ms_e2e / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e},
-            'gpu_launches': int(launches),
+            'gpu_launches': int(launches), 'gpu_launches_per_step': int(launches_per_step),
+            'execution': ('one CUDA graph replay per step' if graphed is not None else 'eager launches'),
+            'eager_ms_per_step': ms_eager,
             'clocks': clocks,
             'roofline': {'kernel': '+'.join(roof_names), 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
                          'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src,
                          'launches': r_calls, 'avg_launch_ms': r_ms / max(r_calls, 1),
-                         'timed': 'live CUDA events in the timed region' if live else 'profiling pass',
+                         'timed': 'CUDA events around every launch of this kernel family on its stream, eager pass of the '
+                                  'same step in this run (the timed region replays the step as one CUDA graph)',
                          'note': 'recurrent-GEMM FLOPs 2*2dirs*T*B*H*4H per launch; this kernel is bound by the '
                                  'serial time-step chain (latency), not by tensor throughput'},
         }
@@ -394,6 +412,7 @@ def main():
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--frames', type=int, default=1000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA graph replay')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -34,6 +34,15 @@ __device__ __forceinline__ uint32_t rt_mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void rt_st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// Remote 16-byte store whose completion is counted (complete_tx) on an mbarrier of the destination CTA: data and
+// signal travel together, and unlike barrier.cluster.arrive.release nothing waits for unrelated global stores.
+__device__ __forceinline__ void rt_st_async_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void rt_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rt_smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void rt_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void rt_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void rt_fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -115,7 +124,8 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
   uint8_t* hbuf = smem + FWD_H_OFF;
   float* actbuf = (float*)(smem + FWD_ACT_OFF);
   uint64_t* mma_bar = (uint64_t*)(smem + FWD_BAR_OFF);
-  uint32_t* tmem_slot = (uint32_t*)(smem + FWD_BAR_OFF + 16);
+  uint64_t* hfull = mma_bar + 1;                 // [2]: h buffer b holds a complete h_t (8 x 1 KB st.async landed)
+  uint32_t* tmem_slot = (uint32_t*)(smem + FWD_BAR_OFF + 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = rt_cluster_rank();
@@ -134,7 +144,10 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
   for (int i = tid; i < 16384 / 16; i += RT_THREADS) reinterpret_cast<uint4*>(hbuf)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     rt_mbar_init(mma_bar, 1);
+    rt_mbar_init(&hfull[0], 1);
+    rt_mbar_init(&hfull[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    rt_mbar_expect_tx(&hfull[1], 8192);        // step 0 fills buffer 1
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rt_smem_u32(tmem_slot)), "r"(32u) : "memory");
@@ -145,7 +158,8 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
   __syncthreads();
   rt_tc_after();
   const uint32_t tmem_base = *tmem_slot;
-  rt_cluster_arrive();      // pairs with the wait of step 0: every CTA has zeroed its h buffers
+  rt_cluster_arrive();      // every CTA has initialised its barriers and zeroed its h buffers
+  rt_cluster_wait();
 
   // ---- per-thread roles
   // (1) gate phase: thread owns gate row lr = tid (gate = warp, unit = lane) for all 16 sequences
@@ -159,15 +173,19 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
   const int ubase = rank * RT_UPC + 4 * ug;
   float c_st[4] = {0.f, 0.f, 0.f, 0.f}, h_st[4] = {0.f, 0.f, 0.f, 0.f};
   const uint32_t hbuf_u32 = rt_smem_u32(hbuf);
+  const uint32_t hfull_u32 = rt_smem_u32(hfull);
+  uint32_t hph[2] = {0u, 0u};
   // destination chunk (16 B = 8 units) of this thread pair inside one h buffer
   const uint32_t k0 = rank * RT_UPC + 4 * (ug & ~1);
   const uint32_t h_chunk_off = (k0 >> 6) * 2048 + rt_swz(cb, k0 & 63);
 
-  float x[16];
+  // x-projection prefetch: 16 independent loads issued back to back one step ahead, kept as raw bf16 bits and
+  // converted only when consumed, so their DRAM latency never sits on the recurrent critical path.
+  unsigned short xr[16];
   auto load_x = [&](int t) {
-    const __nv_bfloat16* xp = xproj + (((size_t)dir * Tn + t) * B) * (4 * RT_H) + grow_g;
+    const unsigned short* xp = reinterpret_cast<const unsigned short*>(xproj) + (((size_t)dir * Tn + t) * B) * (4 * RT_H) + grow_g;
 #pragma unroll
-    for (int b = 0; b < RT_NB; ++b) x[b] = (b0 + b < B) ? __bfloat162float(xp[(size_t)(b0 + b) * (4 * RT_H)]) : 0.f;
+    for (int b = 0; b < RT_NB; ++b) xr[b] = __ldg(xp + (size_t)min(b0 + b, B - 1) * (4 * RT_H));
   };
   if (Tn > 0) load_x(dir ? Tn - 1 : 0);
 
@@ -175,8 +193,11 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
   uint32_t phase = 0;
   for (int s = 0; s < Tn; ++s) {
     const int t = dir ? (Tn - 1 - s) : s;
-    rt_cluster_wait();                       // h_{t-1} slices of all 8 CTAs have landed in hbuf[cur]
     if (tid == 0) {
+      if (s > 0) {                           // h_{t-1} slices of all 8 CTAs have landed in hbuf[cur]
+        rt_mbar_wait(&hfull[cur], hph[cur]);
+        hph[cur] ^= 1;
+      }
       rt_fence_async();
       rt_tc_after();
       const uint32_t wa = rt_smem_u32(Wsm), hb = hbuf_u32 + cur * 8192;
@@ -189,13 +210,15 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
     rt_mbar_wait(mma_bar, phase);
     phase ^= 1;
     rt_tc_after();
+    // hbuf[cur] has been consumed by the MMAs: arm it for h_{t+1} (written during the next step)
+    if (tid == 0 && s + 2 < Tn) rt_mbar_expect_tx(&hfull[cur], 8192);
     float g[16];
     rt_tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16), g);
     rt_tc_before();
     // gate non-linearity: warp 2 holds the candidate gate (tanh), the others sigmoid (PyTorch order i,f,g,o)
 #pragma unroll
     for (int b = 0; b < RT_NB; ++b) {
-      const float v = g[b] + x[b];
+      const float v = g[b] + __uint_as_float((uint32_t)xr[b] << 16);
       actbuf[(warp * RT_NB + b) * RT_UPC + lane] = (warp == 2) ? rt_tanh(v) : rt_sigmoid(v);
     }
     if (s + 1 < Tn) load_x(dir ? (Tn - 2 - s) : (s + 1));     // prefetch next step's x-projection
@@ -220,14 +243,13 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
     // ---- scatter this pair's 8 units of h_t into the next-step B operand of every CTA in the cluster
     const uint32_t p0 = rt_pack(h_st[0], h_st[1]), p1 = rt_pack(h_st[2], h_st[3]);
     const uint32_t q0 = __shfl_down_sync(0xffffffffu, p0, 1), q1 = __shfl_down_sync(0xffffffffu, p1, 1);
-    if ((ug & 1) == 0) {
+    if ((ug & 1) == 0 && s + 1 < Tn) {
       const uint32_t dst = hbuf_u32 + (cur ^ 1) * 8192 + h_chunk_off;
+      const uint32_t bar = hfull_u32 + (cur ^ 1) * 8;
 #pragma unroll
-      for (uint32_t r = 0; r < RT_C; ++r) rt_st_cluster_v4(rt_mapa(dst, r), p0, p1, q0, q1);
+      for (uint32_t r = 0; r < RT_C; ++r) rt_st_async_v4(rt_mapa(dst, r), p0, p1, q0, q1, rt_mapa(bar, r));
     }
-    rt_fence_async();
-    rt_cluster_arrive();
-    // ---- global stores overlap the cluster barrier
+    // ---- global stores: nothing on the recurrent critical path waits for them
     if (b_ok) {
       const size_t row = ((size_t)dir * Tn + t) * B + bglob;
       if (acts) {
@@ -245,9 +267,9 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
     }
     cur ^= 1;
   }
-  rt_cluster_wait();         // peers are done addressing this CTA's shared memory
   rt_tc_before();
-  __syncthreads();
+  rt_cluster_arrive();       // nobody exits while a peer could still address its shared memory
+  rt_cluster_wait();
   if (warp == 0) {
     rt_tc_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
@@ -270,7 +292,8 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
   uint8_t* Bsm = smem + BWD_B_OFF;
   float* red = (float*)(smem + BWD_RED_OFF);
   uint64_t* mma_bar = (uint64_t*)(smem + BWD_BAR_OFF);
-  uint32_t* tmem_slot = (uint32_t*)(smem + BWD_BAR_OFF + 16);
+  uint64_t* rfull = mma_bar + 1;                 // [2]: red buffer b holds all 8 partial blocks (8 x 2 KB)
+  uint32_t* tmem_slot = (uint32_t*)(smem + BWD_BAR_OFF + 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = rt_cluster_rank();
@@ -293,7 +316,10 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
   for (int i = tid; i < (4096 + 32768) / 16; i += RT_THREADS) reinterpret_cast<uint4*>(Bsm)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     rt_mbar_init(mma_bar, 1);
+    rt_mbar_init(&rfull[0], 1);
+    rt_mbar_init(&rfull[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    rt_mbar_expect_tx(&rfull[1], 16384);       // step 0 sends its partials into buffer 1
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rt_smem_u32(tmem_slot)), "r"(32u) : "memory");
@@ -305,6 +331,7 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
   rt_tc_after();
   const uint32_t tmem_base = *tmem_slot;
   rt_cluster_arrive();
+  rt_cluster_wait();
 
   // thread owns unit ul = lane of this CTA and sequences 4*warp .. 4*warp+3 in the pointwise phase
   const int ul = lane, u = rank * RT_UPC + ul;
@@ -314,31 +341,47 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
   for (int q = 0; q < 4; ++q) len_b[q] = (b0 + 4 * warp + q < B) ? lens[b0 + 4 * warp + q] : 0;
   float dcrec[4] = {0.f, 0.f, 0.f, 0.f};
   const uint32_t red_u32 = rt_smem_u32(red);
+  const uint32_t rfull_u32 = rt_smem_u32(rfull);
+  uint32_t rph[2] = {0u, 0u};
   const size_t G4 = 4 * RT_H;
+
+  // software-pipelined loads of the saved forward state: unconditional (clamped indices), issued one step ahead
+  float pa[4][4], pct[4], pcp[4];
+  unsigned short pdy[4];
+  auto prefetch = [&](int t) {
+    const int tp = min(max(dir ? t + 1 : t - 1, 0), Tn - 1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int b = min(b0 + 4 * warp + q, B - 1);
+      const size_t row = ((size_t)dir * Tn + t) * B + b;
+      const float* a = acts + row * G4 + u;
+      pa[0][q] = __ldg(a); pa[1][q] = __ldg(a + RT_H); pa[2][q] = __ldg(a + 2 * RT_H); pa[3][q] = __ldg(a + 3 * RT_H);
+      pct[q] = __ldg(cs + row * RT_H + u);
+      pcp[q] = __ldg(cs + (((size_t)dir * Tn + tp) * B + b) * RT_H + u);
+      pdy[q] = __ldg(reinterpret_cast<const unsigned short*>(dout) + (size_t)(t / pair) * out_ld_t + (size_t)b * out_ld_b +
+                     (size_t)(t % pair) * 2 * RT_H + dir * RT_H + u);
+    }
+  };
+  if (Tn > 0) prefetch(dir ? 0 : Tn - 1);
 
   int cur = 0;
   uint32_t phase = 0;
   for (int s = 0; s < Tn; ++s) {
     const int t = dir ? s : (Tn - 1 - s);
     const int tp = dir ? t + 1 : t - 1;
-    // ---- issue this step's loads before waiting on the cluster: they do not depend on the recurrence
+    // ---- this step's saved activations were prefetched during the previous step (raw registers)
     float ai[4], af[4], ag[4], ao[4], ct[4], cp[4], dy[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int b = b0 + 4 * warp + q;
-      const bool valid = t < len_b[q];
-      if (valid) {
-        const size_t row = ((size_t)dir * Tn + t) * B + b;
-        const float* a = acts + row * G4 + u;
-        ai[q] = a[0]; af[q] = a[RT_H]; ag[q] = a[2 * RT_H]; ao[q] = a[3 * RT_H];
-        ct[q] = cs[row * RT_H + u];
-        cp[q] = (tp >= 0 && tp < Tn) ? cs[(((size_t)dir * Tn + tp) * B + b) * RT_H + u] : 0.f;
-        dy[q] = __bfloat162float(dout[(size_t)(t / pair) * out_ld_t + (size_t)b * out_ld_b + (size_t)(t % pair) * 2 * RT_H + dir * RT_H + u]);
-      } else {
-        ai[q] = af[q] = ag[q] = ao[q] = ct[q] = cp[q] = dy[q] = 0.f;
-      }
+      ai[q] = pa[0][q]; af[q] = pa[1][q]; ag[q] = pa[2][q]; ao[q] = pa[3][q];
+      ct[q] = pct[q];
+      cp[q] = (tp >= 0 && tp < Tn) ? pcp[q] : 0.f;
+      dy[q] = __uint_as_float((uint32_t)pdy[q] << 16);
     }
-    rt_cluster_wait();                       // partial dh of the previous step from all 8 CTAs is in red[cur]
+    if (s > 0) {                             // partial dh of the previous step from all 8 CTAs is in red[cur]
+      rt_mbar_wait(&rfull[cur], rph[cur]);
+      rph[cur] ^= 1;
+    }
     float dg[4][4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -366,10 +409,12 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
         if (b0 + b < B) dgates[(((size_t)dir * Tn + t) * B + b0 + b) * G4 + gte * RT_H + u] = v;
       }
     }
+    if (s + 1 < Tn) prefetch(dir ? s + 1 : Tn - 2 - s);      // next step's state, consumed after the next wait
     rt_fence_async();
     rt_tc_before();
     __syncthreads();
     if (tid == 0) {
+      if (s + 2 < Tn) rt_mbar_expect_tx(&rfull[cur], 16384);   // red[cur] fully read: arm it for step s+1's partials
       rt_tc_after();
       const uint32_t aa = rt_smem_u32(Asm), bb = rt_smem_u32(Bsm);
 #pragma unroll
@@ -385,24 +430,26 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
     rt_tc_after();
     // ---- partial dh_{t-1}[unit, seq] for all 256 units: send each 32-unit block to the CTA that owns it
     const int nxt = cur ^ 1;
+    if (s + 1 < Tn) {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      float p[16];
-      rt_tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + mt * RT_NB, p);
-      const uint32_t owner = mt * 4 + warp;                 // unit mt*128 + warp*32 + lane lives on CTA `owner`
-      const uint32_t dst = rt_mapa(red_u32 + (uint32_t)((((nxt * RT_C + rank) * RT_UPC + lane) * RT_NB) * 4), owner);
+      for (int mt = 0; mt < 2; ++mt) {
+        float p[16];
+        rt_tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + mt * RT_NB, p);
+        const uint32_t owner = mt * 4 + warp;               // unit mt*128 + warp*32 + lane lives on CTA `owner`
+        const uint32_t dst = rt_mapa(red_u32 + (uint32_t)((((nxt * RT_C + rank) * RT_UPC + lane) * RT_NB) * 4), owner);
+        const uint32_t bar = rt_mapa(rfull_u32 + nxt * 8, owner);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        rt_st_cluster_v4(dst + j * 16, __float_as_uint(p[4 * j]), __float_as_uint(p[4 * j + 1]),
-                         __float_as_uint(p[4 * j + 2]), __float_as_uint(p[4 * j + 3]));
+        for (int j = 0; j < 4; ++j)
+          rt_st_async_v4(dst + j * 16, __float_as_uint(p[4 * j]), __float_as_uint(p[4 * j + 1]),
+                         __float_as_uint(p[4 * j + 2]), __float_as_uint(p[4 * j + 3]), bar);
+      }
     }
     rt_tc_before();
-    rt_cluster_arrive();
     cur = nxt;
   }
-  rt_cluster_wait();
   rt_tc_before();
-  __syncthreads();
+  rt_cluster_arrive();
+  rt_cluster_wait();
   if (warp == 0) {
     rt_tc_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");

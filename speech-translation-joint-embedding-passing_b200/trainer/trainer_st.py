@@ -33,6 +33,16 @@ class Trainer_ST(object):
         self.max_grad_norm = max_grad_norm
 
     def _train_batch(self, model, batch_items, dataset=None, step=0, total_steps=0):
+        resloss_de = self._train_batch_device(model, batch_items)
+        if self.optimizer is not None:
+            self.optimizer.step()
+            model.zero_grad()
+        # one D2H read per batch (the reference reads .item() per minibatch, trainer_st.py:287)
+        return {'nll_loss_de': float(resloss_de)}
+
+    def _train_batch_device(self, model, batch_items):
+        """The same step without any host synchronisation (returns the loss as a device scalar), so it
+        can be captured into a CUDA graph (b200st.graph.GraphedTrainStep)."""
         batch_src_ids = batch_items['srcid'][0]
         batch_tgt_ids = batch_items['tgtid'][0]
         batch_acous_feats = batch_items['acous_feat'][0]
@@ -47,8 +57,11 @@ class Trainer_ST(object):
             i_start = bidx * self.minibatch_size
             i_end = min(i_start + self.minibatch_size, batch_size)
             acous_lengths = batch_acous_lengths[i_start:i_end]
-            acous_len = max(int(n) for n in acous_lengths)
-            acous_len = acous_len + 8 - acous_len % 8                        # trainer_st.py:252
+            if torch.is_tensor(acous_lengths) and acous_lengths.is_cuda:     # device-resident lengths: no sync
+                acous_len = batch_acous_feats.size(1)
+            else:
+                acous_len = max(int(n) for n in acous_lengths)
+                acous_len = acous_len + 8 - acous_len % 8                    # trainer_st.py:252
             src_ids = batch_src_ids[i_start:i_end].to(device=self.device, non_blocking=True)
             tgt_ids = batch_tgt_ids[i_start:i_end].to(device=self.device, non_blocking=True)
             acous_feats = batch_acous_feats[i_start:i_end, :acous_len].to(device=self.device,
@@ -73,8 +86,4 @@ class Trainer_ST(object):
             resloss_de = resloss_de + loss_de.acc_loss.detach()
         if self.reducer is not None:
             self.reducer.finish()
-        if self.optimizer is not None:
-            self.optimizer.step()
-            model.zero_grad()
-        # one D2H read per batch (the reference reads .item() per minibatch, trainer_st.py:287)
-        return {'nll_loss_de': float(resloss_de)}
+        return resloss_de
