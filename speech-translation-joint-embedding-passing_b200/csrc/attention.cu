@@ -131,6 +131,159 @@ __global__ void mha_bwd_kv_kernel(const T* __restrict__ dout, int64_t ldo, const
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tiled variants for the training shapes (Lq, Lk <= ~128, d <= 128): one CTA per (batch, head) keeps
+// Q, K, V (and dO, P, dS in backward) in shared memory as fp32, so every global element is read once with
+// coalesced row loads and the three small products run out of shared memory with broadcast/conflict-free
+// access (rows padded to d+1).  At L = 50, d = 64 a head is ~0.4 MFLOP: far below one tensor-core tile's
+// fixed cost, so the CUDA cores are the right unit here; the grid (B*H = 512 CTAs) fills the 148 SMs.
+// ------------------------------------------------------------------------------------------------
+constexpr int MHA_T_THREADS = 256;
+
+template <typename T>
+__device__ __forceinline__ void mha_load_rows(float* dst, int pitch, const T* __restrict__ src, int64_t ld,
+                                              int rows, int d, float scale) {
+  for (int idx = threadIdx.x; idx < rows * d; idx += MHA_T_THREADS) {
+    const int r = idx / d, c = idx - r * d;
+    dst[r * pitch + c] = to_f(src[(int64_t)r * ld + c]) * scale;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(MHA_T_THREADS)
+mha_fwd_tiled_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, int64_t ldk,
+                     const T* __restrict__ v, int64_t ldv, const uint8_t* __restrict__ mask, int64_t mask_sb,
+                     int64_t mask_sq, T* __restrict__ o, int64_t ldo, T* __restrict__ p, int H, int Lq, int Lk,
+                     int d, float temperature) {
+  extern __shared__ float sm[];
+  const int dp = d + 1, lp = Lk + 1;
+  float* Qs = sm;                  // [Lq][dp]  (already divided by the temperature)
+  float* Ks = Qs + Lq * dp;        // [Lk][dp]
+  float* Vs = Ks + Lk * dp;        // [Lk][dp]
+  float* Ss = Vs + Lk * dp;        // [Lq][lp]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // q / temperature: division (not reciprocal multiply) to follow layers.py:216 bit for bit
+  for (int idx = threadIdx.x; idx < Lq * d; idx += MHA_T_THREADS) {
+    const int r = idx / d, c = idx - r * d;
+    Qs[r * dp + c] = to_f(q[((int64_t)b * Lq + r) * ldq + (int64_t)h * d + c]) / temperature;
+  }
+  mha_load_rows(Ks, dp, k + (int64_t)b * Lk * ldk + (int64_t)h * d, ldk, Lk, d, 1.f);
+  mha_load_rows(Vs, dp, v + (int64_t)b * Lk * ldv + (int64_t)h * d, ldv, Lk, d, 1.f);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < Lq * Lk; idx += MHA_T_THREADS) {
+    const int i = idx / Lk, j = idx - i * Lk;
+    const float* qr = Qs + i * dp;
+    const float* kr = Ks + j * dp;
+    float s = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < d; ++c) s = fmaf(qr[c], kr[c], s);
+    if (mask && mask[b * mask_sb + i * mask_sq + j] == 0) s = -1e9f;        // layers.py:224
+    Ss[i * lp + j] = s;
+  }
+  __syncthreads();
+  for (int i = w; i < Lq; i += MHA_T_THREADS / 32) {
+    float* sr = Ss + i * lp;
+    float mx = -INFINITY;
+    for (int j = lane; j < Lk; j += 32) mx = fmaxf(mx, sr[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < Lk; j += 32) { const float e = expf(sr[j] - mx); sr[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    T* pr = p ? p + (((int64_t)b * H + h) * Lq + i) * Lk : nullptr;
+    for (int j = lane; j < Lk; j += 32) {
+      const float pv = sr[j] * inv;
+      sr[j] = pv;
+      if (pr) pr[j] = from_f<T>(pv);
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < Lq * d; idx += MHA_T_THREADS) {
+    const int i = idx / d, c = idx - i * d;
+    const float* pr = Ss + i * lp;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < Lk; ++j) acc = fmaf(pr[j], Vs[j * dp + c], acc);
+    o[((int64_t)b * Lq + i) * ldo + (int64_t)h * d + c] = from_f<T>(acc);
+  }
+}
+
+// dP = dO V^T;  dS = P * (dP - rowsum(P dP));  dQ = dS K / temp;  dK = dS^T (Q / temp);  dV = P^T dO.
+template <typename T>
+__global__ void __launch_bounds__(MHA_T_THREADS)
+mha_bwd_tiled_kernel(const T* __restrict__ dout, int64_t ldo, const T* __restrict__ q, int64_t ldq,
+                     const T* __restrict__ k, int64_t ldk, const T* __restrict__ v, int64_t ldv,
+                     const T* __restrict__ p, T* __restrict__ dq, int64_t lddq, T* __restrict__ dk, int64_t lddk,
+                     T* __restrict__ dv, int64_t lddv, int H, int Lq, int Lk, int d, float temperature) {
+  extern __shared__ float sm[];
+  const int dp = d + 1, lp = Lk + 1;
+  float* Qs = sm;                  // [Lq][dp]  q / temperature
+  float* Ks = Qs + Lq * dp;        // [Lk][dp]
+  float* Vs = Ks + Lk * dp;        // [Lk][dp]
+  float* dOs = Vs + Lk * dp;       // [Lq][dp]
+  float* Ps = dOs + Lq * dp;       // [Lq][lp]
+  float* dSs = Ps + Lq * lp;       // [Lq][lp]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int idx = threadIdx.x; idx < Lq * d; idx += MHA_T_THREADS) {
+    const int r = idx / d, c = idx - r * d;
+    Qs[r * dp + c] = to_f(q[((int64_t)b * Lq + r) * ldq + (int64_t)h * d + c]) / temperature;
+  }
+  mha_load_rows(Ks, dp, k + (int64_t)b * Lk * ldk + (int64_t)h * d, ldk, Lk, d, 1.f);
+  mha_load_rows(Vs, dp, v + (int64_t)b * Lk * ldv + (int64_t)h * d, ldv, Lk, d, 1.f);
+  mha_load_rows(dOs, dp, dout + (int64_t)b * Lq * ldo + (int64_t)h * d, ldo, Lq, d, 1.f);
+  const T* pb = p + ((int64_t)b * H + h) * Lq * Lk;
+  for (int idx = threadIdx.x; idx < Lq * Lk; idx += MHA_T_THREADS) {
+    const int i = idx / Lk, j = idx - i * Lk;
+    Ps[i * lp + j] = to_f(pb[idx]);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < Lq * Lk; idx += MHA_T_THREADS) {
+    const int i = idx / Lk, j = idx - i * Lk;
+    const float* dr = dOs + i * dp;
+    const float* vr = Vs + j * dp;
+    float s = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < d; ++c) s = fmaf(dr[c], vr[c], s);
+    dSs[i * lp + j] = s;
+  }
+  __syncthreads();
+  for (int i = w; i < Lq; i += MHA_T_THREADS / 32) {
+    float delta = 0.f;
+    for (int j = lane; j < Lk; j += 32) delta += dSs[i * lp + j] * Ps[i * lp + j];
+    delta = warp_sum(delta);
+    for (int j = lane; j < Lk; j += 32) dSs[i * lp + j] = Ps[i * lp + j] * (dSs[i * lp + j] - delta);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < Lq * d; idx += MHA_T_THREADS) {          // dQ
+    const int i = idx / d, c = idx - i * d;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < Lk; ++j) acc = fmaf(dSs[i * lp + j], Ks[j * dp + c], acc);
+    dq[((int64_t)b * Lq + i) * lddq + (int64_t)h * d + c] = from_f<T>(acc / temperature);
+  }
+  for (int idx = threadIdx.x; idx < Lk * d; idx += MHA_T_THREADS) {          // dK, dV
+    const int j = idx / d, c = idx - j * d;
+    float ak = 0.f, av = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < Lq; ++i) {
+      ak = fmaf(dSs[i * lp + j], Qs[i * dp + c], ak);
+      av = fmaf(Ps[i * lp + j], dOs[i * dp + c], av);
+    }
+    dk[((int64_t)b * Lk + j) * lddk + (int64_t)h * d + c] = from_f<T>(ak);
+    dv[((int64_t)b * Lk + j) * lddv + (int64_t)h * d + c] = from_f<T>(av);
+  }
+}
+
+static size_t mha_fwd_tiled_smem(int64_t Lq, int64_t Lk, int64_t d) {
+  return ((Lq + 2 * Lk) * (d + 1) + Lq * (Lk + 1)) * sizeof(float);
+}
+static size_t mha_bwd_tiled_smem(int64_t Lq, int64_t Lk, int64_t d) {
+  return ((2 * Lq + 2 * Lk) * (d + 1) + 2 * Lq * (Lk + 1)) * sizeof(float);
+}
+
 // ------------------------------------------------------------------------------------------------
 // LAS attention step: one CTA per batch row.  dynamic smem: (D + 2 * Tk) floats.
 // ------------------------------------------------------------------------------------------------
@@ -222,6 +375,155 @@ __global__ void las_attn_bwd_kernel(const T* __restrict__ dctx, const T* __restr
   }
 }
 
+
+// ---- 16-byte vectorised row access (8 bf16 or 2 x 4 fp32 per call)
+__device__ __forceinline__ void load8(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float* v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void store8(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* v) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// Vectorised LAS attention step (D, Dv multiples of 8): one CTA (256 threads) per sequence.
+//   scores: one warp per key, lanes stride over 16-byte chunks of the key row;
+//   context: thread (group g, chunk c) accumulates keys j = g mod 4 for 8 output columns, groups reduced in smem.
+// dynamic smem: (D + Tk + 4 * Dv) floats.
+template <typename T>
+__global__ void __launch_bounds__(256)
+las_attn_fwd_vec_kernel(const T* __restrict__ q, const T* __restrict__ wk, const T* __restrict__ vals,
+                        const int32_t* __restrict__ klens, T* __restrict__ ctx, float* __restrict__ probs, int Tk,
+                        int D, int Dv) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ float scratch[32];
+  float* qs = sm;             // [D]
+  float* sc = qs + D;         // [Tk]
+  float* part = sc + ((Tk + 3) & ~3);   // [4][Dv]
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int c = threadIdx.x; c < D; c += 256) qs[c] = to_f(q[(int64_t)b * D + c]);
+  __syncthreads();
+  const int klen = klens ? klens[b] : Tk;
+  const T* wkb = wk + (int64_t)b * Tk * D;
+  for (int j = w; j < Tk; j += 8) {
+    float s = 0.f;
+    if (j < klen) {
+      const T* r = wkb + (int64_t)j * D;
+      for (int c = lane * 8; c < D; c += 256) {
+        float v[8];
+        load8(r + c, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(qs[c + i], v[i], s);
+      }
+      s = warp_sum(s);
+    }
+    if (lane == 0) sc[j] = (j >= klen) ? -1e12f : s;                     // attention.py:250-252
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < Tk; j += 256) mx = fmaxf(mx, sc[j]);
+  mx = block_max(mx, scratch);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < Tk; j += 256) { const float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
+  sum = block_sum(sum, scratch);
+  const float inv = 1.f / sum;
+  for (int j = threadIdx.x; j < Tk; j += 256) { const float pv = sc[j] * inv; sc[j] = pv; probs[(int64_t)b * Tk + j] = pv; }
+  __syncthreads();
+  const T* vb = vals + (int64_t)b * Tk * Dv;
+  const int nchunk = Dv >> 3;
+  for (int item = threadIdx.x; item < 4 * nchunk; item += 256) {
+    const int g = item / nchunk, c = (item - g * nchunk) * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = g; j < Tk; j += 4) {
+      const float pj = sc[j];
+      if (pj == 0.f) continue;            // masked keys (and exact zeros) contribute nothing
+      float v[8];
+      load8(vb + (int64_t)j * Dv + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(pj, v[i], acc[i]);
+    }
+    store8(part + g * Dv + c, acc);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Dv; c += 256)
+    ctx[(int64_t)b * Dv + c] = from_f<T>((part[c] + part[Dv + c]) + (part[2 * Dv + c] + part[3 * Dv + c]));
+}
+
+// dynamic smem: (Dv + Tk + 4 * D) floats
+template <typename T>
+__global__ void __launch_bounds__(256)
+las_attn_bwd_vec_kernel(const T* __restrict__ dctx, const T* __restrict__ wk, const T* __restrict__ vals,
+                        const float* __restrict__ probs, float* __restrict__ dscore, T* __restrict__ dq, int Tk, int D,
+                        int Dv) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ float scratch[32];
+  float* dcs = sm;            // [Dv]
+  float* sc = dcs + Dv;       // [Tk]
+  float* part = sc + ((Tk + 3) & ~3);   // [4][D]
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int c = threadIdx.x; c < Dv; c += 256) dcs[c] = to_f(dctx[(int64_t)b * Dv + c]);
+  __syncthreads();
+  const T* vb = vals + (int64_t)b * Tk * Dv;
+  const float* pb = probs + (int64_t)b * Tk;
+  for (int j = w; j < Tk; j += 8) {
+    float s = 0.f;
+    if (pb[j] != 0.f) {                    // dscore = p * (dp - delta): rows with p == 0 need no dp
+      const T* r = vb + (int64_t)j * Dv;
+      for (int c = lane * 8; c < Dv; c += 256) {
+        float v[8];
+        load8(r + c, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(dcs[c + i], v[i], s);
+      }
+      s = warp_sum(s);
+    }
+    if (lane == 0) sc[j] = s;
+  }
+  __syncthreads();
+  float delta = 0.f;
+  for (int j = threadIdx.x; j < Tk; j += 256) delta += sc[j] * pb[j];
+  delta = block_sum(delta, scratch);
+  for (int j = threadIdx.x; j < Tk; j += 256) {
+    const float g = pb[j] * (sc[j] - delta);
+    sc[j] = g;
+    dscore[(int64_t)b * Tk + j] = g;
+  }
+  __syncthreads();
+  const T* wkb = wk + (int64_t)b * Tk * D;
+  const int nchunk = D >> 3;
+  for (int item = threadIdx.x; item < 4 * nchunk; item += 256) {
+    const int g = item / nchunk, c = (item - g * nchunk) * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = g; j < Tk; j += 4) {
+      const float gj = sc[j];
+      if (gj == 0.f) continue;
+      float v[8];
+      load8(wkb + (int64_t)j * D + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(gj, v[i], acc[i]);
+    }
+    store8(part + g * D + c, acc);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += 256)
+    dq[(int64_t)b * D + c] = from_f<T>((part[c] + part[D + c]) + (part[2 * D + c] + part[3 * D + c]));
+}
+
 template <typename T>
 __global__ void argmax_rows_kernel(const T* __restrict__ x, int64_t ld, int cols,
                                    int64_t* __restrict__ idx, int64_t idx_stride) {
@@ -277,6 +579,21 @@ int b200st_mha_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t
                    float temperature, b200st_stream_t stream) {
   if (B <= 0 || Lq <= 0) return 0;
   if (Lk <= 0) return set_error("mha_fwd: empty key sequence");
+  {
+    const size_t tsm = mha_fwd_tiled_smem(Lq, Lk, d);
+    if (tsm <= 100 * 1024) {     // training shapes: whole head in shared memory
+      dim3 tg((unsigned)H, (unsigned)B);
+      B200ST_DISPATCH(dtype, T, {
+        if (tsm > 48 * 1024)
+          B200ST_CUDA(cudaFuncSetAttribute((const void*)mha_fwd_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        mha_fwd_tiled_kernel<T><<<tg, MHA_T_THREADS, tsm, (cudaStream_t)stream>>>(
+            (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, mask, mask_sb, mask_sq, (T*)o, ldo, (T*)p,
+            (int)H, (int)Lq, (int)Lk, (int)d, temperature);
+      });
+      B200ST_LAUNCH_CHECK("mha_fwd_tiled");
+      return 0;
+    }
+  }
   const size_t smem = MHA_WARPS * (d + Lk) * sizeof(float);
   if (smem > 48 * 1024) return set_error("mha_fwd: Lk=%lld d=%lld exceeds the single-pass kernel", (long long)Lk, (long long)d);
   dim3 grid((unsigned)ceil_div(Lq, MHA_WARPS), (unsigned)H, (unsigned)B);
@@ -295,6 +612,21 @@ int b200st_mha_bwd(int dtype, const void* dout, int64_t ldo, const void* q, int6
                    int64_t H, int64_t Lq, int64_t Lk, int64_t d, float temperature,
                    b200st_stream_t stream) {
   if (B <= 0 || Lq <= 0 || Lk <= 0) return 0;
+  {
+    const size_t tsm = mha_bwd_tiled_smem(Lq, Lk, d);
+    if (tsm <= 160 * 1024) {
+      dim3 tg((unsigned)H, (unsigned)B);
+      B200ST_DISPATCH(dtype, T, {
+        if (tsm > 48 * 1024)
+          B200ST_CUDA(cudaFuncSetAttribute((const void*)mha_bwd_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        mha_bwd_tiled_kernel<T><<<tg, MHA_T_THREADS, tsm, (cudaStream_t)stream>>>(
+            (const T*)dout, ldo, (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, (const T*)p, (T*)dq, lddq,
+            (T*)dk, lddk, (T*)dv, lddv, (int)H, (int)Lq, (int)Lk, (int)d, temperature);
+      });
+      B200ST_LAUNCH_CHECK("mha_bwd_tiled");
+      return 0;
+    }
+  }
   const size_t smem = MHA_WARPS * (d + Lk) * sizeof(float);
   if (smem > 48 * 1024) return set_error("mha_bwd: Lk=%lld d=%lld exceeds the single-pass kernel", (long long)Lk, (long long)d);
   dim3 gq((unsigned)ceil_div(Lq, MHA_WARPS), (unsigned)H, (unsigned)B);
@@ -316,6 +648,17 @@ int b200st_las_attn_fwd(int dtype, const void* q, const void* wk, const void* va
                         const int32_t* klens, void* ctx, float* probs, int64_t B, int64_t Tk, int64_t D,
                         int64_t Dv, b200st_stream_t stream) {
   if (B <= 0) return 0;
+  {
+    const size_t vs = (D + ((Tk + 3) & ~3) + 4 * Dv) * sizeof(float);
+    if (D % 8 == 0 && Dv % 8 == 0 && vs <= 48 * 1024) {
+      B200ST_DISPATCH(dtype, T, {
+        las_attn_fwd_vec_kernel<T><<<(unsigned)B, 256, vs, (cudaStream_t)stream>>>(
+            (const T*)q, (const T*)wk, (const T*)vals, klens, (T*)ctx, probs, (int)Tk, (int)D, (int)Dv);
+      });
+      B200ST_LAUNCH_CHECK("las_attn_fwd_vec");
+      return 0;
+    }
+  }
   const size_t smem = (D + Tk) * sizeof(float);
   if (smem > 48 * 1024) return set_error("las_attn_fwd: D+Tk too large");
   B200ST_DISPATCH(dtype, T, {
@@ -330,6 +673,17 @@ int b200st_las_attn_bwd(int dtype, const void* dctx, const void* wk, const void*
                         const float* probs, float* dscore, void* dq, int64_t B, int64_t Tk, int64_t D,
                         int64_t Dv, b200st_stream_t stream) {
   if (B <= 0) return 0;
+  {
+    const size_t vs = (Dv + ((Tk + 3) & ~3) + 4 * D) * sizeof(float);
+    if (D % 8 == 0 && Dv % 8 == 0 && vs <= 48 * 1024) {
+      B200ST_DISPATCH(dtype, T, {
+        las_attn_bwd_vec_kernel<T><<<(unsigned)B, 256, vs, (cudaStream_t)stream>>>(
+            (const T*)dctx, (const T*)wk, (const T*)vals, probs, dscore, (T*)dq, (int)Tk, (int)D, (int)Dv);
+      });
+      B200ST_LAUNCH_CHECK("las_attn_bwd_vec");
+      return 0;
+    }
+  }
   const size_t smem = (Dv + Tk) * sizeof(float);
   if (smem > 48 * 1024) return set_error("las_attn_bwd: Dv+Tk too large");
   B200ST_DISPATCH(dtype, T, {

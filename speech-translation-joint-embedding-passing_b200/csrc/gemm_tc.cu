@@ -22,7 +22,6 @@ namespace b200st {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_STAGES = 4;
 constexpr int TC_THREADS = 256;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -94,21 +93,25 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN>
+template <int BN, int STAGES>
 struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = TC_STAGES * STAGE;
-  static constexpr int TOTAL = BAR_OFF + (2 * TC_STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+  static constexpr int BAR_OFF = STAGES * STAGE;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
 };
 
-template <int BN, bool A_MN, bool B_MN, typename TC, bool ATOMIC>
+// Tile configurations (BN, STAGES): the deep-pipeline / narrow-N ones exist because most GEMMs on this path are
+// latency-bound (M = 64 decoder steps, M ~ 2-3k Transformer rows with K = 512): what matters there is bytes in
+// flight per SM and the number of CTAs, not MMA throughput.
+template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC, bool ATOMIC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                TC* __restrict__ C, int64_t ldc, const TC* R, int64_t ldr, const float* __restrict__ bias,
                int relu, float alpha, int M, int N, int K, int kb_per_split) {
-  using S = TcSmem<BN>;
+  using S = TcSmem<BN, STAGES>;
+  constexpr int TC_STAGES = STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
@@ -298,22 +301,23 @@ bool gemm_tc_eligible(int dtype_ab, int ta, int tb, int64_t M, int64_t N, int64_
   return get_encode() != nullptr;
 }
 
-template <int BN, bool A_MN, bool B_MN, typename TC>
+template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC>
 static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const CUtensorMap& ma, const CUtensorMap& mb,
                      void* C, int64_t ldc, const void* R, int64_t ldr, const float* bias, int relu, int splits,
                      int kb_per_split, cudaStream_t st) {
-  using S = TcSmem<BN>;
+  using S = TcSmem<BN, STAGES>;
+  static_assert(S::TOTAL <= 227 * 1024, "tile configuration exceeds shared memory");
   dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, TC_BM), (unsigned)splits);
   if (splits > 1) {
     if constexpr (sizeof(TC) == 4) {
-      auto kern = gemm_tc_kernel<BN, A_MN, B_MN, float, true>;
+      auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, float, true>;
       B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
       kern<<<grid, TC_THREADS, S::TOTAL, st>>>(ma, mb, (float*)C, ldc, nullptr, 0, nullptr, 0, alpha, (int)M, (int)N, (int)K, kb_per_split);
     } else {
       return set_error("gemm_tc: split-K needs an fp32 output");
     }
   } else {
-    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TC, false>;
+    auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, TC, false>;
     B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     kern<<<grid, TC_THREADS, S::TOTAL, st>>>(ma, mb, (TC*)C, ldc, (const TC*)R, ldr, bias, relu, alpha, (int)M, (int)N, (int)K, kb_per_split);
   }
@@ -327,15 +331,26 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   // op(A) is M x K: ta=0 -> stored [M,K] (K-major); ta=1 -> stored [K,M] (M-major).
   // op(B) is K x N: tb=1 -> stored [N,K] (K-major); tb=0 -> stored [K,N] (N-major).
   const bool a_mn = ta != 0, b_mn = tb == 0;
-  const int BN = (N <= 64) ? 64 : 128;
+  const int kb_total = (int)ceil_div(K, TC_BK);
+  const int64_t m_tiles = ceil_div(M, TC_BM);
+  // ---- tile configuration
+  //  cfg 0: 128 x 128, 4 stages  — throughput shape (many tiles)
+  //  cfg 1: 128 x  64, 6 stages  — mid-size problems that would not fill the 148 SMs with 128-wide tiles
+  //  cfg 2: 128 x  32, 10 stages — single-M-tile (decoder step, M <= 128) with K-major B: narrow N, deep pipeline
+  //  cfg 3: 128 x  64, 8 stages  — single-M-tile with N-major B (128B-swizzled MN-major boxes are 64 wide)
+  int cfg;
+  if (m_tiles == 1 && N > 32) cfg = b_mn ? 3 : 2;
+  else if (N <= 64 || m_tiles * ceil_div(N, 128) < 148) cfg = 1;
+  else cfg = 0;
+  if (N <= 32 && !b_mn) cfg = 2;
+  const int BN = cfg == 0 ? 128 : (cfg == 2 ? 32 : 64);
   CUtensorMap ma, mb;
   if (a_mn) { if (make_map(&ma, A, K, M, lda, TC_BK)) return -1; }
   else      { if (make_map(&ma, A, M, K, lda, TC_BM)) return -1; }
   if (b_mn) { if (make_map(&mb, B, K, N, ldb, TC_BK)) return -1; }
   else      { if (make_map(&mb, B, N, K, ldb, BN)) return -1; }
   // split-K when the output has few tiles and K is long (weight gradients): fp32 output, plain sum only.
-  const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
-  const int kb_total = (int)ceil_div(K, TC_BK);
+  const int64_t tiles = m_tiles * ceil_div(N, BN);
   int splits = 1;
   if (dtype_c == B200ST_F32 && !bias && !relu && !R && tiles < 96 && kb_total >= 16) {
     splits = (int)(296 / tiles);
@@ -345,18 +360,28 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   int kb_per_split = (int)ceil_div(kb_total, splits);
   splits = (int)ceil_div(kb_total, kb_per_split);
   if (splits > 1) B200ST_CUDA(cudaMemset2DAsync(C, ldc * 4, 0, N * 4, M, st));
-#define TC_GO(BN_, AMN, BMN)                                                                               \
+#define TC_GO(BN_, ST_, AMN, BMN)                                                                          \
   do {                                                                                                     \
     if (dtype_c == B200ST_F32)                                                                             \
-      return launch_tc<BN_, AMN, BMN, float>(M, N, K, alpha, ma, mb, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
-    return launch_tc<BN_, AMN, BMN, __nv_bfloat16>(M, N, K, alpha, ma, mb, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
+      return launch_tc<BN_, ST_, AMN, BMN, float>(M, N, K, alpha, ma, mb, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
+    return launch_tc<BN_, ST_, AMN, BMN, __nv_bfloat16>(M, N, K, alpha, ma, mb, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
   } while (0)
-#define TC_BNSEL(AMN, BMN) do { if (BN == 64) TC_GO(64, AMN, BMN); else TC_GO(128, AMN, BMN); } while (0)
-  if (!a_mn && !b_mn) TC_BNSEL(false, false);
-  if (!a_mn && b_mn) TC_BNSEL(false, true);
-  if (a_mn && !b_mn) TC_BNSEL(true, false);
-  TC_BNSEL(true, true);
-#undef TC_BNSEL
+#define TC_CFG(AMN, BMN)                                                   \
+  do {                                                                     \
+    if (cfg == 0) TC_GO(128, 4, AMN, BMN);                                 \
+    if (cfg == 1) TC_GO(64, 6, AMN, BMN);                                  \
+    if (cfg == 3) TC_GO(64, 8, AMN, BMN);                                  \
+  } while (0)
+  if (cfg == 2) {               // K-major B only
+    if (!a_mn) TC_GO(32, 10, false, false);
+    TC_GO(32, 10, true, false);
+  }
+  if (!a_mn && !b_mn) TC_CFG(false, false);
+  if (!a_mn && b_mn) TC_CFG(false, true);
+  if (a_mn && !b_mn) TC_CFG(true, false);
+  TC_CFG(true, true);
+  return set_error("gemm_tc: no tile configuration");
+#undef TC_CFG
 #undef TC_GO
 }
 
