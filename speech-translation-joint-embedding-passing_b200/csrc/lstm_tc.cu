@@ -85,6 +85,32 @@ __device__ __forceinline__ void rt_tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void rt_tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void rt_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Sum of NACC independent accumulators (16 columns each, NACC*16 apart... consecutive) -> v[16].
+// The K loop is spread round-robin over NACC accumulators so that consecutive tcgen05.mma do not form one long
+// dependent accumulate chain; the partial sums are added here.
+template <int NACC>
+__device__ __forceinline__ void rt_tmem_ld_sum(uint32_t taddr, float* v) {
+  uint32_t r[NACC][16];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) rt_tmem_ld16_nowait(taddr + a * 16, r[a]);
+  rt_tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float s = __uint_as_float(r[0][i]);
+#pragma unroll
+    for (int a = 1; a < NACC; ++a) s += __uint_as_float(r[a][i]);
+    v[i] = s;
+  }
+}
 // K-major, 128B-swizzled operand descriptor: SBO = 8 rows * 128 B (see gemm_tc.cu / mma_sm100_desc.hpp)
 __device__ __forceinline__ uint64_t rt_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -150,7 +176,7 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
     rt_mbar_expect_tx(&hfull[1], 8192);        // step 0 fills buffer 1
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rt_smem_u32(tmem_slot)), "r"(32u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rt_smem_u32(tmem_slot)), "r"(64u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   rt_fence_async();
@@ -203,8 +229,8 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
       const uint32_t wa = rt_smem_u32(Wsm), hb = hbuf_u32 + cur * 8192;
 #pragma unroll
       for (int ks = 0; ks < 16; ++ks)
-        rt_mma(tmem_base, rt_desc(wa + (ks >> 2) * 16384 + (ks & 3) * 32), rt_desc(hb + (ks >> 2) * 2048 + (ks & 3) * 32),
-               RT_IDESC, ks > 0 ? 1u : 0u);
+        rt_mma(tmem_base + (ks & 3) * 16, rt_desc(wa + (ks >> 2) * 16384 + (ks & 3) * 32),
+               rt_desc(hb + (ks >> 2) * 2048 + (ks & 3) * 32), RT_IDESC, ks >= 4 ? 1u : 0u);
       rt_commit(mma_bar);
     }
     rt_mbar_wait(mma_bar, phase);
@@ -213,7 +239,7 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
     // hbuf[cur] has been consumed by the MMAs: arm it for h_{t+1} (written during the next step)
     if (tid == 0 && s + 2 < Tn) rt_mbar_expect_tx(&hfull[cur], 8192);
     float g[16];
-    rt_tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16), g);
+    rt_tmem_ld_sum<4>(tmem_base + ((uint32_t)(warp * 32) << 16), g);
     rt_tc_before();
     // gate non-linearity: warp 2 holds the candidate gate (tanh), the others sigmoid (PyTorch order i,f,g,o)
 #pragma unroll
@@ -272,7 +298,7 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
   rt_cluster_wait();
   if (warp == 0) {
     rt_tc_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
   }
 }
 
@@ -322,7 +348,7 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
     rt_mbar_expect_tx(&rfull[1], 16384);       // step 0 sends its partials into buffer 1
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rt_smem_u32(tmem_slot)), "r"(32u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rt_smem_u32(tmem_slot)), "r"(64u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   rt_fence_async();
@@ -409,7 +435,6 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
         if (b0 + b < B) dgates[(((size_t)dir * Tn + t) * B + b0 + b) * G4 + gte * RT_H + u] = v;
       }
     }
-    if (s + 1 < Tn) prefetch(dir ? s + 1 : Tn - 2 - s);      // next step's state, consumed after the next wait
     rt_fence_async();
     rt_tc_before();
     __syncthreads();
@@ -421,10 +446,12 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
-          rt_mma(tmem_base + mt * RT_NB, rt_desc(aa + (mt * 2 + (ks >> 2)) * 16384 + (ks & 3) * 32),
-                 rt_desc(bb + (ks >> 2) * 2048 + (ks & 3) * 32), RT_IDESC, ks > 0 ? 1u : 0u);
+          rt_mma(tmem_base + (mt * 2 + (ks & 1)) * RT_NB, rt_desc(aa + (mt * 2 + (ks >> 2)) * 16384 + (ks & 3) * 32),
+                 rt_desc(bb + (ks >> 2) * 2048 + (ks & 3) * 32), RT_IDESC, ks >= 2 ? 1u : 0u);
       rt_commit(mma_bar);
     }
+    // next step's saved state: issued here so that no fence between now and its use has to wait for it
+    if (s + 1 < Tn) prefetch(dir ? s + 1 : Tn - 2 - s);
     rt_mbar_wait(mma_bar, phase);
     phase ^= 1;
     rt_tc_after();
@@ -434,7 +461,7 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         float p[16];
-        rt_tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + mt * RT_NB, p);
+        rt_tmem_ld_sum<2>(tmem_base + ((uint32_t)(warp * 32) << 16) + mt * 2 * RT_NB, p);
         const uint32_t owner = mt * 4 + warp;               // unit mt*128 + warp*32 + lane lives on CTA `owner`
         const uint32_t dst = rt_mapa(red_u32 + (uint32_t)((((nxt * RT_C + rank) * RT_UPC + lane) * RT_NB) * 4), owner);
         const uint32_t bar = rt_mapa(rfull_u32 + nxt * 8, owner);
@@ -452,7 +479,7 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
   rt_cluster_wait();
   if (warp == 0) {
     rt_tc_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
   }
 }
 

@@ -65,6 +65,9 @@ class Golden:
         return p
 
     def inputs(self):
+        override = os.environ.get('B200ST_TEST_INPUTS')
+        if override and os.path.exists(override):
+            return torch.load(override)
         i = self.group('in')
         i['acous_lens'] = [int(v) for v in i['acous_lens']]
         return i
