@@ -199,28 +199,34 @@ def cpu_step(P, cfg, data):
 
 
 def cpu_baseline(args, budget_s=25.0, steps=1, warmup=0):
-    """Times `steps` oracle steps on a bounded sample of the workload (same shapes, smaller batch)."""
+    """Times `steps` oracle steps on a bounded sample of the workload (same shapes, smaller batch).
+    The batch is chosen from a one-utterance probe so that the whole call stays within ~budget_s seconds."""
     from oracle import st_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = st_config()
     P = {k: v.requires_grad_(True) for k, v in O.init_params(cfg, seed=333).items()}
     probe = O.synthetic_batch(cfg, 1, args.frames, seed=1)
-    t0 = time.perf_counter(); cpu_step(P, cfg, probe); t1 = time.perf_counter() - t0   # also warms threads
-    per_utt = t1
+    t0 = time.perf_counter(); cpu_step(P, cfg, probe); t_probe = time.perf_counter() - t0   # also warms the threads
     total_steps = steps + warmup
-    b = int(max(1, min(args.batch, budget_s / max(per_utt, 1e-3) / max(total_steps, 1))))
-    b = min(b, 8) if total_steps == 1 else b
-    data = O.synthetic_batch(cfg, b, args.frames, seed=333)
-    for _ in range(warmup):
-        cpu_step(P, cfg, data)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_step(P, cfg, data)
-    dt = (time.perf_counter() - t0) / steps
+    # cost model: t(b) ~ t_probe * (0.5 + 0.5 * b)  (the 1890 serial LSTM steps have a large batch-independent part)
+    b = 1
+    while b < min(args.batch, 8) and t_probe * (0.5 + 0.5 * (b * 2)) * total_steps <= budget_s - t_probe:
+        b *= 2
+    if t_probe * total_steps > budget_s:        # even batch 1 blows the budget: the probe IS the measurement
+        dt, b, steps_done = t_probe, 1, 1
+    else:
+        data = O.synthetic_batch(cfg, b, args.frames, seed=333)
+        for _ in range(warmup):
+            cpu_step(P, cfg, data)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_step(P, cfg, data)
+        dt = (time.perf_counter() - t0) / steps
+        steps_done = steps
     return {'value': b / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
             'sample': f'configs[2] shapes ({args.frames} frames, V=10k, 6+6 layers), batch {b} of {args.batch}, '
-                      f'{steps} timed step(s) of fwd+bwd, fp32, torch.set_num_threads({cores}); the reference is '
+                      f'{steps_done} timed step(s) of fwd+bwd, fp32, torch.set_num_threads({cores}); the reference is '
                       f'pure Python/PyTorch and cannot travel to the GPU box, so its algorithm is timed through '
                       f'oracle/st_oracle.py (same torch primitives at the same call sites)',
             'ms_per_step': dt * 1e3, 'batch': b}
@@ -230,14 +236,14 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cb = cpu_baseline(args, budget_s=150.0, steps=max(1, args.steps), warmup=max(0, args.warmup))
+    cb = cpu_baseline(args, budget_s=120.0, steps=max(1, args.steps), warmup=max(0, args.warmup))
     line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': cb['ms_per_step'],
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic', 'config': workload(args), 'cpu_baseline': {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
             'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -397,9 +403,33 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(args)
             line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        # A process group whose collectives were captured into a CUDA graph can block in teardown; results are
+        # already printed, so synchronise, drop the graph and leave without running NCCL's destructors.
+        del graphed
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stderr.flush()
+        os._exit(0)
+
+
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """Only the final JSON line may reach stdout (NCCL / libraries print banners there): route fd 1 to stderr for the
+    duration of the run and keep a handle on the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
 
 
 def main():
@@ -414,6 +444,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA graph replay')
     args = ap.parse_args()
+    _capture_stdout()
     if args.impl == 'reference':
         run_reference(args)
     else:

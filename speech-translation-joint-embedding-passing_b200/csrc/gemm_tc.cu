@@ -106,7 +106,7 @@ struct TcSmem {
 // latency-bound (M = 64 decoder steps, M ~ 2-3k Transformer rows with K = 512): what matters there is bytes in
 // flight per SM and the number of CTAs, not MMA throughput.
 template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC, bool ATOMIC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, (BN * TC_BK * 2 + TC_BM * TC_BK * 2) * STAGES <= 100 * 1024 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                TC* __restrict__ C, int64_t ldc, const TC* R, int64_t ldr, const float* __restrict__ bias,
                int relu, float alpha, int M, int N, int K, int kb_per_split) {
@@ -187,63 +187,80 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       tc_commit(tmem_full);            // accumulator complete
     }
   } else if (warp >= 4) {
+    // ---- epilogue: TMEM -> registers -> per-warp staging tile in the (now idle) pipeline buffers -> coalesced
+    // global stores.  Each warp owns the 32 accumulator rows of its TMEM lane quarter; staging makes every store
+    // instruction write whole contiguous row segments instead of 32 scattered 16-byte pieces.
     const int wq = warp - 4;           // == warp % 4: the TMEM lane quarter this warp may access
-    mbar_wait(tmem_full, 0);
+    constexpr int SP = BN + 4;         // staging row pitch (floats): float4-aligned, conflict-free
+    float* stg = reinterpret_cast<float*>(smem) + wq * 32 * SP;
+    mbar_wait(tmem_full, 0);           // all MMAs retired: accumulator complete, smem stages no longer read
     tc_fence_after();
-    const int row = m0 + wq * 32 + lane;
-    const bool row_ok = row < M;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, r);
-      if (!row_ok || n_iter <= 0) continue;
-      const int col0 = n0 + c0;
-      if (col0 >= N) continue;
-      TC* crow = C + (int64_t)row * ldc + col0;
-      const TC* rrow = R ? R + (int64_t)row * ldr + col0 : nullptr;
-      const int nvalid = min(32, N - col0);
-      if (ATOMIC) {
-        for (int j = 0; j < nvalid; ++j) atomicAdd(reinterpret_cast<float*>(crow) + j, alpha * __uint_as_float(r[j]));
-      } else {
-        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = alpha * __uint_as_float(r[j]);
-          if (bias && j < nvalid) x += bias[col0 + j];
-          if (relu) x = fmaxf(x, 0.f);
-          v[j] = x;
-        }
-        const bool vec_ok = nvalid == 32 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) &&
-                            (!rrow || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
-        if (vec_ok) {
-          if constexpr (sizeof(TC) == 4) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (rrow) { const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rrow) + j); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(crow) + j) = o;
-            }
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(&stg[lane * SP + c0 + j]) =
+            make_float4(alpha * __uint_as_float(r[j]), alpha * __uint_as_float(r[j + 1]),
+                        alpha * __uint_as_float(r[j + 2]), alpha * __uint_as_float(r[j + 3]));
+    }
+    __syncwarp();
+    if (n_iter > 0) {
+      constexpr int LPR = BN / 4;        // lanes per row (4 columns each)
+      constexpr int RPP = 32 / LPR;      // rows per pass
+      const int cc = (lane % LPR) * 4;
+      const int col = n0 + cc;
+#pragma unroll 1
+      for (int rr = lane / LPR; rr < 32; rr += RPP) {
+        const int row = m0 + wq * 32 + rr;
+        if (row >= M || col >= N) continue;
+        const float4 a = *reinterpret_cast<const float4*>(&stg[rr * SP + cc]);
+        float v[4] = {a.x, a.y, a.z, a.w};
+        const int nv = min(4, N - col);
+        TC* cp = C + (int64_t)row * ldc + col;
+        if (ATOMIC) {
+          float* fp = reinterpret_cast<float*>(cp);
+          if (nv == 4 && (reinterpret_cast<uintptr_t>(fp) & 15) == 0) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(fp), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
           } else {
+            for (int j = 0; j < nv; ++j) atomicAdd(fp + j, v[j]);
+          }
+          continue;
+        }
+        if (bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (rrow) {
-                const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(rrow) + j);
-                const __nv_bfloat162* qq = reinterpret_cast<const __nv_bfloat162*>(&q);
+          for (int j = 0; j < 4; ++j) if (j < nv) v[j] += bias[col + j];
+        }
+        if (relu) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) { const float2 f = __bfloat1622float2(qq[t]); v[j + 2 * t] += f.x; v[j + 2 * t + 1] += f.y; }
-              }
-              uint4 o;
-              __nv_bfloat162* oo = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) oo[t] = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(crow) + j) = o;
-            }
+          for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        const TC* rp = R ? R + (int64_t)row * ldr + col : nullptr;
+        if constexpr (sizeof(TC) == 4) {
+          const bool vec = nv == 4 && (reinterpret_cast<uintptr_t>(cp) & 15) == 0 && (!rp || (reinterpret_cast<uintptr_t>(rp) & 15) == 0);
+          if (vec) {
+            if (rp) { const float4 q = *reinterpret_cast<const float4*>(rp); v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w; }
+            *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+            for (int j = 0; j < nv; ++j) reinterpret_cast<float*>(cp)[j] = v[j] + (rp ? to_f(rp[j]) : 0.f);
           }
         } else {
-          for (int j = 0; j < nvalid; ++j) {
-            float x = v[j];
-            if (rrow) x += to_f(rrow[j]);
-            crow[j] = from_f<TC>(x);
+          const bool vec = nv == 4 && (reinterpret_cast<uintptr_t>(cp) & 7) == 0 && (!rp || (reinterpret_cast<uintptr_t>(rp) & 7) == 0);
+          if (vec) {
+            if (rp) {
+              const uint2 q = *reinterpret_cast<const uint2*>(rp);
+              const __nv_bfloat162* qq = reinterpret_cast<const __nv_bfloat162*>(&q);
+              const float2 f0 = __bfloat1622float2(qq[0]), f1 = __bfloat1622float2(qq[1]);
+              v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
+            }
+            uint2 o;
+            __nv_bfloat162* oo = reinterpret_cast<__nv_bfloat162*>(&o);
+            oo[0] = __floats2bfloat162_rn(v[0], v[1]);
+            oo[1] = __floats2bfloat162_rn(v[2], v[3]);
+            *reinterpret_cast<uint2*>(cp) = o;
+          } else {
+            for (int j = 0; j < nv; ++j) cp[j] = from_f<TC>(v[j] + (rp ? to_f(rp[j]) : 0.f));
           }
         }
       }
@@ -334,8 +351,8 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   const int kb_total = (int)ceil_div(K, TC_BK);
   const int64_t m_tiles = ceil_div(M, TC_BM);
   // ---- tile configuration
-  //  cfg 0: 128 x 128, 4 stages  — throughput shape (many tiles)
-  //  cfg 1: 128 x  64, 6 stages  — mid-size problems that would not fill the 148 SMs with 128-wide tiles
+  //  cfg 0: 128 x 128, 3 stages, 2 CTAs/SM — throughput shape (one CTA's epilogue overlaps the other's mainloop)
+  //  cfg 1: 128 x  64, 4 stages, 2 CTAs/SM — mid-size problems that would not fill the 148 SMs with 128-wide tiles
   //  cfg 2: 128 x  32, 10 stages — single-M-tile (decoder step, M <= 128) with K-major B: narrow N, deep pipeline
   //  cfg 3: 128 x  64, 8 stages  — single-M-tile with N-major B (128B-swizzled MN-major boxes are 64 wide)
   int cfg;
@@ -368,8 +385,8 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   } while (0)
 #define TC_CFG(AMN, BMN)                                                   \
   do {                                                                     \
-    if (cfg == 0) TC_GO(128, 4, AMN, BMN);                                 \
-    if (cfg == 1) TC_GO(64, 6, AMN, BMN);                                  \
+    if (cfg == 0) TC_GO(128, 3, AMN, BMN);                                 \
+    if (cfg == 1) TC_GO(64, 4, AMN, BMN);                                  \
     if (cfg == 3) TC_GO(64, 8, AMN, BMN);                                  \
   } while (0)
   if (cfg == 2) {               // K-major B only
