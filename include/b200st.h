@@ -104,6 +104,9 @@ int b200st_blstm_fwd(int dtype, const void* xproj, const float* w_hh_f, const fl
                      const int32_t* lens, void* out, int64_t out_ld_t, int64_t out_ld_b, int pair,
                      void* hs, float* acts, float* cs, int64_t T, int64_t B, int64_t H,
                      b200st_stream_t stream);
+/* Debug aid: register (or clear with NULL) a device buffer of >= 128 int64; the tensor-core recurrence kernels then
+ * record clock64() at fixed points of time steps 64..71 (16 slots per step) for the first CTA. */
+int b200st_debug_timeline(void* buf);
 /* Recurrence kernel selection: 0 = auto (bf16 activations with H = 256 -> tcgen05 kernel), 1 = CUDA cores only.
  * Returns the previous mode (test hook). */
 int b200st_set_blstm_backend(int mode);
@@ -125,6 +128,9 @@ int b200st_las_attn_bwd(int dtype, const void* dctx, const void* wk, const void*
 /* argmax over the last dim (Dec.py:331 topk(1), Seq2seq.py:255 topk(1)); first index wins ties. */
 int b200st_argmax_rows(int dtype, const void* x, int64_t ld, int64_t rows, int64_t cols,
                        int64_t* idx, int64_t idx_stride, b200st_stream_t stream);
+/* arg-max + the Dec.decode lengths rule below in one launch (lengths may be NULL). */
+int b200st_argmax_rows_lengths(int dtype, const void* x, int64_t ld, int64_t rows, int64_t cols, int64_t* idx,
+                               int64_t idx_stride, int32_t* lengths, int step, b200st_stream_t stream);
 /* Dec.decode lengths rule (Dec.py:334-340) kept on device: if sym in {EOS,PAD} and lengths[b] > step
  * then lengths[b] = step + 1. */
 int b200st_las_update_lengths(const int64_t* sym, int64_t sym_stride, int32_t* lengths, int step,

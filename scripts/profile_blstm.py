@@ -24,3 +24,22 @@ for it in range(3):
     torch.cuda.synchronize()
     print(f'T={T} B={B}: fwd {e0.elapsed_time(e1):.3f} ms ({e0.elapsed_time(e1) / T * 1e3:.2f} us/step)  '
           f'bwd {e1.elapsed_time(e2):.3f} ms ({e1.elapsed_time(e2) / T * 1e3:.2f} us/step)')
+
+# ---- in-kernel timeline of steps 64..71 (cycles between recorded points, first CTA)
+import ctypes
+buf = torch.zeros(128, dtype=torch.int64, device='cuda')
+k.lib.b200st_debug_timeline(ctypes.c_void_p(buf.data_ptr()))
+for name, fn, npts in (('fwd', lambda: k.blstm_fwd(xproj, wf, wr, lens, out, B * 4 * H, 4 * H, 2), 9),
+                       ('bwd', lambda: k.blstm_bwd(torch.randn_like(out), B * 4 * H, 4 * H, 2, acts, cs, wf, wr, lens, torch.bfloat16), 8)):
+    buf.zero_(); fn(); torch.cuda.synchronize()
+    tl = buf.cpu().view(8, 16)[:, :npts]
+    d = (tl[:, 1:] - tl[:, :-1]).float()
+    step = (tl[1:, 0] - tl[:-1, 0]).float()
+    full = buf.cpu().view(8, 16)
+    if name == 'fwd':
+        print('fwd issuer: wait_h', int((full[:,1]-full[:,0]).median()), 'fence', int((full[:,10]-full[:,1]).median()), 'mma_issue', int((full[:,11]-full[:,10]).median()), 'commit', int((full[:,2]-full[:,11]).median()), 'mma_done_wait', int((full[:,3]-full[:,2]).median()),
+              '| epilogue: ld', int((full[:,4]-full[:,9]).median()), 'act', int((full[:,5]-full[:,4]).median()), 'bar', int((full[:,6]-full[:,5]).median()), 'cell+send', int((full[:,7]-full[:,6]).median()), 'stores', int((full[:,8]-full[:,7]).median()),
+              '| mma_done->epilogue_start', int((full[:,9]-full[:,3]).median()), 'send->next_h_ready', int((full[1:,1]-full[:-1,7]).median()))
+    print(name, 'cycles between points (median over steps 64..71):', [int(x) for x in d.median(0).values.tolist()],
+          'step period', int(step.median()))
+k.lib.b200st_debug_timeline(None)

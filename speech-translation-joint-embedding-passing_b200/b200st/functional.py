@@ -402,8 +402,7 @@ class _LASDecoder(Function):
             k.gemm(CTX[s], wf[:, :H2], trans_b=True, out=CV[s + 1])
             k.gemm(dec_out, wf[:, H2:], trans_b=True, residual=CV[s + 1], out=CV[s + 1])
             k.gemm(CV[s + 1], wo, trans_b=True, bias=b_out, out=LOGITS[s])       # Dec.py:434
-            k.argmax_rows(LOGITS[s], sym_dst[s])                                 # Dec.py:331
-            k.las_update_lengths(sym_dst[s], lengths, s)                         # Dec.py:334-340
+            k.argmax_rows(LOGITS[s], sym_dst[s], lengths=lengths, step=s)        # Dec.py:331 + 334-340
         if ids_tf is None:
             SYM = IDS[1:]
         embs = k.transpose01(CV[1:])                                             # [B,S,D]

@@ -257,14 +257,17 @@ class CudaKernels:
                    'las_attn_bwd')
         return dscore, dq
 
-    def argmax_rows(self, x, idx_out):
-        """x [rows, cols] (row-strided); idx_out: int64 1-D view (any stride) of length rows."""
-        self._need_cuda(x, idx_out)
+    def argmax_rows(self, x, idx_out, lengths=None, step=0):
+        """x [rows, cols] (row-strided); idx_out: int64 1-D view (any stride) of length rows.  With `lengths`
+        (int32 [rows]) the LAS decode-length rule (Dec.py:334-340) is applied in the same launch."""
+        self._need_cuda(x, idx_out, lengths)
         _rows(x)
         assert idx_out.dtype == torch.int64 and idx_out.dim() == 1 and idx_out.numel() == x.size(0)
-        _lib.check(self.lib.b200st_argmax_rows(_dt(x), _p(x), x.stride(0), x.size(0), x.size(1),
-                                               _p(idx_out), idx_out.stride(0) if idx_out.numel() > 1 else 1,
-                                               self._stream()), 'argmax_rows')
+        if lengths is not None:
+            assert lengths.dtype == torch.int32 and lengths.is_contiguous() and lengths.numel() == x.size(0)
+        _lib.check(self.lib.b200st_argmax_rows_lengths(
+            _dt(x), _p(x), x.stride(0), x.size(0), x.size(1), _p(idx_out),
+            idx_out.stride(0) if idx_out.numel() > 1 else 1, _p(lengths), int(step), self._stream()), 'argmax_rows')
         return idx_out
 
     def las_update_lengths(self, sym, lengths, step):

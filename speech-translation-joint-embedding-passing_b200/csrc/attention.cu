@@ -559,6 +559,52 @@ __global__ void argmax_rows_kernel(const T* __restrict__ x, int64_t ld, int cols
   }
 }
 
+
+// Vectorised row arg-max (cols % 8 == 0, 16-byte aligned rows) with the LAS decode-length rule fused in:
+// if lengths != nullptr: (sym in {EOS, PAD} and lengths[r] > step) -> lengths[r] = step + 1   (Dec.py:334-340).
+template <typename T>
+__global__ void __launch_bounds__(256)
+argmax_rows_vec_kernel(const T* __restrict__ x, int64_t ld, int cols, int64_t* __restrict__ idx, int64_t idx_stride,
+                       int32_t* __restrict__ lengths, int step) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const int64_t r = blockIdx.x;
+  const T* xr = x + r * ld;
+  float mx = -INFINITY;
+  int mi = 0x7fffffff;
+  for (int c = threadIdx.x * 8; c < cols; c += 256 * 8) {
+    float v[8];
+    load8(xr + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (v[i] > mx) { mx = v[i]; mi = c + i; }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (ov > mx || (ov == mx && oi < mi)) { mx = ov; mi = oi; }
+  }
+  if (lane == 0) { sv[w] = mx; si[w] = mi; }
+  __syncthreads();
+  if (w == 0) {
+    float v = lane < 8 ? sv[lane] : -INFINITY;
+    int i = lane < 8 ? si[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+      if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+    if (lane == 0) {
+      const int sym = (i == 0x7fffffff) ? 0 : i;
+      idx[r * idx_stride] = sym;
+      if (lengths && (sym == 3 /*EOS*/ || sym == 0 /*PAD*/) && lengths[r] > step) lengths[r] = step + 1;
+    }
+  }
+}
+
 __global__ void las_update_lengths_kernel(const int64_t* __restrict__ sym, int64_t sym_stride,
                                           int32_t* __restrict__ lengths, int step, int64_t B) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -702,6 +748,23 @@ int b200st_argmax_rows(int dtype, const void* x, int64_t ld, int64_t rows, int64
                                                                             idx, idx_stride);
   });
   B200ST_LAUNCH_CHECK("argmax_rows");
+  return 0;
+}
+
+int b200st_argmax_rows_lengths(int dtype, const void* x, int64_t ld, int64_t rows, int64_t cols, int64_t* idx,
+                               int64_t idx_stride, int32_t* lengths, int step, b200st_stream_t stream) {
+  if (rows <= 0) return 0;
+  const bool vec = cols % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x & 15) == 0;
+  if (vec) {
+    B200ST_DISPATCH(dtype, T, {
+      argmax_rows_vec_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const T*)x, ld, (int)cols, idx,
+                                                                                  idx_stride, lengths, step);
+    });
+    B200ST_LAUNCH_CHECK("argmax_rows_vec");
+    return 0;
+  }
+  if (b200st_argmax_rows(dtype, x, ld, rows, cols, idx, idx_stride, stream)) return -1;
+  if (lengths) return b200st_las_update_lengths(idx, idx_stride, lengths, step, rows, stream);
   return 0;
 }
 

@@ -310,6 +310,7 @@ int blstm_fwd_tc(const void* xproj, const float* w_hh_f, const float* w_hh_r, co
 int blstm_bwd_tc(const void* dout, int64_t out_ld_t, int64_t out_ld_b, int pair, const float* acts, const float* cs,
                  const float* w_hh_f, const float* w_hh_r, const int32_t* lens, void* dgates, int64_t T_, int64_t B,
                  cudaStream_t st);
+int set_timeline(void* buf);
 static int g_blstm_backend = 0;   // 0 auto, 1 CUDA cores only
 
 }  // namespace b200st
@@ -317,6 +318,8 @@ static int g_blstm_backend = 0;   // 0 auto, 1 CUDA cores only
 using namespace b200st;
 
 extern "C" {
+
+int b200st_debug_timeline(void* buf) { return set_timeline(buf); }
 
 int b200st_set_blstm_backend(int mode) {
   const int old = g_blstm_backend;

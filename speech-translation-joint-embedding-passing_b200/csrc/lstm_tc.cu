@@ -22,7 +22,13 @@ constexpr int RT_H = 256;        // hidden units per direction
 constexpr int RT_C = 8;          // CTAs per cluster
 constexpr int RT_UPC = 32;       // units per CTA
 constexpr int RT_NB = 16;        // sequences per cluster (= UMMA N)
-constexpr int RT_THREADS = 128;
+constexpr int RT_THREADS = 128;       // 4 epilogue warps (one TMEM lane quarter each)
+constexpr int RT_BLOCK = 160;         // + 1 issuer warp: waits for operands, issues tcgen05.mma, arms barriers
+
+// Optional in-kernel timeline (debug aid, b200st_debug_timeline): when a buffer is registered, thread 0 of the first
+// CTA records clock64() at fixed points of time steps 64..71.  Costs one predictable branch per point otherwise.
+__device__ long long* g_rt_timeline = nullptr;
+#define RT_TL(i) do { if (tl_on && s >= 64 && s < 72) tl[(s - 64) * 16 + (i)] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t rt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t rt_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -45,7 +51,7 @@ __device__ __forceinline__ void rt_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 }
 __device__ __forceinline__ void rt_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void rt_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ void rt_fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void rt_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void rt_tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void rt_tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void rt_mbar_init(uint64_t* bar, uint32_t count) {
@@ -72,6 +78,57 @@ __device__ __forceinline__ void rt_mma(uint32_t tmem_d, uint64_t da, uint64_t db
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+// Issuer-warp variants: executed by ALL 32 lanes of a convergent warp, the instruction itself is predicated on the
+// elected lane.  Keeping the control flow warp-uniform lets the compiler hold descriptors / TMEM addresses in uniform
+// registers (UTCHMMA operands); a divergent `if (lane == 0)` region forces a vector->uniform move before every MMA.
+__device__ __forceinline__ uint32_t rt_elect() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void rt_mma_if(uint32_t leader, uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(leader) : "memory");
+}
+// TS form: A operand read from tensor memory (lane = row, 32-bit column = two consecutive K elements), B from smem.
+// With N = 16 the SS form is bound by streaming the 4 KB A tile out of shared memory (~110 cycles per MMA measured);
+// a TMEM-resident A removes that, and the recurrent weights never change during the sequence.
+__device__ __forceinline__ void rt_mma_ts_if(uint32_t leader, uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void rt_tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void rt_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+constexpr uint32_t RT_D_COLS = 64;      // accumulators live in TMEM columns [0, 64)
+constexpr uint32_t RT_A_COL = 64;       // resident A operand (recurrent weights) in columns [64, 192)
+constexpr uint32_t RT_TMEM_COLS = 256;
+
+__device__ __forceinline__ void rt_commit_if(uint32_t leader, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(rt_smem_u32(bar)), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void rt_expect_tx_if(uint32_t leader, uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+      ::"r"(rt_smem_u32(bar)), "r"(bytes), "r"(leader) : "memory");
 }
 __device__ __forceinline__ void rt_tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
@@ -134,19 +191,42 @@ __device__ __forceinline__ uint32_t rt_swz(uint32_t row, uint32_t k_in_tile) {
   return row * 128 + ((((k_in_tile >> 3) ^ (row & 7))) << 4);
 }
 
-// shared memory map (forward): W [4 kb][128 rows][128 B] 64 KB | hbuf [2][4 kb][16 rows][128 B] 16 KB |
-// actbuf float [4 gates][16 seqs][32 units] 8 KB | barrier + tmem slot
-constexpr int FWD_W_OFF = 0, FWD_H_OFF = 65536, FWD_ACT_OFF = FWD_H_OFF + 16384, FWD_BAR_OFF = FWD_ACT_OFF + 8192;
-constexpr int FWD_SMEM = FWD_BAR_OFF + 64 + 1024;
+// Issue the 16 forward MMAs of one time step.  CONST_BASE >= 0 bakes the TMEM accumulator addresses in as
+// immediates: UTCHMMA takes its TMEM address from a *uniform* register, and an address that was loaded from shared
+// memory costs an ELECT + R2UR.BROADCAST round trip in front of every MMA (measured: ~116 cycles per MMA issue
+// instead of ~35).  The allocator returns column 0 for the first allocation on an SM, which is the common case.
+template <int CONST_BASE>
+__device__ __forceinline__ void rt_issue_fwd(uint32_t leader, uint32_t tmem_base, uint32_t hb) {
+  const uint32_t base = CONST_BASE >= 0 ? (uint32_t)CONST_BASE : tmem_base;
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks)       // A: W slice [128 rows x 256 k] = 128 columns, 8 columns per K=16 step
+    rt_mma_ts_if(leader, base + (ks & 3) * 16, base + RT_A_COL + ks * 8,
+                 rt_desc(hb + (ks >> 2) * 2048 + (ks & 3) * 32), RT_IDESC, ks >= 4 ? 1u : 0u);
+}
+template <int CONST_BASE>
+__device__ __forceinline__ void rt_issue_bwd(uint32_t leader, uint32_t tmem_base, uint32_t bb) {
+  const uint32_t base = CONST_BASE >= 0 ? (uint32_t)CONST_BASE : tmem_base;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)        // A: W_hh^T tile mt [128 units x 128 own gate rows] = 64 columns
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+      rt_mma_ts_if(leader, base + (mt * 2 + (ks & 1)) * RT_NB, base + RT_A_COL + mt * 64 + ks * 8,
+                   rt_desc(bb + (ks >> 2) * 2048 + (ks & 3) * 32), RT_IDESC, ks >= 2 ? 1u : 0u);
+}
 
-__global__ void __cluster_dims__(RT_C, 1, 1) __launch_bounds__(RT_THREADS, 1)
+// shared memory map (forward): hbuf [2][4 kb][16 rows][128 B] 16 KB | actbuf float [4 gates][16 seqs][32 units] 8 KB |
+// barriers + tmem slot.  (The W_hh slice lives in TMEM.)  The request is padded above half an SM's shared memory so
+// that exactly one CTA is resident per SM and the TMEM allocation starts at column 0 (constant-address fast path).
+constexpr int FWD_H_OFF = 0, FWD_ACT_OFF = FWD_H_OFF + 16384, FWD_BAR_OFF = FWD_ACT_OFF + 8192;
+constexpr int FWD_SMEM = 120 * 1024;
+
+__global__ void __cluster_dims__(RT_C, 1, 1) __launch_bounds__(RT_BLOCK, 1)
 blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __restrict__ w_hh_f,
                     const float* __restrict__ w_hh_r, const int32_t* __restrict__ lens,
                     __nv_bfloat16* __restrict__ out, int64_t out_ld_t, int64_t out_ld_b, int pair,
                     __nv_bfloat16* __restrict__ hs, float* __restrict__ acts, float* __restrict__ cs, int Tn, int B) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* Wsm = smem + FWD_W_OFF;
   uint8_t* hbuf = smem + FWD_H_OFF;
   float* actbuf = (float*)(smem + FWD_ACT_OFF);
   uint64_t* mma_bar = (uint64_t*)(smem + FWD_BAR_OFF);
@@ -158,16 +238,7 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
   const int grp = blockIdx.y, dir = blockIdx.z;
   const float* w = dir ? w_hh_r : w_hh_f;
 
-  // ---- resident weights: local row lr = gate*32 + ul  <->  W_hh row gate*256 + 32*rank + ul
-  for (int chunk = tid; chunk < 128 * 32; chunk += RT_THREADS) {
-    const int lr = chunk >> 5, kc = chunk & 31;
-    const int grow = (lr >> 5) * RT_H + rank * RT_UPC + (lr & 31);
-    const float4* src = reinterpret_cast<const float4*>(w + (size_t)grow * RT_H + kc * 8);
-    const float4 a = src[0], b = src[1];
-    uint4 v = make_uint4(rt_pack(a.x, a.y), rt_pack(a.z, a.w), rt_pack(b.x, b.y), rt_pack(b.z, b.w));
-    *reinterpret_cast<uint4*>(Wsm + (kc >> 3) * 16384 + rt_swz(lr, (kc & 7) * 8)) = v;
-  }
-  for (int i = tid; i < 16384 / 16; i += RT_THREADS) reinterpret_cast<uint4*>(hbuf)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 16384 / 16; i += RT_BLOCK) reinterpret_cast<uint4*>(hbuf)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     rt_mbar_init(mma_bar, 1);
     rt_mbar_init(&hfull[0], 1);
@@ -176,7 +247,7 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
     rt_mbar_expect_tx(&hfull[1], 8192);        // step 0 fills buffer 1
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rt_smem_u32(tmem_slot)), "r"(64u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rt_smem_u32(tmem_slot)), "r"(RT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   rt_fence_async();
@@ -184,9 +255,64 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
   __syncthreads();
   rt_tc_after();
   const uint32_t tmem_base = *tmem_slot;
+  // ---- resident weights -> TMEM: thread (warp w < 4, lane l) owns TMEM lane lr = 32 w + l = gate*32 + ul, i.e. W_hh
+  // row gate*256 + 32*rank + ul, packed two K elements per 32-bit column (K-major A operand of the TS-form MMA)
+  if (warp < 4) {
+    const float* wrow = w + (size_t)(warp * RT_H + rank * RT_UPC + lane) * RT_H;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 a = *reinterpret_cast<const float4*>(wrow + c * 32 + j * 8);
+        const float4 b = *reinterpret_cast<const float4*>(wrow + c * 32 + j * 8 + 4);
+        pk[4 * j] = rt_pack(a.x, a.y); pk[4 * j + 1] = rt_pack(a.z, a.w);
+        pk[4 * j + 2] = rt_pack(b.x, b.y); pk[4 * j + 3] = rt_pack(b.z, b.w);
+      }
+      rt_tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + RT_A_COL + c * 16, pk);
+    }
+    rt_tmem_wait_st();
+  }
+  rt_tc_before();
+  __syncthreads();
+  rt_tc_after();
   rt_cluster_arrive();      // every CTA has initialised its barriers and zeroed its h buffers
   rt_cluster_wait();
 
+  long long* tl = g_rt_timeline;
+  if (warp == 4) {
+    // ================= issuer warp (convergent; the elected lane issues) =================
+    const uint32_t leader = rt_elect();
+    const bool tl_on = tl != nullptr && leader && rank == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    const uint32_t hb0 = rt_smem_u32(hbuf);
+    uint32_t hph[2] = {0u, 0u};
+    int cur = 0;
+    uint32_t phase = 0;
+    for (int s = 0; s < Tn; ++s) {
+      RT_TL(0);
+      if (s > 0) {                             // h_{t-1} slices of all 8 CTAs have landed in hbuf[cur]
+        rt_mbar_wait(&hfull[cur], hph[cur]);
+        hph[cur] ^= 1;
+      }
+      RT_TL(1);
+      rt_fence_async();
+      rt_tc_after();
+      RT_TL(10);
+      const uint32_t hb = hb0 + cur * 8192;
+      if (tmem_base == 0) rt_issue_fwd<0>(leader, 0, hb);
+      else rt_issue_fwd<-1>(leader, tmem_base, hb);
+      RT_TL(11);
+      rt_commit_if(leader, mma_bar);
+      RT_TL(2);
+      // arm hbuf[cur] for h_{t+1}: its refill cannot start before every CTA has consumed this step's outputs
+      if (s + 2 < Tn) rt_expect_tx_if(leader, &hfull[cur], 8192);
+      rt_mbar_wait(mma_bar, phase);            // keep at most one step of MMAs in flight
+      phase ^= 1;
+      RT_TL(3);
+      cur ^= 1;
+    }
+  } else {
+  // ================= epilogue warps =================
   // ---- per-thread roles
   // (1) gate phase: thread owns gate row lr = tid (gate = warp, unit = lane) for all 16 sequences
   const int grow_g = warp * RT_H + rank * RT_UPC + lane;
@@ -200,7 +326,6 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
   float c_st[4] = {0.f, 0.f, 0.f, 0.f}, h_st[4] = {0.f, 0.f, 0.f, 0.f};
   const uint32_t hbuf_u32 = rt_smem_u32(hbuf);
   const uint32_t hfull_u32 = rt_smem_u32(hfull);
-  uint32_t hph[2] = {0u, 0u};
   // destination chunk (16 B = 8 units) of this thread pair inside one h buffer
   const uint32_t k0 = rank * RT_UPC + 4 * (ug & ~1);
   const uint32_t h_chunk_off = (k0 >> 6) * 2048 + rt_swz(cb, k0 & 63);
@@ -215,40 +340,28 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
   };
   if (Tn > 0) load_x(dir ? Tn - 1 : 0);
 
+  const bool tl_on = tl != nullptr && tid == 0 && rank == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   int cur = 0;
   uint32_t phase = 0;
   for (int s = 0; s < Tn; ++s) {
     const int t = dir ? (Tn - 1 - s) : s;
-    if (tid == 0) {
-      if (s > 0) {                           // h_{t-1} slices of all 8 CTAs have landed in hbuf[cur]
-        rt_mbar_wait(&hfull[cur], hph[cur]);
-        hph[cur] ^= 1;
-      }
-      rt_fence_async();
-      rt_tc_after();
-      const uint32_t wa = rt_smem_u32(Wsm), hb = hbuf_u32 + cur * 8192;
-#pragma unroll
-      for (int ks = 0; ks < 16; ++ks)
-        rt_mma(tmem_base + (ks & 3) * 16, rt_desc(wa + (ks >> 2) * 16384 + (ks & 3) * 32),
-               rt_desc(hb + (ks >> 2) * 2048 + (ks & 3) * 32), RT_IDESC, ks >= 4 ? 1u : 0u);
-      rt_commit(mma_bar);
-    }
     rt_mbar_wait(mma_bar, phase);
     phase ^= 1;
     rt_tc_after();
-    // hbuf[cur] has been consumed by the MMAs: arm it for h_{t+1} (written during the next step)
-    if (tid == 0 && s + 2 < Tn) rt_mbar_expect_tx(&hfull[cur], 8192);
+    RT_TL(9);
     float g[16];
     rt_tmem_ld_sum<4>(tmem_base + ((uint32_t)(warp * 32) << 16), g);
     rt_tc_before();
+    RT_TL(4);
     // gate non-linearity: warp 2 holds the candidate gate (tanh), the others sigmoid (PyTorch order i,f,g,o)
 #pragma unroll
     for (int b = 0; b < RT_NB; ++b) {
       const float v = g[b] + __uint_as_float((uint32_t)xr[b] << 16);
       actbuf[(warp * RT_NB + b) * RT_UPC + lane] = (warp == 2) ? rt_tanh(v) : rt_sigmoid(v);
     }
-    if (s + 1 < Tn) load_x(dir ? (Tn - 2 - s) : (s + 1));     // prefetch next step's x-projection
+    RT_TL(5);
     asm volatile("bar.sync 1, 128;" ::: "memory");
+    RT_TL(6);
     // ---- cell update for (sequence cb, units ubase..ubase+3)
     const bool valid = t < len_b;
     const float4 gi = *reinterpret_cast<const float4*>(&actbuf[(0 * RT_NB + cb) * RT_UPC + 4 * ug]);
@@ -275,6 +388,8 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
 #pragma unroll
       for (uint32_t r = 0; r < RT_C; ++r) rt_st_async_v4(rt_mapa(dst, r), p0, p1, q0, q1, rt_mapa(bar, r));
     }
+    RT_TL(7);
+    if (s + 1 < Tn) load_x(dir ? (Tn - 2 - s) : (s + 1));     // prefetch next step's x-projection (raw bits)
     // ---- global stores: nothing on the recurrent critical path waits for them
     if (b_ok) {
       const size_t row = ((size_t)dir * Tn + t) * B + bglob;
@@ -291,30 +406,31 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
                                 (size_t)(t % pair) * 2 * RT_H + dir * RT_H + ubase) = hv;
       if (hs) *reinterpret_cast<uint2*>(hs + (((size_t)dir * (Tn + 1) + (dir ? t : t + 1)) * B + bglob) * RT_H + ubase) = hv;
     }
+    RT_TL(8);
     cur ^= 1;
   }
+  }  // epilogue warps
   rt_tc_before();
   rt_cluster_arrive();       // nobody exits while a peer could still address its shared memory
   rt_cluster_wait();
   if (warp == 0) {
     rt_tc_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(RT_TMEM_COLS) : "memory");
   }
 }
 
-// shared memory map (backward): A = W_hh^T [2 m-tiles][2 kb][128 rows][128 B] 64 KB | B = own dG [2 kb][16][128 B] 4 KB |
-// red float [2][8 src][32 units][16 seqs] 32 KB | barrier + tmem slot
-constexpr int BWD_A_OFF = 0, BWD_B_OFF = 65536, BWD_RED_OFF = BWD_B_OFF + 4096, BWD_BAR_OFF = BWD_RED_OFF + 32768;
-constexpr int BWD_SMEM = BWD_BAR_OFF + 64 + 1024;
+// shared memory map (backward): B = own dG [2 kb][16][128 B] 4 KB | red float [2][8 src][32 units][16 seqs] 32 KB |
+// barriers + tmem slot.  (W_hh^T lives in TMEM.)  Padded like the forward kernel: one CTA per SM.
+constexpr int BWD_B_OFF = 0, BWD_RED_OFF = BWD_B_OFF + 4096, BWD_BAR_OFF = BWD_RED_OFF + 32768;
+constexpr int BWD_SMEM = 120 * 1024;
 
-__global__ void __cluster_dims__(RT_C, 1, 1) __launch_bounds__(RT_THREADS, 1)
+__global__ void __cluster_dims__(RT_C, 1, 1) __launch_bounds__(RT_BLOCK, 1)
 blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, int64_t out_ld_b, int pair,
                     const float* __restrict__ acts, const float* __restrict__ cs, const float* __restrict__ w_hh_f,
                     const float* __restrict__ w_hh_r, const int32_t* __restrict__ lens,
                     __nv_bfloat16* __restrict__ dgates, int Tn, int B) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* Asm = smem + BWD_A_OFF;
   uint8_t* Bsm = smem + BWD_B_OFF;
   float* red = (float*)(smem + BWD_RED_OFF);
   uint64_t* mma_bar = (uint64_t*)(smem + BWD_BAR_OFF);
@@ -326,20 +442,7 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
   const int grp = blockIdx.y, dir = blockIdx.z;
   const float* w = dir ? w_hh_r : w_hh_f;
 
-  // ---- resident W_hh^T: A[mt][kb] row = unit % 128, k = own gate row kl = gate*32 + ul
-  for (int chunk = tid; chunk < 256 * 16; chunk += RT_THREADS) {
-    const int u = chunk & 255, klg = chunk >> 8;           // 8 consecutive kl per chunk; lanes run along u (coalesced)
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int kl = klg * 8 + i;
-      const int grow = (kl >> 5) * RT_H + rank * RT_UPC + (kl & 31);
-      v[i] = w[(size_t)grow * RT_H + u];
-    }
-    const uint4 pk = make_uint4(rt_pack(v[0], v[1]), rt_pack(v[2], v[3]), rt_pack(v[4], v[5]), rt_pack(v[6], v[7]));
-    *reinterpret_cast<uint4*>(Asm + ((u >> 7) * 2 + (klg >> 3)) * 16384 + rt_swz(u & 127, (klg & 7) * 8)) = pk;
-  }
-  for (int i = tid; i < (4096 + 32768) / 16; i += RT_THREADS) reinterpret_cast<uint4*>(Bsm)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (4096 + 32768) / 16; i += RT_BLOCK) reinterpret_cast<uint4*>(Bsm)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     rt_mbar_init(mma_bar, 1);
     rt_mbar_init(&rfull[0], 1);
@@ -348,7 +451,7 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
     rt_mbar_expect_tx(&rfull[1], 16384);       // step 0 sends its partials into buffer 1
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rt_smem_u32(tmem_slot)), "r"(64u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rt_smem_u32(tmem_slot)), "r"(RT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   rt_fence_async();
@@ -356,9 +459,51 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
   __syncthreads();
   rt_tc_after();
   const uint32_t tmem_base = *tmem_slot;
+  // ---- resident W_hh^T -> TMEM: tile mt, lane = unit (mt*128 + 32 w + l), K = own gate rows kl = gate*32 + ul
+  // (W_hh row gate*256 + 32*rank + ul), two K elements per 32-bit column.  Lanes run along units: coalesced reads.
+  if (warp < 4) {
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      const int uu = mt * 128 + warp * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {           // 32 kl per pass = gate c, ul 0..31
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int kl = c * 32 + 2 * j;
+          const float v0 = w[(size_t)((kl >> 5) * RT_H + rank * RT_UPC + (kl & 31)) * RT_H + uu];
+          const float v1 = w[(size_t)(((kl + 1) >> 5) * RT_H + rank * RT_UPC + ((kl + 1) & 31)) * RT_H + uu];
+          pk[j] = rt_pack(v0, v1);
+        }
+        rt_tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + RT_A_COL + mt * 64 + c * 16, pk);
+      }
+    }
+    rt_tmem_wait_st();
+  }
+  rt_tc_before();
+  __syncthreads();
+  rt_tc_after();
   rt_cluster_arrive();
   rt_cluster_wait();
 
+  long long* tl = g_rt_timeline;
+  if (warp == 4) {
+    // ================= issuer warp (convergent; the elected lane issues) =================
+    const uint32_t leader = rt_elect();
+    const uint32_t bb = rt_smem_u32(Bsm);
+    int cur = 0;
+    for (int s = 0; s < Tn; ++s) {
+      __syncthreads();                         // the epilogue warps have written this step's gate gradients (B operand)
+      if (s + 2 < Tn) rt_expect_tx_if(leader, &rfull[cur], 16384);   // red[cur] fully read: arm it for step s+1's partials
+      rt_fence_async();
+      rt_tc_after();
+      if (tmem_base == 0) rt_issue_bwd<0>(leader, 0, bb);
+      else rt_issue_bwd<-1>(leader, tmem_base, bb);
+      rt_commit_if(leader, mma_bar);
+      cur ^= 1;
+    }
+  } else {
+  // ================= epilogue warps =================
   // thread owns unit ul = lane of this CTA and sequences 4*warp .. 4*warp+3 in the pointwise phase
   const int ul = lane, u = rank * RT_UPC + ul;
   const int b0 = grp * RT_NB;
@@ -390,11 +535,13 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
   };
   if (Tn > 0) prefetch(dir ? 0 : Tn - 1);
 
+  const bool tl_on = tl != nullptr && tid == 0 && rank == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   int cur = 0;
   uint32_t phase = 0;
   for (int s = 0; s < Tn; ++s) {
     const int t = dir ? s : (Tn - 1 - s);
     const int tp = dir ? t + 1 : t - 1;
+    RT_TL(0);
     // ---- this step's saved activations were prefetched during the previous step (raw registers)
     float ai[4], af[4], ag[4], ao[4], ct[4], cp[4], dy[4];
 #pragma unroll
@@ -408,6 +555,7 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
       rt_mbar_wait(&rfull[cur], rph[cur]);
       rph[cur] ^= 1;
     }
+    RT_TL(1);
     float dg[4][4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -435,26 +583,19 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
         if (b0 + b < B) dgates[(((size_t)dir * Tn + t) * B + b0 + b) * G4 + gte * RT_H + u] = v;
       }
     }
+    RT_TL(2);
     rt_fence_async();
     rt_tc_before();
     __syncthreads();
-    if (tid == 0) {
-      if (s + 2 < Tn) rt_mbar_expect_tx(&rfull[cur], 16384);   // red[cur] fully read: arm it for step s+1's partials
-      rt_tc_after();
-      const uint32_t aa = rt_smem_u32(Asm), bb = rt_smem_u32(Bsm);
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          rt_mma(tmem_base + (mt * 2 + (ks & 1)) * RT_NB, rt_desc(aa + (mt * 2 + (ks >> 2)) * 16384 + (ks & 3) * 32),
-                 rt_desc(bb + (ks >> 2) * 2048 + (ks & 3) * 32), RT_IDESC, ks >= 2 ? 1u : 0u);
-      rt_commit(mma_bar);
-    }
+    RT_TL(3);
     // next step's saved state: issued here so that no fence between now and its use has to wait for it
+    RT_TL(4);
     if (s + 1 < Tn) prefetch(dir ? s + 1 : Tn - 2 - s);
+    RT_TL(5);
     rt_mbar_wait(mma_bar, phase);
     phase ^= 1;
     rt_tc_after();
+    RT_TL(6);
     // ---- partial dh_{t-1}[unit, seq] for all 256 units: send each 32-unit block to the CTA that owns it
     const int nxt = cur ^ 1;
     if (s + 1 < Tn) {
@@ -472,15 +613,23 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
       }
     }
     rt_tc_before();
+    RT_TL(7);
     cur = nxt;
   }
+  }  // epilogue warps
   rt_tc_before();
   rt_cluster_arrive();
   rt_cluster_wait();
   if (warp == 0) {
     rt_tc_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(RT_TMEM_COLS) : "memory");
   }
+}
+
+int set_timeline(void* buf) {
+  long long* p = (long long*)buf;
+  cudaError_t e = cudaMemcpyToSymbol(g_rt_timeline, &p, sizeof(p));
+  return e == cudaSuccess ? 0 : set_error("debug_timeline: %s", cudaGetErrorString(e));
 }
 
 bool blstm_tc_eligible(int dtype, int64_t H, int64_t out_ld_t, int64_t out_ld_b) {
@@ -492,7 +641,7 @@ int blstm_fwd_tc(const void* xproj, const float* w_hh_f, const float* w_hh_r, co
                  cudaStream_t st) {
   B200ST_CUDA(cudaFuncSetAttribute((const void*)blstm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
   dim3 grid(RT_C, (unsigned)ceil_div(B, RT_NB), 2);
-  blstm_fwd_tc_kernel<<<grid, RT_THREADS, FWD_SMEM, st>>>((const __nv_bfloat16*)xproj, w_hh_f, w_hh_r, lens,
+  blstm_fwd_tc_kernel<<<grid, RT_BLOCK, FWD_SMEM, st>>>((const __nv_bfloat16*)xproj, w_hh_f, w_hh_r, lens,
                                                            (__nv_bfloat16*)out, out_ld_t, out_ld_b, pair,
                                                            (__nv_bfloat16*)hs, acts, cs, (int)T_, (int)B);
   B200ST_LAUNCH_CHECK("blstm_fwd_tc");
@@ -504,7 +653,7 @@ int blstm_bwd_tc(const void* dout, int64_t out_ld_t, int64_t out_ld_b, int pair,
                  cudaStream_t st) {
   B200ST_CUDA(cudaFuncSetAttribute((const void*)blstm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
   dim3 grid(RT_C, (unsigned)ceil_div(B, RT_NB), 2);
-  blstm_bwd_tc_kernel<<<grid, RT_THREADS, BWD_SMEM, st>>>((const __nv_bfloat16*)dout, out_ld_t, out_ld_b, pair, acts, cs,
+  blstm_bwd_tc_kernel<<<grid, RT_BLOCK, BWD_SMEM, st>>>((const __nv_bfloat16*)dout, out_ld_t, out_ld_b, pair, acts, cs,
                                                            w_hh_f, w_hh_r, lens, (__nv_bfloat16*)dgates, (int)T_, (int)B);
   B200ST_LAUNCH_CHECK("blstm_bwd_tc");
   return 0;

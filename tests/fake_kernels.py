@@ -218,8 +218,10 @@ class FakeKernels:
             dscore_out.copy_(ds); ds = dscore_out
         return ds, dq
 
-    def argmax_rows(self, x, idx_out):
+    def argmax_rows(self, x, idx_out, lengths=None, step=0):
         idx_out.copy_(x.float().argmax(dim=1))
+        if lengths is not None:
+            self.las_update_lengths(idx_out, lengths, step)
         return idx_out
 
     def las_update_lengths(self, sym, lengths, step):

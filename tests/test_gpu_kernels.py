@@ -191,6 +191,12 @@ def test_argmax_and_lengths(ks):
     col = torch.empty(9, 3, dtype=torch.int64, device='cuda')
     c.argmax_rows(x, col[:, 1])
     assert torch.equal(col[:, 1], x.argmax(1))
+    big = rnd(5, 10000, dtype=torch.bfloat16)
+    big[0, 3] = 100.0; big[2, 0] = 100.0; big[4, 3] = 100.0; big[3, 9999] = 100.0
+    ln = torch.tensor([7, 7, 7, 7, 2], dtype=torch.int32, device='cuda')
+    out = torch.empty(5, dtype=torch.int64, device='cuda')
+    c.argmax_rows(big, out, lengths=ln, step=3)
+    assert out.tolist() == [3, int(big[1].float().argmax()), 0, 9999, 3] and ln.tolist() == [4, 7, 4, 7, 2]
     sym = torch.tensor([3, 5, 0, 9, 3], device='cuda')
     lengths = torch.tensor([7, 7, 7, 7, 2], dtype=torch.int32, device='cuda')
     c.las_update_lengths(sym, lengths, 3)
