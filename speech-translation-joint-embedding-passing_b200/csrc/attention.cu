@@ -150,43 +150,137 @@ __device__ __forceinline__ void mha_load_rows(float* dst, int pitch, const T* __
   }
 }
 
+// Load `rows` x d row-major global rows into shared memory TRANSPOSED: dst[c * pitch + r].
+template <typename T>
+__device__ __forceinline__ void mha_load_rows_t(float* dst, int pitch, const T* __restrict__ src, int64_t ld,
+                                                int rows, int d) {
+  for (int idx = threadIdx.x; idx < rows * d; idx += MHA_T_THREADS) {
+    const int r = idx / d, c = idx - r * d;
+    dst[c * pitch + r] = to_f(src[(int64_t)r * ld + c]);
+  }
+}
+
+// Register-blocked inner products out of shared memory.
+//   ab_t:  out[i][j] = sum_c A[i][c] * Bt[c][j]   (A row-major pitch pa, Bt transposed pitch pb): 2 x 4 per thread,
+//          the four j share one 16-byte load, the A values are warp broadcasts.
+__device__ __forceinline__ void mha_ab_t(float* out, int po, const float* A, int pa, const float* Bt, int pb, int Li,
+                                         int Lj, int d) {
+  const int tj = (Lj + 3) >> 2, ti = (Li + 1) >> 1;
+  for (int idx = threadIdx.x; idx < ti * tj; idx += MHA_T_THREADS) {
+    const int i0 = (idx / tj) * 2, j0 = (idx % tj) * 4;
+    const float* a0 = A + i0 * pa;
+    const float* a1 = A + min(i0 + 1, Li - 1) * pa;
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 4
+    for (int c = 0; c < d; ++c) {
+      const float4 y = *reinterpret_cast<const float4*>(Bt + c * pb + j0);
+      const float x0 = a0[c], x1 = a1[c];
+      acc[0][0] = fmaf(x0, y.x, acc[0][0]); acc[0][1] = fmaf(x0, y.y, acc[0][1]);
+      acc[0][2] = fmaf(x0, y.z, acc[0][2]); acc[0][3] = fmaf(x0, y.w, acc[0][3]);
+      acc[1][0] = fmaf(x1, y.x, acc[1][0]); acc[1][1] = fmaf(x1, y.y, acc[1][1]);
+      acc[1][2] = fmaf(x1, y.z, acc[1][2]); acc[1][3] = fmaf(x1, y.w, acc[1][3]);
+    }
+    *reinterpret_cast<float4*>(out + i0 * po + j0) = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+    if (i0 + 1 < Li)
+      *reinterpret_cast<float4*>(out + (i0 + 1) * po + j0) = make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
+  }
+}
+//   pv:    out[i][c] = scale * sum_j P[i][j] * V[j][c]  (P pitch pp, V row-major pitch d): 4 rows x 2 columns per thread,
+//          columns adjacent across lanes (conflict-free V reads, coalesced global stores), P values broadcast.
+template <typename T>
+__device__ __forceinline__ void mha_pv(T* __restrict__ out, int64_t ldo, const float* P, int pp, const float* V, int Li,
+                                       int Lj, int d, float scale) {
+  const int ti = (Li + 3) >> 2, tc = d >> 1;
+  for (int idx = threadIdx.x; idx < ti * tc; idx += MHA_T_THREADS) {
+    const int i0 = (idx / tc) * 4, c0 = idx % tc;
+    const float* p0 = P + i0 * pp;
+    const float* p1 = P + min(i0 + 1, Li - 1) * pp;
+    const float* p2 = P + min(i0 + 2, Li - 1) * pp;
+    const float* p3 = P + min(i0 + 3, Li - 1) * pp;
+    float acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll 4
+    for (int j = 0; j < Lj; ++j) {
+      const float v0 = V[j * d + c0], v1 = V[j * d + c0 + tc];
+      const float x0 = p0[j], x1 = p1[j], x2 = p2[j], x3 = p3[j];
+      acc[0][0] = fmaf(x0, v0, acc[0][0]); acc[0][1] = fmaf(x0, v1, acc[0][1]);
+      acc[1][0] = fmaf(x1, v0, acc[1][0]); acc[1][1] = fmaf(x1, v1, acc[1][1]);
+      acc[2][0] = fmaf(x2, v0, acc[2][0]); acc[2][1] = fmaf(x2, v1, acc[2][1]);
+      acc[3][0] = fmaf(x3, v0, acc[3][0]); acc[3][1] = fmaf(x3, v1, acc[3][1]);
+    }
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      if (i0 + ii >= Li) break;
+      T* r = out + (int64_t)(i0 + ii) * ldo;
+      r[c0] = from_f<T>(acc[ii][0] * scale);
+      r[c0 + tc] = from_f<T>(acc[ii][1] * scale);
+    }
+  }
+}
+//   ptv:   out[j][c] = sum_i P[i][j] * X[i][c]   (column j of P times rows of X): 2 key rows x 2 columns per thread.
+template <typename T>
+__device__ __forceinline__ void mha_ptv(T* __restrict__ out, int64_t ldo, const float* P, int pp, const float* X, int Li,
+                                        int Lj, int d) {
+  const int tj = (Lj + 1) >> 1, tc = d >> 1;
+  for (int idx = threadIdx.x; idx < tj * tc; idx += MHA_T_THREADS) {
+    const int j0 = (idx / tc) * 2, c0 = idx % tc;
+    const int j1 = min(j0 + 1, Lj - 1);
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll 4
+    for (int i = 0; i < Li; ++i) {
+      const float s0 = P[i * pp + j0], s1 = P[i * pp + j1];
+      const float xa = X[i * d + c0], xb = X[i * d + c0 + tc];
+      acc[0][0] = fmaf(s0, xa, acc[0][0]); acc[0][1] = fmaf(s0, xb, acc[0][1]);
+      acc[1][0] = fmaf(s1, xa, acc[1][0]); acc[1][1] = fmaf(s1, xb, acc[1][1]);
+    }
+    T* r0 = out + (int64_t)j0 * ldo;
+    r0[c0] = from_f<T>(acc[0][0]); r0[c0 + tc] = from_f<T>(acc[0][1]);
+    if (j0 + 1 < Lj) {
+      T* r1 = out + (int64_t)(j0 + 1) * ldo;
+      r1[c0] = from_f<T>(acc[1][0]); r1[c0 + tc] = from_f<T>(acc[1][1]);
+    }
+  }
+}
+
+// shared-memory pitch of an [L x Lk] score tile: multiple of 4 floats (16-byte row alignment), >= Lk + 3 so that the
+// 4-wide tiles of the last key group stay inside the row
+__host__ __device__ inline int mha_lkp(int Lk) { return ((Lk + 3) & ~3) + 4; }
+
 template <typename T>
 __global__ void __launch_bounds__(MHA_T_THREADS)
 mha_fwd_tiled_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, int64_t ldk,
                      const T* __restrict__ v, int64_t ldv, const uint8_t* __restrict__ mask, int64_t mask_sb,
                      int64_t mask_sq, T* __restrict__ o, int64_t ldo, T* __restrict__ p, int H, int Lq, int Lk,
                      int d, float temperature) {
-  extern __shared__ float sm[];
-  const int dp = d + 1, lp = Lk + 1;
-  float* Qs = sm;                  // [Lq][dp]  (already divided by the temperature)
-  float* Ks = Qs + Lq * dp;        // [Lk][dp]
-  float* Vs = Ks + Lk * dp;        // [Lk][dp]
-  float* Ss = Vs + Lk * dp;        // [Lq][lp]
+  extern __shared__ __align__(16) float sm[];
+  const int lkp = mha_lkp(Lk);
+  float* Qs = sm;                  // [Lq][d]    q / temperature
+  float* Kt = Qs + Lq * d;         // [d][lkp]   K transposed
+  float* Vs = Kt + d * lkp;        // [Lk][d]
+  float* Ss = Vs + Lk * d;         // [Lq][lkp]
   const int h = blockIdx.x, b = blockIdx.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   // q / temperature: division (not reciprocal multiply) to follow layers.py:216 bit for bit
   for (int idx = threadIdx.x; idx < Lq * d; idx += MHA_T_THREADS) {
     const int r = idx / d, c = idx - r * d;
-    Qs[r * dp + c] = to_f(q[((int64_t)b * Lq + r) * ldq + (int64_t)h * d + c]) / temperature;
+    Qs[idx] = to_f(q[((int64_t)b * Lq + r) * ldq + (int64_t)h * d + c]) / temperature;
   }
-  mha_load_rows(Ks, dp, k + (int64_t)b * Lk * ldk + (int64_t)h * d, ldk, Lk, d, 1.f);
-  mha_load_rows(Vs, dp, v + (int64_t)b * Lk * ldv + (int64_t)h * d, ldv, Lk, d, 1.f);
+  for (int idx = threadIdx.x; idx < d * lkp; idx += MHA_T_THREADS) Kt[idx] = 0.f;   // padding columns must be finite
   __syncthreads();
-  for (int idx = threadIdx.x; idx < Lq * Lk; idx += MHA_T_THREADS) {
-    const int i = idx / Lk, j = idx - i * Lk;
-    const float* qr = Qs + i * dp;
-    const float* kr = Ks + j * dp;
-    float s = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < d; ++c) s = fmaf(qr[c], kr[c], s);
-    if (mask && mask[b * mask_sb + i * mask_sq + j] == 0) s = -1e9f;        // layers.py:224
-    Ss[i * lp + j] = s;
-  }
+  mha_load_rows_t(Kt, lkp, k + (int64_t)b * Lk * ldk + (int64_t)h * d, ldk, Lk, d);
+  mha_load_rows(Vs, d, v + (int64_t)b * Lk * ldv + (int64_t)h * d, ldv, Lk, d, 1.f);
+  __syncthreads();
+  mha_ab_t(Ss, lkp, Qs, d, Kt, lkp, Lq, Lk, d);
   __syncthreads();
   for (int i = w; i < Lq; i += MHA_T_THREADS / 32) {
-    float* sr = Ss + i * lp;
+    float* sr = Ss + i * lkp;
+    const uint8_t* mr = mask ? mask + b * mask_sb + i * mask_sq : nullptr;
     float mx = -INFINITY;
-    for (int j = lane; j < Lk; j += 32) mx = fmaxf(mx, sr[j]);
+    for (int j = lane; j < Lk; j += 32) {
+      float sv = sr[j];
+      if (mr && mr[j] == 0) sv = -1e9f;                                  // layers.py:224
+      sr[j] = sv;
+      mx = fmaxf(mx, sv);
+    }
     mx = warp_max(mx);
     float sum = 0.f;
     for (int j = lane; j < Lk; j += 32) { const float e = expf(sr[j] - mx); sr[j] = e; sum += e; }
@@ -200,14 +294,7 @@ mha_fwd_tiled_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
     }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < Lq * d; idx += MHA_T_THREADS) {
-    const int i = idx / d, c = idx - i * d;
-    const float* pr = Ss + i * lp;
-    float acc = 0.f;
-#pragma unroll 4
-    for (int j = 0; j < Lk; ++j) acc = fmaf(pr[j], Vs[j * dp + c], acc);
-    o[((int64_t)b * Lq + i) * ldo + (int64_t)h * d + c] = from_f<T>(acc);
-  }
+  mha_pv(o + (int64_t)b * Lq * ldo + (int64_t)h * d, ldo, Ss, lkp, Vs, Lq, Lk, d, 1.f);
 }
 
 // dP = dO V^T;  dS = P * (dP - rowsum(P dP));  dQ = dS K / temp;  dK = dS^T (Q / temp);  dV = P^T dO.
@@ -217,71 +304,52 @@ mha_bwd_tiled_kernel(const T* __restrict__ dout, int64_t ldo, const T* __restric
                      const T* __restrict__ k, int64_t ldk, const T* __restrict__ v, int64_t ldv,
                      const T* __restrict__ p, T* __restrict__ dq, int64_t lddq, T* __restrict__ dk, int64_t lddk,
                      T* __restrict__ dv, int64_t lddv, int H, int Lq, int Lk, int d, float temperature) {
-  extern __shared__ float sm[];
-  const int dp = d + 1, lp = Lk + 1;
-  float* Qs = sm;                  // [Lq][dp]  q / temperature
-  float* Ks = Qs + Lq * dp;        // [Lk][dp]
-  float* Vs = Ks + Lk * dp;        // [Lk][dp]
-  float* dOs = Vs + Lk * dp;       // [Lq][dp]
-  float* Ps = dOs + Lq * dp;       // [Lq][lp]
-  float* dSs = Ps + Lq * lp;       // [Lq][lp]
+  extern __shared__ __align__(16) float sm[];
+  const int lkp = mha_lkp(Lk);
+  float* Qs = sm;                  // [Lq][d]    q / temperature
+  float* Ks = Qs + Lq * d;         // [Lk][d]
+  float* Vt = Ks + Lk * d;         // [d][lkp]   V transposed
+  float* dOs = Vt + d * lkp;       // [Lq][d]
+  float* Ps = dOs + Lq * d;        // [Lq][lkp]
+  float* dSs = Ps + Lq * lkp;      // [Lq][lkp]
   const int h = blockIdx.x, b = blockIdx.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int idx = threadIdx.x; idx < Lq * d; idx += MHA_T_THREADS) {
     const int r = idx / d, c = idx - r * d;
-    Qs[r * dp + c] = to_f(q[((int64_t)b * Lq + r) * ldq + (int64_t)h * d + c]) / temperature;
+    Qs[idx] = to_f(q[((int64_t)b * Lq + r) * ldq + (int64_t)h * d + c]) / temperature;
   }
-  mha_load_rows(Ks, dp, k + (int64_t)b * Lk * ldk + (int64_t)h * d, ldk, Lk, d, 1.f);
-  mha_load_rows(Vs, dp, v + (int64_t)b * Lk * ldv + (int64_t)h * d, ldv, Lk, d, 1.f);
-  mha_load_rows(dOs, dp, dout + (int64_t)b * Lq * ldo + (int64_t)h * d, ldo, Lq, d, 1.f);
+  for (int idx = threadIdx.x; idx < d * lkp; idx += MHA_T_THREADS) Vt[idx] = 0.f;
+  __syncthreads();
+  mha_load_rows(Ks, d, k + (int64_t)b * Lk * ldk + (int64_t)h * d, ldk, Lk, d, 1.f);
+  mha_load_rows_t(Vt, lkp, v + (int64_t)b * Lk * ldv + (int64_t)h * d, ldv, Lk, d);
+  mha_load_rows(dOs, d, dout + (int64_t)b * Lq * ldo + (int64_t)h * d, ldo, Lq, d, 1.f);
   const T* pb = p + ((int64_t)b * H + h) * Lq * Lk;
   for (int idx = threadIdx.x; idx < Lq * Lk; idx += MHA_T_THREADS) {
     const int i = idx / Lk, j = idx - i * Lk;
-    Ps[i * lp + j] = to_f(pb[idx]);
+    Ps[i * lkp + j] = to_f(pb[idx]);
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < Lq * Lk; idx += MHA_T_THREADS) {
-    const int i = idx / Lk, j = idx - i * Lk;
-    const float* dr = dOs + i * dp;
-    const float* vr = Vs + j * dp;
-    float s = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < d; ++c) s = fmaf(dr[c], vr[c], s);
-    dSs[i * lp + j] = s;
-  }
+  mha_ab_t(dSs, lkp, dOs, d, Vt, lkp, Lq, Lk, d);          // dP
   __syncthreads();
   for (int i = w; i < Lq; i += MHA_T_THREADS / 32) {
     float delta = 0.f;
-    for (int j = lane; j < Lk; j += 32) delta += dSs[i * lp + j] * Ps[i * lp + j];
+    for (int j = lane; j < Lk; j += 32) delta += dSs[i * lkp + j] * Ps[i * lkp + j];
     delta = warp_sum(delta);
-    for (int j = lane; j < Lk; j += 32) dSs[i * lp + j] = Ps[i * lp + j] * (dSs[i * lp + j] - delta);
+    for (int j = lane; j < Lk; j += 32) dSs[i * lkp + j] = Ps[i * lkp + j] * (dSs[i * lkp + j] - delta);
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < Lq * d; idx += MHA_T_THREADS) {          // dQ
-    const int i = idx / d, c = idx - i * d;
-    float acc = 0.f;
-#pragma unroll 4
-    for (int j = 0; j < Lk; ++j) acc = fmaf(dSs[i * lp + j], Ks[j * dp + c], acc);
-    dq[((int64_t)b * Lq + i) * lddq + (int64_t)h * d + c] = from_f<T>(acc / temperature);
-  }
-  for (int idx = threadIdx.x; idx < Lk * d; idx += MHA_T_THREADS) {          // dK, dV
-    const int j = idx / d, c = idx - j * d;
-    float ak = 0.f, av = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < Lq; ++i) {
-      ak = fmaf(dSs[i * lp + j], Qs[i * dp + c], ak);
-      av = fmaf(Ps[i * lp + j], dOs[i * dp + c], av);
-    }
-    dk[((int64_t)b * Lk + j) * lddk + (int64_t)h * d + c] = from_f<T>(ak);
-    dv[((int64_t)b * Lk + j) * lddv + (int64_t)h * d + c] = from_f<T>(av);
-  }
+  mha_pv(dq + (int64_t)b * Lq * lddq + (int64_t)h * d, lddq, dSs, lkp, Ks, Lq, Lk, d, 1.f / temperature);
+  mha_ptv(dk + (int64_t)b * Lk * lddk + (int64_t)h * d, lddk, dSs, lkp, Qs, Lq, Lk, d);
+  mha_ptv(dv + (int64_t)b * Lk * lddv + (int64_t)h * d, lddv, Ps, lkp, dOs, Lq, Lk, d);
 }
 
 static size_t mha_fwd_tiled_smem(int64_t Lq, int64_t Lk, int64_t d) {
-  return ((Lq + 2 * Lk) * (d + 1) + Lq * (Lk + 1)) * sizeof(float);
+  const int64_t lkp = mha_lkp((int)Lk);
+  return (Lq * d + d * lkp + Lk * d + Lq * lkp) * sizeof(float);
 }
 static size_t mha_bwd_tiled_smem(int64_t Lq, int64_t Lk, int64_t d) {
-  return ((2 * Lq + 2 * Lk) * (d + 1) + 2 * Lq * (Lk + 1)) * sizeof(float);
+  const int64_t lkp = mha_lkp((int)Lk);
+  return (2 * Lq * d + Lk * d + d * lkp + 2 * Lq * lkp) * sizeof(float);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -627,7 +695,7 @@ int b200st_mha_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t
   if (Lk <= 0) return set_error("mha_fwd: empty key sequence");
   {
     const size_t tsm = mha_fwd_tiled_smem(Lq, Lk, d);
-    if (tsm <= 100 * 1024) {     // training shapes: whole head in shared memory
+    if (tsm <= 100 * 1024 && d % 4 == 0) {     // training shapes: whole head in shared memory
       dim3 tg((unsigned)H, (unsigned)B);
       B200ST_DISPATCH(dtype, T, {
         if (tsm > 48 * 1024)
@@ -660,7 +728,7 @@ int b200st_mha_bwd(int dtype, const void* dout, int64_t ldo, const void* q, int6
   if (B <= 0 || Lq <= 0 || Lk <= 0) return 0;
   {
     const size_t tsm = mha_bwd_tiled_smem(Lq, Lk, d);
-    if (tsm <= 160 * 1024) {
+    if (tsm <= 160 * 1024 && d % 4 == 0) {
       dim3 tg((unsigned)H, (unsigned)B);
       B200ST_DISPATCH(dtype, T, {
         if (tsm > 48 * 1024)
