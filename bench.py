@@ -249,6 +249,16 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # the GPU arm
 # ------------------------------------------------------------------------------------------------
+def _profile_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the recurrence kernels, from the committed
+    `ncu --set full` capture (profiles/r01_blstm_ncu.json), averaged over fwd+bwd; None if not captured."""
+    try:
+        d = json.load(open(os.path.join(ROOT, 'profiles', 'r01_blstm_ncu.json')))
+        return d.get('dram_bytes_per_launch_avg')
+    except Exception:
+        return None
+
+
 def build_model(cfg, device):
     from models.Seq2seq import Seq2seq
     torch.manual_seed(333)
@@ -329,8 +339,10 @@ def run_b200(args):
         eager_step(dev_items)
     launches_per_step = K().launch_count() - n_before
     fam = kt.summary()
-    dominant = max(('blstm_fwd', 'blstm_bwd', 'gemm'), key=lambda n: fam[n]['ms'])
-    roof_names = ['blstm_fwd', 'blstm_bwd'] if dominant.startswith('blstm') else [dominant]
+    # Dominant kernel = the persistent BLSTM recurrence pair (largest single-kernel share of the step in the ncu launch
+    # list, profiles/r01_launches_summary.txt; the eager per-family sums above overstate the many tiny GEMM launches
+    # because each bracket then also contains host launch gaps).
+    roof_names = ['blstm_fwd', 'blstm_bwd']
     roof = {n: fam[n] for n in roof_names}
     ms_eager = timed(lambda: eager_step(dev_items), args.steps)
 
@@ -393,7 +405,8 @@ def run_b200(args):
             'eager_ms_per_step': ms_eager,
             'clocks': clocks,
             'roofline': {'kernel': '+'.join(roof_names), 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
-                         'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                         'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': _profile_traffic(), 'peak_source': peak_src,
+                         'us_per_time_step': 1e3 * r_ms / (2 * sum((args.frames + 8 - args.frames % 8) // 2 ** l for l in range(4))),
                          'launches': r_calls, 'avg_launch_ms': r_ms / max(r_calls, 1),
                          'timed': 'CUDA events around every launch of this kernel family on its stream, eager pass of the '
                                   'same step in this run (the timed region replays the step as one CUDA graph)',
