@@ -93,9 +93,9 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int BM = TC_BM>
 struct TcSmem {
-  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int A_BYTES = BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE;
@@ -105,12 +105,15 @@ struct TcSmem {
 // Tile configurations (BN, STAGES): the deep-pipeline / narrow-N ones exist because most GEMMs on this path are
 // latency-bound (M = 64 decoder steps, M ~ 2-3k Transformer rows with K = 512): what matters there is bytes in
 // flight per SM and the number of CTAs, not MMA throughput.
-template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC, bool ATOMIC>
-__global__ void __launch_bounds__(TC_THREADS, (BN * TC_BK * 2 + TC_BM * TC_BK * 2) * STAGES <= 100 * 1024 ? 2 : 1)
+// BM = 128, or 64 for single-M-tile problems with M <= 64 (the decoder steps): the SS-form MMA is paced by streaming
+// the A tile out of shared memory, so not reading 64 zero-padded rows halves the per-MMA cost.  For M = 64 the
+// accumulator row i lives in TMEM lane (i / 16) * 32 + (i % 16) (measured: scripts/probes/umma_m64_probe.cu).
+template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC, bool ATOMIC, int BM = TC_BM>
+__global__ void __launch_bounds__(TC_THREADS, (BN * TC_BK * 2 + BM * TC_BK * 2) * STAGES <= 100 * 1024 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                TC* __restrict__ C, int64_t ldc, const TC* R, int64_t ldr, const float* __restrict__ bias,
                int relu, float alpha, int M, int N, int K, int kb_per_split) {
-  using S = TcSmem<BN, STAGES>;
+  using S = TcSmem<BN, STAGES, BM>;
   constexpr int TC_STAGES = STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -120,7 +123,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kb_total = (K + TC_BK - 1) / TC_BK;
   const int kb_begin = blockIdx.z * kb_per_split;
   const int kb_end = min(kb_total, kb_begin + kb_per_split);
@@ -152,7 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int k0 = (kb_begin + it) * TC_BK;
         if (A_MN) {
 #pragma unroll
-          for (int c = 0; c < TC_BM / 64; ++c) tma_load_2d(sa + c * (TC_BK * 128), &tma_a, m0 + c * 64, k0, &full[s]);
+          for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (TC_BK * 128), &tma_a, m0 + c * 64, k0, &full[s]);
         } else {
           tma_load_2d(sa, &tma_a, k0, m0, &full[s]);
         }
@@ -166,7 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(TC_BM, BN, A_MN, B_MN);
+      constexpr uint32_t idesc = umma_idesc(BM, BN, A_MN, B_MN);
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % TC_STAGES;
         const uint32_t ph = (it / TC_STAGES) & 1;
@@ -209,11 +212,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (n_iter > 0) {
       constexpr int LPR = BN / 4;        // lanes per row (4 columns each)
       constexpr int RPP = 32 / LPR;      // rows per pass
+      constexpr int RPW = BM == 64 ? 16 : 32;   // accumulator rows held by one warp's TMEM lane quarter
       const int cc = (lane % LPR) * 4;
       const int col = n0 + cc;
 #pragma unroll 1
-      for (int rr = lane / LPR; rr < 32; rr += RPP) {
-        const int row = m0 + wq * 32 + rr;
+      for (int rr = lane / LPR; rr < RPW; rr += RPP) {
+        const int row = m0 + wq * RPW + rr;
         if (row >= M || col >= N) continue;
         const float4 a = *reinterpret_cast<const float4*>(&stg[rr * SP + cc]);
         float v[4] = {a.x, a.y, a.z, a.w};
@@ -318,23 +322,23 @@ bool gemm_tc_eligible(int dtype_ab, int ta, int tb, int64_t M, int64_t N, int64_
   return get_encode() != nullptr;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC>
+template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC, int BM = TC_BM>
 static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const CUtensorMap& ma, const CUtensorMap& mb,
                      void* C, int64_t ldc, const void* R, int64_t ldr, const float* bias, int relu, int splits,
                      int kb_per_split, cudaStream_t st) {
-  using S = TcSmem<BN, STAGES>;
+  using S = TcSmem<BN, STAGES, BM>;
   static_assert(S::TOTAL <= 227 * 1024, "tile configuration exceeds shared memory");
-  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, TC_BM), (unsigned)splits);
+  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), (unsigned)splits);
   if (splits > 1) {
     if constexpr (sizeof(TC) == 4) {
-      auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, float, true>;
+      auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, float, true, BM>;
       B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
       kern<<<grid, TC_THREADS, S::TOTAL, st>>>(ma, mb, (float*)C, ldc, nullptr, 0, nullptr, 0, alpha, (int)M, (int)N, (int)K, kb_per_split);
     } else {
       return set_error("gemm_tc: split-K needs an fp32 output");
     }
   } else {
-    auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, TC, false>;
+    auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, TC, false, BM>;
     B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     kern<<<grid, TC_THREADS, S::TOTAL, st>>>(ma, mb, (TC*)C, ldc, (const TC*)R, ldr, bias, relu, alpha, (int)M, (int)N, (int)K, kb_per_split);
   }
@@ -361,9 +365,10 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   else cfg = 0;
   if (N <= 32 && !b_mn) cfg = 2;
   const int BN = cfg == 0 ? 128 : (cfg == 2 ? 32 : 64);
+  const bool m64 = (cfg == 2 || cfg == 3) && M <= 64;       // half-height A tile for the decoder-step GEMMs
   CUtensorMap ma, mb;
   if (a_mn) { if (make_map(&ma, A, K, M, lda, TC_BK)) return -1; }
-  else      { if (make_map(&ma, A, M, K, lda, TC_BM)) return -1; }
+  else      { if (make_map(&ma, A, M, K, lda, m64 ? 64 : TC_BM)) return -1; }
   if (b_mn) { if (make_map(&mb, B, K, N, ldb, TC_BK)) return -1; }
   else      { if (make_map(&mb, B, N, K, ldb, BN)) return -1; }
   // split-K when the output has few tiles and K is long (weight gradients): fp32 output, plain sum only.
@@ -383,12 +388,23 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
       return launch_tc<BN_, ST_, AMN, BMN, float>(M, N, K, alpha, ma, mb, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
     return launch_tc<BN_, ST_, AMN, BMN, __nv_bfloat16>(M, N, K, alpha, ma, mb, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
   } while (0)
+#define TC_GO64(BN_, ST_, AMN, BMN)                                                                        \
+  do {                                                                                                     \
+    if (dtype_c == B200ST_F32)                                                                             \
+      return launch_tc<BN_, ST_, AMN, BMN, float, 64>(M, N, K, alpha, ma, mb, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
+    return launch_tc<BN_, ST_, AMN, BMN, __nv_bfloat16, 64>(M, N, K, alpha, ma, mb, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
+  } while (0)
 #define TC_CFG(AMN, BMN)                                                   \
   do {                                                                     \
     if (cfg == 0) TC_GO(128, 3, AMN, BMN);                                 \
     if (cfg == 1) TC_GO(64, 4, AMN, BMN);                                  \
     if (cfg == 3) TC_GO(64, 8, AMN, BMN);                                  \
   } while (0)
+  if (m64) {                    // M <= 64: half-height tiles, deeper pipelines (12 KB / 16 KB per stage)
+    if (cfg == 2) { if (!a_mn) TC_GO64(32, 12, false, false); TC_GO64(32, 12, true, false); }
+    if (!a_mn && b_mn) TC_GO64(64, 10, false, true);
+    if (a_mn && b_mn) TC_GO64(64, 10, true, true);
+  }
   if (cfg == 2) {               // K-major B only
     if (!a_mn) TC_GO(32, 10, false, false);
     TC_GO(32, 10, true, false);
@@ -400,6 +416,7 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   return set_error("gemm_tc: no tile configuration");
 #undef TC_CFG
 #undef TC_GO
+#undef TC_GO64
 }
 
 }  // namespace b200st
