@@ -81,12 +81,13 @@ int b200st_mha_bwd(int dtype, const void* dout, int64_t ldo, const void* q, int6
                    b200st_stream_t stream);
 
 /* ---- LSTM cell pointwise (one step of torch.nn.LSTM, Dec.py:393-419) ----------------------------
- * gates [B,4H] = pre-activations (x W_ih^T + h W_hh^T + b_ih + b_hh), PyTorch order i,f,g,o.
+ * gates (+ gates_b + gates_c, NULLs skipped) [B,4H] = pre-activations x W_ih^T + h W_hh^T + b_ih + b_hh, possibly
+ * delivered as partial products that were computed concurrently; PyTorch order i,f,g,o.
  * acts [B,4H] fp32 = post-activation gates, c/c_prev fp32 [B,H] (c_prev NULL = zeros),
  * h [B,H] dtype; if residual != NULL, out_res = h + residual (Dec.py:417-418). */
-int b200st_lstm_cell_fwd(int dtype, const void* gates, const float* c_prev, void* h, float* c,
-                         float* acts, const void* residual, void* out_res, int64_t B, int64_t H,
-                         b200st_stream_t stream);
+int b200st_lstm_cell_fwd(int dtype, const void* gates, const void* gates_b, const void* gates_c,
+                         const float* c_prev, void* h, float* c, float* acts, const void* residual,
+                         void* out_res, int64_t B, int64_t H, b200st_stream_t stream);
 /* dh = dh_a + dh_b + dh_c (NULLs skipped); dc_next NULL = zeros; c_prev NULL = zeros. */
 int b200st_lstm_cell_bwd(int dtype, const void* dh_a, const void* dh_b, const void* dh_c,
                          const float* dc_next, const float* acts, const float* c_prev, const float* c,

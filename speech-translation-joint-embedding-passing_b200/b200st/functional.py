@@ -377,32 +377,49 @@ class _LASDecoder(Function):
         else:
             ids_in = ids_tf.t()[:S].contiguous()
             sym_dst = SYM
-        G = e(B, 4 * D)
+        # Per-step critical path (5 GEMMs): emb W_a -> cell0 -> x W_ih1 -> cell1 -> x W_ih2 -> cell2 -> attention ->
+        # ctx W_fa -> vocabulary -> arg-max.  Everything that only depends on the PREVIOUS step (h_i W_hh_i, cv W_b) or
+        # is independent of the attention (dec_out W_fb) is forked onto side streams as soon as its input exists.
+        side = rt.side_streams(dev, n_layers + 1)
+        Gx = [e(B, 4 * D) for _ in range(n_layers)]          # x-part (+ bias) of the gate pre-activations
+        Gh = [e(B, 4 * D) for _ in range(n_layers)]          # h_{s-1} W_hh^T
+        Gcv = e(B, 4 * D)                                     # cell_value_{s-1} W_ih0[:, E:]^T
+        CVb = e(B, D)                                         # dec_out W_ffn[:, 2H:]^T
         for s in range(S):
             k.embedding_fwd(ids_in[s], emb_table, dt, out=EMB[s])
             x = EMB[s]
             for i in range(n_layers):
                 # gates = x W_ih^T + b_ih + b_hh + h W_hh^T   (torch.nn.LSTM step, Dec.py:393-415)
                 if i == 0:      # x = cat(emb, prev cell_value) (Dec.py:383) without materialising the concat
-                    k.gemm(x, wih[0][:, :E], trans_b=True, bias=bias[0], out=G)
-                    if s > 0:
-                        k.gemm(CV[s], wih[0][:, E:], trans_b=True, residual=G, out=G)
+                    k.gemm(x, wih[0][:, :E], trans_b=True, bias=bias[0], out=Gx[0])
                 else:
-                    k.gemm(x, wih[i], trans_b=True, bias=bias[i], out=G)
+                    k.gemm(x, wih[i], trans_b=True, bias=bias[i], out=Gx[i])
                 if s > 0:
-                    k.gemm(Hst[i][s], whh[i], trans_b=True, residual=G, out=G)
+                    rt.join(side[i])
                 res_in = x if RES[i] is not None else None
-                _, _, _, out_res = k.lstm_cell_fwd(G, Cst[i][s], residual=res_in, h_out=Hst[i][s + 1],
+                _, _, _, out_res = k.lstm_cell_fwd(Gx[i], Cst[i][s], residual=res_in, h_out=Hst[i][s + 1],
                                                    c_out=Cst[i][s + 1], acts_out=ACT[i][s],
-                                                   res_out=RES[i][s] if RES[i] is not None else None)
+                                                   res_out=RES[i][s] if RES[i] is not None else None,
+                                                   gates_b=Gh[i] if s > 0 else None,
+                                                   gates_c=Gcv if (i == 0 and s > 0) else None)
+                if s + 1 < S:
+                    with rt.fork(side[i]):                    # next step's recurrent part, off the critical path
+                        k.gemm(Hst[i][s + 1], whh[i], trans_b=True, out=Gh[i])
                 x = out_res if out_res is not None else Hst[i][s + 1]
             dec_out = x
+            with rt.fork(side[n_layers]):
+                k.gemm(dec_out, wf[:, H2:], trans_b=True, out=CVb)
             k.las_attn_fwd(dec_out, wk, enc, klens, ctx_out=CTX[s], probs_out=PROBS[s])
             # cell_value = acous_ffn(cat(context, dec_out)) (Dec.py:431-433), again without the concat
-            k.gemm(CTX[s], wf[:, :H2], trans_b=True, out=CV[s + 1])
-            k.gemm(dec_out, wf[:, H2:], trans_b=True, residual=CV[s + 1], out=CV[s + 1])
+            rt.join(side[n_layers])
+            k.gemm(CTX[s], wf[:, :H2], trans_b=True, residual=CVb, out=CV[s + 1])
+            if s + 1 < S:
+                with rt.fork(side[0]):
+                    k.gemm(CV[s + 1], wih[0][:, E:], trans_b=True, out=Gcv)
             k.gemm(CV[s + 1], wo, trans_b=True, bias=b_out, out=LOGITS[s])       # Dec.py:434
             k.argmax_rows(LOGITS[s], sym_dst[s], lengths=lengths, step=s)        # Dec.py:331 + 334-340
+        for st in side:
+            rt.join(st)
         if ids_tf is None:
             SYM = IDS[1:]
         embs = k.transpose01(CV[1:])                                             # [B,S,D]
@@ -463,32 +480,46 @@ class _LASDecoder(Function):
         DCTX = e(S, B, H2)
         DSC = e(S, B, Tk, dtype=f32)
         DEMB = e(S, B, E)
-        dh_next: List[Optional[torch.Tensor]] = [None] * n_layers
+        # Per-step critical path (4 GEMMs): dcv W_fa -> attention bwd -> cell2 bwd -> dG2 W_ih2 -> cell1 bwd -> dG1 W_ih1
+        # -> cell0 bwd -> dG0 W_ih0[:, E:] (into DCV[s-1]).  The recurrent products dG_i W_hh_i (needed one step later),
+        # dcv W_fb (needed after the attention backward) and dG0 W_ih0[:, :E] (needed after the loop) run on side streams.
+        side = rt.side_streams(dev, n_layers + 1)
+        DHN = [e(B, D) for _ in range(n_layers)]             # dh flowing to the previous step, per layer
+        D_OUT = e(B, D)
+        have_dhn = [False] * n_layers
         dc_next: List[Optional[torch.Tensor]] = [None] * n_layers
         for s in reversed(range(S)):
             dcv = DCV[s]
             # cell_value = ctx Wf[:, :2H]^T + dec_out Wf[:, 2H:]^T
+            with rt.fork(side[n_layers]):
+                k.gemm(dcv, wf[:, H2:], out=D_OUT)
             k.gemm(dcv, wf[:, :H2], out=DCTX[s])
-            d_out = k.gemm(dcv, wf[:, H2:])                                      # [B,D]
             _, dq_att = k.las_attn_bwd(DCTX[s], wk, enc, PROBS[s], dscore_out=DSC[s])
+            rt.join(side[n_layers])
             # dec_out = y_{n-1};  y_i = h_i (+ y_{i-1} on residual layers, Dec.py:417-418)
-            dy_parts = [d_out, dq_att]
+            dy_parts = [D_OUT, dq_att]
             for i in reversed(range(n_layers)):
-                _, dc_next[i] = k.lstm_cell_bwd(dy_parts + [dh_next[i]], dc_next[i], ACT[i][s], Cst[i][s],
-                                                Cst[i][s + 1], dt, dgates_out=DG[i][s])
+                if have_dhn[i]:
+                    rt.join(side[i])
+                _, dc_next[i] = k.lstm_cell_bwd(dy_parts + [DHN[i] if have_dhn[i] else None], dc_next[i], ACT[i][s],
+                                                Cst[i][s], Cst[i][s + 1], dt, dgates_out=DG[i][s])
                 dgi = DG[i][s]
-                if s > 0:
-                    dh_next[i] = k.gemm(dgi, whh[i])
+                with rt.fork(side[i]):
+                    if s > 0:
+                        k.gemm(dgi, whh[i], out=DHN[i])
+                        have_dhn[i] = True
+                    if i == 0:
+                        k.gemm(dgi, wih[0][:, :E], out=DEMB[s])
                 if i > 0:
                     if RES[i] is not None:      # the skip connection carries dy_i straight to y_{i-1}
                         skip = dy_parts[0] if len(dy_parts) == 1 else k.add(dy_parts[0], dy_parts[1])
                         dy_parts = [k.gemm(dgi, wih[i], residual=skip)]
                     else:
                         dy_parts = [k.gemm(dgi, wih[i])]
-                else:
-                    k.gemm(dgi, wih[0][:, :E], out=DEMB[s])
-                    if s > 0:
-                        k.gemm(dgi, wih[0][:, E:], residual=DCV[s - 1], out=DCV[s - 1])
+                elif s > 0:
+                    k.gemm(dgi, wih[0][:, E:], residual=DCV[s - 1], out=DCV[s - 1])
+        for st in side:
+            rt.join(st)
 
         SB = S * B
         grads_lstm = []

@@ -174,8 +174,10 @@ class CudaKernels:
 
     # -- LSTM -------------------------------------------------------------------------------------
     def lstm_cell_fwd(self, gates, c_prev, residual=None, save_acts=True, h_out=None, c_out=None,
-                      acts_out=None, res_out=None):
-        self._need_cuda(gates, c_prev, residual)
+                      acts_out=None, res_out=None, gates_b=None, gates_c=None):
+        self._need_cuda(gates, c_prev, residual, gates_b, gates_c)
+        for g in (gates_b, gates_c):
+            assert g is None or (g.is_contiguous() and g.shape == gates.shape and g.dtype == gates.dtype)
         B, H4 = gates.shape
         H = H4 // 4
         assert gates.is_contiguous()
@@ -188,7 +190,7 @@ class CudaKernels:
         if residual is not None:
             out_res = res_out if res_out is not None else torch.empty_like(h)
             assert residual.is_contiguous() and out_res.is_contiguous()
-        _lib.check(self.lib.b200st_lstm_cell_fwd(_dt(gates), _p(gates), _p(c_prev), _p(h), _p(c),
+        _lib.check(self.lib.b200st_lstm_cell_fwd(_dt(gates), _p(gates), _p(gates_b), _p(gates_c), _p(c_prev), _p(h), _p(c),
                                                  _p(acts), _p(residual), _p(out_res), B, H,
                                                  self._stream()), 'lstm_cell_fwd')
         return h, c, acts, out_res

@@ -46,3 +46,48 @@ def operand(param: torch.Tensor) -> torch.Tensor:
 
 def clear_cache():
     _cache.clear()
+
+
+# ------------------------------------------------------------------------------------------------
+# side streams: independent kernels of one step are enqueued on forked streams; inside a CUDA graph
+# capture they become parallel branches, in eager mode they overlap through the hardware queues.
+# ------------------------------------------------------------------------------------------------
+_side = {}
+
+
+def side_streams(device, n):
+    """`n` persistent side streams for `device` (None entries on CPU, where fork/join are no-ops)."""
+    if device.type != 'cuda':
+        return [None] * n
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    pool = _side.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
+class fork:
+    """`with fork(stream): launch(...)` — the body runs on `stream`, ordered after everything enqueued so far on the
+    current stream.  `stream is None` (CPU) runs the body inline."""
+
+    def __init__(self, stream):
+        self.stream = stream
+        self.ctx = None
+
+    def __enter__(self):
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(self.stream)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def join(stream):
+    """Make the current stream wait for everything enqueued so far on `stream`."""
+    if stream is not None:
+        torch.cuda.current_stream().wait_stream(stream)

@@ -24,7 +24,8 @@ namespace b200st {
 // single-step cell
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void lstm_cell_fwd_kernel(const T* __restrict__ gates, const float* __restrict__ c_prev,
+__global__ void lstm_cell_fwd_kernel(const T* __restrict__ gates, const T* __restrict__ gates_b,
+                                     const T* __restrict__ gates_c, const float* __restrict__ c_prev,
                                      T* __restrict__ h, float* __restrict__ c, float* __restrict__ acts,
                                      const T* __restrict__ residual, T* __restrict__ out_res, int64_t B,
                                      int H) {
@@ -33,10 +34,19 @@ __global__ void lstm_cell_fwd_kernel(const T* __restrict__ gates, const float* _
   const int64_t b = idx / H;
   const int u = (int)(idx % H);
   const T* g = gates + b * 4 * H;
-  const float i_ = sigmoidf_(to_f(g[u]));
-  const float f_ = sigmoidf_(to_f(g[H + u]));
-  const float g_ = tanhf(to_f(g[2 * H + u]));
-  const float o_ = sigmoidf_(to_f(g[3 * H + u]));
+  float pi = to_f(g[u]), pf = to_f(g[H + u]), pg = to_f(g[2 * H + u]), po = to_f(g[3 * H + u]);
+  if (gates_b) {   // pre-activations may arrive as partial products computed concurrently (x W_ih^T, h W_hh^T, ...)
+    const T* q = gates_b + b * 4 * H;
+    pi += to_f(q[u]); pf += to_f(q[H + u]); pg += to_f(q[2 * H + u]); po += to_f(q[3 * H + u]);
+  }
+  if (gates_c) {
+    const T* q = gates_c + b * 4 * H;
+    pi += to_f(q[u]); pf += to_f(q[H + u]); pg += to_f(q[2 * H + u]); po += to_f(q[3 * H + u]);
+  }
+  const float i_ = sigmoidf_(pi);
+  const float f_ = sigmoidf_(pf);
+  const float g_ = tanhf(pg);
+  const float o_ = sigmoidf_(po);
   const float cp = c_prev ? c_prev[idx] : 0.f;
   const float cn = f_ * cp + i_ * g_;
   const float hn = o_ * tanhf(cn);
@@ -327,13 +337,14 @@ int b200st_set_blstm_backend(int mode) {
   return old;
 }
 
-int b200st_lstm_cell_fwd(int dtype, const void* gates, const float* c_prev, void* h, float* c,
-                         float* acts, const void* residual, void* out_res, int64_t B, int64_t H,
-                         b200st_stream_t stream) {
+int b200st_lstm_cell_fwd(int dtype, const void* gates, const void* gates_b, const void* gates_c,
+                         const float* c_prev, void* h, float* c, float* acts, const void* residual,
+                         void* out_res, int64_t B, int64_t H, b200st_stream_t stream) {
   if (B * H <= 0) return 0;
   B200ST_DISPATCH(dtype, T, {
     lstm_cell_fwd_kernel<T><<<(unsigned)ceil_div(B * H, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)gates, c_prev, (T*)h, c, acts, (const T*)residual, (T*)out_res, B, (int)H);
+        (const T*)gates, (const T*)gates_b, (const T*)gates_c, c_prev, (T*)h, c, acts, (const T*)residual,
+        (T*)out_res, B, (int)H);
   });
   B200ST_LAUNCH_CHECK("lstm_cell_fwd");
   return 0;

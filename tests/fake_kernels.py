@@ -96,8 +96,12 @@ class FakeKernels:
 
     # -- LSTM cell --------------------------------------------------------------------------------
     def lstm_cell_fwd(self, gates, c_prev, residual=None, save_acts=True, h_out=None, c_out=None,
-                      acts_out=None, res_out=None):
-        i, f, g, o = gates.float().chunk(4, dim=-1)
+                      acts_out=None, res_out=None, gates_b=None, gates_c=None):
+        pre = gates.float()
+        for extra in (gates_b, gates_c):
+            if extra is not None:
+                pre = pre + extra.float()
+        i, f, g, o = pre.chunk(4, dim=-1)
         i, f, g, o = torch.sigmoid(i), torch.sigmoid(f), torch.tanh(g), torch.sigmoid(o)
         cp = 0 if c_prev is None else c_prev
         c = f * cp + i * g

@@ -127,6 +127,10 @@ def test_lstm_cell(ks, dtype):
     hr, ccr, actsr, outrr = f.lstm_cell_fwd(gates, cp, residual=res)
     for a, b in ((h, hr), (cc, ccr), (acts, actsr), (outr, outrr)):
         assert rel_err(a, b) < TOL[dtype]
+    gb, gc = rnd(B, 4 * H, dtype=dtype, seed=7), rnd(B, 4 * H, dtype=dtype, seed=8)
+    h3, c3, _, _ = c.lstm_cell_fwd(gates, cp, gates_b=gb, gates_c=gc)
+    hr3, cr3, _, _ = f.lstm_cell_fwd(gates, cp, gates_b=gb, gates_c=gc)
+    assert rel_err(h3, hr3) < TOL[dtype] and rel_err(c3, cr3) < TOL[dtype]
     h0, c0, _, _ = c.lstm_cell_fwd(gates, None)
     hr0, cr0, _, _ = f.lstm_cell_fwd(gates, None)
     assert rel_err(h0, hr0) < TOL[dtype]
