@@ -301,18 +301,28 @@ class _BLSTMLayer(Function):
         T, B, I, H, pair, ld_t, ld_b = ctx.geom
         dg = k.blstm_bwd(_c(dout), ld_t, ld_b, pair, acts, cs, w_hh_f, w_hh_r, lens, x2.dtype)
         dgf, dgr = dg[0].view(T * B, 4 * H), dg[1].view(T * B, 4 * H)
+        f32 = torch.float32
+        dev = dgf.device
+        dw_ih_f, dw_ih_r = torch.empty_like(w_ih_f), torch.empty_like(w_ih_r)
+        dw_hh_f, dw_hh_r = torch.empty_like(w_hh_f), torch.empty_like(w_hh_r)
+        db_f = torch.empty(4 * H, dtype=f32, device=dev)
+        db_r = torch.empty(4 * H, dtype=f32, device=dev)
+        side = rt.side_streams(dev, 2)
+        with rt.fork(side[0]):          # recurrent-weight gradients are split-K GEMMs over T*B rows: they leave SMs idle
+            k.gemm(dgf, hs[0, :T].reshape(T * B, H), trans_a=True, out=dw_hh_f)
+            k.gemm(dgr, hs[1, 1:].reshape(T * B, H), trans_a=True, out=dw_hh_r)
+            k.colsum(dgf, out=db_f)
+            k.colsum(dgr, out=db_r)
+        with rt.fork(side[1]):
+            k.gemm(dgf, x2, trans_a=True, out=dw_ih_f)
+            k.gemm(dgr, x2, trans_a=True, out=dw_ih_r)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = k.gemm(dgf, rt.operand(w_ih_f))
             k.gemm(dgr, rt.operand(w_ih_r), residual=dx, out=dx)
             dx = dx.view(T, B, I)
-        f32 = torch.float32
-        dw_ih_f = k.gemm(dgf, x2, trans_a=True, out_dtype=f32)
-        dw_ih_r = k.gemm(dgr, x2, trans_a=True, out_dtype=f32)
-        dw_hh_f = k.gemm(dgf, hs[0, :T].reshape(T * B, H), trans_a=True, out_dtype=f32)
-        dw_hh_r = k.gemm(dgr, hs[1, 1:].reshape(T * B, H), trans_a=True, out_dtype=f32)
-        db_f = k.colsum(dgf)
-        db_r = k.colsum(dgr)
+        rt.join(side[0])
+        rt.join(side[1])
         return dx, None, dw_ih_f, dw_hh_f, db_f, db_f, dw_ih_r, dw_hh_r, db_r, db_r, None, None
 
 

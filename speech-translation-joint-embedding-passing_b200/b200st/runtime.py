@@ -56,8 +56,10 @@ _side = {}
 
 
 def side_streams(device, n):
-    """`n` persistent side streams for `device` (None entries on CPU, where fork/join are no-ops)."""
-    if device.type != 'cuda':
+    """`n` persistent side streams for `device`.  Returns None entries (fork/join become no-ops, everything runs
+    inline) on CPU and whenever no CUDA graph is being captured: eagerly, the event traffic of forking costs more
+    host time than the overlap wins, while inside a capture the forks are free and become parallel graph branches."""
+    if device.type != 'cuda' or not torch.cuda.is_current_stream_capturing():
         return [None] * n
     key = (device.index if device.index is not None else torch.cuda.current_device())
     pool = _side.setdefault(key, [])
