@@ -251,6 +251,8 @@ mha_fwd_tiled_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
                      const T* __restrict__ v, int64_t ldv, const uint8_t* __restrict__ mask, int64_t mask_sb,
                      int64_t mask_sq, T* __restrict__ o, int64_t ldo, T* __restrict__ p, int H, int Lq, int Lk,
                      int d, float temperature) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __align__(16) float sm[];
   const int lkp = mha_lkp(Lk);
   float* Qs = sm;                  // [Lq][d]    q / temperature
@@ -304,6 +306,8 @@ mha_bwd_tiled_kernel(const T* __restrict__ dout, int64_t ldo, const T* __restric
                      const T* __restrict__ k, int64_t ldk, const T* __restrict__ v, int64_t ldv,
                      const T* __restrict__ p, T* __restrict__ dq, int64_t lddq, T* __restrict__ dk, int64_t lddk,
                      T* __restrict__ dv, int64_t lddv, int H, int Lq, int Lk, int d, float temperature) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __align__(16) float sm[];
   const int lkp = mha_lkp(Lk);
   float* Qs = sm;                  // [Lq][d]    q / temperature
@@ -476,6 +480,8 @@ __global__ void __launch_bounds__(256)
 las_attn_fwd_vec_kernel(const T* __restrict__ q, const T* __restrict__ wk, const T* __restrict__ vals,
                         const int32_t* __restrict__ klens, T* __restrict__ ctx, float* __restrict__ probs, int Tk,
                         int D, int Dv) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __align__(16) float sm[];
   __shared__ float scratch[32];
   float* qs = sm;             // [D]
@@ -537,6 +543,8 @@ __global__ void __launch_bounds__(256)
 las_attn_bwd_vec_kernel(const T* __restrict__ dctx, const T* __restrict__ wk, const T* __restrict__ vals,
                         const float* __restrict__ probs, float* __restrict__ dscore, T* __restrict__ dq, int Tk, int D,
                         int Dv) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __align__(16) float sm[];
   __shared__ float scratch[32];
   float* dcs = sm;            // [Dv]
@@ -634,6 +642,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 argmax_rows_vec_kernel(const T* __restrict__ x, int64_t ld, int cols, int64_t* __restrict__ idx, int64_t idx_stride,
                        int32_t* __restrict__ lengths, int step) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float sv[32];
   __shared__ int si[32];
   const int64_t r = blockIdx.x;
@@ -700,9 +710,9 @@ int b200st_mha_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t
       B200ST_DISPATCH(dtype, T, {
         if (tsm > 48 * 1024)
           B200ST_CUDA(cudaFuncSetAttribute((const void*)mha_fwd_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-        mha_fwd_tiled_kernel<T><<<tg, MHA_T_THREADS, tsm, (cudaStream_t)stream>>>(
-            (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, mask, mask_sb, mask_sq, (T*)o, ldo, (T*)p,
-            (int)H, (int)Lq, (int)Lk, (int)d, temperature);
+        B200ST_CUDA(launch_pdl(mha_fwd_tiled_kernel<T>, tg, dim3(MHA_T_THREADS), tsm, (cudaStream_t)stream,
+                               (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, mask, mask_sb, mask_sq, (T*)o, ldo,
+                               (T*)p, (int)H, (int)Lq, (int)Lk, (int)d, temperature));
       });
       B200ST_LAUNCH_CHECK("mha_fwd_tiled");
       return 0;
@@ -733,9 +743,9 @@ int b200st_mha_bwd(int dtype, const void* dout, int64_t ldo, const void* q, int6
       B200ST_DISPATCH(dtype, T, {
         if (tsm > 48 * 1024)
           B200ST_CUDA(cudaFuncSetAttribute((const void*)mha_bwd_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-        mha_bwd_tiled_kernel<T><<<tg, MHA_T_THREADS, tsm, (cudaStream_t)stream>>>(
-            (const T*)dout, ldo, (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, (const T*)p, (T*)dq, lddq,
-            (T*)dk, lddk, (T*)dv, lddv, (int)H, (int)Lq, (int)Lk, (int)d, temperature);
+        B200ST_CUDA(launch_pdl(mha_bwd_tiled_kernel<T>, tg, dim3(MHA_T_THREADS), tsm, (cudaStream_t)stream,
+                               (const T*)dout, ldo, (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, (const T*)p,
+                               (T*)dq, lddq, (T*)dk, lddk, (T*)dv, lddv, (int)H, (int)Lq, (int)Lk, (int)d, temperature));
       });
       B200ST_LAUNCH_CHECK("mha_bwd_tiled");
       return 0;
@@ -766,8 +776,8 @@ int b200st_las_attn_fwd(int dtype, const void* q, const void* wk, const void* va
     const size_t vs = (D + ((Tk + 3) & ~3) + 4 * Dv) * sizeof(float);
     if (D % 8 == 0 && Dv % 8 == 0 && vs <= 48 * 1024) {
       B200ST_DISPATCH(dtype, T, {
-        las_attn_fwd_vec_kernel<T><<<(unsigned)B, 256, vs, (cudaStream_t)stream>>>(
-            (const T*)q, (const T*)wk, (const T*)vals, klens, (T*)ctx, probs, (int)Tk, (int)D, (int)Dv);
+        B200ST_CUDA(launch_pdl(las_attn_fwd_vec_kernel<T>, dim3((unsigned)B), dim3(256), vs, (cudaStream_t)stream,
+                               (const T*)q, (const T*)wk, (const T*)vals, klens, (T*)ctx, probs, (int)Tk, (int)D, (int)Dv));
       });
       B200ST_LAUNCH_CHECK("las_attn_fwd_vec");
       return 0;
@@ -791,8 +801,8 @@ int b200st_las_attn_bwd(int dtype, const void* dctx, const void* wk, const void*
     const size_t vs = (Dv + ((Tk + 3) & ~3) + 4 * D) * sizeof(float);
     if (D % 8 == 0 && Dv % 8 == 0 && vs <= 48 * 1024) {
       B200ST_DISPATCH(dtype, T, {
-        las_attn_bwd_vec_kernel<T><<<(unsigned)B, 256, vs, (cudaStream_t)stream>>>(
-            (const T*)dctx, (const T*)wk, (const T*)vals, probs, dscore, (T*)dq, (int)Tk, (int)D, (int)Dv);
+        B200ST_CUDA(launch_pdl(las_attn_bwd_vec_kernel<T>, dim3((unsigned)B), dim3(256), vs, (cudaStream_t)stream,
+                               (const T*)dctx, (const T*)wk, (const T*)vals, probs, dscore, (T*)dq, (int)Tk, (int)D, (int)Dv));
       });
       B200ST_LAUNCH_CHECK("las_attn_bwd_vec");
       return 0;
@@ -825,8 +835,8 @@ int b200st_argmax_rows_lengths(int dtype, const void* x, int64_t ld, int64_t row
   const bool vec = cols % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x & 15) == 0;
   if (vec) {
     B200ST_DISPATCH(dtype, T, {
-      argmax_rows_vec_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const T*)x, ld, (int)cols, idx,
-                                                                                  idx_stride, lengths, step);
+      B200ST_CUDA(launch_pdl(argmax_rows_vec_kernel<T>, dim3((unsigned)rows), dim3(256), 0, (cudaStream_t)stream,
+                             (const T*)x, ld, (int)cols, idx, idx_stride, lengths, step));
     });
     B200ST_LAUNCH_CHECK("argmax_rows_vec");
     return 0;

@@ -31,6 +31,31 @@ void count_launch(int n = 1);
     else return b200st::set_error("unsupported dtype %d", (int)(dtype));                 \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------
+// Hot-loop kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the grid may be scheduled
+// while its predecessor in the stream is still draining, so launch latency and per-CTA prologue (barrier init, TMEM
+// allocation, descriptor prefetch) overlap the predecessor's tail.  `pdl_wait()` (griddepcontrol.wait) blocks until
+// every prerequisite grid has completed and its memory is visible; it is placed before the first access to any
+// buffer another kernel may have written or may still be reading, so the data semantics stay strictly serial.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);

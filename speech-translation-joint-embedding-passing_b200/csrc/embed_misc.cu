@@ -9,6 +9,8 @@ template <typename T>
 __global__ void embedding_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table,
                                      T* __restrict__ out, int64_t ld_out, int64_t n, int dim,
                                      int64_t vocab) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t i = blockIdx.x;
   int64_t id = ids[i];
   if (id < 0 || id >= vocab) id = 0;   // out-of-range ids read the PAD row instead of faulting
@@ -47,6 +49,8 @@ __global__ void mix_gather_concat_kernel(const int64_t* __restrict__ ids,
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
                            int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     out[i] = from_f<T>(to_f(a[i]) + to_f(b[i]));
@@ -81,6 +85,8 @@ __global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, int
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, float* __restrict__ out,
                               int64_t rows, int64_t cols, int64_t rows_per_block) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float part[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + lane;
@@ -103,6 +109,8 @@ __global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, float* __rest
 template <typename T>
 __global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx,
                                 int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     dx[i] = to_f(y[i]) > 0.f ? dy[i] : from_f<T>(0.f);
@@ -143,8 +151,8 @@ int b200st_embedding_fwd(int dtype, const int64_t* ids, const float* table, void
                          int64_t n, int64_t dim, int64_t vocab, b200st_stream_t stream) {
   if (n <= 0) return 0;
   B200ST_DISPATCH(dtype, T, {
-    embedding_fwd_kernel<T><<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(ids, table, (T*)out, ld_out,
-                                                                           n, (int)dim, vocab);
+    B200ST_CUDA(launch_pdl(embedding_fwd_kernel<T>, dim3((unsigned)n), dim3(128), 0, (cudaStream_t)stream, ids, table,
+                           (T*)out, ld_out, n, (int)dim, vocab));
   });
   B200ST_LAUNCH_CHECK("embedding_fwd");
   return 0;
@@ -177,8 +185,8 @@ int b200st_mix_gather_concat(int dtype, const int64_t* ids, const float* table, 
 int b200st_add(int dtype, const void* a, const void* b, void* out, int64_t n, b200st_stream_t stream) {
   if (n <= 0) return 0;
   B200ST_DISPATCH(dtype, T, {
-    add_kernel<T><<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b,
-                                                                       (T*)out, n);
+    B200ST_CUDA(launch_pdl(add_kernel<T>, dim3(flat_grid(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const T*)a,
+                           (const T*)b, (T*)out, n));
   });
   B200ST_LAUNCH_CHECK("add");
   return 0;
@@ -248,7 +256,7 @@ int b200st_colsum(int dtype, const void* x, int64_t ld, float* out, int64_t rows
   const int64_t rpb = ceil_div(rows, row_blocks);
   dim3 grid((unsigned)col_tiles, (unsigned)ceil_div(rows, rpb));
   B200ST_DISPATCH(dtype, T, {
-    colsum_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ld, out, rows, cols, rpb);
+    B200ST_CUDA(launch_pdl(colsum_kernel<T>, grid, dim3(256), 0, st, (const T*)x, ld, out, rows, cols, rpb));
   });
   B200ST_LAUNCH_CHECK("colsum");
   return 0;
@@ -258,8 +266,8 @@ int b200st_relu_bwd(int dtype, const void* dy, const void* y, void* dx, int64_t 
                     b200st_stream_t stream) {
   if (n <= 0) return 0;
   B200ST_DISPATCH(dtype, T, {
-    relu_bwd_kernel<T><<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)y,
-                                                                            (T*)dx, n);
+    B200ST_CUDA(launch_pdl(relu_bwd_kernel<T>, dim3(flat_grid(n, 256)), dim3(256), 0, (cudaStream_t)stream,
+                           (const T*)dy, (const T*)y, (T*)dx, n));
   });
   B200ST_LAUNCH_CHECK("relu_bwd");
   return 0;

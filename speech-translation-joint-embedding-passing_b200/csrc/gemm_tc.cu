@@ -142,6 +142,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation) overlapped the previous kernel's tail; operands, residual
+  // and the output buffer may only be touched from here on.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -333,14 +337,16 @@ static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const CUtenso
     if constexpr (sizeof(TC) == 4) {
       auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, float, true, BM>;
       B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-      kern<<<grid, TC_THREADS, S::TOTAL, st>>>(ma, mb, (float*)C, ldc, nullptr, 0, nullptr, 0, alpha, (int)M, (int)N, (int)K, kb_per_split);
+      B200ST_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), S::TOTAL, st, ma, mb, (float*)C, ldc, (const float*)nullptr,
+                             (int64_t)0, (const float*)nullptr, 0, alpha, (int)M, (int)N, (int)K, kb_per_split));
     } else {
       return set_error("gemm_tc: split-K needs an fp32 output");
     }
   } else {
     auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, TC, false, BM>;
     B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    kern<<<grid, TC_THREADS, S::TOTAL, st>>>(ma, mb, (TC*)C, ldc, (const TC*)R, ldr, bias, relu, alpha, (int)M, (int)N, (int)K, kb_per_split);
+    B200ST_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), S::TOTAL, st, ma, mb, (TC*)C, ldc, (const TC*)R, ldr, bias, relu,
+                           alpha, (int)M, (int)N, (int)K, kb_per_split));
   }
   B200ST_LAUNCH_CHECK("gemm_tc");
   return 0;
@@ -359,12 +365,14 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   //  cfg 1: 128 x  64, 4 stages, 2 CTAs/SM — mid-size problems that would not fill the 148 SMs with 128-wide tiles
   //  cfg 2: 128 x  32, 10 stages — single-M-tile (decoder step, M <= 128) with K-major B: narrow N, deep pipeline
   //  cfg 3: 128 x  64, 8 stages  — single-M-tile with N-major B (128B-swizzled MN-major boxes are 64 wide)
+  // single-M-tile problems with a very wide N (the per-step vocabulary projection): keep the grid within one wave
+  const bool wide = m_tiles == 1 && M <= 64 && !b_mn && ceil_div(N, 64) > 148;
   int cfg;
   if (m_tiles == 1 && N > 32) cfg = b_mn ? 3 : 2;
   else if (N <= 64 || m_tiles * ceil_div(N, 128) < 148) cfg = 1;
   else cfg = 0;
   if (N <= 32 && !b_mn) cfg = 2;
-  const int BN = cfg == 0 ? 128 : (cfg == 2 ? 32 : 64);
+  const int BN = (cfg == 0 || wide) ? 128 : (cfg == 2 ? 32 : 64);
   const bool m64 = (cfg == 2 || cfg == 3) && M <= 64;       // half-height A tile for the decoder-step GEMMs
   CUtensorMap ma, mb;
   if (a_mn) { if (make_map(&ma, A, K, M, lda, TC_BK)) return -1; }
@@ -400,6 +408,7 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
     if (cfg == 1) TC_GO(64, 4, AMN, BMN);                                  \
     if (cfg == 3) TC_GO(64, 8, AMN, BMN);                                  \
   } while (0)
+  if (wide) { if (!a_mn) TC_GO64(128, 6, false, false); TC_GO64(128, 6, true, false); }
   if (m64) {                    // M <= 64: half-height tiles, deeper pipelines (12 KB / 16 KB per stage)
     if (cfg == 2) { if (!a_mn) TC_GO64(32, 12, false, false); TC_GO64(32, 12, true, false); }
     if (!a_mn && b_mn) TC_GO64(64, 10, false, true);

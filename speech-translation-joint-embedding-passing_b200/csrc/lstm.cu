@@ -29,6 +29,8 @@ __global__ void lstm_cell_fwd_kernel(const T* __restrict__ gates, const T* __res
                                      T* __restrict__ h, float* __restrict__ c, float* __restrict__ acts,
                                      const T* __restrict__ residual, T* __restrict__ out_res, int64_t B,
                                      int H) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   const int64_t b = idx / H;
@@ -65,6 +67,8 @@ __global__ void lstm_cell_bwd_kernel(const T* __restrict__ dh_a, const T* __rest
                                      const float* __restrict__ acts, const float* __restrict__ c_prev,
                                      const float* __restrict__ c, T* __restrict__ dgates,
                                      float* __restrict__ dc_prev, int64_t B, int H) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   const int64_t b = idx / H;
@@ -342,9 +346,9 @@ int b200st_lstm_cell_fwd(int dtype, const void* gates, const void* gates_b, cons
                          void* out_res, int64_t B, int64_t H, b200st_stream_t stream) {
   if (B * H <= 0) return 0;
   B200ST_DISPATCH(dtype, T, {
-    lstm_cell_fwd_kernel<T><<<(unsigned)ceil_div(B * H, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)gates, (const T*)gates_b, (const T*)gates_c, c_prev, (T*)h, c, acts, (const T*)residual,
-        (T*)out_res, B, (int)H);
+    B200ST_CUDA(launch_pdl(lstm_cell_fwd_kernel<T>, dim3((unsigned)ceil_div(B * H, 256)), dim3(256), 0, (cudaStream_t)stream,
+                           (const T*)gates, (const T*)gates_b, (const T*)gates_c, c_prev, (T*)h, c, acts,
+                           (const T*)residual, (T*)out_res, B, (int)H));
   });
   B200ST_LAUNCH_CHECK("lstm_cell_fwd");
   return 0;
@@ -355,9 +359,9 @@ int b200st_lstm_cell_bwd(int dtype, const void* dh_a, const void* dh_b, const vo
                          void* dgates, float* dc_prev, int64_t B, int64_t H, b200st_stream_t stream) {
   if (B * H <= 0) return 0;
   B200ST_DISPATCH(dtype, T, {
-    lstm_cell_bwd_kernel<T><<<(unsigned)ceil_div(B * H, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)dh_a, (const T*)dh_b, (const T*)dh_c, dc_next, acts, c_prev, c, (T*)dgates, dc_prev,
-        B, (int)H);
+    B200ST_CUDA(launch_pdl(lstm_cell_bwd_kernel<T>, dim3((unsigned)ceil_div(B * H, 256)), dim3(256), 0, (cudaStream_t)stream,
+                           (const T*)dh_a, (const T*)dh_b, (const T*)dh_c, dc_next, acts, c_prev, c, (T*)dgates,
+                           dc_prev, B, (int)H));
   });
   B200ST_LAUNCH_CHECK("lstm_cell_bwd");
   return 0;

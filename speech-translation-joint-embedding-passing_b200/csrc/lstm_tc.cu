@@ -578,9 +578,8 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint32_t b = 4 * warp + q;
-        const __nv_bfloat16 v = __float2bfloat16_rn(dg[gte][q]);
-        *reinterpret_cast<__nv_bfloat16*>(Bsm + (kl >> 6) * 2048 + rt_swz(b, kl & 63) + (kl & 7) * 2) = v;
-        if (b0 + b < B) dgates[(((size_t)dir * Tn + t) * B + b0 + b) * G4 + gte * RT_H + u] = v;
+        *reinterpret_cast<__nv_bfloat16*>(Bsm + (kl >> 6) * 2048 + rt_swz(b, kl & 63) + (kl & 7) * 2) =
+            __float2bfloat16_rn(dg[gte][q]);
       }
     }
     RT_TL(2);
@@ -588,6 +587,15 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
     rt_tc_before();
     __syncthreads();
     RT_TL(3);
+    // the global copy of the gate gradients (for the weight-gradient GEMMs) is written while the MMAs run
+#pragma unroll
+    for (int gte = 0; gte < 4; ++gte)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t b = 4 * warp + q;
+        if (b0 + b < B)
+          dgates[(((size_t)dir * Tn + t) * B + b0 + b) * G4 + gte * RT_H + u] = __float2bfloat16_rn(dg[gte][q]);
+      }
     // next step's saved state: issued here so that no fence between now and its use has to wait for it
     RT_TL(4);
     if (s + 1 < Tn) prefetch(dir ? s + 1 : Tn - 2 - s);

@@ -13,6 +13,8 @@ __global__ void layernorm_fwd_kernel(const T* __restrict__ x, const float* __res
                                      const float* __restrict__ beta, T* __restrict__ y,
                                      float* __restrict__ mean, float* __restrict__ rstd, int64_t rows,
                                      int cols, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -40,6 +42,8 @@ __global__ void layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restri
                                      const float* __restrict__ rstd, T* __restrict__ dx,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                      int64_t rows, int cols, int rows_per_block) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float sm[];   // [2][cols]
   float* sg = sm;
   float* sb = sm + cols;
@@ -245,8 +249,8 @@ int b200st_layernorm_fwd(int dtype, const void* x, const float* gamma, const flo
   if (rows <= 0) return 0;
   const int wpb = 4;
   B200ST_DISPATCH(dtype, T, {
-    layernorm_fwd_kernel<T><<<(unsigned)ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-        (const T*)x, gamma, beta, (T*)y, mean, rstd, rows, (int)cols, eps);
+    B200ST_CUDA(launch_pdl(layernorm_fwd_kernel<T>, dim3((unsigned)ceil_div(rows, wpb)), dim3(wpb * 32), 0,
+                           (cudaStream_t)stream, (const T*)x, gamma, beta, (T*)y, mean, rstd, rows, (int)cols, eps));
   });
   B200ST_LAUNCH_CHECK("layernorm_fwd");
   return 0;
@@ -262,8 +266,9 @@ int b200st_layernorm_bwd(int dtype, const void* dy, const void* x, const float* 
   int rpb = (int)ceil_div(rows, 296);
   if (rpb < 4) rpb = 4;
   B200ST_DISPATCH(dtype, T, {
-    layernorm_bwd_kernel<T><<<(unsigned)ceil_div(rows, rpb), 128, smem, (cudaStream_t)stream>>>(
-        (const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta, rows, (int)cols, rpb);
+    B200ST_CUDA(launch_pdl(layernorm_bwd_kernel<T>, dim3((unsigned)ceil_div(rows, rpb)), dim3(128), smem,
+                           (cudaStream_t)stream, (const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta,
+                           rows, (int)cols, rpb));
   });
   B200ST_LAUNCH_CHECK("layernorm_bwd");
   return 0;
