@@ -46,6 +46,25 @@ __device__ __forceinline__ void rt_st_async_v4(uint32_t addr, uint32_t a, uint32
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(bar) : "memory");
 }
+// explicit shared-space accesses: pointers derived from the aligned dynamic-smem base lose their address space and
+// would compile to generic LD/ST
+__device__ __forceinline__ void rt_sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void rt_sts_b16(uint32_t a, unsigned short v) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
+__device__ __forceinline__ uint2 rt_lds_v2u(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 rt_lds_v4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+// volatile (position-pinned) read-only global loads / register moves for the two-step-ahead prefetch pipeline
+__device__ __forceinline__ float rt_ldg_f32(const float* p) { float v; asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; }
+__device__ __forceinline__ unsigned short rt_ldg_u16(const unsigned short* p) { unsigned short v; asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p)); return v; }
+__device__ __forceinline__ float rt_mov_f32(float x) { float v; asm volatile("mov.f32 %0, %1;" : "=f"(v) : "f"(x)); return v; }
+__device__ __forceinline__ unsigned short rt_mov_u16(unsigned short x) { unsigned short v; asm volatile("mov.b16 %0, %1;" : "=h"(v) : "h"(x)); return v; }
 __device__ __forceinline__ void rt_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rt_smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -326,6 +345,7 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
   float c_st[4] = {0.f, 0.f, 0.f, 0.f}, h_st[4] = {0.f, 0.f, 0.f, 0.f};
   const uint32_t hbuf_u32 = rt_smem_u32(hbuf);
   const uint32_t hfull_u32 = rt_smem_u32(hfull);
+  const uint32_t act_u32 = rt_smem_u32(actbuf);
   // destination chunk (16 B = 8 units) of this thread pair inside one h buffer
   const uint32_t k0 = rank * RT_UPC + 4 * (ug & ~1);
   const uint32_t h_chunk_off = (k0 >> 6) * 2048 + rt_swz(cb, k0 & 63);
@@ -333,10 +353,16 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
   // x-projection prefetch: 16 independent loads issued back to back one step ahead, kept as raw bf16 bits and
   // converted only when consumed, so their DRAM latency never sits on the recurrent critical path.
   unsigned short xr[16];
+  const bool full_grp = b0 + RT_NB <= B;
   auto load_x = [&](int t) {
     const unsigned short* xp = reinterpret_cast<const unsigned short*>(xproj) + (((size_t)dir * Tn + t) * B) * (4 * RT_H) + grow_g;
+    if (full_grp) {                 // one base address, compile-time row offsets
 #pragma unroll
-    for (int b = 0; b < RT_NB; ++b) xr[b] = __ldg(xp + (size_t)min(b0 + b, B - 1) * (4 * RT_H));
+      for (int b = 0; b < RT_NB; ++b) xr[b] = __ldg(xp + (size_t)(b0 + b) * (4 * RT_H));
+    } else {
+#pragma unroll
+      for (int b = 0; b < RT_NB; ++b) xr[b] = __ldg(xp + (size_t)min(b0 + b, B - 1) * (4 * RT_H));
+    }
   };
   if (Tn > 0) load_x(dir ? Tn - 1 : 0);
 
@@ -355,19 +381,22 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
     RT_TL(4);
     // gate non-linearity: warp 2 holds the candidate gate (tanh), the others sigmoid (PyTorch order i,f,g,o)
 #pragma unroll
-    for (int b = 0; b < RT_NB; ++b) {
-      const float v = g[b] + __uint_as_float((uint32_t)xr[b] << 16);
-      actbuf[(warp * RT_NB + b) * RT_UPC + lane] = (warp == 2) ? rt_tanh(v) : rt_sigmoid(v);
-    }
+    for (int b = 0; b < RT_NB; ++b) g[b] += __uint_as_float((uint32_t)xr[b] << 16);
+    // next step's x-projection (raw bits): issued as soon as xr is consumed, a full step ahead of its use, so that no
+    // scoreboard wait at the top of the next iteration can sit behind its DRAM latency
+    if (s + 1 < Tn) load_x(dir ? (Tn - 2 - s) : (s + 1));
+#pragma unroll
+    for (int b = 0; b < RT_NB; ++b)
+      rt_sts_f32(act_u32 + (uint32_t)(((warp * RT_NB + b) * RT_UPC + lane) * 4), (warp == 2) ? rt_tanh(g[b]) : rt_sigmoid(g[b]));
     RT_TL(5);
     asm volatile("bar.sync 1, 128;" ::: "memory");
     RT_TL(6);
     // ---- cell update for (sequence cb, units ubase..ubase+3)
     const bool valid = t < len_b;
-    const float4 gi = *reinterpret_cast<const float4*>(&actbuf[(0 * RT_NB + cb) * RT_UPC + 4 * ug]);
-    const float4 gf = *reinterpret_cast<const float4*>(&actbuf[(1 * RT_NB + cb) * RT_UPC + 4 * ug]);
-    const float4 gg = *reinterpret_cast<const float4*>(&actbuf[(2 * RT_NB + cb) * RT_UPC + 4 * ug]);
-    const float4 go = *reinterpret_cast<const float4*>(&actbuf[(3 * RT_NB + cb) * RT_UPC + 4 * ug]);
+    const float4 gi = rt_lds_v4(act_u32 + (uint32_t)(((0 * RT_NB + cb) * RT_UPC + 4 * ug) * 4));
+    const float4 gf = rt_lds_v4(act_u32 + (uint32_t)(((1 * RT_NB + cb) * RT_UPC + 4 * ug) * 4));
+    const float4 gg = rt_lds_v4(act_u32 + (uint32_t)(((2 * RT_NB + cb) * RT_UPC + 4 * ug) * 4));
+    const float4 go = rt_lds_v4(act_u32 + (uint32_t)(((3 * RT_NB + cb) * RT_UPC + 4 * ug) * 4));
     const float ai[4] = {gi.x, gi.y, gi.z, gi.w}, af[4] = {gf.x, gf.y, gf.z, gf.w};
     const float ag[4] = {gg.x, gg.y, gg.z, gg.w}, ao[4] = {go.x, go.y, go.z, go.w};
     float ho[4];
@@ -389,7 +418,6 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
       for (uint32_t r = 0; r < RT_C; ++r) rt_st_async_v4(rt_mapa(dst, r), p0, p1, q0, q1, rt_mapa(bar, r));
     }
     RT_TL(7);
-    if (s + 1 < Tn) load_x(dir ? (Tn - 2 - s) : (s + 1));     // prefetch next step's x-projection (raw bits)
     // ---- global stores: nothing on the recurrent critical path waits for them
     if (b_ok) {
       const size_t row = ((size_t)dir * Tn + t) * B + bglob;
@@ -419,7 +447,7 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
   }
 }
 
-// shared memory map (backward): B = own dG [2 kb][16][128 B] 4 KB | red float [2][8 src][32 units][16 seqs] 32 KB |
+// shared memory map (backward): B = own dG [2 kb][16][128 B] 4 KB | red bf16 [2][8 src][2 quad pairs][32 units][8] 16 KB (region sized 32 KB) |
 // barriers + tmem slot.  (W_hh^T lives in TMEM.)  Padded like the forward kernel: one CTA per SM.
 constexpr int BWD_B_OFF = 0, BWD_RED_OFF = BWD_B_OFF + 4096, BWD_BAR_OFF = BWD_RED_OFF + 32768;
 constexpr int BWD_SMEM = 120 * 1024;
@@ -448,7 +476,7 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
     rt_mbar_init(&rfull[0], 1);
     rt_mbar_init(&rfull[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    rt_mbar_expect_tx(&rfull[1], 16384);       // step 0 sends its partials into buffer 1
+    rt_mbar_expect_tx(&rfull[1], 8192);        // step 0 sends its partials into buffer 1
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rt_smem_u32(tmem_slot)), "r"(RT_TMEM_COLS) : "memory");
@@ -494,7 +522,7 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
     int cur = 0;
     for (int s = 0; s < Tn; ++s) {
       __syncthreads();                         // the epilogue warps have written this step's gate gradients (B operand)
-      if (s + 2 < Tn) rt_expect_tx_if(leader, &rfull[cur], 16384);   // red[cur] fully read: arm it for step s+1's partials
+      if (s + 2 < Tn) rt_expect_tx_if(leader, &rfull[cur], 8192);   // red[cur] fully read: arm it for step s+1's partials
       rt_fence_async();
       rt_tc_after();
       if (tmem_base == 0) rt_issue_bwd<0>(leader, 0, bb);
@@ -513,27 +541,57 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
   float dcrec[4] = {0.f, 0.f, 0.f, 0.f};
   const uint32_t red_u32 = rt_smem_u32(red);
   const uint32_t rfull_u32 = rt_smem_u32(rfull);
+  const uint32_t bsm_u32 = rt_smem_u32(Bsm);
   uint32_t rph[2] = {0u, 0u};
   const size_t G4 = 4 * RT_H;
 
-  // software-pipelined loads of the saved forward state: unconditional (clamped indices), issued one step ahead
-  float pa[4][4], pct[4], pcp[4];
-  unsigned short pdy[4];
+  // software-pipelined loads of the saved forward state: unconditional (clamped indices), issued TWO steps ahead into
+  // the staging set (qa..), moved into the consume set (pa..) one step later while the MMAs run -- no scoreboard wait
+  // for DRAM latency ever lands on the recurrent critical path.
+  float pa[4][4], pct[4], pcp[4], qa[4][4], qct[4], qcp[4];
+  unsigned short pdy[4], qdy[4];
+  const bool full_grp = b0 + RT_NB <= B;
   auto prefetch = [&](int t) {
     const int tp = min(max(dir ? t + 1 : t - 1, 0), Tn - 1);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int b = min(b0 + 4 * warp + q, B - 1);
-      const size_t row = ((size_t)dir * Tn + t) * B + b;
+    const unsigned short* dyp = reinterpret_cast<const unsigned short*>(dout) + (size_t)(t / pair) * out_ld_t +
+                                (size_t)(t % pair) * 2 * RT_H + dir * RT_H + u;
+    if (full_grp) {                 // one base address per tensor, compile-time offsets
+      const size_t row = ((size_t)dir * Tn + t) * B + b0 + 4 * warp;
       const float* a = acts + row * G4 + u;
-      pa[0][q] = __ldg(a); pa[1][q] = __ldg(a + RT_H); pa[2][q] = __ldg(a + 2 * RT_H); pa[3][q] = __ldg(a + 3 * RT_H);
-      pct[q] = __ldg(cs + row * RT_H + u);
-      pcp[q] = __ldg(cs + (((size_t)dir * Tn + tp) * B + b) * RT_H + u);
-      pdy[q] = __ldg(reinterpret_cast<const unsigned short*>(dout) + (size_t)(t / pair) * out_ld_t + (size_t)b * out_ld_b +
-                     (size_t)(t % pair) * 2 * RT_H + dir * RT_H + u);
+      const float* c = cs + row * RT_H + u;
+      const float* cpv = cs + (((size_t)dir * Tn + tp) * B + b0 + 4 * warp) * RT_H + u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        qa[0][q] = rt_ldg_f32(a + q * G4); qa[1][q] = rt_ldg_f32(a + q * G4 + RT_H);
+        qa[2][q] = rt_ldg_f32(a + q * G4 + 2 * RT_H); qa[3][q] = rt_ldg_f32(a + q * G4 + 3 * RT_H);
+        qct[q] = rt_ldg_f32(c + q * RT_H);
+        qcp[q] = rt_ldg_f32(cpv + q * RT_H);
+        qdy[q] = rt_ldg_u16(dyp + (size_t)(b0 + 4 * warp + q) * out_ld_b);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int b = min(b0 + 4 * warp + q, B - 1);
+        const size_t row = ((size_t)dir * Tn + t) * B + b;
+        const float* a = acts + row * G4 + u;
+        qa[0][q] = rt_ldg_f32(a); qa[1][q] = rt_ldg_f32(a + RT_H); qa[2][q] = rt_ldg_f32(a + 2 * RT_H); qa[3][q] = rt_ldg_f32(a + 3 * RT_H);
+        qct[q] = rt_ldg_f32(cs + row * RT_H + u);
+        qcp[q] = rt_ldg_f32(cs + (((size_t)dir * Tn + tp) * B + b) * RT_H + u);
+        qdy[q] = rt_ldg_u16(dyp + (size_t)b * out_ld_b);
+      }
     }
   };
-  if (Tn > 0) prefetch(dir ? 0 : Tn - 1);
+  auto advance = [&]() {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      pa[0][q] = rt_mov_f32(qa[0][q]); pa[1][q] = rt_mov_f32(qa[1][q]); pa[2][q] = rt_mov_f32(qa[2][q]);
+      pa[3][q] = rt_mov_f32(qa[3][q]);
+      pct[q] = rt_mov_f32(qct[q]); pcp[q] = rt_mov_f32(qcp[q]); pdy[q] = rt_mov_u16(qdy[q]);
+    }
+  };
+  auto t_of = [&](int s) { return dir ? s : (Tn - 1 - s); };
+  if (Tn > 0) { prefetch(t_of(0)); advance(); }
+  if (Tn > 1) prefetch(t_of(1));
 
   const bool tl_on = tl != nullptr && tid == 0 && rank == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   int cur = 0;
@@ -557,11 +615,16 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
     }
     RT_TL(1);
     float dg[4][4];
+    float dhs[4] = {dy[0], dy[1], dy[2], dy[3]};
+#pragma unroll
+    for (int i = 0; i < RT_C; ++i) {           // red[buf][src][seq-quad pair][unit][2 quads x 4 bf16]: one 8 B read per source
+      const uint2 r2 = rt_lds_v2u(red_u32 + (uint32_t)((((cur * RT_C + i) * 2 + (warp >> 1)) * RT_UPC + ul) * 16 + (warp & 1) * 8));
+      dhs[0] += __uint_as_float(r2.x << 16); dhs[1] += __uint_as_float(r2.x & 0xffff0000u);
+      dhs[2] += __uint_as_float(r2.y << 16); dhs[3] += __uint_as_float(r2.y & 0xffff0000u);
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      float dh = dy[q];
-#pragma unroll
-      for (int i = 0; i < RT_C; ++i) dh += red[((cur * RT_C + i) * RT_UPC + ul) * RT_NB + 4 * warp + q];
+      const float dh = dhs[q];
       const bool valid = t < len_b[q];
       const float tc = rt_tanh(ct[q]);
       const float dc = dcrec[q] + dh * ao[q] * (1.f - tc * tc);
@@ -578,8 +641,8 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint32_t b = 4 * warp + q;
-        *reinterpret_cast<__nv_bfloat16*>(Bsm + (kl >> 6) * 2048 + rt_swz(b, kl & 63) + (kl & 7) * 2) =
-            __float2bfloat16_rn(dg[gte][q]);
+        rt_sts_b16(bsm_u32 + (kl >> 6) * 2048 + rt_swz(b, kl & 63) + (kl & 7) * 2,
+                   __bfloat16_as_ushort(__float2bfloat16_rn(dg[gte][q])));
       }
     }
     RT_TL(2);
@@ -598,7 +661,8 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
       }
     // next step's saved state: issued here so that no fence between now and its use has to wait for it
     RT_TL(4);
-    if (s + 1 < Tn) prefetch(dir ? s + 1 : Tn - 2 - s);
+    advance();                                  // step s+1's state (loaded a full step ago) -> consume set
+    if (s + 2 < Tn) prefetch(t_of(s + 2));
     RT_TL(5);
     rt_mbar_wait(mma_bar, phase);
     phase ^= 1;
@@ -612,12 +676,13 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
         float p[16];
         rt_tmem_ld_sum<2>(tmem_base + ((uint32_t)(warp * 32) << 16) + mt * 2 * RT_NB, p);
         const uint32_t owner = mt * 4 + warp;               // unit mt*128 + warp*32 + lane lives on CTA `owner`
-        const uint32_t dst = rt_mapa(red_u32 + (uint32_t)((((nxt * RT_C + rank) * RT_UPC + lane) * RT_NB) * 4), owner);
+        const uint32_t dst = rt_mapa(red_u32 + (uint32_t)((((nxt * RT_C + rank) * 2) * RT_UPC + lane) * 16), owner);
         const uint32_t bar = rt_mapa(rfull_u32 + nxt * 8, owner);
+        // partial sums travel as bf16 (the SM-to-SM network moves ~24 B/clk per CTA: 8 KB instead of 16 KB per step)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          rt_st_async_v4(dst + j * 16, __float_as_uint(p[4 * j]), __float_as_uint(p[4 * j + 1]),
-                         __float_as_uint(p[4 * j + 2]), __float_as_uint(p[4 * j + 3]), bar);
+        for (int j = 0; j < 2; ++j)
+          rt_st_async_v4(dst + j * (RT_UPC * 16), rt_pack(p[8 * j], p[8 * j + 1]), rt_pack(p[8 * j + 2], p[8 * j + 3]),
+                         rt_pack(p[8 * j + 4], p[8 * j + 5]), rt_pack(p[8 * j + 6], p[8 * j + 7]), bar);
       }
     }
     rt_tc_before();
