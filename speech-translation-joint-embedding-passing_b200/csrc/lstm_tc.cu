@@ -352,19 +352,25 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
 
   // x-projection prefetch: 16 independent loads issued back to back one step ahead, kept as raw bf16 bits and
   // converted only when consumed, so their DRAM latency never sits on the recurrent critical path.
-  unsigned short xr[16];
+  unsigned short xr[16], xq[16];     // consume set / staging set (loaded two steps ahead)
   const bool full_grp = b0 + RT_NB <= B;
   auto load_x = [&](int t) {
     const unsigned short* xp = reinterpret_cast<const unsigned short*>(xproj) + (((size_t)dir * Tn + t) * B) * (4 * RT_H) + grow_g;
     if (full_grp) {                 // one base address, compile-time row offsets
 #pragma unroll
-      for (int b = 0; b < RT_NB; ++b) xr[b] = __ldg(xp + (size_t)(b0 + b) * (4 * RT_H));
+      for (int b = 0; b < RT_NB; ++b) xq[b] = rt_ldg_u16(xp + (size_t)(b0 + b) * (4 * RT_H));
     } else {
 #pragma unroll
-      for (int b = 0; b < RT_NB; ++b) xr[b] = __ldg(xp + (size_t)min(b0 + b, B - 1) * (4 * RT_H));
+      for (int b = 0; b < RT_NB; ++b) xq[b] = rt_ldg_u16(xp + (size_t)min(b0 + b, B - 1) * (4 * RT_H));
     }
   };
-  if (Tn > 0) load_x(dir ? Tn - 1 : 0);
+  auto advance_x = [&]() {
+#pragma unroll
+    for (int b = 0; b < RT_NB; ++b) xr[b] = rt_mov_u16(xq[b]);
+  };
+  auto t_of = [&](int s) { return dir ? (Tn - 1 - s) : s; };
+  if (Tn > 0) { load_x(t_of(0)); advance_x(); }
+  if (Tn > 1) load_x(t_of(1));
 
   const bool tl_on = tl != nullptr && tid == 0 && rank == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   int cur = 0;
@@ -382,9 +388,6 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
     // gate non-linearity: warp 2 holds the candidate gate (tanh), the others sigmoid (PyTorch order i,f,g,o)
 #pragma unroll
     for (int b = 0; b < RT_NB; ++b) g[b] += __uint_as_float((uint32_t)xr[b] << 16);
-    // next step's x-projection (raw bits): issued as soon as xr is consumed, a full step ahead of its use, so that no
-    // scoreboard wait at the top of the next iteration can sit behind its DRAM latency
-    if (s + 1 < Tn) load_x(dir ? (Tn - 2 - s) : (s + 1));
 #pragma unroll
     for (int b = 0; b < RT_NB; ++b)
       rt_sts_f32(act_u32 + (uint32_t)(((warp * RT_NB + b) * RT_UPC + lane) * 4), (warp == 2) ? rt_tanh(g[b]) : rt_sigmoid(g[b]));
@@ -415,9 +418,16 @@ blstm_fwd_tc_kernel(const __nv_bfloat16* __restrict__ xproj, const float* __rest
       const uint32_t dst = hbuf_u32 + (cur ^ 1) * 8192 + h_chunk_off;
       const uint32_t bar = hfull_u32 + (cur ^ 1) * 8;
 #pragma unroll
-      for (uint32_t r = 0; r < RT_C; ++r) rt_st_async_v4(rt_mapa(dst, r), p0, p1, q0, q1, rt_mapa(bar, r));
+      for (uint32_t i = 0; i < RT_C; ++i) {       // rotated destination order: no receiver is hit by all 8 senders at once
+        const uint32_t r = (i + rank) & (RT_C - 1);
+        rt_st_async_v4(rt_mapa(dst, r), p0, p1, q0, q1, rt_mapa(bar, r));
+      }
     }
     RT_TL(7);
+    // x-projection pipeline (position-pinned asm): step s+1's bits, loaded a full step ago, move to the consume set;
+    // step s+2's loads are issued.  No scoreboard wait on DRAM latency can reach the recurrent critical path.
+    advance_x();
+    if (s + 2 < Tn) load_x(t_of(s + 2));
     // ---- global stores: nothing on the recurrent critical path waits for them
     if (b_ok) {
       const size_t row = ((size_t)dir * Tn + t) * B + bglob;
