@@ -40,6 +40,10 @@ for name, fn, npts in (('fwd', lambda: k.blstm_fwd(xproj, wf, wr, lens, out, B *
         print('fwd issuer: wait_h', int((full[:,1]-full[:,0]).median()), 'fence', int((full[:,10]-full[:,1]).median()), 'mma_issue', int((full[:,11]-full[:,10]).median()), 'commit', int((full[:,2]-full[:,11]).median()), 'mma_done_wait', int((full[:,3]-full[:,2]).median()),
               '| epilogue: ld', int((full[:,4]-full[:,9]).median()), 'act', int((full[:,5]-full[:,4]).median()), 'bar', int((full[:,6]-full[:,5]).median()), 'cell+send', int((full[:,7]-full[:,6]).median()), 'stores', int((full[:,8]-full[:,7]).median()),
               '| mma_done->epilogue_start', int((full[:,9]-full[:,3]).median()), 'send->next_h_ready', int((full[1:,1]-full[:-1,7]).median()))
+    print(name, 'per-step periods', [int(x) for x in step.tolist()])
+    print(name, 'raw rows (relative to first point of step 64):')
+    for r in full.tolist():
+        print('   ', [int(x - full[0, 0].item()) if x else 0 for x in r[:12]])
     print(name, 'cycles between points (median over steps 64..71):', [int(x) for x in d.median(0).values.tolist()],
           'step period', int(step.median()))
 k.lib.b200st_debug_timeline(None)

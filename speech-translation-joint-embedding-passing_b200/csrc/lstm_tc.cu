@@ -55,6 +55,11 @@ __device__ __forceinline__ uint2 rt_lds_v2u(uint32_t a) {
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
   return v;
 }
+__device__ __forceinline__ uint4 rt_lds_v4u(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ float4 rt_lds_v4(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
@@ -558,23 +563,23 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
   // software-pipelined loads of the saved forward state: unconditional (clamped indices), issued TWO steps ahead into
   // the staging set (qa..), moved into the consume set (pa..) one step later while the MMAs run -- no scoreboard wait
   // for DRAM latency ever lands on the recurrent critical path.
-  float pa[4][4], pct[4], pcp[4], qa[4][4], qct[4], qcp[4];
+  float pa[4][4], pct[4], pcp[4], qa[4][4], qcp[4];
   unsigned short pdy[4], qdy[4];
   const bool full_grp = b0 + RT_NB <= B;
   auto prefetch = [&](int t) {
     const int tp = min(max(dir ? t + 1 : t - 1, 0), Tn - 1);
-    const unsigned short* dyp = reinterpret_cast<const unsigned short*>(dout) + (size_t)(t / pair) * out_ld_t +
-                                (size_t)(t % pair) * 2 * RT_H + dir * RT_H + u;
+    // pair is 1 (plain layer) or 2 (pyramid frame-pair concat) in practice: no integer division on the hot path
+    const int tq = pair == 1 ? t : (pair == 2 ? (t >> 1) : t / pair), tr = pair == 1 ? 0 : (pair == 2 ? (t & 1) : t % pair);
+    const unsigned short* dyp = reinterpret_cast<const unsigned short*>(dout) + (size_t)tq * out_ld_t +
+                                (size_t)tr * 2 * RT_H + dir * RT_H + u;
     if (full_grp) {                 // one base address per tensor, compile-time offsets
       const size_t row = ((size_t)dir * Tn + t) * B + b0 + 4 * warp;
       const float* a = acts + row * G4 + u;
-      const float* c = cs + row * RT_H + u;
       const float* cpv = cs + (((size_t)dir * Tn + tp) * B + b0 + 4 * warp) * RT_H + u;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         qa[0][q] = rt_ldg_f32(a + q * G4); qa[1][q] = rt_ldg_f32(a + q * G4 + RT_H);
         qa[2][q] = rt_ldg_f32(a + q * G4 + 2 * RT_H); qa[3][q] = rt_ldg_f32(a + q * G4 + 3 * RT_H);
-        qct[q] = rt_ldg_f32(c + q * RT_H);
         qcp[q] = rt_ldg_f32(cpv + q * RT_H);
         qdy[q] = rt_ldg_u16(dyp + (size_t)(b0 + 4 * warp + q) * out_ld_b);
       }
@@ -585,7 +590,6 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
         const size_t row = ((size_t)dir * Tn + t) * B + b;
         const float* a = acts + row * G4 + u;
         qa[0][q] = rt_ldg_f32(a); qa[1][q] = rt_ldg_f32(a + RT_H); qa[2][q] = rt_ldg_f32(a + 2 * RT_H); qa[3][q] = rt_ldg_f32(a + 3 * RT_H);
-        qct[q] = rt_ldg_f32(cs + row * RT_H + u);
         qcp[q] = rt_ldg_f32(cs + (((size_t)dir * Tn + tp) * B + b) * RT_H + u);
         qdy[q] = rt_ldg_u16(dyp + (size_t)b * out_ld_b);
       }
@@ -596,12 +600,29 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
     for (int q = 0; q < 4; ++q) {
       pa[0][q] = rt_mov_f32(qa[0][q]); pa[1][q] = rt_mov_f32(qa[1][q]); pa[2][q] = rt_mov_f32(qa[2][q]);
       pa[3][q] = rt_mov_f32(qa[3][q]);
-      pct[q] = rt_mov_f32(qct[q]); pcp[q] = rt_mov_f32(qcp[q]); pdy[q] = rt_mov_u16(qdy[q]);
+      pcp[q] = rt_mov_f32(qcp[q]); pdy[q] = rt_mov_u16(qdy[q]);
     }
   };
   auto t_of = [&](int s) { return dir ? s : (Tn - 1 - s); };
-  if (Tn > 0) { prefetch(t_of(0)); advance(); }
+  if (Tn > 0) {
+    prefetch(t_of(0)); advance();
+    // c_t is loaded for the first step only: afterwards it is the previous step's c_{t-1} (carried in registers)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      pct[q] = __ldg(cs + (((size_t)dir * Tn + t_of(0)) * B + min(b0 + 4 * warp + q, B - 1)) * RT_H + u);
+  }
   if (Tn > 1) prefetch(t_of(1));
+
+  // staged-tile -> global copy roles: chunk c = tid + 128 i covers sequence c / 16, k = 8 (c % 16) .. +7
+  uint32_t cp_src[2], cp_dst[2];
+  bool cp_ok[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint32_t c = tid + i * RT_THREADS, seq = c >> 4, k0 = (c & 15) * 8;
+    cp_src[i] = bsm_u32 + (k0 >> 6) * 2048 + rt_swz(seq, k0 & 63);
+    cp_dst[i] = seq * (uint32_t)G4 + (k0 >> 5) * RT_H + rank * RT_UPC + (k0 & 31);
+    cp_ok[i] = b0 + (int)seq < B;
+  }
 
   const bool tl_on = tl != nullptr && tid == 0 && rank == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   int cur = 0;
@@ -617,12 +638,15 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
       ai[q] = pa[0][q]; af[q] = pa[1][q]; ag[q] = pa[2][q]; ao[q] = pa[3][q];
       ct[q] = pct[q];
       cp[q] = (tp >= 0 && tp < Tn) ? pcp[q] : 0.f;
+      pct[q] = pcp[q];                         // next step's c_t
       dy[q] = __uint_as_float((uint32_t)pdy[q] << 16);
     }
     if (s > 0) {                             // partial dh of the previous step from all 8 CTAs is in red[cur]
       rt_mbar_wait(&rfull[cur], rph[cur]);
       rph[cur] ^= 1;
     }
+    // every epilogue warp has finished copying the previous step's staged tile before anyone overwrites it
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     RT_TL(1);
     float dg[4][4];
     float dhs[4] = {dy[0], dy[1], dy[2], dy[3]};
@@ -660,15 +684,17 @@ blstm_bwd_tc_kernel(const __nv_bfloat16* __restrict__ dout, int64_t out_ld_t, in
     rt_tc_before();
     __syncthreads();
     RT_TL(3);
-    // the global copy of the gate gradients (for the weight-gradient GEMMs) is written while the MMAs run
+    // the global copy of the gate gradients (for the weight-gradient GEMMs) is written while the MMAs run: the tile
+    // just staged for the MMA ([16 seqs][128 k] bf16, swizzled) is copied out in 16-byte chunks, 2 per thread
+    // (a per-thread register store would take 16 two-byte store instructions)
+    {
+      __nv_bfloat16* drow = dgates + (((size_t)dir * Tn + t) * B + b0) * G4;
 #pragma unroll
-    for (int gte = 0; gte < 4; ++gte)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t b = 4 * warp + q;
-        if (b0 + b < B)
-          dgates[(((size_t)dir * Tn + t) * B + b0 + b) * G4 + gte * RT_H + u] = __float2bfloat16_rn(dg[gte][q]);
+      for (int i = 0; i < 2; ++i) {
+        const uint4 v = rt_lds_v4u(cp_src[i]);
+        if (cp_ok[i]) *reinterpret_cast<uint4*>(drow + cp_dst[i]) = v;
       }
+    }
     // next step's saved state: issued here so that no fence between now and its use has to wait for it
     RT_TL(4);
     advance();                                  // step s+1's state (loaded a full step ago) -> consume set
