@@ -65,6 +65,10 @@ class CudaKernels:
         """0 auto (tcgen05 recurrence for bf16/H=256), 1 CUDA cores only.  Returns the previous mode."""
         return int(self.lib.b200st_set_blstm_backend(int(mode)))
 
+    def set_mha_backend(self, mode: int) -> int:
+        """0 auto (tcgen05 attention core for bf16, d=64, L<=64), 1 CUDA-core tiles only.  Returns the previous mode."""
+        return int(self.lib.b200st_set_mha_backend(int(mode)))
+
     # -- GEMM -------------------------------------------------------------------------------------
     def gemm(self, a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=None,
              relu=False, residual=None, alpha=1.0):

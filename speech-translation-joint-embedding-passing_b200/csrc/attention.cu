@@ -347,6 +347,15 @@ mha_bwd_tiled_kernel(const T* __restrict__ dout, int64_t ldo, const T* __restric
   mha_ptv(dv + (int64_t)b * Lk * lddv + (int64_t)h * d, lddv, Ps, lkp, dOs, Lq, Lk, d);
 }
 
+// tensor-core variants (attention_tc.cu): return 1 when the shape is not covered
+int mha_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const uint8_t* mask,
+               int64_t mask_sb, int64_t mask_sq, void* o, int64_t ldo, void* p, int64_t B, int64_t H, int64_t Lq,
+               int64_t Lk, int64_t d, float temperature, cudaStream_t st);
+int mha_bwd_tc(const void* dout, int64_t ldo, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+               int64_t ldv, const void* p, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+               int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d, float temperature, cudaStream_t st);
+static int g_mha_backend = 0;     // 0 = auto (tensor cores for bf16 when the shape fits), 1 = SIMT tiles only
+
 static size_t mha_fwd_tiled_smem(int64_t Lq, int64_t Lk, int64_t d) {
   const int64_t lkp = mha_lkp((int)Lk);
   return (Lq * d + d * lkp + Lk * d + Lq * lkp) * sizeof(float);
@@ -703,6 +712,11 @@ int b200st_mha_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t
                    float temperature, b200st_stream_t stream) {
   if (B <= 0 || Lq <= 0) return 0;
   if (Lk <= 0) return set_error("mha_fwd: empty key sequence");
+  if (dtype == B200ST_BF16 && g_mha_backend == 0) {
+    const int rc = mha_fwd_tc(q, ldq, k, ldk, v, ldv, mask, mask_sb, mask_sq, o, ldo, p, B, H, Lq, Lk, d, temperature,
+                              (cudaStream_t)stream);
+    if (rc <= 0) return rc;           // launched (0) or failed (-1); 1 = shape not covered, use the SIMT tiles
+  }
   {
     const size_t tsm = mha_fwd_tiled_smem(Lq, Lk, d);
     if (tsm <= 100 * 1024 && d % 4 == 0) {     // training shapes: whole head in shared memory
@@ -730,12 +744,23 @@ int b200st_mha_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t
   return 0;
 }
 
+int b200st_set_mha_backend(int mode) {
+  const int old = g_mha_backend;
+  if (mode == 0 || mode == 1) g_mha_backend = mode;
+  return old;
+}
+
 int b200st_mha_bwd(int dtype, const void* dout, int64_t ldo, const void* q, int64_t ldq,
                    const void* k, int64_t ldk, const void* v, int64_t ldv, const void* p, void* ds,
                    void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B,
                    int64_t H, int64_t Lq, int64_t Lk, int64_t d, float temperature,
                    b200st_stream_t stream) {
   if (B <= 0 || Lq <= 0 || Lk <= 0) return 0;
+  if (dtype == B200ST_BF16 && g_mha_backend == 0) {
+    const int rc = mha_bwd_tc(dout, ldo, q, ldq, k, ldk, v, ldv, p, dq, lddq, dk, lddk, dv, lddv, B, H, Lq, Lk, d,
+                              temperature, (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
   {
     const size_t tsm = mha_bwd_tiled_smem(Lq, Lk, d);
     if (tsm <= 160 * 1024 && d % 4 == 0) {

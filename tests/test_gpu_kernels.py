@@ -84,7 +84,9 @@ def test_layernorm(ks, dtype, rows, cols):
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('B,H,Lq,Lk,d,mask_kind', [(2, 4, 7, 7, 8, 'causal'), (3, 8, 50, 31, 64, 'key'),
                                                    (64, 8, 50, 50, 64, 'causal'), (2, 8, 9, 12, 6, None),
-                                                   (2, 2, 5, 150, 64, 'key')])
+                                                   (2, 2, 5, 150, 64, 'key'), (2, 8, 32, 32, 64, None),
+                                                   (2, 8, 64, 64, 64, 'causal'), (3, 8, 33, 49, 64, 'key'),
+                                                   (5, 8, 1, 17, 64, 'key')])
 def test_mha(ks, dtype, B, H, Lq, Lk, d, mask_kind):
     c, f = ks
     qkv = rnd(B, max(Lq, Lk), 3 * H * d, dtype=dtype)            # packed buffer: exercises row strides
@@ -107,6 +109,31 @@ def test_mha(ks, dtype, B, H, Lq, Lk, d, mask_kind):
     dqr, dkr, dvr = f.mha_bwd(do, q, k, v, pr, H, temp)
     for a, b in ((dq, dqr), (dk, dkr), (dv, dvr)):
         assert rel_err(a, b) < TOL[dtype]
+
+
+@pytest.mark.parametrize('Lq,Lk,mask_kind', [(50, 50, 'causal'), (50, 32, 'key'), (32, 32, 'key')])
+def test_mha_tensor_core_matches_cuda_core_tiles(ks, Lq, Lk, mask_kind):
+    """The tcgen05 attention core (bf16, d=64, L<=64) against the CUDA-core tile kernels on the training shapes."""
+    c, f = ks
+    B, H, d = 16, 8, 64
+    q, k, v = rnd(B, Lq, H * d, dtype=torch.bfloat16), rnd(B, Lk, H * d, dtype=torch.bfloat16, seed=1), rnd(B, Lk, H * d, dtype=torch.bfloat16, seed=2)
+    if mask_kind == 'key':
+        lens = torch.randint(1, Lk + 1, (B,), device='cuda')
+        mask = (torch.arange(Lk, device='cuda')[None, :] < lens[:, None]).unsqueeze(1).to(torch.uint8)
+    else:
+        ids = torch.randint(0, 3, (B, Lk), device='cuda'); ids[:, 0] = 2
+        mask = f.token_mask(ids, 0, True)
+    do = rnd(B, Lq, H * d, dtype=torch.bfloat16, seed=9)
+    res = []
+    for mode in (0, 1):
+        old = c.set_mha_backend(mode)
+        try:
+            o, p = c.mha_fwd(q, k, v, mask, H, 8.0)
+            res.append((o, p) + tuple(c.mha_bwd(do, q, k, v, p, H, 8.0)))
+        finally:
+            c.set_mha_backend(old)
+    for a, b in zip(*res):
+        assert rel_err(a, b) < 1e-2
 
 
 def test_mha_fully_masked_row_is_uniform(ks):
