@@ -31,6 +31,24 @@ void count_launch(int n = 1);
     else return b200st::set_error("unsupported dtype %d", (int)(dtype));                 \
   } while (0)
 
+// four consecutive elements (16-byte aligned for fp32, 8-byte for bf16) <-> fp32 registers
+__device__ __forceinline__ void load4(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, float* v) {
+  const uint2 a = *reinterpret_cast<const uint2*>(p);
+  v[0] = __uint_as_float(a.x << 16); v[1] = __uint_as_float(a.x & 0xffff0000u);
+  v[2] = __uint_as_float(a.y << 16); v[3] = __uint_as_float(a.y & 0xffff0000u);
+}
+__device__ __forceinline__ void store4(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float* v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
 // ---- programmatic dependent launch (PDL) -----------------------------------------------------------------
 // Hot-loop kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the grid may be scheduled
 // while its predecessor in the stream is still draining, so launch latency and per-CTA prologue (barrier init, TMEM

@@ -80,6 +80,85 @@ __global__ void layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restri
   }
 }
 
+// Register-accumulating variant for cols % 128 == 0, cols <= 128 * NV: lane l of every warp owns the column quads
+// {(32 i + l) * 4 .. +3}, i < NV, so the dgamma / dbeta partial sums of all the rows a warp walks stay in registers
+// (the strip kernel above pays two shared-memory atomics per ELEMENT); they are merged once per CTA.
+template <typename T, int NV>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_reg_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
+                         float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int cols,
+                         int rows_per_block) {
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ float sm[];   // [2][cols]
+  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nq = cols >> 7;        // quads per lane actually used (<= NV)
+  float gam[NV][4], ag[NV][4], ab[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g4 = i < nq ? *reinterpret_cast<const float4*>(gamma + (32 * i + lane) * 4) : make_float4(0, 0, 0, 0);
+    gam[i][0] = g4.x; gam[i][1] = g4.y; gam[i][2] = g4.z; gam[i][3] = g4.w;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ag[i][j] = ab[i][j] = 0.f;
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  for (int64_t row = r0 + w; row < r0 + rows_per_block && row < rows; row += nw) {
+    const T* dyr = dy + row * cols;
+    const T* xr = x + row * cols;
+    const float mu = mean[row], rs = rstd[row];
+    float d[NV][4], xh[NV][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i < nq) {
+        load4(dyr + (32 * i + lane) * 4, d[i]);
+        load4(xr + (32 * i + lane) * 4, xh[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          xh[i][j] = (xh[i][j] - mu) * rs;
+          const float g = d[i][j] * gam[i][j];
+          s1 += g;
+          s2 += g * xh[i][j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / cols;
+    s2 = warp_sum(s2) / cols;
+    T* dxr = dx + row * cols;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i < nq) {
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[j] = rs * (d[i][j] * gam[i][j] - s1 - xh[i][j] * s2);
+          ag[i][j] += d[i][j] * xh[i][j];
+          ab[i][j] += d[i][j];
+        }
+        store4(dxr + (32 * i + lane) * 4, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (i < nq) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&sm[(32 * i + lane) * 4 + j], ag[i][j]);
+        atomicAdd(&sm[cols + (32 * i + lane) * 4 + j], ab[i][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    atomicAdd(&dgamma[c], sm[c]);
+    atomicAdd(&dbeta[c], sm[cols + c]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Vocabulary rows.  The row is staged once in shared memory as fp32.
 // ------------------------------------------------------------------------------------------------
@@ -263,6 +342,23 @@ int b200st_layernorm_bwd(int dtype, const void* dy, const void* x, const float* 
   const size_t smem = 2 * cols * sizeof(float);
   if (smem > 48 * 1024) return set_error("layernorm_bwd: cols %lld too large", (long long)cols);
   // ~2 CTAs per SM worth of row strips keeps the final atomics few while filling the chip.
+  if (cols % 128 == 0 && cols <= 1024 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dx & 15) == 0 &&
+      ((uintptr_t)gamma & 15) == 0) {
+    const int rpb = 16;             // 8 warps x 2 rows
+    B200ST_DISPATCH(dtype, T, {
+      if (cols <= 512) {
+        B200ST_CUDA(launch_pdl(layernorm_bwd_reg_kernel<T, 4>, dim3((unsigned)ceil_div(rows, rpb)), dim3(256), smem,
+                               (cudaStream_t)stream, (const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta,
+                               rows, (int)cols, rpb));
+      } else {
+        B200ST_CUDA(launch_pdl(layernorm_bwd_reg_kernel<T, 8>, dim3((unsigned)ceil_div(rows, rpb)), dim3(256), smem,
+                               (cudaStream_t)stream, (const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta,
+                               rows, (int)cols, rpb));
+      }
+    });
+    B200ST_LAUNCH_CHECK("layernorm_bwd_reg");
+    return 0;
+  }
   int rpb = (int)ceil_div(rows, 296);
   if (rpb < 4) rpb = 4;
   B200ST_DISPATCH(dtype, T, {

@@ -143,10 +143,12 @@ class Seq2seq(nn.Module):
         enc_outputs, *_ = self.enc_src(emb_src, src_mask=src_mask)
         return enc_outputs
 
-    def _decoder_de(self, emb_tgt, enc_outputs, tgt_mask=None, src_mask=None, beam_width=1):
+    def _decoder_de(self, emb_tgt, enc_outputs, tgt_mask=None, src_mask=None, beam_width=1, logits_only=False):
         """Seq2seq.py:249-257: decoder stack, vocabulary projection, log-softmax and top-k (top-1 fused)."""
         dec_outputs_tgt, *_ = self.dec_tgt(emb_tgt, enc_outputs, tgt_mask=tgt_mask, src_mask=src_mask)
         logits_tgt = BF.linear(dec_outputs_tgt, self.out_tgt.weight)
+        if logits_only:
+            return dec_outputs_tgt, logits_tgt, None, None, None
         logps_tgt, preds_top1 = BF.log_softmax_argmax(logits_tgt)
         if beam_width == 1:
             preds_tgt = preds_top1
@@ -167,7 +169,11 @@ class Seq2seq(nn.Module):
     # training forward (Seq2seq.py:396-509)
     # ------------------------------------------------------------------------------------------
     def forward_train(self, src, tgt=None, acous_feats=None, acous_lens=None, mode='ST', use_gpu=True,
-                      lm_mode='null', lm_model=None):
+                      lm_mode='null', lm_model=None, st_loss_scale=None):
+        """Reference signature (Seq2seq.py:396) plus one optional extension: with `st_loss_scale` (1-element fp32
+        device tensor) the ST branch returns out_dict['loss_st'] = st_loss_scale * sum over non-PAD targets of
+        -log p(tgt[:, 1:]) computed by the fused softmax + NLL kernel straight from the logits (the value
+        trainer_st.py:268-288 forms from logps_st), and skips materialising logps_st / preds_st."""
         out_dict = {}
         device = check_device(use_gpu)
         mode = mode.upper()
@@ -212,11 +218,20 @@ class Seq2seq(nn.Module):
             src_mask_input = self._length_mask(self._as_device_lengths(lengths, emb_src.device),
                                                emb_src.size(1))
             enc_outputs = self._encoder_en(emb_src, src_mask=src_mask_input)
-            _, _, logps_tgt, preds_tgt, _ = self._decoder_de(emb_tgt, enc_outputs, tgt_mask=tgt_mask,
-                                                             src_mask=src_mask_input)
             out_dict['emb_st'] = emb_src
-            out_dict['preds_st'] = preds_tgt
-            out_dict['logps_st'] = logps_tgt
+            if st_loss_scale is not None:
+                _, logits_tgt, _, _, _ = self._decoder_de(emb_tgt, enc_outputs, tgt_mask=tgt_mask,
+                                                          src_mask=src_mask_input, logits_only=True)
+                # position i predicts tgt[:, i+1]; the last position has no target (mask 0, never read)
+                nxt = torch.cat([tgt[:, 1:], tgt[:, :1]], dim=1)
+                keep = nxt.ne(PAD)
+                keep[:, -1] = False
+                out_dict['loss_st'] = BF.fused_softmax_nll(logits_tgt, nxt, keep.to(torch.uint8), st_loss_scale)
+            else:
+                _, _, logps_tgt, preds_tgt, _ = self._decoder_de(emb_tgt, enc_outputs, tgt_mask=tgt_mask,
+                                                                 src_mask=src_mask_input)
+                out_dict['preds_st'] = preds_tgt
+                out_dict['logps_st'] = logps_tgt
 
         if 'lengths_asr' in out_dict and torch.is_tensor(out_dict['lengths_asr']):
             out_dict['lengths_asr'] = out_dict['lengths_asr'].cpu().numpy().astype(np.int64)

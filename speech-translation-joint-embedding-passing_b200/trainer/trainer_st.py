@@ -19,7 +19,8 @@ from utils.misc import check_device
 class Trainer_ST(object):
 
     def __init__(self, use_gpu=True, batch_size=64, minibatch_partition=1, eval_with_mask=True,
-                 normalise_loss=True, loss_coeff=None, optimizer=None, reducer=None, max_grad_norm=1.0):
+                 normalise_loss=True, loss_coeff=None, optimizer=None, reducer=None, max_grad_norm=1.0,
+                 fused_loss=True):
         self.use_gpu = use_gpu
         self.device = check_device(use_gpu)
         self.batch_size = batch_size
@@ -31,6 +32,9 @@ class Trainer_ST(object):
         self.optimizer = optimizer
         self.reducer = reducer
         self.max_grad_norm = max_grad_norm
+        # fused softmax + masked NLL (+ its gradient) straight from the logits instead of log_softmax -> NLLLoss;
+        # same value and gradient, no [B, L, V] log-probability tensor
+        self.fused_loss = fused_loss
 
     def _train_batch(self, model, batch_items, dataset=None, step=0, total_steps=0):
         resloss_de = self._train_batch_device(model, batch_items)
@@ -67,6 +71,16 @@ class Trainer_ST(object):
             acous_feats = batch_acous_feats[i_start:i_end, :acous_len].to(device=self.device,
                                                                           non_blocking=True)
             non_padding_mask_tgt = tgt_ids.data.ne(PAD)
+            if self.fused_loss and self.eval_with_mask and self.normalise_loss:
+                # same loss (trainer_st.py:268-288), formed by the fused softmax + NLL kernel from the logits
+                scale = (self.loss_coeff['nll_st'] / n_minibatch) / torch.sum(non_padding_mask_tgt[:, 1:]).to(torch.float32)
+                out_dict = model.forward_train(src_ids, tgt=tgt_ids, acous_feats=acous_feats,
+                                               acous_lens=acous_lengths, mode='ST', use_gpu=self.use_gpu,
+                                               st_loss_scale=scale.reshape(1))
+                loss = out_dict['loss_st']
+                loss.backward()
+                resloss_de = resloss_de + loss.detach()
+                continue
             out_dict = model.forward_train(src_ids, tgt=tgt_ids, acous_feats=acous_feats,
                                            acous_lens=acous_lengths, mode='ST', use_gpu=self.use_gpu)
             logps_de = out_dict['logps_st'][:, :-1, :]

@@ -57,6 +57,27 @@ def test_backward_st_matches_reference(golden, fake_backend):
         assert g is None or float(g.abs().sum()) == 0.0, name
 
 
+@pytest.mark.parametrize('fused', [True, False])
+def test_trainer_step_matches_reference_grads(golden, fake_backend, fused):
+    """Trainer_ST._train_batch_device (fused softmax+NLL from the logits, or the reference's logps -> NLLLoss
+    route) reproduces the reference loss and gradients (trainer_st.py:253-288)."""
+    from trainer.trainer_st import Trainer_ST
+    m = build_model(golden.cfg, golden.params())
+    m.train()
+    b = golden.inputs()
+    items = {'srcid': [b['src']], 'tgtid': [b['tgt']], 'acous_feat': [b['acous_feats']],
+             'acouslen': [int(n) for n in b['acous_lens']]}
+    tr = Trainer_ST(use_gpu=False, batch_size=b['src'].size(0), fused_loss=fused)
+    loss = tr._train_batch_device(m, items)
+    assert abs(float(loss) - float(golden['st/loss'])) < 1e-4 * abs(float(golden['st/loss']))
+    ref = golden.group('st_grad')
+    named = dict(m.named_parameters())
+    gnorm = sum(float(g.double().norm() ** 2) for g in ref.values()) ** 0.5
+    for name, g in ref.items():
+        err = float((named[name].grad.double() - g.double()).norm())
+        assert err < 1e-4 * max(float(g.double().norm()), 1e-3 * gnorm), (name, err)
+
+
 def test_las_forward_matches_reference(golden, fake_backend):
     m = build_model(golden.cfg, golden.params())
     I = golden.inputs()
