@@ -73,8 +73,10 @@ int b200st_mha_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t
                    const void* v, int64_t ldv, const uint8_t* mask, int64_t mask_sb, int64_t mask_sq,
                    void* o, int64_t ldo, void* p, int64_t B, int64_t H, int64_t Lq, int64_t Lk,
                    int64_t d, float temperature, b200st_stream_t stream);
-/* Attention-core kernel selection: 0 = auto (bf16, d = 64, Lq and Lk <= 64 -> tcgen05 kernel, one (batch, head) per
- * CTA with S / O / dP / dV / dQ / dK accumulated in TMEM), 1 = CUDA-core tiles only.  Returns the previous mode. */
+/* Attention kernel selection (test hook), a bit mask: bit 0 set = Transformer attention core on CUDA-core tiles only
+ * (default: bf16, d = 64, Lq and Lk <= 64 -> tcgen05 kernel, one (batch, head) per CTA with S / O / dP / dV / dQ / dK
+ * accumulated in TMEM); bit 1 set = LAS attention step with one CTA per sequence (default for bf16: a 4-CTA cluster
+ * per sequence, keys split across the CTAs and merged through distributed shared memory).  Returns the previous mask. */
 int b200st_set_mha_backend(int mode);
 /* ds: workspace [B,H,Lq,Lk] (same dtype as p); dq/dk/dv written (not accumulated). */
 int b200st_mha_bwd(int dtype, const void* dout, int64_t ldo, const void* q, int64_t ldq,

@@ -66,7 +66,8 @@ class CudaKernels:
         return int(self.lib.b200st_set_blstm_backend(int(mode)))
 
     def set_mha_backend(self, mode: int) -> int:
-        """0 auto (tcgen05 attention core for bf16, d=64, L<=64), 1 CUDA-core tiles only.  Returns the previous mode."""
+        """Bit mask: 1 = Transformer attention core on CUDA-core tiles only (default tcgen05 for bf16, d=64, L<=64);
+        2 = LAS attention step with one CTA per sequence (default: 4-CTA key-split cluster).  Returns the previous mask."""
         return int(self.lib.b200st_set_mha_backend(int(mode)))
 
     # -- GEMM -------------------------------------------------------------------------------------

@@ -354,6 +354,7 @@ int mha_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const voi
 int mha_bwd_tc(const void* dout, int64_t ldo, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                int64_t ldv, const void* p, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d, float temperature, cudaStream_t st);
+static int g_las_backend = 0;     // 0 = auto (key-split cluster kernels for bf16), 1 = one CTA per sequence
 static int g_mha_backend = 0;     // 0 = auto (tensor cores for bf16 when the shape fits), 1 = SIMT tiles only
 
 static size_t mha_fwd_tiled_smem(int64_t Lq, int64_t Lk, int64_t d) {
@@ -609,6 +610,196 @@ las_attn_bwd_vec_kernel(const T* __restrict__ dctx, const T* __restrict__ wk, co
     dq[(int64_t)b * D + c] = from_f<T>((part[c] + part[D + c]) + (part[2 * D + c] + part[3 * D + c]));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Key-split LAS attention step: a cluster of LAS_CS CTAs per sequence, each owning a contiguous slice of the keys.
+// One sequence reads 2 x Tk x 512 x 2 B (~260 KB) of keys + values per step; a single CTA per sequence is bound by
+// its own load latency (64 CTAs, ~30 us).  Here 4 x B CTAs keep 4-8 independent 16-byte loads in flight per thread
+// and the per-slice softmax statistics / partial context are merged flash-decoding style through distributed
+// shared memory: slice r sends (max_r, sum_r) to every CTA and its unnormalised partial context columns to the CTA
+// that owns them; after ONE cluster barrier every CTA normalises its probabilities and its quarter of the context.
+// ------------------------------------------------------------------------------------------------
+constexpr int LAS_CS = 4;
+__device__ __forceinline__ uint32_t las_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void las_st_remote(const float* local, uint32_t rank, float v) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(local), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+// split barrier: every CTA of the cluster must be running before its shared memory may be written remotely
+__device__ __forceinline__ void las_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void las_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void las_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float dot8(const float* a, const uint4& u) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); s = fmaf(a[2 * i], f.x, s); s = fmaf(a[2 * i + 1], f.y, s); }
+  return s;
+}
+__device__ __forceinline__ void axpy8(float* acc, float w, const uint4& u) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); acc[2 * i] = fmaf(w, f.x, acc[2 * i]); acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]); }
+}
+// warp-per-key dot products of `vec` (smem, fp32, n floats) with rows [k0, k0+nk) of `rows` (bf16, row stride n),
+// four keys (= eight 16-byte loads per lane for n = 512) in flight; keys with use(j) == false get `skip`
+template <typename F>
+__device__ __forceinline__ void las_key_dots(float* out, const float* vec, const __nv_bfloat16* rows, int n, int nk, float skip, F use) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int jj = w; jj < nk; jj += 32) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    bool on[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) on[i] = (jj + 8 * i < nk) && use(jj + 8 * i);
+    for (int c = lane * 8; c < n; c += 256) {
+      uint4 u[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        u[i] = on[i] ? __ldg(reinterpret_cast<const uint4*>(rows + (int64_t)(jj + 8 * i) * n + c)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[i] += dot8(vec + c, u[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float t = warp_sum(s[i]);
+      if (lane == 0 && jj + 8 * i < nk) out[jj + 8 * i] = on[i] ? t : skip;
+    }
+  }
+}
+// part[g][n] (g < 4) = sum over keys j = g mod 4 of wgt[j] * rows[j][:]; thread (g, 8-column chunk), 8 loads in flight
+__device__ __forceinline__ void las_weighted_rows(float* part, const float* wgt, const __nv_bfloat16* rows, int n, int nk) {
+  const int nchunk = n >> 3;
+  for (int item = threadIdx.x; item < 4 * nchunk; item += 256) {
+    const int g = item / nchunk, c = (item - g * nchunk) * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j0 = g; j0 < nk; j0 += 32) {
+      uint4 u[8];
+      float wv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = j0 + 4 * i;
+        wv[i] = j < nk ? wgt[j] : 0.f;
+        u[i] = wv[i] != 0.f ? __ldg(reinterpret_cast<const uint4*>(rows + (int64_t)j * n + c)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) axpy8(acc, wv[i], u[i]);
+    }
+    store8(part + g * n + c, acc);
+  }
+}
+
+// dynamic smem floats: D (q) + 64 (scores) + 4*Dv (part) + Dv (red: LAS_CS x Dv/LAS_CS) + 2*LAS_CS (stat)
+__global__ void __cluster_dims__(LAS_CS, 1, 1) __launch_bounds__(256)
+las_attn_fwd_cl_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ wk,
+                       const __nv_bfloat16* __restrict__ vals, const int32_t* __restrict__ klens,
+                       __nv_bfloat16* __restrict__ ctx, float* __restrict__ probs, int Tk, int D, int Dv) {
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ __align__(16) float sm[];
+  __shared__ float scratch[32];
+  float* qs = sm;                  // [D]
+  float* sc = qs + D;              // [64] scores -> exp(score - local max)
+  float* part = sc + 64;           // [4][Dv]
+  float* red = part + 4 * Dv;      // [LAS_CS][Dv / LAS_CS] partial contexts for the columns this CTA owns
+  float* stat = red + Dv;          // [LAS_CS][2] (max, sum) of every slice
+  const uint32_t rank = las_rank();
+  const int b = blockIdx.y;
+  const int kpc = (Tk + LAS_CS - 1) / LAS_CS;
+  const int k0 = rank * kpc, nk = max(0, min(Tk, k0 + kpc) - k0);
+  las_cluster_arrive();            // "I am running": waited for just before the first remote store
+  for (int c = threadIdx.x; c < D; c += 256) qs[c] = to_f(q[(int64_t)b * D + c]);
+  __syncthreads();
+  const int klen = klens ? klens[b] : Tk;
+  las_key_dots(sc, qs, wk + ((int64_t)b * Tk + k0) * D, D, nk, -1e12f, [&](int j) { return k0 + j < klen; });   // attention.py:250-252
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < nk; j += 256) mx = fmaxf(mx, sc[j]);
+  mx = block_max(mx, scratch);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < nk; j += 256) { const float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
+  sum = block_sum(sum, scratch);
+  las_cluster_wait();
+  if (threadIdx.x < LAS_CS) { las_st_remote(&stat[2 * rank], threadIdx.x, mx); las_st_remote(&stat[2 * rank + 1], threadIdx.x, sum); }
+  __syncthreads();
+  las_weighted_rows(part, sc, vals + ((int64_t)b * Tk + k0) * Dv, Dv, nk);
+  __syncthreads();
+  const int cpo = Dv / LAS_CS;     // columns per owner
+  for (int c = threadIdx.x; c < Dv; c += 256)
+    las_st_remote(&red[rank * cpo + (c % cpo)], (uint32_t)(c / cpo), (part[c] + part[Dv + c]) + (part[2 * Dv + c] + part[3 * Dv + c]));
+  las_cluster_sync();
+  float M = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < LAS_CS; ++r) M = fmaxf(M, stat[2 * r]);
+  float L = 0.f, f[LAS_CS];
+#pragma unroll
+  for (int r = 0; r < LAS_CS; ++r) { f[r] = stat[2 * r + 1] > 0.f ? expf(stat[2 * r] - M) : 0.f; L += f[r] * stat[2 * r + 1]; }
+  const float inv = 1.f / L;
+  for (int j = threadIdx.x; j < nk; j += 256) probs[(int64_t)b * Tk + k0 + j] = sc[j] * f[rank] * inv;
+  for (int c = threadIdx.x; c < cpo; c += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < LAS_CS; ++r) a = fmaf(f[r], red[r * cpo + c], a);
+    ctx[(int64_t)b * Dv + rank * cpo + c] = __float2bfloat16_rn(a * inv);
+  }
+}
+
+// dynamic smem floats: Dv (dctx) + 64 (dp -> dscore) + 64 (p) + 4*D (part) + D (red) + LAS_CS (stat)
+__global__ void __cluster_dims__(LAS_CS, 1, 1) __launch_bounds__(256)
+las_attn_bwd_cl_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* __restrict__ wk,
+                       const __nv_bfloat16* __restrict__ vals, const float* __restrict__ probs,
+                       float* __restrict__ dscore, __nv_bfloat16* __restrict__ dq, int Tk, int D, int Dv) {
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ __align__(16) float sm[];
+  __shared__ float scratch[32];
+  float* dcs = sm;                 // [Dv]
+  float* sc = dcs + Dv;            // [64]
+  float* ps = sc + 64;             // [64]
+  float* part = ps + 64;           // [4][D]
+  float* red = part + 4 * D;       // [LAS_CS][D / LAS_CS]
+  float* stat = red + D;           // [LAS_CS] partial sum_j p_j dp_j
+  const uint32_t rank = las_rank();
+  const int b = blockIdx.y;
+  const int kpc = (Tk + LAS_CS - 1) / LAS_CS;
+  const int k0 = rank * kpc, nk = max(0, min(Tk, k0 + kpc) - k0);
+  las_cluster_arrive();
+  for (int c = threadIdx.x; c < Dv; c += 256) dcs[c] = to_f(dctx[(int64_t)b * Dv + c]);
+  for (int j = threadIdx.x; j < nk; j += 256) ps[j] = probs[(int64_t)b * Tk + k0 + j];
+  __syncthreads();
+  // dp_j = dctx . V_j (rows with p == 0 need no dp: dscore = p * (dp - delta))
+  las_key_dots(sc, dcs, vals + ((int64_t)b * Tk + k0) * Dv, Dv, nk, 0.f, [&](int j) { return ps[j] != 0.f; });
+  __syncthreads();
+  float dl = 0.f;
+  for (int j = threadIdx.x; j < nk; j += 256) dl += sc[j] * ps[j];
+  dl = block_sum(dl, scratch);
+  las_cluster_wait();
+  if (threadIdx.x < LAS_CS) las_st_remote(&stat[rank], threadIdx.x, dl);
+  las_cluster_sync();
+  float delta = 0.f;
+#pragma unroll
+  for (int r = 0; r < LAS_CS; ++r) delta += stat[r];
+  for (int j = threadIdx.x; j < nk; j += 256) {
+    const float g = ps[j] * (sc[j] - delta);
+    sc[j] = g;
+    dscore[(int64_t)b * Tk + k0 + j] = g;
+  }
+  __syncthreads();
+  las_weighted_rows(part, sc, wk + ((int64_t)b * Tk + k0) * D, D, nk);
+  __syncthreads();
+  const int cpo = D / LAS_CS;
+  for (int c = threadIdx.x; c < D; c += 256)
+    las_st_remote(&red[rank * cpo + (c % cpo)], (uint32_t)(c / cpo), (part[c] + part[D + c]) + (part[2 * D + c] + part[3 * D + c]));
+  las_cluster_sync();
+  for (int c = threadIdx.x; c < cpo; c += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < LAS_CS; ++r) a += red[r * cpo + c];
+    dq[(int64_t)b * D + rank * cpo + c] = __float2bfloat16_rn(a);
+  }
+}
+
 template <typename T>
 __global__ void argmax_rows_kernel(const T* __restrict__ x, int64_t ld, int cols,
                                    int64_t* __restrict__ idx, int64_t idx_stride) {
@@ -745,8 +936,8 @@ int b200st_mha_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t
 }
 
 int b200st_set_mha_backend(int mode) {
-  const int old = g_mha_backend;
-  if (mode == 0 || mode == 1) g_mha_backend = mode;
+  const int old = g_mha_backend | (g_las_backend << 1);
+  if (mode >= 0 && mode <= 3) { g_mha_backend = mode & 1; g_las_backend = (mode >> 1) & 1; }
   return old;
 }
 
@@ -797,6 +988,17 @@ int b200st_las_attn_fwd(int dtype, const void* q, const void* wk, const void* va
                         const int32_t* klens, void* ctx, float* probs, int64_t B, int64_t Tk, int64_t D,
                         int64_t Dv, b200st_stream_t stream) {
   if (B <= 0) return 0;
+  if (dtype == B200ST_BF16 && g_las_backend == 0 && D % 8 == 0 && Dv % (8 * LAS_CS) == 0 && Tk <= 64 * LAS_CS && Tk >= LAS_CS &&
+      B <= 65535 && ((uintptr_t)wk & 15) == 0 && ((uintptr_t)vals & 15) == 0) {
+    const size_t cs = (D + 64 + 5 * Dv + 2 * LAS_CS) * sizeof(float);
+    if (cs <= 48 * 1024) {
+      B200ST_CUDA(launch_pdl(las_attn_fwd_cl_kernel, dim3(LAS_CS, (unsigned)B), dim3(256), cs, (cudaStream_t)stream,
+                             (const __nv_bfloat16*)q, (const __nv_bfloat16*)wk, (const __nv_bfloat16*)vals, klens,
+                             (__nv_bfloat16*)ctx, probs, (int)Tk, (int)D, (int)Dv));
+      B200ST_LAUNCH_CHECK("las_attn_fwd_cl");
+      return 0;
+    }
+  }
   {
     const size_t vs = (D + ((Tk + 3) & ~3) + 4 * Dv) * sizeof(float);
     if (D % 8 == 0 && Dv % 8 == 0 && vs <= 48 * 1024) {
@@ -822,6 +1024,17 @@ int b200st_las_attn_bwd(int dtype, const void* dctx, const void* wk, const void*
                         const float* probs, float* dscore, void* dq, int64_t B, int64_t Tk, int64_t D,
                         int64_t Dv, b200st_stream_t stream) {
   if (B <= 0) return 0;
+  if (dtype == B200ST_BF16 && g_las_backend == 0 && D % (8 * LAS_CS) == 0 && Dv % 8 == 0 && Tk <= 64 * LAS_CS && Tk >= LAS_CS &&
+      B <= 65535 && ((uintptr_t)wk & 15) == 0 && ((uintptr_t)vals & 15) == 0) {
+    const size_t cs = (Dv + 128 + 5 * D + LAS_CS) * sizeof(float);
+    if (cs <= 48 * 1024) {
+      B200ST_CUDA(launch_pdl(las_attn_bwd_cl_kernel, dim3(LAS_CS, (unsigned)B), dim3(256), cs, (cudaStream_t)stream,
+                             (const __nv_bfloat16*)dctx, (const __nv_bfloat16*)wk, (const __nv_bfloat16*)vals, probs,
+                             dscore, (__nv_bfloat16*)dq, (int)Tk, (int)D, (int)Dv));
+      B200ST_LAUNCH_CHECK("las_attn_bwd_cl");
+      return 0;
+    }
+  }
   {
     const size_t vs = (Dv + ((Tk + 3) & ~3) + 4 * D) * sizeof(float);
     if (D % 8 == 0 && Dv % 8 == 0 && vs <= 48 * 1024) {

@@ -212,6 +212,35 @@ def test_las_attention(ks, dtype):
     assert rel_err(ds, dsr) < TOL[dtype] and rel_err(dq, dqr) < TOL[dtype]
 
 
+@pytest.mark.parametrize('B,Tk,D,Dv', [(64, 126, 512, 512), (5, 37, 64, 96), (3, 4, 32, 32), (2, 256, 512, 512)])
+def test_las_attention_key_split_cluster(ks, B, Tk, D, Dv):
+    """bf16 LAS attention step on the 4-CTA key-split cluster kernels (training shape first) against the torch
+    restatement and against the one-CTA-per-sequence kernels; includes klen = 0 (uniform row) and klen = Tk."""
+    c, f = ks
+    dt = torch.bfloat16
+    q, wk, vals = rnd(B, D, dtype=dt), rnd(B, Tk, D, dtype=dt, seed=1), rnd(B, Tk, Dv, dtype=dt, seed=2)
+    klens = torch.randint(1, Tk + 1, (B,), device='cuda').to(torch.int32)
+    klens[0] = Tk
+    klens[-1] = 0
+    dctx = rnd(B, Dv, dtype=dt, seed=3)
+    res = []
+    for mode in (0, 2):
+        old = c.set_mha_backend(mode)
+        try:
+            cx, p = c.las_attn_fwd(q, wk, vals, klens)
+            ds, dq = c.las_attn_bwd(dctx, wk, vals, p)
+            res.append((cx, p, ds, dq))
+        finally:
+            c.set_mha_backend(old)
+    cxr, pr = f.las_attn_fwd(q, wk, vals, klens)
+    dsr, dqr = f.las_attn_bwd(dctx, wk, vals, res[0][1])
+    for a, b in zip(res[0], (cxr, pr, dsr, dqr)):
+        assert rel_err(a, b) < TOL[dt]
+    for a, b in zip(*res):
+        assert rel_err(a, b) < TOL[dt]
+    assert abs(float(res[0][1][-1].sum()) - 1.0) < 1e-3 and float((res[0][1][-1] - 1.0 / Tk).abs().max()) < 1e-6
+
+
 def test_argmax_and_lengths(ks):
     c, f = ks
     x = rnd(9, 1000)
