@@ -214,6 +214,152 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
 }
 
+// ---- cluster split-K for the decoder-step shapes (M <= 64, long K, few N tiles) ---------------------------------
+// A [64 x N] output with K = 2048 and N = 512 has 8 output tiles: 8 CTAs would each stream 256 KB of weights alone
+// (~12 us, latency-bound).  Here the K range of every tile is split over a cluster of CS CTAs along grid.z (CS x more
+// CTAs, each a 2-4 k-block pipeline); the fp32 partial tiles are reduce-scattered through distributed shared memory
+// -- rank r receives rows [r * 64/CS, (r+1) * 64/CS) of every partial -- and each rank finishes (alpha, bias, ReLU,
+// residual) and stores its rows.  No zero-filled fp32 output, no atomics, no second kernel.
+template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_clk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                   TC* __restrict__ C, int64_t ldc, const TC* R, int64_t ldr, const float* __restrict__ bias,
+                   int relu, float alpha, int M, int N, int K, int kb_per_split) {
+  constexpr int BM = 64;
+  using S = TcSmem<BN, STAGES, BM>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  float* red = reinterpret_cast<float*>(smem + S::BAR_OFF + 256);   // [CS][64 / CS][BN] partial rows this rank owns
+
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // "running": waited for before any DSMEM store
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const uint32_t cs = gridDim.z, rank = blockIdx.z;             // the cluster spans grid.z exactly
+  const int kb_total = (K + TC_BK - 1) / TC_BK;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(kb_total, kb_begin + kb_per_split);
+  const int n_iter = max(0, kb_end - kb_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* sa = smem + s * S::STAGE;
+        uint8_t* sb = sa + S::A_BYTES;
+        mbar_expect_tx(&full[s], S::STAGE);
+        const int k0 = (kb_begin + it) * TC_BK;
+        if (A_MN) tma_load_2d(sa, &tma_a, 0, k0, &full[s]);
+        else tma_load_2d(sa, &tma_a, k0, 0, &full[s]);
+        if (B_MN) {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (TC_BK * 128), &tma_b, n0 + c * 64, k0, &full[s]);
+        } else {
+          tma_load_2d(sb, &tma_b, k0, n0, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(BM, BN, A_MN, B_MN);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * S::STAGE);
+        const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t da = A_MN ? umma_desc(sa + k * 2048, TC_BK * 128, 1024) : umma_desc(sa + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? umma_desc(sb + k * 2048, TC_BK * 128, 1024) : umma_desc(sb + k * 32, 16, 1024);
+          tc_mma_f16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(&empty[s]);
+      }
+      tc_commit(tmem_full);
+    }
+  } else if (warp >= 4) {
+    // partial tile -> owners: accumulator row i sits in TMEM lane (i / 16) * 32 + (i % 16); lanes 0..15 of warp wq
+    // hold rows 16 wq .. 16 wq + 15 and send them, 16 bytes per store, to the rank that owns the row
+    const int wq = warp - 4;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t rpo = BM / cs;                     // rows per owner
+    const uint32_t row = wq * 16 + (lane & 15);
+    const uint32_t owner = row / rpo, lrow = row % rpo;
+    uint32_t dst = smem_u32(red + ((size_t)rank * rpo + lrow) * BN), rdst;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(dst), "r"(owner));
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, r);
+      if (lane < 16) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const uint32_t z = n_iter > 0 ? 0xffffffffu : 0u;     // an empty K slice contributes zeros
+          asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rdst + (c0 + j) * 4), "r"(r[j] & z),
+                       "r"(r[j + 1] & z), "r"(r[j + 2] & z), "r"(r[j + 3] & z) : "memory");
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  // ---- every rank: sum the CS partials of its rows, epilogue, store
+  {
+    const int rpo = BM / (int)cs;
+    constexpr int QPR = BN / 4;                       // float4 quads per row
+    for (int item = threadIdx.x; item < rpo * QPR; item += TC_THREADS) {
+      const int lrow = item / QPR, cc = (item % QPR) * 4;
+      const int row = (int)rank * rpo + lrow, col = n0 + cc;
+      if (row >= M || col >= N) continue;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int r = 0; r < (int)cs; ++r) {
+        const float4 a = *reinterpret_cast<const float4*>(&red[((size_t)r * rpo + lrow) * BN + cc]);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+      }
+      const int nv = min(4, N - col);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] *= alpha;
+        if (bias && j < nv) v[j] += bias[col + j];
+        if (relu) v[j] = fmaxf(v[j], 0.f);
+      }
+      TC* cp = C + (int64_t)row * ldc + col;
+      const TC* rp = R ? R + (int64_t)row * ldr + col : nullptr;
+      for (int j = 0; j < nv; ++j) cp[j] = from_f<TC>(v[j] + (rp ? to_f(rp[j]) : 0.f));
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -284,6 +430,25 @@ static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const CUtenso
   return 0;
 }
 
+template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC>
+static int launch_tc_clk(int64_t M, int64_t N, int64_t K, float alpha, const CUtensorMap& ma, const CUtensorMap& mb,
+                         void* C, int64_t ldc, const void* R, int64_t ldr, const float* bias, int relu, int cs,
+                         int kb_per_split, cudaStream_t st) {
+  using S = TcSmem<BN, STAGES, 64>;
+  static_assert((2 * STAGES + 1) * 8 + 16 <= 256, "barrier block");
+  constexpr int SMEM = S::BAR_OFF + 256 + 64 * BN * 4 + 1024;
+  auto kern = gemm_tc_clk_kernel<BN, STAGES, A_MN, B_MN, TC>;
+  B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  dim3 grid((unsigned)ceil_div(N, BN), 1, (unsigned)cs);
+  B200ST_CUDA(launch_pdl_cluster_z(kern, grid, dim3(TC_THREADS), SMEM, st, (unsigned)cs, ma, mb, (TC*)C, ldc, (const TC*)R,
+                                   ldr, bias, relu, alpha, (int)M, (int)N, (int)K, kb_per_split));
+  B200ST_LAUNCH_CHECK("gemm_tc_clk");
+  return 0;
+}
+
+static int g_clk_enabled = 1;
+void gemm_tc_set_cluster_splitk(int on) { g_clk_enabled = on; }
+
 int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const void* A, int64_t lda,
             const void* B, int64_t ldb, void* C, int64_t ldc, const void* R, int64_t ldr, const float* bias, int relu,
             cudaStream_t st) {
@@ -311,6 +476,21 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   else      { if (make_map(&ma, A, M, K, lda, m64 ? 64 : TC_BM)) return -1; }
   if (b_mn) { if (make_map(&mb, B, K, N, ldb, TC_BK)) return -1; }
   else      { if (make_map(&mb, B, N, K, ldb, BN)) return -1; }
+  // cluster split-K: decoder-step shapes whose few N tiles would each stream a long K alone
+  const int64_t tiles_1cta = ceil_div(N, BN);       // CTAs the non-split configuration would launch
+  if (g_clk_enabled && m64 && !a_mn && kb_total >= 8 && (tiles_1cta <= 16 || (tiles_1cta <= 32 && kb_total >= 16))) {
+    int cs = kb_total >= 16 ? 8 : 4;
+    while (cs > 2 && ceil_div(N, 64) * cs > 160) cs >>= 1;
+    const int kps = (int)ceil_div(kb_total, cs);
+    CUtensorMap mb64 = mb;
+    if (!b_mn && BN != 64) { if (make_map(&mb64, B, N, K, ldb, 64)) return -1; }
+    if (b_mn) {
+      if (dtype_c == B200ST_F32) return launch_tc_clk<64, 4, false, true, float>(M, N, K, alpha, ma, mb64, C, ldc, R, ldr, bias, relu, cs, kps, st);
+      return launch_tc_clk<64, 4, false, true, __nv_bfloat16>(M, N, K, alpha, ma, mb64, C, ldc, R, ldr, bias, relu, cs, kps, st);
+    }
+    if (dtype_c == B200ST_F32) return launch_tc_clk<64, 4, false, false, float>(M, N, K, alpha, ma, mb64, C, ldc, R, ldr, bias, relu, cs, kps, st);
+    return launch_tc_clk<64, 4, false, false, __nv_bfloat16>(M, N, K, alpha, ma, mb64, C, ldc, R, ldr, bias, relu, cs, kps, st);
+  }
   // split-K when the output has few tiles and K is long (weight gradients): fp32 output, plain sum only.
   const int64_t tiles = m_tiles * ceil_div(N, BN);
   int splits = 1;

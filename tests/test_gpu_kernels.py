@@ -335,7 +335,10 @@ def test_glue(ks, dtype):
 
 @pytest.mark.parametrize('ta,tb', [(False, True), (False, False), (True, False), (True, True)])
 @pytest.mark.parametrize('M,N,K', [(128, 128, 64), (100, 72, 80), (3200, 512, 512), (64, 2048, 712),
-                                   (64, 10000, 512), (1024, 80, 4096), (1024, 1024, 16384), (37, 24, 8)])
+                                   (64, 10000, 512), (1024, 80, 4096), (1024, 1024, 16384), (37, 24, 8),
+                                   # decoder-step shapes served by the cluster split-K kernel (M <= 64, K >= 512)
+                                   (64, 512, 2048), (64, 1024, 2048), (37, 200, 1000), (64, 512, 512), (5, 72, 2048),
+                                   (64, 2048, 1536)])
 def test_gemm_tensor_core(ks, ta, tb, M, N, K):
     """tcgen05/TMA/TMEM kernel (forced) vs fp32 matmul of the same bf16 operands: K-major and MN-major
     operand staging, M/N/K tails (TMA zero fill), bf16 and fp32 (split-K atomics) outputs."""
