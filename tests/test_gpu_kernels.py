@@ -325,6 +325,9 @@ def test_glue(ks, dtype):
     acc = torch.ones(130, device='cuda')
     c.colsum(big, out=acc, accumulate=True)
     assert rel_err(acc, f.colsum(big) + 1) < 1e-4
+    for r_, c_ in ((3200, 2048), (77, 520), (1, 8), (4100, 1000)):       # 16-byte-vector path (bf16) + tails
+        wide = rnd(r_, c_ + 8, dtype=dtype)[:, :c_]                       # ld > cols
+        assert rel_err(c.colsum(wide), f.colsum(wide)) < 1e-4
     assert torch.equal(c.relu_bwd(a, b), f.relu_bwd(a, b))
     ids = torch.randint(0, 4, (6, 9), device='cuda')
     assert torch.equal(c.token_mask(ids, 0, True), f.token_mask(ids, 0, True))
