@@ -41,7 +41,8 @@ struct TcSmem {
 // the A tile out of shared memory, so not reading 64 zero-padded rows halves the per-MMA cost.  For M = 64 the
 // accumulator row i lives in TMEM lane (i / 16) * 32 + (i % 16) (measured: scripts/probes/umma_m64_probe.cu).
 template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC, bool ATOMIC, int BM = TC_BM>
-__global__ void __launch_bounds__(TC_THREADS, (BN * TC_BK * 2 + BM * TC_BK * 2) * STAGES <= 100 * 1024 ? 2 : 1)
+__global__ void __launch_bounds__(TC_THREADS, (BN * TC_BK * 2 + BM * TC_BK * 2) * STAGES <= 50 * 1024 ? 4 :
+                                              ((BN * TC_BK * 2 + BM * TC_BK * 2) * STAGES <= 100 * 1024 ? 2 : 1))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                TC* __restrict__ C, int64_t ldc, const TC* R, int64_t ldr, const float* __restrict__ bias,
                int relu, float alpha, int M, int N, int K, int kb_per_split) {
@@ -151,56 +152,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       constexpr int RPW = BM == 64 ? 16 : 32;   // accumulator rows held by one warp's TMEM lane quarter
       const int cc = (lane % LPR) * 4;
       const int col = n0 + cc;
+      // residual rows are fetched UP rows ahead of their use: a dependent load per row pass would leave the whole
+      // epilogue waiting on one global-memory latency per row
+      constexpr int UP = 4;
+      const bool has_r = R != nullptr && !ATOMIC;
 #pragma unroll 1
-      for (int rr = lane / LPR; rr < RPW; rr += RPP) {
-        const int row = m0 + wq * RPW + rr;
-        if (row >= M || col >= N) continue;
-        const float4 a = *reinterpret_cast<const float4*>(&stg[rr * SP + cc]);
-        float v[4] = {a.x, a.y, a.z, a.w};
-        const int nv = min(4, N - col);
-        TC* cp = C + (int64_t)row * ldc + col;
-        if (ATOMIC) {
-          float* fp = reinterpret_cast<float*>(cp);
-          if (nv == 4 && (reinterpret_cast<uintptr_t>(fp) & 15) == 0) {
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(fp), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
-          } else {
-            for (int j = 0; j < nv; ++j) atomicAdd(fp + j, v[j]);
-          }
-          continue;
-        }
-        if (bias) {
+      for (int rr0 = lane / LPR; rr0 < RPW; rr0 += RPP * UP) {
+        float radd[UP][4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (j < nv) v[j] += bias[col + j];
-        }
-        if (relu) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        const TC* rp = R ? R + (int64_t)row * ldr + col : nullptr;
-        if constexpr (sizeof(TC) == 4) {
-          const bool vec = nv == 4 && (reinterpret_cast<uintptr_t>(cp) & 15) == 0 && (!rp || (reinterpret_cast<uintptr_t>(rp) & 15) == 0);
-          if (vec) {
-            if (rp) { const float4 q = *reinterpret_cast<const float4*>(rp); v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w; }
-            *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-            for (int j = 0; j < nv; ++j) reinterpret_cast<float*>(cp)[j] = v[j] + (rp ? to_f(rp[j]) : 0.f);
-          }
-        } else {
-          const bool vec = nv == 4 && (reinterpret_cast<uintptr_t>(cp) & 7) == 0 && (!rp || (reinterpret_cast<uintptr_t>(rp) & 7) == 0);
-          if (vec) {
-            if (rp) {
-              const uint2 q = *reinterpret_cast<const uint2*>(rp);
-              const __nv_bfloat162* qq = reinterpret_cast<const __nv_bfloat162*>(&q);
-              const float2 f0 = __bfloat1622float2(qq[0]), f1 = __bfloat1622float2(qq[1]);
-              v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
+        for (int u = 0; u < UP; ++u) {
+          radd[u][0] = radd[u][1] = radd[u][2] = radd[u][3] = 0.f;
+          const int rr = rr0 + u * RPP;
+          const int row = m0 + wq * RPW + rr;
+          if (has_r && rr < RPW && row < M && col < N) {
+            const TC* rp = R + (int64_t)row * ldr + col;
+            const int nv = min(4, N - col);
+            if constexpr (sizeof(TC) == 4) {
+              if (nv == 4 && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+                const float4 q = *reinterpret_cast<const float4*>(rp);
+                radd[u][0] = q.x; radd[u][1] = q.y; radd[u][2] = q.z; radd[u][3] = q.w;
+              } else {
+                for (int j = 0; j < nv; ++j) radd[u][j] = to_f(rp[j]);
+              }
+            } else {
+              if (nv == 4 && (reinterpret_cast<uintptr_t>(rp) & 7) == 0) {
+                const uint2 q = *reinterpret_cast<const uint2*>(rp);
+                radd[u][0] = __uint_as_float(q.x << 16); radd[u][1] = __uint_as_float(q.x & 0xffff0000u);
+                radd[u][2] = __uint_as_float(q.y << 16); radd[u][3] = __uint_as_float(q.y & 0xffff0000u);
+              } else {
+                for (int j = 0; j < nv; ++j) radd[u][j] = to_f(rp[j]);
+              }
             }
-            uint2 o;
-            __nv_bfloat162* oo = reinterpret_cast<__nv_bfloat162*>(&o);
-            oo[0] = __floats2bfloat162_rn(v[0], v[1]);
-            oo[1] = __floats2bfloat162_rn(v[2], v[3]);
-            *reinterpret_cast<uint2*>(cp) = o;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UP; ++u) {
+          const int rr = rr0 + u * RPP;
+          const int row = m0 + wq * RPW + rr;
+          if (rr >= RPW || row >= M || col >= N) continue;
+          const float4 a = *reinterpret_cast<const float4*>(&stg[rr * SP + cc]);
+          float v[4] = {a.x, a.y, a.z, a.w};
+          const int nv = min(4, N - col);
+          TC* cp = C + (int64_t)row * ldc + col;
+          if (ATOMIC) {
+            float* fp = reinterpret_cast<float*>(cp);
+            if (nv == 4 && (reinterpret_cast<uintptr_t>(fp) & 15) == 0) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(fp), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+            } else {
+              for (int j = 0; j < nv; ++j) atomicAdd(fp + j, v[j]);
+            }
+            continue;
+          }
+          if (bias) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < nv) v[j] += bias[col + j];
+          }
+          if (relu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] += radd[u][j];
+          if constexpr (sizeof(TC) == 4) {
+            if (nv == 4 && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+              *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+              for (int j = 0; j < nv; ++j) reinterpret_cast<float*>(cp)[j] = v[j];
+            }
           } else {
-            for (int j = 0; j < nv; ++j) cp[j] = from_f<TC>(v[j] + (rp ? to_f(rp[j]) : 0.f));
+            if (nv == 4 && (reinterpret_cast<uintptr_t>(cp) & 7) == 0) {
+              uint2 o;
+              __nv_bfloat162* oo = reinterpret_cast<__nv_bfloat162*>(&o);
+              oo[0] = __floats2bfloat162_rn(v[0], v[1]);
+              oo[1] = __floats2bfloat162_rn(v[2], v[3]);
+              *reinterpret_cast<uint2*>(cp) = o;
+            } else {
+              for (int j = 0; j < nv; ++j) cp[j] = from_f<TC>(v[j]);
+            }
           }
         }
       }
@@ -469,6 +497,9 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   else if (N <= 64 || m_tiles * ceil_div(N, 128) < 148) cfg = 1;
   else cfg = 0;
   if (N <= 32 && !b_mn) cfg = 2;
+  // cfg 4: 128 x 64, 2 stages, 4 CTAs/SM -- many M tiles with a one- or two-block K (the first BLSTM layer's input
+  // projection, K = acoustic dim): a tile is all prologue + epilogue latency, so what helps is more tiles in flight
+  if (cfg != 2 && kb_total <= 2 && m_tiles >= 64) cfg = 4;
   const int BN = (cfg == 0 || wide) ? 128 : (cfg == 2 ? 32 : 64);
   const bool m64 = (cfg == 2 || cfg == 3) && M <= 64;       // half-height A tile for the decoder-step GEMMs
   CUtensorMap ma, mb;
@@ -519,6 +550,7 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
     if (cfg == 0) TC_GO(128, 3, AMN, BMN);                                 \
     if (cfg == 1) TC_GO(64, 4, AMN, BMN);                                  \
     if (cfg == 3) TC_GO(64, 8, AMN, BMN);                                  \
+    if (cfg == 4) TC_GO(64, 2, AMN, BMN);                                  \
   } while (0)
   if (wide) { if (!a_mn) TC_GO64(128, 6, false, false); TC_GO64(128, 6, true, false); }
   if (m64) {                    // M <= 64: half-height tiles, deeper pipelines (12 KB / 16 KB per stage)
