@@ -8,7 +8,8 @@ k = CudaKernels()
 shapes = [(64, 10000, 512, 0, 1), (64, 2048, 512, 0, 1), (64, 2048, 200, 0, 1), (64, 512, 512, 0, 1), (64, 512, 2048, 0, 0),
           (64, 200, 2048, 0, 0), (64, 512, 512, 0, 0), (3200, 512, 512, 0, 1), (3200, 512, 512, 0, 0), (1984, 512, 512, 0, 1),
           (3200, 1024, 512, 0, 1), (3200, 10000, 512, 0, 1), (32256, 1024, 1024, 0, 1), (32256, 1024, 1024, 0, 0),
-          (64512, 1024, 80, 0, 1), (1024, 1024, 32256, 1, 0), (1024, 256, 64512, 1, 0), (512, 512, 3200, 1, 0)]
+          (64512, 1024, 80, 0, 1), (1024, 1024, 32256, 1, 0), (1024, 256, 64512, 1, 0), (512, 512, 3200, 1, 0), (2048, 512, 3200, 1, 0), (512, 2048, 2048, 1, 0),
+          (512, 512, 2048, 1, 0), (2048, 1024, 64, 1, 0), (2048, 512, 64, 1, 0)]
 for (M, N, K, ta, tb) in shapes:
     a = torch.randn((K, M) if ta else (M, K), device='cuda').bfloat16()
     b = torch.randn((N, K) if tb else (K, N), device='cuda').bfloat16()

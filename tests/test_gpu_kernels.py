@@ -341,7 +341,9 @@ def test_glue(ks, dtype):
                                    (64, 10000, 512), (1024, 80, 4096), (1024, 1024, 16384), (37, 24, 8),
                                    # decoder-step shapes served by the cluster split-K kernel (M <= 64, K >= 512)
                                    (64, 512, 2048), (64, 1024, 2048), (37, 200, 1000), (64, 512, 512), (5, 72, 2048),
-                                   (64, 2048, 1536)])
+                                   (64, 2048, 1536),
+                                   # weight-gradient shapes (ta, !tb, fp32 out): cluster split-K with 128-row tiles
+                                   (512, 512, 3200), (2048, 512, 2048), (512, 2048, 3200), (1024, 256, 8064)])
 def test_gemm_tensor_core(ks, ta, tb, M, N, K):
     """tcgen05/TMA/TMEM kernel (forced) vs fp32 matmul of the same bf16 operands: K-major and MN-major
     operand staging, M/N/K tails (TMA zero fill), bf16 and fp32 (split-K atomics) outputs."""
