@@ -63,6 +63,11 @@ int b200st_layernorm_fwd(int dtype, const void* x, const float* gamma, const flo
 int b200st_layernorm_bwd(int dtype, const void* dy, const void* x, const float* gamma,
                          const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
                          int64_t rows, int64_t cols, b200st_stream_t stream);
+/* Same, plus `add` (same shape/dtype as dx, may be NULL): dx = add + LayerNorm gradient.  Lets a residual block's
+ * backward hand the skip-connection gradient to the kernel instead of running a separate add. */
+int b200st_layernorm_bwd_add(int dtype, const void* dy, const void* x, const float* gamma,
+                             const float* mean, const float* rstd, const void* add, void* dx,
+                             float* dgamma, float* dbeta, int64_t rows, int64_t cols, b200st_stream_t stream);
 
 /* ---- multi-head scaled-dot-product attention core (layers.py:162-170,213-229) -------------------
  * q,k,v are the projection outputs viewed as [B, L, H, d] with row strides ldq/ldk/ldv (elements);

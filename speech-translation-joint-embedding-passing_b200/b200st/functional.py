@@ -112,6 +112,109 @@ def mha_core(q, k, v, mask, n_head, temperature):
 
 
 # ------------------------------------------------------------------------------------------------
+# Whole residual sub-layers as ONE autograd node each.  Same kernels as the pieces above; what the fusion buys is
+# launch count on a path that is latency-bound (12 layers x ~30 small kernels): K and V come out of one GEMM on the
+# concatenated w_ks|w_vs, their input gradient out of one GEMM, the skip-connection gradient is added inside the
+# LayerNorm-backward kernel and (self-attention) inside the K|V input-gradient GEMM's epilogue, and the two
+# LayerNorm parameter gradients share one zero-filled buffer.
+# ------------------------------------------------------------------------------------------------
+class _MHABlock(Function):
+    """out = fc(attention(w_qs(LN(q)), w_ks(kv), w_vs(kv))) + q;  MultiHeadAttention.forward, layers.py:148-197
+    (LayerNorm on the query input only, K/V from the raw input, no biases, dropout p = 0)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature):
+        k = K()
+        B, Lq, D = q.shape
+        Lk = kv.size(1)
+        self_attn = kv is q
+        q2 = _c(q).reshape(-1, D)
+        kv2 = q2 if self_attn else _c(kv).reshape(-1, D)
+        qn, mean, rstd = k.layernorm_fwd(q2, ln_w, ln_b, eps)
+        HD = w_q.size(0)
+        qp = k.gemm(qn, rt.operand(w_q), trans_b=True)
+        kvp = k.gemm(kv2, rt.operand_cat(w_k, w_v), trans_b=True)                 # [B*Lk, 2*HD] = K | V
+        kv3 = kvp.view(B, Lk, 2 * HD)
+        o, p = k.mha_fwd(qp.view(B, Lq, HD), kv3[:, :, :HD], kv3[:, :, HD:], mask, n_head, temperature)
+        o2 = o.view(-1, HD)
+        out = k.gemm(o2, rt.operand(w_fc), trans_b=True, residual=q2)
+        ctx.self_attn, ctx.n_head, ctx.temperature, ctx.dims = self_attn, n_head, temperature, (B, Lq, Lk, D, HD)
+        ctx.kv_shape = kv.shape
+        ctx.save_for_backward(q2, None if self_attn else kv2, qn, mean, rstd, qp, kvp, p, o2, ln_w, w_q, w_k, w_v, w_fc)
+        ctx.mark_non_differentiable(p)
+        return out.view(B, Lq, D), p
+
+    @staticmethod
+    def backward(ctx, dout, _dp):
+        k = K()
+        q2, kv2, qn, mean, rstd, qp, kvp, p, o2, ln_w, w_q, w_k, w_v, w_fc = ctx.saved_tensors
+        B, Lq, Lk, D, HD = ctx.dims
+        if kv2 is None:
+            kv2 = q2
+        dout2 = _c(dout).reshape(-1, D)
+        do = k.gemm(dout2, rt.operand(w_fc))
+        dw_fc = k.gemm(dout2, o2, trans_a=True, out_dtype=torch.float32)
+        dqp = torch.empty_like(qp)
+        dkvp = torch.empty_like(kvp)
+        kv3, dkv3 = kvp.view(B, Lk, 2 * HD), dkvp.view(B, Lk, 2 * HD)
+        k.mha_bwd(do.view(B, Lq, HD), qp.view(B, Lq, HD), kv3[:, :, :HD], kv3[:, :, HD:], p, ctx.n_head,
+                  ctx.temperature, dq=dqp.view(B, Lq, HD), dk=dkv3[:, :, :HD], dv=dkv3[:, :, HD:])
+        dw_q = k.gemm(dqp, qn, trans_a=True, out_dtype=torch.float32)
+        dw_kv = k.gemm(dkvp, kv2, trans_a=True, out_dtype=torch.float32)         # [2*HD, D]
+        dqn = k.gemm(dqp, rt.operand(w_q))
+        dln = torch.zeros((2, D), dtype=torch.float32, device=q2.device)
+        dq = k.layernorm_bwd(dqn, q2, ln_w, mean, rstd, dln[0], dln[1], add=dout2)   # + skip-connection gradient
+        wkv = rt.operand_cat(w_k, w_v)
+        if ctx.self_attn:
+            dq = k.gemm(dkvp, wkv, residual=dq)
+            dkv = None
+        else:
+            dkv = k.gemm(dkvp, wkv).view(ctx.kv_shape)
+        return (dq.view(B, Lq, D), dkv, None, dln[0], dln[1], None, dw_q, dw_kv[:HD], dw_kv[HD:], dw_fc, None, None)
+
+
+def mha_block(q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature):
+    """Returns (out [B, Lq, D], attention probabilities [B, H, Lq, Lk]).  Pass the SAME tensor object as q and kv
+    for self-attention: its two gradient contributions are then merged inside the GEMM epilogue."""
+    return _MHABlock.apply(q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature)
+
+
+class _FFNBlock(Function):
+    """x + w_2(relu(w_1(LN(x))));  PositionwiseFeedForward.forward, layers.py:232-252."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, eps, w1, b1, w2, b2):
+        k = K()
+        D = x.size(-1)
+        x2 = _c(x).reshape(-1, D)
+        y, mean, rstd = k.layernorm_fwd(x2, ln_w, ln_b, eps)
+        h = k.gemm(y, rt.operand(w1), trans_b=True, bias=b1, relu=True)
+        out = k.gemm(h, rt.operand(w2), trans_b=True, bias=b2, residual=x2)
+        ctx.save_for_backward(x2, y, mean, rstd, h, ln_w, w1, w2)
+        return out.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        k = K()
+        x2, y, mean, rstd, h, ln_w, w1, w2 = ctx.saved_tensors
+        D = x2.size(1)
+        dout2 = _c(dout).reshape(-1, D)
+        dz = k.relu_bwd(k.gemm(dout2, rt.operand(w2)), h)
+        dw2 = k.gemm(dout2, h, trans_a=True, out_dtype=torch.float32)
+        db2 = k.colsum(dout2)
+        dy = k.gemm(dz, rt.operand(w1))
+        dw1 = k.gemm(dz, y, trans_a=True, out_dtype=torch.float32)
+        db1 = k.colsum(dz)
+        dln = torch.zeros((2, D), dtype=torch.float32, device=x2.device)
+        dx = k.layernorm_bwd(dy, x2, ln_w, mean, rstd, dln[0], dln[1], add=dout2)
+        return dx.view(dout.shape), dln[0], dln[1], None, dw1, db1, dw2, db2
+
+
+def ffn_block(x, ln_w, ln_b, eps, w1, b1, w2, b2):
+    return _FFNBlock.apply(x, ln_w, ln_b, eps, w1, b1, w2, b2)
+
+
+# ------------------------------------------------------------------------------------------------
 # Embedding lookups: Seq2seq.py:188,207; Dec.py:166,223
 # ------------------------------------------------------------------------------------------------
 class _Embedding(Function):

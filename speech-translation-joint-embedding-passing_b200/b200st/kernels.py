@@ -124,13 +124,14 @@ class CudaKernels:
                    'layernorm_fwd')
         return y, mean, rstd
 
-    def layernorm_bwd(self, dy, x, gamma, mean, rstd, dgamma, dbeta):
-        assert dy.is_contiguous() and x.is_contiguous()
+    def layernorm_bwd(self, dy, x, gamma, mean, rstd, dgamma, dbeta, add=None):
+        """dx = [add +] LayerNorm gradient; dgamma / dbeta (fp32, pre-zeroed or running sums) are accumulated into."""
+        assert dy.is_contiguous() and x.is_contiguous() and (add is None or (add.is_contiguous() and add.dtype == x.dtype))
         rows, cols = x.numel() // x.size(-1), x.size(-1)
         dx = torch.empty_like(x)
-        _lib.check(self.lib.b200st_layernorm_bwd(_dt(x), _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd),
-                                                 _p(dx), _p(dgamma), _p(dbeta), rows, cols,
-                                                 self._stream()), 'layernorm_bwd')
+        _lib.check(self.lib.b200st_layernorm_bwd_add(_dt(x), _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(add),
+                                                     _p(dx), _p(dgamma), _p(dbeta), rows, cols,
+                                                     self._stream()), 'layernorm_bwd')
         return dx
 
     # -- multi-head attention core ----------------------------------------------------------------
@@ -162,18 +163,20 @@ class CudaKernels:
                    'mha_fwd')
         return o, p
 
-    def mha_bwd(self, dout, q, k, v, p, n_head, temperature):
+    def mha_bwd(self, dout, q, k, v, p, n_head, temperature, dq=None, dk=None, dv=None):
+        """dq/dk/dv may be caller-provided [B, L, HD] views with a dense last dim (e.g. column slices of one fused
+        [B*L, 2*HD] K|V gradient buffer)."""
         B, Lq, HD = q.shape
         Lk = k.size(1)
         d = HD // n_head
         assert dout.is_contiguous()
         ds = torch.empty_like(p)
-        dq = torch.empty((B, Lq, HD), dtype=q.dtype, device=q.device)
-        dk = torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device)
-        dv = torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device)
+        dq = torch.empty((B, Lq, HD), dtype=q.dtype, device=q.device) if dq is None else dq
+        dk = torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device) if dk is None else dk
+        dv = torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device) if dv is None else dv
         _lib.check(self.lib.b200st_mha_bwd(_dt(q), _p(dout), HD, _p(q), self._bld(q), _p(k),
-                                           self._bld(k), _p(v), self._bld(v), _p(p), _p(ds), _p(dq), HD,
-                                           _p(dk), HD, _p(dv), HD, B, n_head, Lq, Lk, d,
+                                           self._bld(k), _p(v), self._bld(v), _p(p), _p(ds), _p(dq), self._bld(dq),
+                                           _p(dk), self._bld(dk), _p(dv), self._bld(dv), B, n_head, Lq, Lk, d,
                                            float(temperature), self._stream()), 'mha_bwd')
         return dq, dk, dv
 
@@ -399,12 +402,14 @@ class CudaKernels:
                                                self._stream()), 'transpose01')
         return out
 
-    def cast(self, x, dtype):
+    def cast(self, x, dtype, out=None):
         self._need_cuda(x)
-        if x.dtype == dtype:
+        if x.dtype == dtype and out is None:
             return x
         assert x.is_contiguous()
-        out = torch.empty(x.shape, dtype=dtype, device=x.device)
+        if out is None:
+            out = torch.empty(x.shape, dtype=dtype, device=x.device)
+        assert out.is_contiguous() and out.numel() == x.numel() and out.dtype == dtype
         _lib.check(self.lib.b200st_cast(_dt(x), _dt(out), _p(x), _p(out), x.numel(), self._stream()),
                    'cast')
         return out

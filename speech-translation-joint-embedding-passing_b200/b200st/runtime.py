@@ -44,6 +44,30 @@ def operand(param: torch.Tensor) -> torch.Tensor:
     return shadow
 
 
+def operand_cat(*params: torch.Tensor) -> torch.Tensor:
+    """Row-wise concatenation [sum(out_i), in] of several weight matrices in the compute dtype (e.g. w_ks | w_vs so
+    that K and V are projected by ONE GEMM).  Cached like `operand`; rebuilt when any member's version changes."""
+    key = ('cat',) + tuple(id(p) for p in params)
+    vers = tuple(p._version for p in params)
+    ptrs = tuple(p.data_ptr() for p in params)
+    hit = _cache.get(key)
+    if hit is not None and all(r() is p for r, p in zip(hit[0], params)) and hit[1] == vers and hit[2] == ptrs:
+        return hit[3]
+    from .kernels import K
+    rows = [p.size(0) for p in params]
+    buf = torch.empty((sum(rows), params[0].size(1)), dtype=_compute_dtype, device=params[0].device)
+    r0 = 0
+    for p, n in zip(params, rows):
+        src = p.detach().contiguous()
+        if src.dtype == _compute_dtype:
+            buf[r0:r0 + n].copy_(src)
+        else:
+            K().cast(src, _compute_dtype, out=buf[r0:r0 + n])
+        r0 += n
+    _cache[key] = (tuple(weakref.ref(p) for p in params), vers, ptrs, buf)
+    return buf
+
+
 def clear_cache():
     _cache.clear()
 

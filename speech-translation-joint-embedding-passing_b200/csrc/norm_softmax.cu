@@ -39,7 +39,7 @@ __global__ void layernorm_fwd_kernel(const T* __restrict__ x, const float* __res
 template <typename T>
 __global__ void layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                      const float* __restrict__ gamma, const float* __restrict__ mean,
-                                     const float* __restrict__ rstd, T* __restrict__ dx,
+                                     const float* __restrict__ rstd, const T* __restrict__ add, T* __restrict__ dx,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                      int64_t rows, int cols, int rows_per_block) {
   pdl_wait();
@@ -68,7 +68,7 @@ __global__ void layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restri
     for (int c = lane; c < cols; c += 32) {
       const float d = to_f(dyr[c]);
       const float xh = (to_f(xr[c]) - mu) * rs;
-      dxr[c] = from_f<T>(rs * (d * gamma[c] - s1 - xh * s2));
+      dxr[c] = from_f<T>(rs * (d * gamma[c] - s1 - xh * s2) + (add ? to_f(add[row * cols + c]) : 0.f));
       atomicAdd(&sg[c], d * xh);
       atomicAdd(&sb[c], d);
     }
@@ -86,7 +86,8 @@ __global__ void layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restri
 template <typename T, int NV>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_reg_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
-                         const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ add,
+                         T* __restrict__ dx,
                          float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int cols,
                          int rows_per_block) {
   pdl_wait();
@@ -131,10 +132,11 @@ layernorm_bwd_reg_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       if (i < nq) {
-        float o[4];
+        float o[4], ad[4] = {0.f, 0.f, 0.f, 0.f};
+        if (add) load4(add + row * cols + (32 * i + lane) * 4, ad);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          o[j] = rs * (d[i][j] * gam[i][j] - s1 - xh[i][j] * s2);
+          o[j] = rs * (d[i][j] * gam[i][j] - s1 - xh[i][j] * s2) + ad[j];
           ag[i][j] += d[i][j] * xh[i][j];
           ab[i][j] += d[i][j];
         }
@@ -335,24 +337,24 @@ int b200st_layernorm_fwd(int dtype, const void* x, const float* gamma, const flo
   return 0;
 }
 
-int b200st_layernorm_bwd(int dtype, const void* dy, const void* x, const float* gamma,
-                         const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
-                         int64_t rows, int64_t cols, b200st_stream_t stream) {
+int b200st_layernorm_bwd_add(int dtype, const void* dy, const void* x, const float* gamma,
+                             const float* mean, const float* rstd, const void* add, void* dx, float* dgamma,
+                             float* dbeta, int64_t rows, int64_t cols, b200st_stream_t stream) {
   if (rows <= 0) return 0;
   const size_t smem = 2 * cols * sizeof(float);
   if (smem > 48 * 1024) return set_error("layernorm_bwd: cols %lld too large", (long long)cols);
   // ~2 CTAs per SM worth of row strips keeps the final atomics few while filling the chip.
   if (cols % 128 == 0 && cols <= 1024 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dx & 15) == 0 &&
-      ((uintptr_t)gamma & 15) == 0) {
+      ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)add & 15) == 0) {
     const int rpb = 16;             // 8 warps x 2 rows
     B200ST_DISPATCH(dtype, T, {
       if (cols <= 512) {
         B200ST_CUDA(launch_pdl(layernorm_bwd_reg_kernel<T, 4>, dim3((unsigned)ceil_div(rows, rpb)), dim3(256), smem,
-                               (cudaStream_t)stream, (const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta,
+                               (cudaStream_t)stream, (const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)add, (T*)dx, dgamma, dbeta,
                                rows, (int)cols, rpb));
       } else {
         B200ST_CUDA(launch_pdl(layernorm_bwd_reg_kernel<T, 8>, dim3((unsigned)ceil_div(rows, rpb)), dim3(256), smem,
-                               (cudaStream_t)stream, (const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta,
+                               (cudaStream_t)stream, (const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)add, (T*)dx, dgamma, dbeta,
                                rows, (int)cols, rpb));
       }
     });
@@ -363,11 +365,17 @@ int b200st_layernorm_bwd(int dtype, const void* dy, const void* x, const float* 
   if (rpb < 4) rpb = 4;
   B200ST_DISPATCH(dtype, T, {
     B200ST_CUDA(launch_pdl(layernorm_bwd_kernel<T>, dim3((unsigned)ceil_div(rows, rpb)), dim3(128), smem,
-                           (cudaStream_t)stream, (const T*)dy, (const T*)x, gamma, mean, rstd, (T*)dx, dgamma, dbeta,
+                           (cudaStream_t)stream, (const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)add, (T*)dx, dgamma, dbeta,
                            rows, (int)cols, rpb));
   });
   B200ST_LAUNCH_CHECK("layernorm_bwd");
   return 0;
+}
+
+int b200st_layernorm_bwd(int dtype, const void* dy, const void* x, const float* gamma,
+                         const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                         int64_t rows, int64_t cols, b200st_stream_t stream) {
+  return b200st_layernorm_bwd_add(dtype, dy, x, gamma, mean, rstd, nullptr, dx, dgamma, dbeta, rows, cols, stream);
 }
 
 int b200st_log_softmax_fwd(int dtype, const void* x, void* y, int64_t rows, int64_t cols,

@@ -73,13 +73,17 @@ class MultiheadAttention(nn.Module):
         assert self.d_k == self.d_v, 'the fused attention core assumes d_k == d_v (always true upstream)'
         _no_dropout(self.dropout, 'MultiheadAttention')
         _no_dropout(self.attention.dropout, 'ScaledDotProductAttention (hard-wired p=0.1, layers.py:207)')
+        if mask is not None and mask.dtype == torch.bool:
+            mask = mask.view(torch.uint8) if mask.is_contiguous() else mask.to(torch.uint8)
+        if k is v:           # every call site of the reference (self- and cross-attention): one fused sub-layer node
+            return BF.mha_block(q, k, mask, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps,
+                                self.w_qs.weight, self.w_ks.weight, self.w_vs.weight, self.fc.weight, self.n_head,
+                                self.attention.temperature)
         residual = q
         qn = BF.layer_norm(q, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
         qp = BF.linear(qn, self.w_qs.weight)
         kp = BF.linear(k, self.w_ks.weight)
         vp = BF.linear(v, self.w_vs.weight)
-        if mask is not None and mask.dtype == torch.bool:
-            mask = mask.view(torch.uint8) if mask.is_contiguous() else mask.to(torch.uint8)
         o, attn = BF.mha_core(qp, kp, vp, mask, self.n_head, self.attention.temperature)
         out = BF.linear(o, self.fc.weight, residual=residual)      # fc, dropout(p=0), += residual
         return out, attn
@@ -119,9 +123,8 @@ class PositionwiseFeedForward(nn.Module):
 
     def forward(self, x):
         _no_dropout(self.dropout, 'PositionwiseFeedForward')
-        y = BF.layer_norm(x, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
-        y = BF.linear(y, self.w_1.weight, self.w_1.bias, relu=True)
-        return BF.linear(y, self.w_2.weight, self.w_2.bias, residual=x)
+        return BF.ffn_block(x, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps,
+                            self.w_1.weight, self.w_1.bias, self.w_2.weight, self.w_2.bias)
 
 
 # ---- helpers (layers.py:260-309) ---------------------------------------------------------------

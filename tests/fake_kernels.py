@@ -52,7 +52,7 @@ class FakeKernels:
         y = (xf - mean[..., None]) * rstd[..., None] * gamma + beta
         return y.to(x.dtype), mean.reshape(-1), rstd.reshape(-1)
 
-    def layernorm_bwd(self, dy, x, gamma, mean, rstd, dgamma, dbeta):
+    def layernorm_bwd(self, dy, x, gamma, mean, rstd, dgamma, dbeta, add=None):
         cols = x.size(-1)
         xf, dyf = x.float().reshape(-1, cols), dy.float().reshape(-1, cols)
         xh = (xf - mean[:, None]) * rstd[:, None]
@@ -60,6 +60,8 @@ class FakeKernels:
         dx = rstd[:, None] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
         dgamma += (dyf * xh).sum(0)
         dbeta += dyf.sum(0)
+        if add is not None:
+            dx = dx + add.float().reshape(-1, cols)
         return dx.to(x.dtype).view(x.shape)
 
     # -- attention --------------------------------------------------------------------------------
@@ -77,7 +79,8 @@ class FakeKernels:
         o = torch.matmul(p, vf).transpose(1, 2).reshape(B, Lq, HD)
         return o.to(q.dtype), (p.to(q.dtype) if want_probs else None)
 
-    def mha_bwd(self, dout, q, k, v, p, n_head, temperature):
+    def mha_bwd(self, dout, q, k, v, p, n_head, temperature, dq=None, dk=None, dv=None):
+        outs = (dq, dk, dv)
         B, Lq, HD = q.shape
         Lk = k.size(1)
         d = HD // n_head
@@ -92,7 +95,11 @@ class FakeKernels:
         dk = torch.matmul(ds.transpose(2, 3), qf)
         dv = torch.matmul(pf.transpose(2, 3), do)
         back = lambda t, L: t.transpose(1, 2).reshape(B, L, HD).to(q.dtype)
-        return back(dq, Lq), back(dk, Lk), back(dv, Lk)
+        res = [back(dq, Lq), back(dk, Lk), back(dv, Lk)]
+        for i, o in enumerate(outs):
+            if o is not None:
+                o.copy_(res[i]); res[i] = o
+        return tuple(res)
 
     # -- LSTM cell --------------------------------------------------------------------------------
     def lstm_cell_fwd(self, gates, c_prev, residual=None, save_acts=True, h_out=None, c_out=None,
@@ -299,8 +306,11 @@ class FakeKernels:
     def transpose01(self, x, out_dtype=None):
         return x.transpose(0, 1).contiguous().to(out_dtype or x.dtype)
 
-    def cast(self, x, dtype):
-        return x.to(dtype)
+    def cast(self, x, dtype, out=None):
+        if out is None:
+            return x.to(dtype)
+        out.copy_(x.to(dtype))
+        return out
 
     def colsum(self, x, out=None, accumulate=False):
         s = x.float().sum(0)
