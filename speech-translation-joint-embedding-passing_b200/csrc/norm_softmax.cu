@@ -155,9 +155,11 @@ layernorm_bwd_reg_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    atomicAdd(&dgamma[c], sm[c]);
-    atomicAdd(&dbeta[c], sm[cols + c]);
+  // one 16-byte vector reduction per column quad: the per-address chain of same-location L2 atomics (one per CTA)
+  // is what bounds this kernel once the row work is spread over many CTAs
+  for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dgamma + c), "f"(sm[c]), "f"(sm[c + 1]), "f"(sm[c + 2]), "f"(sm[c + 3]) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbeta + c), "f"(sm[cols + c]), "f"(sm[cols + c + 1]), "f"(sm[cols + c + 2]), "f"(sm[cols + c + 3]) : "memory");
   }
 }
 
@@ -345,8 +347,8 @@ int b200st_layernorm_bwd_add(int dtype, const void* dy, const void* x, const flo
   if (smem > 48 * 1024) return set_error("layernorm_bwd: cols %lld too large", (long long)cols);
   // ~2 CTAs per SM worth of row strips keeps the final atomics few while filling the chip.
   if (cols % 128 == 0 && cols <= 1024 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dx & 15) == 0 &&
-      ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)add & 15) == 0) {
-    const int rpb = 16;             // 8 warps x 2 rows
+      ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)add & 15) == 0 && ((uintptr_t)dgamma & 15) == 0 && ((uintptr_t)dbeta & 15) == 0) {
+    const int rpb = 16;             // 8 warps x 2 rows (measured best: fewer rows per CTA lengthen the dgamma/dbeta atomic chains, more serialise the row loads)
     B200ST_DISPATCH(dtype, T, {
       if (cols <= 512) {
         B200ST_CUDA(launch_pdl(layernorm_bwd_reg_kernel<T, 4>, dim3((unsigned)ceil_div(rows, rpb)), dim3(256), smem,
