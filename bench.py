@@ -249,12 +249,16 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # the GPU arm
 # ------------------------------------------------------------------------------------------------
-def _profile_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the recurrence kernels, from the committed
-    `ncu --set full` capture (profiles/r01_blstm_ncu.json), averaged over fwd+bwd; None if not captured."""
+def _profile_traffic(frames_padded, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the recurrence kernels from the committed
+    `ncu --set full` capture (profiles/r01_blstm_ncu.json: one fwd + one bwd launch at T=1008, B=64), averaged over
+    fwd+bwd and scaled to the AVERAGE launch of this run (the four pyramid layers run T, T/2, T/4, T/8 steps; the
+    kernels' traffic is linear in T*B), like `achieved`; None if not captured."""
     try:
         d = json.load(open(os.path.join(ROOT, 'profiles', 'r01_blstm_ncu.json')))
-        return d.get('dram_bytes_per_launch_avg')
+        ref = d['blstm_fwd_tc']
+        mean_t = sum(frames_padded // 2 ** l for l in range(4)) / 4.0
+        return d['dram_bytes_per_launch_avg'] * (mean_t * batch) / (ref['T'] * ref['B'])
     except Exception:
         return None
 
@@ -405,7 +409,7 @@ def run_b200(args):
             'eager_ms_per_step': ms_eager,
             'clocks': clocks,
             'roofline': {'kernel': '+'.join(roof_names), 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
-                         'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': _profile_traffic(), 'peak_source': peak_src,
+                         'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': _profile_traffic(args.frames + 8 - args.frames % 8, args.batch), 'peak_source': peak_src,
                          'us_per_time_step': 1e3 * r_ms / (2 * sum((args.frames + 8 - args.frames % 8) // 2 ** l for l in range(4))),
                          'launches': r_calls, 'avg_launch_ms': r_ms / max(r_calls, 1),
                          'timed': 'CUDA events around every launch of this kernel family on its stream, eager pass of the '
