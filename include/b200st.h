@@ -39,6 +39,8 @@ int64_t b200st_launch_count(void);
  * op(A) is M x K: trans_a=0 -> A stored [M,K] (lda), trans_a=1 -> A stored [K,M].
  * op(B) is K x N: trans_b=0 -> B stored [K,N] (ldb), trans_b=1 -> B stored [N,K] (an nn.Linear weight).
  * R (same dtype/shape as C, may alias C, may be NULL), bias fp32[N] or NULL.
+ * relu: 0 none, 1 ReLU as written above, 2 "gate": C = (R > 0) ? alpha*op(A)*op(B) + bias : 0 -- R is then the
+ * forward activation whose sign masks the result (ReLU backward, layers.py:247, fused into the dX GEMM).
  * Replaces every nn.Linear / matmul / bmm on the path: layers.py:131-134,158-160,192-194,238-249,
  * Seq2seq.py:124-131,180,195,207,253, Dec.py:96-98,432-436, attention.py:192-193, and the LSTM input
  * projections inside torch.nn.LSTM (Enc.py:50-66, Dec.py:104-118). */
@@ -142,6 +144,11 @@ int b200st_argmax_rows(int dtype, const void* x, int64_t ld, int64_t rows, int64
 /* arg-max + the Dec.decode lengths rule below in one launch (lengths may be NULL). */
 int b200st_argmax_rows_lengths(int dtype, const void* x, int64_t ld, int64_t rows, int64_t cols, int64_t* idx,
                                int64_t idx_stride, int32_t* lengths, int step, b200st_stream_t stream);
+/* Same, and (table != NULL) the chosen token's embedding row table[idx] (fp32 [cols, dim]) is written to
+ * emb[r * ld_emb ..] in `dtype`: the free-running LAS decoder's "feed the arg-max back" (Dec.py:331-341) in one launch. */
+int b200st_argmax_rows_embed(int dtype, const void* x, int64_t ld, int64_t rows, int64_t cols, int64_t* idx,
+                             int64_t idx_stride, int32_t* lengths, int step, const float* table, void* emb,
+                             int64_t ld_emb, int64_t dim, b200st_stream_t stream);
 /* Dec.decode lengths rule (Dec.py:334-340) kept on device: if sym in {EOS,PAD} and lengths[b] > step
  * then lengths[b] = step + 1. */
 int b200st_las_update_lengths(const int64_t* sym, int64_t sym_stride, int32_t* lengths, int step,

@@ -199,7 +199,7 @@ class _FFNBlock(Function):
         x2, y, mean, rstd, h, ln_w, w1, w2 = ctx.saved_tensors
         D = x2.size(1)
         dout2 = _c(dout).reshape(-1, D)
-        dz = k.relu_bwd(k.gemm(dout2, rt.operand(w2)), h)
+        dz = k.gemm(dout2, rt.operand(w2), relu_gate=h)                           # ReLU backward in the epilogue
         dw2 = k.gemm(dout2, h, trans_a=True, out_dtype=torch.float32)
         db2 = k.colsum(dout2)
         dy = k.gemm(dz, rt.operand(w1))
@@ -498,8 +498,12 @@ class _LASDecoder(Function):
         Gh = [e(B, 4 * D) for _ in range(n_layers)]          # h_{s-1} W_hh^T
         Gcv = e(B, 4 * D)                                     # cell_value_{s-1} W_ih0[:, E:]^T
         CVb = e(B, D)                                         # dec_out W_ffn[:, 2H:]^T
+        fused_feed = ids_tf is None          # free running: the arg-max kernel also writes the next step's embedding
+        if fused_feed:
+            k.embedding_fwd(ids_in[0], emb_table, dt, out=EMB[0])
+        else:                                # teacher forcing: every input token is known up front
+            k.embedding_fwd(ids_in.reshape(-1), emb_table, dt, out=EMB.view(S * B, -1))
         for s in range(S):
-            k.embedding_fwd(ids_in[s], emb_table, dt, out=EMB[s])
             x = EMB[s]
             for i in range(n_layers):
                 # gates = x W_ih^T + b_ih + b_hh + h W_hh^T   (torch.nn.LSTM step, Dec.py:393-415)
@@ -530,7 +534,8 @@ class _LASDecoder(Function):
                 with rt.fork(side[0]):
                     k.gemm(CV[s + 1], wih[0][:, E:], trans_b=True, out=Gcv)
             k.gemm(CV[s + 1], wo, trans_b=True, bias=b_out, out=LOGITS[s])       # Dec.py:434
-            k.argmax_rows(LOGITS[s], sym_dst[s], lengths=lengths, step=s)        # Dec.py:331 + 334-340
+            feed = (emb_table, EMB[s + 1]) if (fused_feed and s + 1 < S) else None
+            k.argmax_rows(LOGITS[s], sym_dst[s], lengths=lengths, step=s, embed=feed)   # Dec.py:331 + 334-341
         for st in side:
             rt.join(st)
         if ids_tf is None:

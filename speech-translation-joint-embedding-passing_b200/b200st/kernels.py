@@ -72,9 +72,12 @@ class CudaKernels:
 
     # -- GEMM -------------------------------------------------------------------------------------
     def gemm(self, a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=None,
-             relu=False, residual=None, alpha=1.0):
+             relu=False, residual=None, alpha=1.0, relu_gate=None):
         """out = relu?(alpha * op(a) @ op(b) + bias) + residual.  a, b: 2-D (row-strided) or 3-D batched
         (batch stride arbitrary).  op(a) is [M,K], op(b) is [K,N]."""
+        if relu_gate is not None:       # out = (relu_gate > 0) ? a @ b : 0  -- rides the residual slot with relu mode 2
+            assert residual is None and not relu
+            residual, relu = relu_gate, 2
         self._need_cuda(a, b, out, bias, residual)
         batched = a.dim() == 3
         if batched:
@@ -267,17 +270,27 @@ class CudaKernels:
                    'las_attn_bwd')
         return dscore, dq
 
-    def argmax_rows(self, x, idx_out, lengths=None, step=0):
+    def argmax_rows(self, x, idx_out, lengths=None, step=0, embed=None):
         """x [rows, cols] (row-strided); idx_out: int64 1-D view (any stride) of length rows.  With `lengths`
-        (int32 [rows]) the LAS decode-length rule (Dec.py:334-340) is applied in the same launch."""
+        (int32 [rows]) the LAS decode-length rule (Dec.py:334-340) is applied in the same launch; with
+        `embed = (table fp32 [cols, dim], out [rows, dim])` the chosen token's embedding row is written too."""
         self._need_cuda(x, idx_out, lengths)
         _rows(x)
         assert idx_out.dtype == torch.int64 and idx_out.dim() == 1 and idx_out.numel() == x.size(0)
         if lengths is not None:
             assert lengths.dtype == torch.int32 and lengths.is_contiguous() and lengths.numel() == x.size(0)
-        _lib.check(self.lib.b200st_argmax_rows_lengths(
+        table = emb = None
+        ld_emb = dim = 0
+        if embed is not None:
+            table, emb = embed
+            self._need_cuda(table, emb)
+            assert table.dtype == torch.float32 and table.is_contiguous() and table.size(0) == x.size(1)
+            assert emb.dtype == x.dtype and emb.dim() == 2 and emb.stride(1) == 1 and emb.shape == (x.size(0), table.size(1))
+            ld_emb, dim = emb.stride(0), table.size(1)
+        _lib.check(self.lib.b200st_argmax_rows_embed(
             _dt(x), _p(x), x.stride(0), x.size(0), x.size(1), _p(idx_out),
-            idx_out.stride(0) if idx_out.numel() > 1 else 1, _p(lengths), int(step), self._stream()), 'argmax_rows')
+            idx_out.stride(0) if idx_out.numel() > 1 else 1, _p(lengths), int(step), _p(table), _p(emb), ld_emb, dim,
+            self._stream()), 'argmax_rows')
         return idx_out
 
     def las_update_lengths(self, sym, lengths, step):

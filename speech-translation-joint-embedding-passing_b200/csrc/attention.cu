@@ -841,11 +841,13 @@ __global__ void argmax_rows_kernel(const T* __restrict__ x, int64_t ld, int cols
 template <typename T>
 __global__ void __launch_bounds__(256)
 argmax_rows_vec_kernel(const T* __restrict__ x, int64_t ld, int cols, int64_t* __restrict__ idx, int64_t idx_stride,
-                       int32_t* __restrict__ lengths, int step) {
+                       int32_t* __restrict__ lengths, int step, const float* __restrict__ table, T* __restrict__ emb,
+                       int64_t ld_emb, int dim) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ float sv[32];
   __shared__ int si[32];
+  __shared__ int s_sym;
   const int64_t r = blockIdx.x;
   const T* xr = x + r * ld;
   float mx = -INFINITY;
@@ -878,8 +880,15 @@ argmax_rows_vec_kernel(const T* __restrict__ x, int64_t ld, int cols, int64_t* _
     if (lane == 0) {
       const int sym = (i == 0x7fffffff) ? 0 : i;
       idx[r * idx_stride] = sym;
+      s_sym = sym;
       if (lengths && (sym == 3 /*EOS*/ || sym == 0 /*PAD*/) && lengths[r] > step) lengths[r] = step + 1;
     }
+  }
+  if (table) {        // the free-running decoder feeds this token's embedding to the next step (Dec.py:341): same launch
+    __syncthreads();
+    const float* src = table + (int64_t)s_sym * dim;
+    T* dst = emb + r * ld_emb;
+    for (int c = threadIdx.x; c < dim; c += 256) dst[c] = from_f<T>(src[c]);
   }
 }
 
@@ -1069,18 +1078,28 @@ int b200st_argmax_rows(int dtype, const void* x, int64_t ld, int64_t rows, int64
 
 int b200st_argmax_rows_lengths(int dtype, const void* x, int64_t ld, int64_t rows, int64_t cols, int64_t* idx,
                                int64_t idx_stride, int32_t* lengths, int step, b200st_stream_t stream) {
+  return b200st_argmax_rows_embed(dtype, x, ld, rows, cols, idx, idx_stride, lengths, step, nullptr, nullptr, 0, 0, stream);
+}
+
+int b200st_argmax_rows_embed(int dtype, const void* x, int64_t ld, int64_t rows, int64_t cols, int64_t* idx,
+                             int64_t idx_stride, int32_t* lengths, int step, const float* table, void* emb,
+                             int64_t ld_emb, int64_t dim, b200st_stream_t stream) {
   if (rows <= 0) return 0;
   const bool vec = cols % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x & 15) == 0;
   if (vec) {
     B200ST_DISPATCH(dtype, T, {
       B200ST_CUDA(launch_pdl(argmax_rows_vec_kernel<T>, dim3((unsigned)rows), dim3(256), 0, (cudaStream_t)stream,
-                             (const T*)x, ld, (int)cols, idx, idx_stride, lengths, step));
+                             (const T*)x, ld, (int)cols, idx, idx_stride, lengths, step, table, (T*)emb, ld_emb, (int)dim));
     });
     B200ST_LAUNCH_CHECK("argmax_rows_vec");
     return 0;
   }
   if (b200st_argmax_rows(dtype, x, ld, rows, cols, idx, idx_stride, stream)) return -1;
-  if (lengths) return b200st_las_update_lengths(idx, idx_stride, lengths, step, rows, stream);
+  if (lengths && b200st_las_update_lengths(idx, idx_stride, lengths, step, rows, stream)) return -1;
+  if (table) {
+    if (idx_stride != 1) return set_error("argmax_rows_embed: the unfused route needs dense ids");
+    return b200st_embedding_fwd(dtype, idx, table, emb, ld_emb, rows, dim, cols, stream);
+  }
   return 0;
 }
 

@@ -92,8 +92,11 @@ gemm_simt_kernel(int64_t M, int64_t N, int64_t K, float alpha,
       if (gn >= N) continue;
       float v = alpha * acc[i][j];
       if (bias) v += bias[gn];
-      if (relu) v = fmaxf(v, 0.f);
-      if (R) v += to_f(R[gm * ldr + gn]);
+      if (relu == 1) v = fmaxf(v, 0.f);
+      if (R) {
+        const float r = to_f(R[gm * ldr + gn]);
+        v = relu == 2 ? (r > 0.f ? v : 0.f) : v + r;        // relu == 2: R gates the result (ReLU backward)
+      }
       C[gm * ldc + gn] = from_f<TO>(v);
     }
   }

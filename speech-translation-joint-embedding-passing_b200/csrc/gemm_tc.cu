@@ -207,12 +207,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 4; ++j) if (j < nv) v[j] += bias[col + j];
           }
-          if (relu) {
+          if (relu == 1) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
           }
+          if (relu == 2) {            // R gates the result: (R > 0) ? v : 0  (ReLU backward fused into the dX GEMM)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] += radd[u][j];
+            for (int j = 0; j < 4; ++j) v[j] = radd[u][j] > 0.f ? v[j] : 0.f;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] += radd[u][j];
+          }
           if constexpr (sizeof(TC) == 4) {
             if (nv == 4 && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
               *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
@@ -374,10 +379,14 @@ gemm_tc_clk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       for (int j = 0; j < 4; ++j) {
         v[j] *= alpha;
         if (bias && j < nv) v[j] += bias[col + j];
-        if (relu) v[j] = fmaxf(v[j], 0.f);
+        if (relu == 1) v[j] = fmaxf(v[j], 0.f);
       }
       TC* cp = C + (int64_t)row * ldc + col;
       const TC* rp = R ? R + (int64_t)row * ldr + col : nullptr;
+      if (relu == 2 && rp) {
+        for (int j = 0; j < nv; ++j) cp[j] = from_f<TC>(to_f(rp[j]) > 0.f ? v[j] : 0.f);
+        continue;
+      }
       for (int j = 0; j < nv; ++j) cp[j] = from_f<TC>(v[j] + (rp ? to_f(rp[j]) : 0.f));
     }
   }

@@ -26,7 +26,7 @@ class FakeKernels:
 
     # -- GEMM -------------------------------------------------------------------------------------
     def gemm(self, a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=None,
-             relu=False, residual=None, alpha=1.0):
+             relu=False, residual=None, alpha=1.0, relu_gate=None):
         self.launches += 1
         A = a.float().transpose(-1, -2) if trans_a else a.float()
         Bm = b.float().transpose(-1, -2) if trans_b else b.float()
@@ -37,6 +37,9 @@ class FakeKernels:
             y = torch.relu(y)
         if residual is not None:
             y = y + residual.float()
+        if relu_gate is not None:
+            y = torch.where(relu_gate.float() > 0, y, torch.zeros_like(y))
+            residual = relu_gate
         if out is None:
             od = out_dtype or (residual.dtype if residual is not None else a.dtype)
             return y.to(od)
@@ -229,10 +232,13 @@ class FakeKernels:
             dscore_out.copy_(ds); ds = dscore_out
         return ds, dq
 
-    def argmax_rows(self, x, idx_out, lengths=None, step=0):
+    def argmax_rows(self, x, idx_out, lengths=None, step=0, embed=None):
         idx_out.copy_(x.float().argmax(dim=1))
         if lengths is not None:
             self.las_update_lengths(idx_out, lengths, step)
+        if embed is not None:
+            table, out = embed
+            out.copy_(table[idx_out].to(out.dtype))
         return idx_out
 
     def las_update_lengths(self, sym, lengths, step):

@@ -43,6 +43,19 @@ def test_gemm(ks, dtype, ta, tb, M, N, K):
     assert rel_err(y, yr) < TOL[dtype]
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('M,N,K', [(3200, 2048, 512), (37, 29, 13), (64, 512, 2048)])
+def test_gemm_relu_gate_epilogue(ks, dtype, M, N, K):
+    """relu mode 2: the residual slot carries the forward activation and gates the product (ReLU backward)."""
+    c, f = ks
+    a, b = rnd(M, K, dtype=dtype), rnd(K, N, dtype=dtype, seed=1)
+    h = torch.relu(rnd(M, N, dtype=dtype, seed=2))
+    y = c.gemm(a, b, relu_gate=h)
+    yr = f.gemm(a, b, relu_gate=h)
+    assert rel_err(y, yr) < TOL[dtype]
+    assert float(y[h == 0].abs().sum()) == 0.0
+
+
 def test_gemm_strided_views_and_batched(ks):
     c, f = ks
     w = rnd(96, 50)
@@ -257,6 +270,11 @@ def test_argmax_and_lengths(ks):
     out = torch.empty(5, dtype=torch.int64, device='cuda')
     c.argmax_rows(big, out, lengths=ln, step=3)
     assert out.tolist() == [3, int(big[1].float().argmax()), 0, 9999, 3] and ln.tolist() == [4, 7, 4, 7, 2]
+    table = rnd(10000, 200)
+    emb = torch.empty(5, 200, dtype=torch.bfloat16, device='cuda')
+    out2 = torch.empty(5, dtype=torch.int64, device='cuda')
+    c.argmax_rows(big, out2, embed=(table, emb))                  # arg-max + embedding feed in one launch
+    assert torch.equal(out2, out) and torch.equal(emb, table[out].to(torch.bfloat16))
     sym = torch.tensor([3, 5, 0, 9, 3], device='cuda')
     lengths = torch.tensor([7, 7, 7, 7, 2], dtype=torch.int32, device='cuda')
     c.las_update_lengths(sym, lengths, 3)
