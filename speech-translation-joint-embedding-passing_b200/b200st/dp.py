@@ -52,9 +52,17 @@ class GradAllReducer:
         if grads[0].is_cuda:
             if self._stream is None:
                 self._stream = torch.cuda.Stream()
-            # the bucket becomes ready on the compute stream; ship it from a side stream
+            # the bucket becomes ready on the compute stream; ship it from a side stream.  NCCL: the bucket's gradient
+            # tensors are reduced IN PLACE by one grouped (coalesced) launch with ReduceOp.AVG -- no flatten copy, no
+            # divide pass, no unflatten copies at the end of backward (those used to be the serial tail of the step).
             self._stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._stream):
+                if dist.get_backend(self.group) == 'nccl':
+                    with dist._coalescing_manager(self.group, device=grads[0].device, async_ops=True) as cm:
+                        for g in grads:
+                            dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+                    self._inflight.append((cm, None, grads))
+                    return
                 flat = torch._utils._flatten_dense_tensors(grads)
                 flat.div_(self.world)
                 work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
@@ -71,6 +79,8 @@ class GradAllReducer:
         self._flush()
         for work, flat, grads in self._inflight:
             work.wait()
+            if flat is None:                 # reduced in place
+                continue
             if flat.is_cuda:
                 with torch.cuda.stream(self._stream):
                     for g, s in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
