@@ -52,6 +52,16 @@ int b200st_gemm(int dtype_ab, int dtype_c, int trans_a, int trans_b,
                 const void* R, int64_t ldr, int64_t stride_r,
                 const float* bias, int relu, int64_t batch, b200st_stream_t stream);
 
+/* C = relu?( alpha * (op(A) op(B) + op(A2) op(B2)) + bias ) + R   (unbatched; both pairs share trans_a / trans_b,
+ * M and N; K and K2 are their depths).  One launch with a two-segment K loop into the same accumulator on the
+ * tensor-core path; replaces the pair "dx = dG_f W_ih_f; dx += dG_r W_ih_r" of a bidirectional LSTM layer's input
+ * gradient (autograd of torch.nn.LSTM(bidirectional=True), Enc.py:150-167). */
+int b200st_gemm2(int dtype_ab, int dtype_c, int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, int64_t K2,
+                 float alpha, const void* A, int64_t lda, const void* B, int64_t ldb,
+                 const void* A2, int64_t lda2, const void* B2, int64_t ldb2,
+                 void* C, int64_t ldc, const void* R, int64_t ldr, const float* bias, int relu,
+                 b200st_stream_t stream);
+
 /* GEMM kernel selection: 0 = auto (bf16 operands that TMA can address -> tcgen05 tensor-core kernel, everything
  * else -> exact CUDA-core kernel), 1 = CUDA cores only, 2 = tensor cores required (error if not eligible).
  * Returns the previous mode.  Used by tests to compare the two kernels; the product leaves it at 0. */

@@ -421,9 +421,8 @@ class _BLSTMLayer(Function):
             k.gemm(dgr, x2, trans_a=True, out=dw_ih_r)
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = k.gemm(dgf, rt.operand(w_ih_f))
-            k.gemm(dgr, rt.operand(w_ih_r), residual=dx, out=dx)
-            dx = dx.view(T, B, I)
+            # both directions' contributions in ONE launch (two-segment K loop into the same accumulator)
+            dx = k.gemm2(dgf, rt.operand(w_ih_f), dgr, rt.operand(w_ih_r)).view(T, B, I)
         rt.join(side[0])
         rt.join(side[1])
         return dx, None, dw_ih_f, dw_hh_f, db_f, db_f, dw_ih_r, dw_hh_r, db_r, db_r, None, None

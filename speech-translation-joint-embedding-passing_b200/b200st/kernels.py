@@ -114,6 +114,32 @@ class CudaKernels:
             _p(residual), ldr, sr, _p(bias), int(relu), nb, self._stream()), 'gemm')
         return out
 
+    def gemm2(self, a, b, a2, b2, *, trans_b=False, out=None, out_dtype=None, bias=None, residual=None, alpha=1.0):
+        """out = alpha * (a @ op(b) + a2 @ op(b2)) + bias + residual, 2-D row-strided operands: one launch with a
+        two-segment K loop (tensor-core path) instead of a GEMM plus an accumulate-into GEMM."""
+        self._need_cuda(a, b, a2, b2, out, bias, residual)
+        for t in (a, b, a2, b2):
+            _rows(t)
+        M, K = a.shape
+        K2 = a2.size(1)
+        N = b.size(0) if trans_b else b.size(1)
+        assert a2.size(0) == M and (b.size(1) if trans_b else b.size(0)) == K
+        assert (b2.size(0) if trans_b else b2.size(1)) == N and (b2.size(1) if trans_b else b2.size(0)) == K2
+        assert a.dtype == b.dtype == a2.dtype == b2.dtype
+        if out is None:
+            out = torch.empty((M, N), dtype=out_dtype or (residual.dtype if residual is not None else a.dtype),
+                              device=a.device)
+        _rows(out)
+        ldr = 0
+        if residual is not None:
+            _rows(residual)
+            assert residual.dtype == out.dtype and residual.shape == out.shape
+            ldr = residual.stride(0)
+        _lib.check(self.lib.b200st_gemm2(_dt(a), _dt(out), 0, int(trans_b), M, N, K, K2, float(alpha), _p(a), a.stride(0),
+                                         _p(b), b.stride(0), _p(a2), a2.stride(0), _p(b2), b2.stride(0), _p(out),
+                                         out.stride(0), _p(residual), ldr, _p(bias), 0, self._stream()), 'gemm2')
+        return out
+
     # -- LayerNorm --------------------------------------------------------------------------------
     def layernorm_fwd(self, x, gamma, beta, eps, save_stats=True):
         self._need_cuda(x, gamma, beta)

@@ -165,7 +165,8 @@ bool gemm_tc_eligible(int dtype_ab, int ta, int tb, int64_t M, int64_t N, int64_
                       const void* B, int64_t ldb, int64_t batch);
 int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const void* A, int64_t lda,
             const void* B, int64_t ldb, void* C, int64_t ldc, const void* R, int64_t ldr, const float* bias, int relu,
-            cudaStream_t st);
+            cudaStream_t st, const void* A2 = nullptr, int64_t lda2 = 0, const void* B2 = nullptr, int64_t ldb2 = 0,
+            int64_t K2 = 0);
 static int g_gemm_backend = 0;   // 0 auto, 1 CUDA cores only, 2 tensor cores required
 }  // namespace b200st
 
@@ -195,4 +196,26 @@ extern "C" int b200st_gemm(int dtype_ab, int dtype_c, int trans_a, int trans_b, 
   return gemm_simt(dtype_ab, dtype_c, trans_a, trans_b, M, N, K, alpha, A, lda, stride_a, B,
                    ldb, stride_b, C, ldc, stride_c, R, ldr, stride_r, bias, relu, batch,
                    (cudaStream_t)stream);
+}
+
+// C = relu?(alpha * (op(A) op(B) + op(A2) op(B2)) + bias) + R: one launch with a two-segment K loop on the tensor-core
+// path (first segment K %% 64 == 0), otherwise two GEMMs chained through the residual slot.
+extern "C" int b200st_gemm2(int dtype_ab, int dtype_c, int trans_a, int trans_b, int64_t M, int64_t N, int64_t K,
+                            int64_t K2, float alpha, const void* A, int64_t lda, const void* B, int64_t ldb,
+                            const void* A2, int64_t lda2, const void* B2, int64_t ldb2, void* C, int64_t ldc,
+                            const void* R, int64_t ldr, const float* bias, int relu, b200st_stream_t stream) {
+  using namespace b200st;
+  if (M <= 0 || N <= 0) return 0;
+  const bool ok = g_gemm_backend != 1 && K % 64 == 0 && relu != 2 &&
+                  gemm_tc_eligible(dtype_ab, trans_a, trans_b, M, N, K, A, lda, B, ldb, 1) &&
+                  gemm_tc_eligible(dtype_ab, trans_a, trans_b, M, N, K2, A2, lda2, B2, ldb2, 1);
+  if (ok)
+    return gemm_tc(dtype_c, trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, C, ldc, R, ldr, bias, relu,
+                   (cudaStream_t)stream, A2, lda2, B2, ldb2, K2);
+  if (relu) return set_error("gemm2: the chained fallback cannot apply an activation to the sum");
+  if (b200st_gemm(dtype_ab, dtype_c, trans_a, trans_b, M, N, K, alpha, A, lda, 0, B, ldb, 0, C, ldc, 0, R, ldr, 0,
+                  bias, 0, 1, stream))
+    return -1;
+  return b200st_gemm(dtype_ab, dtype_c, trans_a, trans_b, M, N, K2, alpha, A2, lda2, 0, B2, ldb2, 0, C, ldc, 0, C, ldc,
+                     0, nullptr, 0, 1, stream);
 }

@@ -44,6 +44,7 @@ template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC, bool ATOMIC, in
 __global__ void __launch_bounds__(TC_THREADS, (BN * TC_BK * 2 + BM * TC_BK * 2) * STAGES <= 50 * 1024 ? 4 :
                                               ((BN * TC_BK * 2 + BM * TC_BK * 2) * STAGES <= 100 * 1024 ? 2 : 1))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_b2, int kb_seg1,
                TC* __restrict__ C, int64_t ldc, const TC* R, int64_t ldr, const float* __restrict__ bias,
                int relu, float alpha, int M, int N, int K, int kb_per_split) {
   using S = TcSmem<BN, STAGES, BM>;
@@ -89,18 +90,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         uint8_t* sa = smem + s * S::STAGE;
         uint8_t* sb = sa + S::A_BYTES;
         mbar_expect_tx(&full[s], S::STAGE);
-        const int k0 = (kb_begin + it) * TC_BK;
+        // two-segment K: k-blocks [0, kb_seg1) come from (A, B), the rest from (A2, B2) -- C = A B + A2 B2 in one
+        // accumulator (the two directions' input gradients of a BLSTM layer)
+        const bool seg2 = kb_begin + it >= kb_seg1;
+        const CUtensorMap* pa = seg2 ? &tma_a2 : &tma_a;
+        const CUtensorMap* pb = seg2 ? &tma_b2 : &tma_b;
+        const int k0 = (kb_begin + it - (seg2 ? kb_seg1 : 0)) * TC_BK;
         if (A_MN) {
 #pragma unroll
-          for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (TC_BK * 128), &tma_a, m0 + c * 64, k0, &full[s]);
+          for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (TC_BK * 128), pa, m0 + c * 64, k0, &full[s]);
         } else {
-          tma_load_2d(sa, &tma_a, k0, m0, &full[s]);
+          tma_load_2d(sa, pa, k0, m0, &full[s]);
         }
         if (B_MN) {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (TC_BK * 128), &tma_b, n0 + c * 64, k0, &full[s]);
+          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (TC_BK * 128), pb, n0 + c * 64, k0, &full[s]);
         } else {
-          tma_load_2d(sb, &tma_b, k0, n0, &full[s]);
+          tma_load_2d(sb, pb, k0, n0, &full[s]);
         }
       }
     }
@@ -443,7 +449,7 @@ bool gemm_tc_eligible(int dtype_ab, int ta, int tb, int64_t M, int64_t N, int64_
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC, int BM = TC_BM>
 static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const CUtensorMap& ma, const CUtensorMap& mb,
-                     void* C, int64_t ldc, const void* R, int64_t ldr, const float* bias, int relu, int splits,
+                     const CUtensorMap& ma2, const CUtensorMap& mb2, int kb_seg1, void* C, int64_t ldc, const void* R, int64_t ldr, const float* bias, int relu, int splits,
                      int kb_per_split, cudaStream_t st) {
   using S = TcSmem<BN, STAGES, BM>;
   static_assert(S::TOTAL <= 227 * 1024, "tile configuration exceeds shared memory");
@@ -452,7 +458,7 @@ static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const CUtenso
     if constexpr (sizeof(TC) == 4) {
       auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, float, true, BM>;
       B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-      B200ST_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), S::TOTAL, st, ma, mb, (float*)C, ldc, (const float*)nullptr,
+      B200ST_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), S::TOTAL, st, ma, mb, ma2, mb2, kb_seg1, (float*)C, ldc, (const float*)nullptr,
                              (int64_t)0, (const float*)nullptr, 0, alpha, (int)M, (int)N, (int)K, kb_per_split));
     } else {
       return set_error("gemm_tc: split-K needs an fp32 output");
@@ -460,7 +466,7 @@ static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const CUtenso
   } else {
     auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, TC, false, BM>;
     B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    B200ST_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), S::TOTAL, st, ma, mb, (TC*)C, ldc, (const TC*)R, ldr, bias, relu,
+    B200ST_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), S::TOTAL, st, ma, mb, ma2, mb2, kb_seg1, (TC*)C, ldc, (const TC*)R, ldr, bias, relu,
                            alpha, (int)M, (int)N, (int)K, kb_per_split));
   }
   B200ST_LAUNCH_CHECK("gemm_tc");
@@ -488,7 +494,13 @@ void gemm_tc_set_cluster_splitk(int on) { g_clk_enabled = on; }
 
 int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const void* A, int64_t lda,
             const void* B, int64_t ldb, void* C, int64_t ldc, const void* R, int64_t ldr, const float* bias, int relu,
-            cudaStream_t st) {
+            cudaStream_t st, const void* A2, int64_t lda2, const void* B2, int64_t ldb2, int64_t K2) {
+  // optional second operand pair (same op() forms, K2 deep): C = alpha (op(A) op(B) + op(A2) op(B2)) + ...; the
+  // first segment must end on a k-block boundary
+  const bool dual = A2 != nullptr && K2 > 0;
+  if (dual && K % TC_BK) return set_error("gemm_tc: two-segment GEMM needs K %% 64 == 0 for the first segment");
+  const int64_t K1 = K;
+  if (dual) K += K2;
   // op(A) is M x K: ta=0 -> stored [M,K] (K-major); ta=1 -> stored [K,M] (M-major).
   // op(B) is K x N: tb=1 -> stored [N,K] (K-major); tb=0 -> stored [K,N] (N-major).
   const bool a_mn = ta != 0, b_mn = tb == 0;
@@ -512,13 +524,22 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   const int BN = (cfg == 0 || wide) ? 128 : (cfg == 2 ? 32 : 64);
   const bool m64 = (cfg == 2 || cfg == 3) && M <= 64;       // half-height A tile for the decoder-step GEMMs
   CUtensorMap ma, mb;
-  if (a_mn) { if (make_map(&ma, A, K, M, lda, TC_BK)) return -1; }
-  else      { if (make_map(&ma, A, M, K, lda, m64 ? 64 : TC_BM)) return -1; }
-  if (b_mn) { if (make_map(&mb, B, K, N, ldb, TC_BK)) return -1; }
-  else      { if (make_map(&mb, B, N, K, ldb, BN)) return -1; }
+  if (a_mn) { if (make_map(&ma, A, K1, M, lda, TC_BK)) return -1; }
+  else      { if (make_map(&ma, A, M, K1, lda, m64 ? 64 : TC_BM)) return -1; }
+  if (b_mn) { if (make_map(&mb, B, K1, N, ldb, TC_BK)) return -1; }
+  else      { if (make_map(&mb, B, N, K1, ldb, BN)) return -1; }
+  CUtensorMap ma2 = ma, mb2 = mb;
+  int kb_seg1 = 0x7fffffff;
+  if (dual) {
+    if (a_mn) { if (make_map(&ma2, A2, K2, M, lda2, TC_BK)) return -1; }
+    else      { if (make_map(&ma2, A2, M, K2, lda2, m64 ? 64 : TC_BM)) return -1; }
+    if (b_mn) { if (make_map(&mb2, B2, K2, N, ldb2, TC_BK)) return -1; }
+    else      { if (make_map(&mb2, B2, N, K2, ldb2, BN)) return -1; }
+    kb_seg1 = (int)(K1 / TC_BK);
+  }
   // cluster split-K: decoder-step shapes whose few N tiles would each stream a long K alone
   const int64_t tiles_1cta = ceil_div(N, BN);       // CTAs the non-split configuration would launch
-  if (g_clk_enabled && m64 && !a_mn && kb_total >= 8 && (tiles_1cta <= 16 || (tiles_1cta <= 32 && kb_total >= 16))) {
+  if (g_clk_enabled && !dual && m64 && !a_mn && kb_total >= 8 && (tiles_1cta <= 16 || (tiles_1cta <= 32 && kb_total >= 16))) {
     int cs = kb_total >= 16 ? 8 : 4;
     while (cs > 2 && ceil_div(N, 64) * cs > 160) cs >>= 1;
     const int kps = (int)ceil_div(kb_total, cs);
@@ -534,7 +555,7 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   // split-K when the output has few tiles and K is long (weight gradients): fp32 output, plain sum only.
   const int64_t tiles = m_tiles * ceil_div(N, BN);
   int splits = 1;
-  if (dtype_c == B200ST_F32 && !bias && !relu && !R && tiles < 96 && kb_total >= 16) {
+  if (dtype_c == B200ST_F32 && !dual && !bias && !relu && !R && tiles < 96 && kb_total >= 16) {
     splits = (int)(296 / tiles);
     if (splits > kb_total / 4) splits = kb_total / 4;
     if (splits < 1) splits = 1;
@@ -545,14 +566,14 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
 #define TC_GO(BN_, ST_, AMN, BMN)                                                                          \
   do {                                                                                                     \
     if (dtype_c == B200ST_F32)                                                                             \
-      return launch_tc<BN_, ST_, AMN, BMN, float>(M, N, K, alpha, ma, mb, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
-    return launch_tc<BN_, ST_, AMN, BMN, __nv_bfloat16>(M, N, K, alpha, ma, mb, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
+      return launch_tc<BN_, ST_, AMN, BMN, float>(M, N, K, alpha, ma, mb, ma2, mb2, kb_seg1, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
+    return launch_tc<BN_, ST_, AMN, BMN, __nv_bfloat16>(M, N, K, alpha, ma, mb, ma2, mb2, kb_seg1, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
   } while (0)
 #define TC_GO64(BN_, ST_, AMN, BMN)                                                                        \
   do {                                                                                                     \
     if (dtype_c == B200ST_F32)                                                                             \
-      return launch_tc<BN_, ST_, AMN, BMN, float, 64>(M, N, K, alpha, ma, mb, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
-    return launch_tc<BN_, ST_, AMN, BMN, __nv_bfloat16, 64>(M, N, K, alpha, ma, mb, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
+      return launch_tc<BN_, ST_, AMN, BMN, float, 64>(M, N, K, alpha, ma, mb, ma2, mb2, kb_seg1, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
+    return launch_tc<BN_, ST_, AMN, BMN, __nv_bfloat16, 64>(M, N, K, alpha, ma, mb, ma2, mb2, kb_seg1, C, ldc, R, ldr, bias, relu, splits, kb_per_split, st); \
   } while (0)
 #define TC_CFG(AMN, BMN)                                                   \
   do {                                                                     \

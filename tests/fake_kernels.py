@@ -46,6 +46,20 @@ class FakeKernels:
         out.copy_(y.to(out.dtype))
         return out
 
+    def gemm2(self, a, b, a2, b2, *, trans_b=False, out=None, out_dtype=None, bias=None, residual=None, alpha=1.0):
+        self.launches += 1
+        Bm = b.float().t() if trans_b else b.float()
+        B2 = b2.float().t() if trans_b else b2.float()
+        y = alpha * (a.float() @ Bm + a2.float() @ B2)
+        if bias is not None:
+            y = y + bias
+        if residual is not None:
+            y = y + residual.float()
+        if out is None:
+            return y.to(out_dtype or (residual.dtype if residual is not None else a.dtype))
+        out.copy_(y.to(out.dtype))
+        return out
+
     # -- LayerNorm --------------------------------------------------------------------------------
     def layernorm_fwd(self, x, gamma, beta, eps, save_stats=True):
         xf = x.float()

@@ -56,6 +56,23 @@ def test_gemm_relu_gate_epilogue(ks, dtype, M, N, K):
     assert float(y[h == 0].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('M,N,K,K2,tb', [(8064, 1024, 1024, 1024, False), (300, 80, 1024, 1024, False),
+                                         (64, 512, 128, 200, True), (37, 29, 13, 64, False), (513, 256, 64, 40, True)])
+def test_gemm2_two_segment(ks, dtype, M, N, K, K2, tb):
+    """C = A B + A2 B2 (+ bias + residual) in one launch: two-segment K loop on the tensor-core path, chained
+    GEMMs otherwise (fp32, first segment not a multiple of 64, ...)."""
+    c, f = ks
+    a, a2 = rnd(M, K, dtype=dtype), rnd(M, K2, dtype=dtype, seed=1)
+    b = rnd(N, K, dtype=dtype, seed=2) if tb else rnd(K, N, dtype=dtype, seed=2)
+    b2 = rnd(N, K2, dtype=dtype, seed=3) if tb else rnd(K2, N, dtype=dtype, seed=3)
+    res, bias = rnd(M, N, dtype=dtype, seed=4), rnd(N, seed=5)
+    assert rel_err(c.gemm2(a, b, a2, b2, trans_b=tb), f.gemm2(a, b, a2, b2, trans_b=tb)) < TOL[dtype]
+    y = c.gemm2(a, b, a2, b2, trans_b=tb, bias=bias, residual=res, alpha=0.5)
+    yr = f.gemm2(a, b, a2, b2, trans_b=tb, bias=bias, residual=res, alpha=0.5)
+    assert rel_err(y, yr) < TOL[dtype]
+
+
 def test_gemm_strided_views_and_batched(ks):
     c, f = ks
     w = rnd(96, 50)
