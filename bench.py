@@ -46,7 +46,8 @@ def workload(args):
             'per_gpu_batch': args.batch, 'global_batch': args.batch * args.gpus, 'frames': args.frames,
             'frames_padded': args.frames + 8 - args.frames % 8, 'acous_dim': 80, 'vocab': 10000,
             'dim_model': 512, 'heads': 8, 'layers': '6+6', 'max_seq_len_src': 32, 'tgt_len': 50,
-            'step': 'forward_train(ST) + masked NLL + backward' + (' + grad all-reduce' if args.gpus > 1 else ''),
+            'step': 'Trainer_ST._train_batch: forward_train(ST) + masked NLL + backward' +
+                    (' + grad all-reduce' if args.gpus > 1 else '') + ' + grad-norm clip(1.0) + Adam',
             'parallelism': f'dp{args.gpus}', 'dropout': 0.0}
 
 
@@ -183,18 +184,21 @@ ALL_FAMILIES = ['gemm', 'gemm2', 'layernorm_fwd', 'layernorm_bwd', 'mha_fwd', 'm
                 'blstm_fwd', 'blstm_bwd', 'las_attn_fwd', 'las_attn_bwd', 'argmax_rows', 'las_update_lengths',
                 'embedding_fwd', 'embedding_bwd', 'mix_gather_concat', 'log_softmax_fwd', 'log_softmax_bwd',
                 'masked_nll_fwd', 'masked_nll_bwd', 'add', 'add_posenc', 'transpose01', 'cast', 'colsum',
-                'relu_bwd', 'token_mask', 'length_mask']
+                'relu_bwd', 'token_mask', 'length_mask', 'clip_adam_step']
 
 
 # ------------------------------------------------------------------------------------------------
 # the CPU arm: the reference's algorithm (oracle port, plain PyTorch fp32) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_step(P, cfg, data):
+def cpu_step(P, cfg, data, adam=None):
     from oracle import st_oracle as O
     for v in P.values():
         v.grad = None
     loss, _ = O.train_step_st(P, cfg, data['src'], data['tgt'], data['acous_feats'], data['acous_lens'])
     loss.backward()
+    if adam is not None:                     # Optimizer.step(): modules/optim.py:31-36
+        torch.nn.utils.clip_grad_norm_([v for v in P.values() if v.grad is not None], 1.0)
+        adam.step()
     return float(loss.detach())
 
 
@@ -206,8 +210,9 @@ def cpu_baseline(args, budget_s=25.0, steps=1, warmup=0):
     torch.set_num_threads(cores)
     cfg = st_config()
     P = {k: v.requires_grad_(True) for k, v in O.init_params(cfg, seed=333).items()}
+    adam = torch.optim.Adam(list(P.values()), lr=1e-5)
     probe = O.synthetic_batch(cfg, 1, args.frames, seed=1)
-    t0 = time.perf_counter(); cpu_step(P, cfg, probe); t_probe = time.perf_counter() - t0   # also warms the threads
+    t0 = time.perf_counter(); cpu_step(P, cfg, probe, adam); t_probe = time.perf_counter() - t0   # also warms the threads
     total_steps = steps + warmup
     # cost model: t(b) ~ t_probe * (0.5 + 0.5 * b)  (the 1890 serial LSTM steps have a large batch-independent part)
     b = 1
@@ -218,15 +223,15 @@ def cpu_baseline(args, budget_s=25.0, steps=1, warmup=0):
     else:
         data = O.synthetic_batch(cfg, b, args.frames, seed=333)
         for _ in range(warmup):
-            cpu_step(P, cfg, data)
+            cpu_step(P, cfg, data, adam)
         t0 = time.perf_counter()
         for _ in range(steps):
-            cpu_step(P, cfg, data)
+            cpu_step(P, cfg, data, adam)
         dt = (time.perf_counter() - t0) / steps
         steps_done = steps
     return {'value': b / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
             'sample': f'configs[2] shapes ({args.frames} frames, V=10k, 6+6 layers), batch {b} of {args.batch}, '
-                      f'{steps_done} timed step(s) of fwd+bwd, fp32, torch.set_num_threads({cores}); the reference is '
+                      f'{steps_done} timed step(s) of fwd+bwd+clip+Adam, fp32, torch.set_num_threads({cores}); the reference is '
                       f'pure Python/PyTorch and cannot travel to the GPU box, so its algorithm is timed through '
                       f'oracle/st_oracle.py (same torch primitives at the same call sites)',
             'ms_per_step': dt * 1e3, 'batch': b}
@@ -298,7 +303,11 @@ def run_b200(args):
     cfg = st_config()
     model = build_model(cfg, device)
     reducer = GradAllReducer(model) if world > 1 else None
-    trainer = Trainer_ST(use_gpu=True, batch_size=args.batch, minibatch_partition=1, reducer=reducer)
+    from modules.optim import Optimizer
+    # the reference's optimizer (trainer_base.py:422-426) at its warm-up starting rate (learning_rate_init)
+    optimizer = Optimizer(torch.optim.Adam(model.parameters(), lr=1e-5), max_grad_norm=1.0)
+    trainer = Trainer_ST(use_gpu=True, batch_size=args.batch, minibatch_partition=1, reducer=reducer,
+                         optimizer=optimizer)
 
     host = O.synthetic_batch(cfg, args.batch, args.frames, seed=333 + rank)
     pin = lambda t: t.pin_memory()
@@ -352,10 +361,17 @@ def run_b200(args):
 
     # ---- the measured step: one CUDA graph of forward_train + loss + backward (+ all-reduce)
     graphed = None
+    ms_fb = None
     if not args.no_graph:
         try:
             from b200st.graph import GraphedTrainStep
-            graphed = GraphedTrainStep(model, trainer, dev_items)
+            g_fb = GraphedTrainStep(model, trainer, dev_items)           # forward + backward only (north-star hot path)
+            for _ in range(max(args.warmup, 3)):
+                g_fb()
+            ms_fb = timed(lambda: g_fb(), args.steps)
+            del g_fb
+            model.zero_grad(set_to_none=True)
+            graphed = GraphedTrainStep(model, trainer, dev_items, with_optimizer=True)
         except Exception as ex:            # e.g. a collective that cannot be captured: stay eager, say so
             print(f'[bench] CUDA graph capture failed ({type(ex).__name__}: {ex}); timing the eager step', file=sys.stderr)
             graphed = None
@@ -406,6 +422,10 @@ def run_b200(args):
                     'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e},
             'gpu_launches': int(launches), 'gpu_launches_per_step': int(launches_per_step),
             'execution': ('one CUDA graph replay per step' if graphed is not None else 'eager launches'),
+            'fwd_bwd_only': (None if ms_fb is None else {
+                'ms_per_step': ms_fb, 'value': total_units / (ms_fb / 1e3), 'unit': UNIT,
+                'what': 'the same graph without the optimizer step (forward + loss + backward' +
+                        (' + grad all-reduce)' if world > 1 else ')')}),
             'eager_ms_per_step': ms_eager,
             'clocks': clocks,
             'roofline': {'kernel': '+'.join(roof_names), 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,

@@ -22,8 +22,14 @@ class GraphedTrainStep:
     usage:  g = GraphedTrainStep(model, trainer, example_items);  loss = g(new_items)   # device scalar
     Gradients are left in `p.grad` (static buffers, overwritten by every replay)."""
 
-    def __init__(self, model, trainer, items: Dict, warmup: int = 3):
+    def __init__(self, model, trainer, items: Dict, warmup: int = 3, with_optimizer: bool = False):
+        """with_optimizer: also capture `trainer.optimizer.step()` (fused clip + Adam, modules/optim.py) behind the
+        backward / gradient all-reduce, i.e. the whole of Trainer_ST._train_batch (trainer_st.py:211-299) is one
+        graph.  Warm-up passes do NOT step the optimizer.  Set the learning rate with `trainer.optimizer.set_lr()`
+        before a replay; the step count lives on the device."""
         self.model, self.trainer = model, trainer
+        if with_optimizer and trainer.optimizer is None:
+            raise ValueError('with_optimizer=True needs trainer.optimizer')
         dev = next(model.parameters()).device
         self.static = {
             'srcid': [items['srcid'][0].to(dev).clone()],
@@ -41,11 +47,15 @@ class GraphedTrainStep:
                 trainer._train_batch_device(model, self.static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if with_optimizer:
+            trainer.optimizer._engine().prepare()     # state + pointer tables for the parameters that got a gradient
         model.zero_grad(set_to_none=True)
         rt.clear_cache()                      # weight shadows get (re)built inside the captured region
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = trainer._train_batch_device(model, self.static)
+            if with_optimizer:
+                trainer.optimizer.step()
 
     def load(self, items: Dict, non_blocking: bool = True):
         """Copy a new batch (host pinned or device tensors of the captured shapes) into the static buffers."""

@@ -489,6 +489,29 @@ class CudaKernels:
         return mask
 
 
+    # -- fused clip + Adam (modules/optim.py:31-36) -------------------------------------------------
+    def opt_chunk(self) -> int:
+        return int(self.lib.b200st_opt_chunk())
+
+    def clip_adam_step(self, tensors, table, blockmap, partials, scal, step, lr, *, max_grad_norm, beta1, beta2,
+                       eps, weight_decay):
+        """One optimizer step over every tensor in `table` (device int64 [n][6], see include/b200st.h); `tensors`
+        (lists of params / grads / exp_avg / exp_avg_sq) is what the table points at and is only used by test
+        stand-ins.  step, lr: fp32 device scalars; scal: fp32 [4] device scratch that receives
+        {clip coefficient, lr / bias_correction1, sqrt(bias_correction2), grad norm}."""
+        self._need_cuda(table, blockmap, partials, scal, step, lr)
+        nb = blockmap.size(0)
+        clip = max_grad_norm is not None and max_grad_norm > 0
+        if clip:
+            _lib.check(self.lib.b200st_multi_sqnorm(_p(table), _p(blockmap), nb, _p(partials), self._stream()),
+                       'multi_sqnorm')
+        _lib.check(self.lib.b200st_adam_prepare(_p(partials) if clip else None, nb, float(max_grad_norm or 0.0),
+                                                _p(lr), float(beta1), float(beta2), _p(step), _p(scal),
+                                                self._stream()), 'adam_prepare')
+        _lib.check(self.lib.b200st_multi_adam(_p(table), _p(blockmap), nb, _p(scal), float(beta1), float(beta2),
+                                              float(eps), float(weight_decay), self._stream()), 'multi_adam')
+
+
 _backend = None
 
 

@@ -60,6 +60,33 @@ class FakeKernels:
         out.copy_(y.to(out.dtype))
         return out
 
+    # -- fused clip + Adam ------------------------------------------------------------------------
+    def opt_chunk(self):
+        return 8192
+
+    def clip_adam_step(self, tensors, table, blockmap, partials, scal, step, lr, *, max_grad_norm, beta1, beta2,
+                       eps, weight_decay):
+        """torch.nn.utils.clip_grad_norm_ + torch.optim.Adam (amsgrad off) restated with torch ops on the tensors the
+        device table points at; p.grad is left unscaled (the clip coefficient is applied on the fly)."""
+        self.launches += 3
+        params, grads, ms, vs = tensors
+        norm = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).float()
+        clip = torch.ones((), device=norm.device)
+        if max_grad_norm and max_grad_norm > 0:
+            clip = torch.clamp(max_grad_norm / (norm + 1e-6), max=1.0)
+        step += 1
+        t = float(step)
+        bc1, bc2 = 1 - beta1 ** t, 1 - beta2 ** t
+        scal.copy_(torch.stack([clip, lr[0] / bc1, torch.tensor(bc2 ** 0.5, device=norm.device), norm]))
+        for p, g, m, v in zip(params, grads, ms, vs):
+            g = g * clip
+            if weight_decay:
+                g = g + weight_decay * p.data
+            m.lerp_(g, 1 - beta1)
+            v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+            denom = (v.sqrt() / bc2 ** 0.5).add_(eps)
+            p.data.addcdiv_(m, denom, value=-float(lr[0]) / bc1)
+
     # -- LayerNorm --------------------------------------------------------------------------------
     def layernorm_fwd(self, x, gamma, beta, eps, save_stats=True):
         xf = x.float()
