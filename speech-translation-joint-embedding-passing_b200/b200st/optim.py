@@ -92,9 +92,16 @@ class FusedClipAdam:
                               'scal': torch.zeros(4, dtype=torch.float32, device=dev),
                               'table_host': _pinned(torch.empty((len(rows), 6), dtype=torch.int64), dev),
                               'table': torch.empty((len(rows), 6), dtype=torch.int64, device=dev)}
-        # the pinned staging buffer is persistent: a capture records a copy node that re-reads it on every replay
-        b['table_host'].copy_(torch.tensor(rows, dtype=torch.int64))
-        b['table'].copy_(b['table_host'], non_blocking=True)
+        host = torch.tensor(rows, dtype=torch.int64)
+        if _capturing(dev):
+            # a capture records a copy NODE that re-reads its source on every replay: stage through the persistent
+            # pinned buffer, which is written here and never again while the graph lives
+            b['table_host'].copy_(host)
+            b['table'].copy_(b['table_host'], non_blocking=True)
+        else:
+            # eager: the GPU may still be a step behind, so never overwrite a staging buffer a pending copy reads --
+            # a fresh pinned tensor per rebuild (the caching host allocator recycles it once the copy has run)
+            b['table'].copy_(_pinned(host, dev), non_blocking=True)
 
     def prepare(self):
         """Allocate state and pointer tables for the parameters that currently hold a gradient, without stepping.
