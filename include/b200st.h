@@ -102,6 +102,22 @@ int b200st_mha_bwd(int dtype, const void* dout, int64_t ldo, const void* q, int6
                    int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d, float temperature,
                    b200st_stream_t stream);
 
+/* The same pair with attention dropout: attn = dropout(softmax(.), p) multiplies V (layers.py:226; hard-wired p = 0.1
+ * in training mode, layers.py:207).  The keep mask of element (b, h, i, j) is Philox4x32-10(seed = rng[0], step =
+ * rng[1], site, index ((b*H + h)*Lq + i)*Lk + j) -- see b200st_dropout; backward recomputes it.  `p` still receives
+ * the UN-dropped probabilities (backward needs them).  Implemented by the shared-memory tile kernels. */
+int b200st_mha_fwd_dropout(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                           int64_t ldv, const uint8_t* mask, int64_t mask_sb, int64_t mask_sq, void* o,
+                           int64_t ldo, void* p, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d,
+                           float temperature, float drop_p, const int64_t* rng, int64_t site,
+                           b200st_stream_t stream);
+int b200st_mha_bwd_dropout(int dtype, const void* dout, int64_t ldo, const void* q, int64_t ldq,
+                           const void* k, int64_t ldk, const void* v, int64_t ldv, const void* p, void* ds,
+                           void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B,
+                           int64_t H, int64_t Lq, int64_t Lk, int64_t d, float temperature, float drop_p,
+                           const int64_t* rng, int64_t site, b200st_stream_t stream);
+
+
 /* ---- LSTM cell pointwise (one step of torch.nn.LSTM, Dec.py:393-419) ----------------------------
  * gates (+ gates_b + gates_c, NULLs skipped) [B,4H] = pre-activations x W_ih^T + h W_hh^T + b_ih + b_hh, possibly
  * delivered as partial products that were computed concurrently; PyTorch order i,f,g,o.
@@ -219,6 +235,17 @@ int b200st_token_mask(const int64_t* ids, uint8_t* mask, int64_t B, int64_t L, i
 int b200st_length_mask(const int32_t* lengths, uint8_t* mask, int64_t B, int64_t L,
                        b200st_stream_t stream);
 
+/* ---- dropout (nn.Dropout call sites: Enc.py:159-212, Dec.py:166,386-429, Seq2seq.py:195-209, layers.py:182-249) --
+ * y[r, c] = x[r, c] * keep / (1 - p) (+ residual[r, c]) over a rows x cols view (row strides ldx / ldr / ldy).
+ * keep is a pure function of (rng[0] = seed, rng[1] = step, site, element index r * ld_mask + col_off + c):
+ * Philox4x32-10 with key {seed_lo, seed_hi ^ step_hi}, counter {index/4 (64 bit), site, step_lo}, word index%4,
+ * keep iff word >= p * 2^32.  rng is a 2 x int64 DEVICE array; b200st_rng_advance adds 1 to rng[1] (launched once per
+ * forward pass, so a replayed CUDA graph draws new masks).  Backward = the same call on the gradient (same site). */
+int b200st_dropout(int dtype, const void* x, int64_t ldx, const void* residual, int64_t ldr, void* y, int64_t ldy,
+                   int64_t rows, int64_t cols, int64_t ld_mask, int64_t col_off, float p, const int64_t* rng,
+                   int64_t site, b200st_stream_t stream);
+int b200st_rng_advance(int64_t* rng, b200st_stream_t stream);
+
 /* ---- fused gradient-norm clip + Adam over all parameter tensors -----------------------
  * Replaces torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step() behind Optimizer.step()
  * (modules/optim.py:31-36; constructed at trainer/trainer_base.py:422-426).  `table` is a device array
@@ -232,10 +259,10 @@ int b200st_length_mask(const int32_t* lengths, uint8_t* mask, int64_t B, int64_t
 int b200st_opt_chunk(void);
 int b200st_multi_sqnorm(const int64_t* table, const int32_t* blockmap, int64_t n_blocks, float* partials,
                         b200st_stream_t stream);
-int b200st_adam_prepare(const float* partials, int64_t n_blocks, float max_grad_norm, const float* lr, float beta1,
-                        float beta2, float* step, float* scal, b200st_stream_t stream);
-int b200st_multi_adam(const int64_t* table, const int32_t* blockmap, int64_t n_blocks, const float* scal, float beta1,
-                      float beta2, float eps, float weight_decay, b200st_stream_t stream);
+int b200st_adam_prepare(const float* partials, int64_t n_blocks, float max_grad_norm, const float* lr, double beta1,
+                        double beta2, float* step, float* scal, b200st_stream_t stream);
+int b200st_multi_adam(const int64_t* table, const int32_t* blockmap, int64_t n_blocks, const float* scal, double beta1,
+                      double beta2, double eps, double weight_decay, b200st_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -169,6 +169,17 @@ def init_params(cfg: STConfig, seed: int = 333, dtype=torch.float32, scale: floa
 # --------------------------------------------------------------------------------------------
 # LSTM (reference: torch.nn.LSTM at Enc.py:50-66,153-209 and Dec.py:104-118,395-415)
 # --------------------------------------------------------------------------------------------
+# Dropout hook (training-mode nn.Dropout call sites of the reference).  None = every dropout at p = 0, which is what
+# the golden fixtures and the parity contract use.  Tests that exercise dropout install
+# DROP(x, tag) -> x * mask / (1 - p) with the mask the CUDA path drew for the site called `tag`, so that the comparison
+# stays exact; the tags name the reference call sites (see each _drop call).
+DROP = None
+
+
+def _drop(x, tag: str):
+    return x if DROP is None else DROP(x, tag)
+
+
 def lstm_cell(x, h, c, w_ih, w_hh, b_ih, b_hh):
     """One LSTM step, PyTorch gate order (i, f, g, o).  This is what torch.nn.LSTM computes for a
     length-1 sequence (Dec.py:395-415)."""
@@ -238,6 +249,7 @@ def las_encoder(P: Params, cfg: STConfig, acous_feats, acous_lens, loops: bool =
         # pad_packed_sequence returns max(lens) frames; the reference then reshapes to the full
         # length (Enc.py:159-160), which requires max(lens) == t_l.
         assert out.shape[1] == t_l, 'max padded length must equal the feature length'
+        out = _drop(out, f'las.enc.l{layer}')                               # Enc.py:159,178,195,212
         if layer < 4:
             x = out.reshape(B, t_l // 2, 2 * out.shape[-1])                 # Enc.py:166-167
             lens = lens // 2                                                # Enc.py:170
@@ -265,6 +277,7 @@ def las_decoder(P: Params, cfg: STConfig, acous_outputs, acous_lens, tgt=None,
     S_full = tgt.shape[1]
     lengths = [S_full] * B                                                  # Dec.py:163
     emb_tgt = F.embedding(tgt, P[pre + 'embedder.weight'], padding_idx=PAD)  # Dec.py:166
+    emb_tgt = _drop(emb_tgt, 'las.dec.emb')                                 # embedding_dropout, Dec.py:166
 
     t_k = acous_outputs.shape[1]
     if acous_lens is not None:                                              # Dec.py:173-181
@@ -293,7 +306,7 @@ def las_decoder(P: Params, cfg: STConfig, acous_outputs, acous_lens, tgt=None,
             out = h1
             if 0 < i < cfg.num_unilstm_dec - 1:                             # Dec.py:417-418
                 out = out + x
-            x = out
+            x = _drop(out, f'las.dec.s{idx}.l{i}')                          # Dec.py:403,419
         hc = new_hc
         dec_out = x
         # bilinear attention (attention.py:190-193): score = q . (W k_j)
@@ -303,6 +316,7 @@ def las_decoder(P: Params, cfg: STConfig, acous_outputs, acous_lens, tgt=None,
             scores = scores.masked_fill(key_mask.unsqueeze(1), -1e12)       # attention.py:250-252
         probs = F.softmax(scores, dim=2)                                    # attention.py:268
         context = torch.bmm(probs, acous_outputs).squeeze(1)                # attention.py:273
+        context = _drop(context, f'las.dec.s{idx}.att')                     # Dec.py:429
         ff_in = torch.cat([context, dec_out], dim=-1)                       # Dec.py:431
         cell_value = F.linear(ff_in, P[pre + 'acous_ffn.weight'])           # Dec.py:433
         logits = F.linear(cell_value, P[pre + 'acous_out.weight'], P[pre + 'acous_out.bias'])
@@ -351,9 +365,9 @@ def multihead_attention(P: Params, prefix: str, cfg: STConfig, q_in, k_in, v_in,
     attn = torch.matmul(q / (dk ** 0.5), k.transpose(2, 3))                 # layers.py:216
     if mask is not None:
         attn = attn.masked_fill(mask.unsqueeze(1) == 0, -1e9)               # layers.py:224
-    attn = F.softmax(attn, dim=-1)
+    attn = _drop(F.softmax(attn, dim=-1), prefix + 'attn')                  # layers.py:226 (hard-wired p = 0.1)
     o = torch.matmul(attn, v).transpose(1, 2).contiguous().view(B, Lq, -1)
-    out = F.linear(o, P[prefix + 'fc.weight']) + residual                   # layers.py:194-195
+    out = _drop(F.linear(o, P[prefix + 'fc.weight']), prefix + 'fc') + residual   # layers.py:194-195
     return out, attn
 
 
@@ -363,7 +377,7 @@ def positionwise_ffn(P: Params, prefix: str, x):
     y = F.layer_norm(x, (D,), P[prefix + 'layer_norm.weight'], P[prefix + 'layer_norm.bias'], 1e-6)
     y = F.linear(F.relu(F.linear(y, P[prefix + 'w_1.weight'], P[prefix + 'w_1.bias'])),
                  P[prefix + 'w_2.weight'], P[prefix + 'w_2.bias'])
-    return y + x
+    return _drop(y, prefix + 'ffn') + x                                     # layers.py:249-250
 
 
 def tf_encoder(P: Params, cfg: STConfig, src_emb, src_mask):
@@ -407,13 +421,13 @@ def mix_embeddings(P: Params, src_ids, emb_dyn):
     """The embedding-passing mix, Seq2seq._get_src_emb (Seq2seq.py:183-199):
     enc_emb_proj(cat(E_static[src], e_dyn)), Linear(E+D -> D, no bias), dropout 0."""
     static = F.embedding(src_ids, P['enc_embedder.weight'], padding_idx=PAD)
-    return F.linear(torch.cat([static, emb_dyn], dim=2), P['enc_emb_proj.weight'])
+    return F.linear(_drop(torch.cat([static, emb_dyn], dim=2), 'mix'), P['enc_emb_proj.weight'])   # Seq2seq.py:195
 
 
 def target_embeddings(P: Params, cfg: STConfig, tgt):
     """Seq2seq._get_tgt_emb (Seq2seq.py:202-211)."""
     mask = pad_mask(tgt).to(torch.uint8) & subsequent_mask(tgt.size(-1)).to(torch.uint8)
-    emb = F.embedding(tgt, P['dec_embedder.weight'], padding_idx=PAD)
+    emb = _drop(F.embedding(tgt, P['dec_embedder.weight'], padding_idx=PAD), 'tgt_emb')   # Seq2seq.py:207-209
     if cfg.has_dec_emb_proj:
         emb = F.linear(emb, P['dec_emb_proj.weight'])
     return mask, emb

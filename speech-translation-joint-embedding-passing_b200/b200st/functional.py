@@ -64,6 +64,42 @@ def linear(x, weight, bias=None, relu=False, residual=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# nn.Dropout call sites (Enc.py:159-212, Seq2seq.py:195-209, layers.py:182-249).  The mask is never stored: it is a
+# function of (step seed, site, element index) that the backward launch recomputes (csrc/philox.cuh).
+# ------------------------------------------------------------------------------------------------
+class _Dropout(Function):
+    @staticmethod
+    def forward(ctx, x, p, site, residual):
+        rng = rt.current_rng(x.device)
+        ctx.p, ctx.site, ctx.has_res = p, site, residual is not None
+        ctx.save_for_backward(rng)
+        return K().dropout(_c(x), p, rng, site, residual=None if residual is None else _c(residual))
+
+    @staticmethod
+    def backward(ctx, dy):
+        (rng,) = ctx.saved_tensors
+        dy = _c(dy)
+        return K().dropout(dy, ctx.p, rng, ctx.site), None, None, (dy if ctx.has_res else None)
+
+
+def dropout(x, p, training=True, tag='', residual=None):
+    """dropout(x) (+ residual).  Identity (or a plain add) when p == 0 or not training."""
+    if not training or p <= 0:
+        return x if residual is None else _Add.apply(x, residual)
+    return _Dropout.apply(x, p, rt.next_site(tag, p), residual)
+
+
+class _Add(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return K().add(_c(a), _c(b))
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+# ------------------------------------------------------------------------------------------------
 # LayerNorm: layers.py:139,153,240,245; TFEnc.py:61,89; TFDec.py:58,127
 # ------------------------------------------------------------------------------------------------
 class _LayerNorm(Function):
@@ -92,23 +128,27 @@ def layer_norm(x, weight, bias, eps):
 # ------------------------------------------------------------------------------------------------
 class _MHACore(Function):
     @staticmethod
-    def forward(ctx, q, k, v, mask, n_head, temperature):
-        o, p = K().mha_fwd(q, k, v, mask, n_head, temperature)
-        ctx.n_head, ctx.temperature = n_head, temperature
-        ctx.save_for_backward(q, k, v, p)
+    def forward(ctx, q, k, v, mask, n_head, temperature, p_attn, site):
+        rng = rt.current_rng(q.device) if p_attn > 0 else None
+        o, p = K().mha_fwd(q, k, v, mask, n_head, temperature, dropout=(p_attn, rng, site))
+        ctx.n_head, ctx.temperature, ctx.drop = n_head, temperature, (p_attn, site)
+        ctx.save_for_backward(q, k, v, p, rng)
         ctx.mark_non_differentiable(p)
         return o, p
 
     @staticmethod
     def backward(ctx, do, _dp):
-        q, k, v, p = ctx.saved_tensors
-        dq, dk, dv = K().mha_bwd(_c(do), q, k, v, p, ctx.n_head, ctx.temperature)
-        return dq, dk, dv, None, None, None
+        q, k, v, p, rng = ctx.saved_tensors
+        dq, dk, dv = K().mha_bwd(_c(do), q, k, v, p, ctx.n_head, ctx.temperature,
+                                 dropout=(ctx.drop[0], rng, ctx.drop[1]))
+        return dq, dk, dv, None, None, None, None, None
 
 
-def mha_core(q, k, v, mask, n_head, temperature):
-    """q [B,Lq,H*d], k/v [B,Lk,H*d] (dense last dim), mask uint8/bool [B,1|Lq,Lk] or None."""
-    return _MHACore.apply(q, k, v, mask, n_head, temperature)
+def mha_core(q, k, v, mask, n_head, temperature, p_attn=0.0, tag=''):
+    """q [B,Lq,H*d], k/v [B,Lk,H*d] (dense last dim), mask uint8/bool [B,1|Lq,Lk] or None.  p_attn > 0: attention
+    dropout on the probabilities (layers.py:226); the returned probabilities are the un-dropped ones."""
+    site = rt.next_site(tag + '.attn', p_attn) if p_attn > 0 else 0
+    return _MHACore.apply(q, k, v, mask, n_head, temperature, p_attn, site)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -123,8 +163,12 @@ class _MHABlock(Function):
     (LayerNorm on the query input only, K/V from the raw input, no biases, dropout p = 0)."""
 
     @staticmethod
-    def forward(ctx, q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature):
+    def forward(ctx, q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature, drop):
+        # drop = (p_attn, site_attn, p_fc, site_fc): attention dropout on the probabilities (layers.py:226) and
+        # dropout on the fc output before the residual add (layers.py:194-195); all zeros = the fused fast path
         k = K()
+        p_attn, s_attn, p_fc, s_fc = drop
+        rng = rt.current_rng(q.device) if (p_attn > 0 or p_fc > 0) else None
         B, Lq, D = q.shape
         Lk = kv.size(1)
         self_attn = kv is q
@@ -135,30 +179,38 @@ class _MHABlock(Function):
         qp = k.gemm(qn, rt.operand(w_q), trans_b=True)
         kvp = k.gemm(kv2, rt.operand_cat(w_k, w_v), trans_b=True)                 # [B*Lk, 2*HD] = K | V
         kv3 = kvp.view(B, Lk, 2 * HD)
-        o, p = k.mha_fwd(qp.view(B, Lq, HD), kv3[:, :, :HD], kv3[:, :, HD:], mask, n_head, temperature)
+        o, p = k.mha_fwd(qp.view(B, Lq, HD), kv3[:, :, :HD], kv3[:, :, HD:], mask, n_head, temperature,
+                         dropout=(p_attn, rng, s_attn))
         o2 = o.view(-1, HD)
-        out = k.gemm(o2, rt.operand(w_fc), trans_b=True, residual=q2)
+        if p_fc > 0:
+            out = k.dropout(k.gemm(o2, rt.operand(w_fc), trans_b=True), p_fc, rng, s_fc, residual=q2)
+        else:
+            out = k.gemm(o2, rt.operand(w_fc), trans_b=True, residual=q2)
         ctx.self_attn, ctx.n_head, ctx.temperature, ctx.dims = self_attn, n_head, temperature, (B, Lq, Lk, D, HD)
-        ctx.kv_shape = kv.shape
-        ctx.save_for_backward(q2, None if self_attn else kv2, qn, mean, rstd, qp, kvp, p, o2, ln_w, w_q, w_k, w_v, w_fc)
+        ctx.kv_shape, ctx.drop = kv.shape, drop
+        ctx.save_for_backward(q2, None if self_attn else kv2, qn, mean, rstd, qp, kvp, p, o2, ln_w, w_q, w_k, w_v, w_fc,
+                              rng)
         ctx.mark_non_differentiable(p)
         return out.view(B, Lq, D), p
 
     @staticmethod
     def backward(ctx, dout, _dp):
         k = K()
-        q2, kv2, qn, mean, rstd, qp, kvp, p, o2, ln_w, w_q, w_k, w_v, w_fc = ctx.saved_tensors
+        q2, kv2, qn, mean, rstd, qp, kvp, p, o2, ln_w, w_q, w_k, w_v, w_fc, rng = ctx.saved_tensors
         B, Lq, Lk, D, HD = ctx.dims
+        p_attn, s_attn, p_fc, s_fc = ctx.drop
         if kv2 is None:
             kv2 = q2
         dout2 = _c(dout).reshape(-1, D)
-        do = k.gemm(dout2, rt.operand(w_fc))
-        dw_fc = k.gemm(dout2, o2, trans_a=True, out_dtype=torch.float32)
+        dfc = k.dropout(dout2, p_fc, rng, s_fc) if p_fc > 0 else dout2      # gradient of the fc output
+        do = k.gemm(dfc, rt.operand(w_fc))
+        dw_fc = k.gemm(dfc, o2, trans_a=True, out_dtype=torch.float32)
         dqp = torch.empty_like(qp)
         dkvp = torch.empty_like(kvp)
         kv3, dkv3 = kvp.view(B, Lk, 2 * HD), dkvp.view(B, Lk, 2 * HD)
         k.mha_bwd(do.view(B, Lq, HD), qp.view(B, Lq, HD), kv3[:, :, :HD], kv3[:, :, HD:], p, ctx.n_head,
-                  ctx.temperature, dq=dqp.view(B, Lq, HD), dk=dkv3[:, :, :HD], dv=dkv3[:, :, HD:])
+                  ctx.temperature, dq=dqp.view(B, Lq, HD), dk=dkv3[:, :, :HD], dv=dkv3[:, :, HD:],
+                  dropout=(p_attn, rng, s_attn))
         dw_q = k.gemm(dqp, qn, trans_a=True, out_dtype=torch.float32)
         dw_kv = k.gemm(dkvp, kv2, trans_a=True, out_dtype=torch.float32)         # [2*HD, D]
         dqn = k.gemm(dqp, rt.operand(w_q))
@@ -170,48 +222,59 @@ class _MHABlock(Function):
             dkv = None
         else:
             dkv = k.gemm(dkvp, wkv).view(ctx.kv_shape)
-        return (dq.view(B, Lq, D), dkv, None, dln[0], dln[1], None, dw_q, dw_kv[:HD], dw_kv[HD:], dw_fc, None, None)
+        return (dq.view(B, Lq, D), dkv, None, dln[0], dln[1], None, dw_q, dw_kv[:HD], dw_kv[HD:], dw_fc, None, None,
+                None)
 
 
-def mha_block(q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature):
+def mha_block(q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature, p_attn=0.0, p_fc=0.0, tag=''):
     """Returns (out [B, Lq, D], attention probabilities [B, H, Lq, Lk]).  Pass the SAME tensor object as q and kv
-    for self-attention: its two gradient contributions are then merged inside the GEMM epilogue."""
-    return _MHABlock.apply(q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature)
+    for self-attention: its two gradient contributions are then merged inside the GEMM epilogue.
+    p_attn / p_fc: dropout on the attention probabilities / on the fc output (training mode values, 0 otherwise)."""
+    drop = (p_attn, rt.next_site(tag + '.attn', p_attn) if p_attn > 0 else 0,
+            p_fc, rt.next_site(tag + '.fc', p_fc) if p_fc > 0 else 0)
+    return _MHABlock.apply(q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature, drop)
 
 
 class _FFNBlock(Function):
     """x + w_2(relu(w_1(LN(x))));  PositionwiseFeedForward.forward, layers.py:232-252."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, eps, w1, b1, w2, b2):
+    def forward(ctx, x, ln_w, ln_b, eps, w1, b1, w2, b2, p, site):
         k = K()
         D = x.size(-1)
         x2 = _c(x).reshape(-1, D)
         y, mean, rstd = k.layernorm_fwd(x2, ln_w, ln_b, eps)
         h = k.gemm(y, rt.operand(w1), trans_b=True, bias=b1, relu=True)
-        out = k.gemm(h, rt.operand(w2), trans_b=True, bias=b2, residual=x2)
-        ctx.save_for_backward(x2, y, mean, rstd, h, ln_w, w1, w2)
+        rng = None
+        if p > 0:            # x + dropout(w_2(.)) (layers.py:248-250)
+            rng = rt.current_rng(x.device)
+            out = k.dropout(k.gemm(h, rt.operand(w2), trans_b=True, bias=b2), p, rng, site, residual=x2)
+        else:
+            out = k.gemm(h, rt.operand(w2), trans_b=True, bias=b2, residual=x2)
+        ctx.drop = (p, site)
+        ctx.save_for_backward(x2, y, mean, rstd, h, ln_w, w1, w2, rng)
         return out.view(x.shape)
 
     @staticmethod
     def backward(ctx, dout):
         k = K()
-        x2, y, mean, rstd, h, ln_w, w1, w2 = ctx.saved_tensors
+        x2, y, mean, rstd, h, ln_w, w1, w2, rng = ctx.saved_tensors
         D = x2.size(1)
         dout2 = _c(dout).reshape(-1, D)
-        dz = k.gemm(dout2, rt.operand(w2), relu_gate=h)                           # ReLU backward in the epilogue
-        dw2 = k.gemm(dout2, h, trans_a=True, out_dtype=torch.float32)
-        db2 = k.colsum(dout2)
+        d2 = k.dropout(dout2, ctx.drop[0], rng, ctx.drop[1]) if ctx.drop[0] > 0 else dout2   # gradient of w_2's output
+        dz = k.gemm(d2, rt.operand(w2), relu_gate=h)                              # ReLU backward in the epilogue
+        dw2 = k.gemm(d2, h, trans_a=True, out_dtype=torch.float32)
+        db2 = k.colsum(d2)
         dy = k.gemm(dz, rt.operand(w1))
         dw1 = k.gemm(dz, y, trans_a=True, out_dtype=torch.float32)
         db1 = k.colsum(dz)
         dln = torch.zeros((2, D), dtype=torch.float32, device=x2.device)
         dx = k.layernorm_bwd(dy, x2, ln_w, mean, rstd, dln[0], dln[1], add=dout2)
-        return dx.view(dout.shape), dln[0], dln[1], None, dw1, db1, dw2, db2
+        return dx.view(dout.shape), dln[0], dln[1], None, dw1, db1, dw2, db2, None, None
 
 
-def ffn_block(x, ln_w, ln_b, eps, w1, b1, w2, b2):
-    return _FFNBlock.apply(x, ln_w, ln_b, eps, w1, b1, w2, b2)
+def ffn_block(x, ln_w, ln_b, eps, w1, b1, w2, b2, p=0.0, tag=''):
+    return _FFNBlock.apply(x, ln_w, ln_b, eps, w1, b1, w2, b2, p, rt.next_site(tag + '.ffn', p) if p > 0 else 0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -259,36 +322,48 @@ def add_posenc(x, pe):
 # ------------------------------------------------------------------------------------------------
 class _Mix(Function):
     @staticmethod
-    def forward(ctx, ids, table, dyn, weight):
+    def forward(ctx, ids, table, dyn, weight, p, site):
         b, s = ids.shape
         ids = _c(ids)
         dyn2 = _c(dyn).reshape(b * s, -1)
         cat = K().mix_gather_concat(ids.reshape(-1), table, dyn2)
+        rng = None
+        if p > 0:            # embedding_dropout on the concatenation (Seq2seq.py:195)
+            rng = rt.current_rng(ids.device)
+            K().dropout(cat, p, rng, site, out=cat)
         out = K().gemm(cat, rt.operand(weight), trans_b=True)
-        ctx.save_for_backward(ids, table, cat, weight)
+        ctx.drop = (p, site)
+        ctx.save_for_backward(ids, table, cat, weight, rng)
         return out.view(b, s, weight.size(0))
 
     @staticmethod
     def backward(ctx, dy):
-        ids, table, cat, weight = ctx.saved_tensors
+        ids, table, cat, weight, rng = ctx.saved_tensors
         e = table.size(1)
         d_out = weight.size(0)
         dy2 = _c(dy).reshape(-1, d_out)
         w = rt.operand(weight)
+        p, site = ctx.drop
+        ld = weight.size(1)                                       # E + D: the mask is indexed over the whole concat row
         dtable = ddyn = dw = None
         if ctx.needs_input_grad[1]:
             dstatic = K().gemm(dy2, w[:, :e])                     # [n, E]
+            if p > 0:
+                K().dropout(dstatic, p, rng, site, out=dstatic, ld_mask=ld, col_off=0)
             dtable = torch.zeros_like(table)
             K().embedding_bwd(ids.reshape(-1), dstatic, dtable, PAD)   # padding_idx=PAD, Seq2seq.py:106-107
         if ctx.needs_input_grad[2]:
-            ddyn = K().gemm(dy2, w[:, e:]).view(ids.size(0), ids.size(1), -1)
+            ddyn = K().gemm(dy2, w[:, e:])
+            if p > 0:
+                K().dropout(ddyn, p, rng, site, out=ddyn, ld_mask=ld, col_off=e)
+            ddyn = ddyn.view(ids.size(0), ids.size(1), -1)
         if ctx.needs_input_grad[3]:
-            dw = K().gemm(dy2, cat, trans_a=True, out_dtype=torch.float32)
-        return None, dtable, ddyn, dw
+            dw = K().gemm(dy2, cat, trans_a=True, out_dtype=torch.float32)       # cat holds the dropped values
+        return None, dtable, ddyn, dw, None, None
 
 
-def mix(ids, table, dyn, weight):
-    return _Mix.apply(ids, table, dyn, weight)
+def mix(ids, table, dyn, weight, p=0.0, tag='mix'):
+    return _Mix.apply(ids, table, dyn, weight, p, rt.next_site(tag, p) if p > 0 else 0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -447,9 +522,13 @@ class _LASDecoder(Function):
     """
 
     @staticmethod
-    def forward(ctx, enc, klens, ids_tf, n_steps, need_logps, emb_table, w_att, w_ffn, w_out, b_out,
+    def forward(ctx, enc, klens, ids_tf, n_steps, need_logps, drop, emb_table, w_att, w_ffn, w_out, b_out,
                 *lstm_params):
+        # drop = (p_emb, p): embedding dropout on the input tokens' embeddings (Dec.py:166 -- every teacher-forcing
+        # token, only the BOS embedding when free running, Dec.py:199,223) and dropout on every LSTM layer's output and
+        # on the attention context (Dec.py:403,419,429); the recurrent h/c and the residual sum itself stay un-dropped.
         k = K()
+        p_emb, p_drop = drop
         dt = enc.dtype
         dev = enc.device
         enc = _c(enc)
@@ -502,6 +581,16 @@ class _LASDecoder(Function):
             k.embedding_fwd(ids_in[0], emb_table, dt, out=EMB[0])
         else:                                # teacher forcing: every input token is known up front
             k.embedding_fwd(ids_in.reshape(-1), emb_table, dt, out=EMB.view(S * B, -1))
+        rng = rt.current_rng(dev) if (p_emb > 0 or p_drop > 0) else None
+        site_emb = 0
+        if p_emb > 0:                        # EMB holds the dropped embeddings from here on
+            site_emb = rt.next_site('las.dec.emb', p_emb)
+            tgt_e = EMB[0] if fused_feed else EMB.view(S * B, -1)
+            k.dropout(tgt_e, p_emb, rng, site_emb, out=tgt_e)
+        XD = [e(S, B, D) for _ in range(n_layers)] if p_drop > 0 else None     # dropped layer outputs
+        CTXD = e(S, B, H2) if p_drop > 0 else None                               # dropped attention contexts
+        site_l = [[0] * n_layers for _ in range(S)]
+        site_att = [0] * S
         for s in range(S):
             x = EMB[s]
             for i in range(n_layers):
@@ -522,13 +611,20 @@ class _LASDecoder(Function):
                     with rt.fork(side[i]):                    # next step's recurrent part, off the critical path
                         k.gemm(Hst[i][s + 1], whh[i], trans_b=True, out=Gh[i])
                 x = out_res if out_res is not None else Hst[i][s + 1]
+                if p_drop > 0:
+                    site_l[s][i] = rt.next_site(f'las.dec.s{s}.l{i}', p_drop)
+                    x = k.dropout(x, p_drop, rng, site_l[s][i], out=XD[i][s])
             dec_out = x
             with rt.fork(side[n_layers]):
                 k.gemm(dec_out, wf[:, H2:], trans_b=True, out=CVb)
             k.las_attn_fwd(dec_out, wk, enc, klens, ctx_out=CTX[s], probs_out=PROBS[s])
             # cell_value = acous_ffn(cat(context, dec_out)) (Dec.py:431-433), again without the concat
             rt.join(side[n_layers])
-            k.gemm(CTX[s], wf[:, :H2], trans_b=True, residual=CVb, out=CV[s + 1])
+            ctx_s = CTX[s]
+            if p_drop > 0:
+                site_att[s] = rt.next_site(f'las.dec.s{s}.att', p_drop)
+                ctx_s = k.dropout(CTX[s], p_drop, rng, site_att[s], out=CTXD[s])
+            k.gemm(ctx_s, wf[:, :H2], trans_b=True, residual=CVb, out=CV[s + 1])
             if s + 1 < S:
                 with rt.fork(side[0]):
                     k.gemm(CV[s + 1], wih[0][:, E:], trans_b=True, out=Gcv)
@@ -551,9 +647,13 @@ class _LASDecoder(Function):
         ctx.need_logps = need_logps
         ctx.has_klens = klens is not None
         ctx.n_fixed = 10
+        ctx.drop = (p_emb, p_drop, site_emb, site_l, site_att, fused_feed)
         saved = [enc, klens, ids_in.contiguous(), wk, CV, CTX, PROBS, EMB, logp_tm, emb_table, w_att,
                  w_ffn, w_out]
         saved += Hst + Cst + ACT + [r for r in RES if r is not None]
+        if p_drop > 0:
+            saved += XD + [CTXD]
+        saved.append(rng)
         saved += list(lstm_params)
         ctx.res_layers = [i for i in range(n_layers) if RES[i] is not None]
         ctx.save_for_backward(*saved)
@@ -573,6 +673,12 @@ class _LASDecoder(Function):
         RES = [None] * n_layers
         for i in ctx.res_layers:
             RES[i] = sv[p]; p += 1
+        p_emb, p_drop, site_emb, site_l, site_att, fused_feed = ctx.drop
+        XD = CTXD = None
+        if p_drop > 0:
+            XD = sv[p:p + n_layers]; p += n_layers
+            CTXD = sv[p]; p += 1
+        rng = sv[p]; p += 1
         lstm_params = sv[p:]
         lp = [lstm_params[4 * i:4 * i + 4] for i in range(n_layers)]
         dt, dev, f32 = enc.dtype, enc.device, torch.float32
@@ -611,11 +717,16 @@ class _LASDecoder(Function):
             with rt.fork(side[n_layers]):
                 k.gemm(dcv, wf[:, H2:], out=D_OUT)
             k.gemm(dcv, wf[:, :H2], out=DCTX[s])
+            if p_drop > 0:                       # gradient of the dropped context -> gradient of the context
+                k.dropout(DCTX[s], p_drop, rng, site_att[s], out=DCTX[s])
             _, dq_att = k.las_attn_bwd(DCTX[s], wk, enc, PROBS[s], dscore_out=DSC[s])
             rt.join(side[n_layers])
             # dec_out = y_{n-1};  y_i = h_i (+ y_{i-1} on residual layers, Dec.py:417-418)
             dy_parts = [D_OUT, dq_att]
             for i in reversed(range(n_layers)):
+                if p_drop > 0:                   # dy_parts is the gradient of the DROPPED layer output x_{i+1}
+                    dsum = dy_parts[0] if len(dy_parts) == 1 else k.add(dy_parts[0], dy_parts[1])
+                    dy_parts = [k.dropout(dsum, p_drop, rng, site_l[s][i])]
                 if have_dhn[i]:
                     rt.join(side[i])
                 _, dc_next[i] = k.lstm_cell_bwd(dy_parts + [DHN[i] if have_dhn[i] else None], dc_next[i], ACT[i][s],
@@ -647,16 +758,21 @@ class _LASDecoder(Function):
                 k.gemm(dg2, EMB.view(SB, E), trans_a=True, out=dw_ih[:, :E])
                 k.gemm(dg2, CV[:S].reshape(SB, D), trans_a=True, out=dw_ih[:, E:])
             else:
-                below = RES[i - 1] if RES[i - 1] is not None else Hst[i - 1][1:]
+                below = XD[i - 1] if XD is not None else (RES[i - 1] if RES[i - 1] is not None else Hst[i - 1][1:])
                 dw_ih = k.gemm(dg2, below.reshape(SB, D), trans_a=True, out_dtype=f32)
             dw_hh = k.gemm(dg2, Hst[i][:S].reshape(SB, D), trans_a=True, out_dtype=f32)
             db = k.colsum(dg2)
             grads_lstm += [dw_ih, dw_hh, db, db]
         dec_out_stack = RES[n_layers - 1] if RES[n_layers - 1] is not None else Hst[n_layers - 1][1:]
+        if XD is not None:
+            dec_out_stack = XD[n_layers - 1]
         dcv2 = DCV.view(SB, D)
         dw_ffn = torch.empty_like(w_ffn)
-        k.gemm(dcv2, CTX.view(SB, H2), trans_a=True, out=dw_ffn[:, :H2])
+        k.gemm(dcv2, (CTXD if CTXD is not None else CTX).view(SB, H2), trans_a=True, out=dw_ffn[:, :H2])
         k.gemm(dcv2, dec_out_stack.reshape(SB, D), trans_a=True, out=dw_ffn[:, H2:])
+        if p_emb > 0:
+            d_e = DEMB[0] if fused_feed else DEMB.view(SB, E)
+            k.dropout(d_e, p_emb, rng, site_emb, out=d_e)
         d_table = torch.zeros_like(emb_table)
         k.embedding_bwd(ids_in.reshape(-1), DEMB.view(SB, E), d_table, PAD)      # Dec.py:80-81 padding_idx
         # keys / values: d wk[b] = dscore[:, b]^T dec_out[:, b];  d vals[b] = probs[:, b]^T dctx[:, b]
@@ -667,11 +783,11 @@ class _LASDecoder(Function):
         k.gemm(d_wk.view(B * Tk, D), rt.operand(w_att), residual=d_enc.view(B * Tk, H2),
                out=d_enc.view(B * Tk, H2))
         dw_att = k.gemm(d_wk.view(B * Tk, D), enc.view(B * Tk, H2), trans_a=True, out_dtype=f32)
-        return (d_enc, None, None, None, None, d_table, dw_att, dw_ffn, dw_out, db_out, *grads_lstm)
+        return (d_enc, None, None, None, None, None, d_table, dw_att, dw_ffn, dw_out, db_out, *grads_lstm)
 
 
 def las_decoder(enc, klens, ids_tf, n_steps, need_logps, emb_table, w_att, w_ffn, w_out, b_out,
-                lstm_params):
+                lstm_params, p_emb=0.0, p_drop=0.0):
     flat = [t for layer in lstm_params for t in layer]
-    return _LASDecoder.apply(enc, klens, ids_tf, n_steps, need_logps, emb_table, w_att, w_ffn, w_out,
-                             b_out, *flat)
+    return _LASDecoder.apply(enc, klens, ids_tf, n_steps, need_logps, (p_emb, p_drop), emb_table, w_att, w_ffn,
+                             w_out, b_out, *flat)

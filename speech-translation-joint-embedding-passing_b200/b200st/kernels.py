@@ -171,7 +171,8 @@ class CudaKernels:
             (t.shape, t.stride())
         return t.stride(1)
 
-    def mha_fwd(self, q, k, v, mask, n_head, temperature, want_probs=True):
+    def mha_fwd(self, q, k, v, mask, n_head, temperature, want_probs=True, dropout=None):
+        """dropout: None or (p, rng_state, site) -- attention dropout on the probabilities (layers.py:226)."""
         self._need_cuda(q, k, v, mask)
         B, Lq, HD = q.shape
         Lk = k.size(1)
@@ -186,13 +187,20 @@ class CudaKernels:
                 msq = 0
         else:
             msb = msq = 0
+        if dropout is not None and dropout[0] > 0:
+            dp, rng, site = dropout
+            _lib.check(self.lib.b200st_mha_fwd_dropout(_dt(q), _p(q), self._bld(q), _p(k), self._bld(k), _p(v),
+                                                       self._bld(v), _p(mask), msb, msq, _p(o), HD, _p(p), B,
+                                                       n_head, Lq, Lk, d, float(temperature), float(dp), _p(rng),
+                                                       int(site), self._stream()), 'mha_fwd_dropout')
+            return o, p
         _lib.check(self.lib.b200st_mha_fwd(_dt(q), _p(q), self._bld(q), _p(k), self._bld(k), _p(v),
                                            self._bld(v), _p(mask), msb, msq, _p(o), HD, _p(p), B,
                                            n_head, Lq, Lk, d, float(temperature), self._stream()),
                    'mha_fwd')
         return o, p
 
-    def mha_bwd(self, dout, q, k, v, p, n_head, temperature, dq=None, dk=None, dv=None):
+    def mha_bwd(self, dout, q, k, v, p, n_head, temperature, dq=None, dk=None, dv=None, dropout=None):
         """dq/dk/dv may be caller-provided [B, L, HD] views with a dense last dim (e.g. column slices of one fused
         [B*L, 2*HD] K|V gradient buffer)."""
         B, Lq, HD = q.shape
@@ -203,6 +211,14 @@ class CudaKernels:
         dq = torch.empty((B, Lq, HD), dtype=q.dtype, device=q.device) if dq is None else dq
         dk = torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device) if dk is None else dk
         dv = torch.empty((B, Lk, HD), dtype=q.dtype, device=q.device) if dv is None else dv
+        if dropout is not None and dropout[0] > 0:
+            dp, rng, site = dropout
+            _lib.check(self.lib.b200st_mha_bwd_dropout(_dt(q), _p(dout), HD, _p(q), self._bld(q), _p(k),
+                                                       self._bld(k), _p(v), self._bld(v), _p(p), _p(ds), _p(dq),
+                                                       self._bld(dq), _p(dk), self._bld(dk), _p(dv), self._bld(dv), B,
+                                                       n_head, Lq, Lk, d, float(temperature), float(dp), _p(rng),
+                                                       int(site), self._stream()), 'mha_bwd_dropout')
+            return dq, dk, dv
         _lib.check(self.lib.b200st_mha_bwd(_dt(q), _p(dout), HD, _p(q), self._bld(q), _p(k),
                                            self._bld(k), _p(v), self._bld(v), _p(p), _p(ds), _p(dq), self._bld(dq),
                                            _p(dk), self._bld(dk), _p(dv), self._bld(dv), B, n_head, Lq, Lk, d,
@@ -488,6 +504,40 @@ class CudaKernels:
                    'length_mask')
         return mask
 
+
+    # -- dropout ------------------------------------------------------------------------------------
+    def dropout(self, x, p, rng, site, residual=None, out=None, ld_mask=None, col_off=0):
+        """out = x * keep / (1 - p) (+ residual) over a 2-D row-strided view (any leading dims are flattened when x
+        is contiguous).  keep depends on (rng = device [seed, step], site, row * ld_mask + col_off + col) only; the
+        backward pass is the same call on the gradient.  ld_mask / col_off let a column slice of a wider tensor
+        reuse the mask of the whole (e.g. the two halves of the embedding-passing concat)."""
+        self._need_cuda(x, rng, residual, out)
+        x2 = x if x.dim() == 2 else x.reshape(-1, x.size(-1))
+        _rows(x2)
+        rows, cols = x2.shape
+        if out is None:
+            out = torch.empty((rows, cols), dtype=x.dtype, device=x.device)
+            ret = out.view(x.shape) if x.dim() != 2 else out
+        else:
+            ret = out
+            out = out if out.dim() == 2 else out.view(-1, out.size(-1))
+        _rows(out)
+        assert out.shape == x2.shape and out.dtype == x.dtype
+        r2, ldr = None, 0
+        if residual is not None:
+            r2 = residual if residual.dim() == 2 else residual.reshape(-1, residual.size(-1))
+            _rows(r2)
+            assert r2.shape == x2.shape and r2.dtype == x.dtype
+            ldr = r2.stride(0)
+        _lib.check(self.lib.b200st_dropout(_dt(x), _p(x2), x2.stride(0), _p(r2), ldr, _p(out), out.stride(0), rows, cols,
+                                           int(ld_mask if ld_mask is not None else cols), int(col_off), float(p),
+                                           _p(rng), int(site), self._stream()), 'dropout')
+        return ret
+
+    def rng_advance(self, rng):
+        self._need_cuda(rng)
+        assert rng.dtype == torch.int64 and rng.numel() == 2
+        _lib.check(self.lib.b200st_rng_advance(_p(rng), self._stream()), 'rng_advance')
 
     # -- fused clip + Adam (modules/optim.py:31-36) -------------------------------------------------
     def opt_chunk(self) -> int:

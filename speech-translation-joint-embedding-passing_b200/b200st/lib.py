@@ -18,7 +18,7 @@ HEADER = os.path.join(_ROOT, 'include', 'b200st.h')
 LIB_PATH = os.path.join(_HERE, 'libb200st.so')
 
 _CTYPES = {
-    'int': ctypes.c_int, 'int64_t': ctypes.c_int64, 'float': ctypes.c_float,
+    'int': ctypes.c_int, 'int64_t': ctypes.c_int64, 'float': ctypes.c_float, 'double': ctypes.c_double,
     'b200st_stream_t': ctypes.c_void_p, 'void': None,
 }
 

@@ -5,6 +5,7 @@
 // Sequence lengths on the training path are tiny (<= 50 keys, 126 acoustic frames), so one warp owns a
 // query row end to end: scores, mask, softmax and the P.V product never leave the SM.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace b200st {
 
@@ -250,11 +251,13 @@ __global__ void __launch_bounds__(MHA_T_THREADS)
 mha_fwd_tiled_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, int64_t ldk,
                      const T* __restrict__ v, int64_t ldv, const uint8_t* __restrict__ mask, int64_t mask_sb,
                      int64_t mask_sq, T* __restrict__ o, int64_t ldo, T* __restrict__ p, int H, int Lq, int Lk,
-                     int d, float temperature) {
+                     int d, float temperature, float drop_p, const int64_t* __restrict__ rng, int64_t site) {
   pdl_wait();
   pdl_launch_dependents();
   extern __shared__ __align__(16) float sm[];
   const int lkp = mha_lkp(Lk);
+  DropRng drop;
+  if (drop_p > 0.f) drop.init(rng, site, drop_p);
   float* Qs = sm;                  // [Lq][d]    q / temperature
   float* Kt = Qs + Lq * d;         // [d][lkp]   K transposed
   float* Vs = Kt + d * lkp;        // [Lk][d]
@@ -289,10 +292,13 @@ mha_fwd_tiled_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
     T* pr = p ? p + (((int64_t)b * H + h) * Lq + i) * Lk : nullptr;
+    const uint64_t row0 = (((uint64_t)b * H + h) * Lq + i) * (uint64_t)Lk;
     for (int j = lane; j < Lk; j += 32) {
-      const float pv = sr[j] * inv;
+      float pv = sr[j] * inv;
+      if (pr) pr[j] = from_f<T>(pv);                   // the UN-dropped probabilities are what backward needs
+      // attn = dropout(softmax(.)) (layers.py:226): the dropped probabilities multiply V
+      if (drop_p > 0.f) pv *= drop.factor(row0 + j);
       sr[j] = pv;
-      if (pr) pr[j] = from_f<T>(pv);
     }
   }
   __syncthreads();
@@ -305,11 +311,14 @@ __global__ void __launch_bounds__(MHA_T_THREADS)
 mha_bwd_tiled_kernel(const T* __restrict__ dout, int64_t ldo, const T* __restrict__ q, int64_t ldq,
                      const T* __restrict__ k, int64_t ldk, const T* __restrict__ v, int64_t ldv,
                      const T* __restrict__ p, T* __restrict__ dq, int64_t lddq, T* __restrict__ dk, int64_t lddk,
-                     T* __restrict__ dv, int64_t lddv, int H, int Lq, int Lk, int d, float temperature) {
+                     T* __restrict__ dv, int64_t lddv, int H, int Lq, int Lk, int d, float temperature,
+                     float drop_p, const int64_t* __restrict__ rng, int64_t site) {
   pdl_wait();
   pdl_launch_dependents();
   extern __shared__ __align__(16) float sm[];
   const int lkp = mha_lkp(Lk);
+  DropRng drop;
+  if (drop_p > 0.f) drop.init(rng, site, drop_p);
   float* Qs = sm;                  // [Lq][d]    q / temperature
   float* Ks = Qs + Lq * d;         // [Lk][d]
   float* Vt = Ks + Lk * d;         // [d][lkp]   V transposed
@@ -337,6 +346,23 @@ mha_bwd_tiled_kernel(const T* __restrict__ dout, int64_t ldo, const T* __restric
   __syncthreads();
   for (int i = w; i < Lq; i += MHA_T_THREADS / 32) {
     float delta = 0.f;
+    if (drop_p > 0.f) {
+      // forward used P~ = m * P (m = keep / (1 - p)): dP = m * dP~;  dS = P * (dP - sum_j P dP);  dV needs P~, so the
+      // probability tile is rewritten to P~ once dS has been formed
+      const uint64_t row0 = (((uint64_t)b * H + h) * Lq + i) * (uint64_t)Lk;
+      for (int j = lane; j < Lk; j += 32) {
+        const float dp = dSs[i * lkp + j] * drop.factor(row0 + j);
+        delta += dp * Ps[i * lkp + j];
+        dSs[i * lkp + j] = dp;
+      }
+      delta = warp_sum(delta);
+      for (int j = lane; j < Lk; j += 32) {
+        const float pr = Ps[i * lkp + j];
+        dSs[i * lkp + j] = pr * (dSs[i * lkp + j] - delta);
+        Ps[i * lkp + j] = pr * drop.factor(row0 + j);
+      }
+      continue;
+    }
     for (int j = lane; j < Lk; j += 32) delta += dSs[i * lkp + j] * Ps[i * lkp + j];
     delta = warp_sum(delta);
     for (int j = lane; j < Lk; j += 32) dSs[i * lkp + j] = Ps[i * lkp + j] * (dSs[i * lkp + j] - delta);
@@ -906,13 +932,14 @@ using namespace b200st;
 
 extern "C" {
 
-int b200st_mha_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
-                   int64_t ldv, const uint8_t* mask, int64_t mask_sb, int64_t mask_sq, void* o,
-                   int64_t ldo, void* p, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d,
-                   float temperature, b200st_stream_t stream) {
+static int mha_fwd_impl(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                        int64_t ldv, const uint8_t* mask, int64_t mask_sb, int64_t mask_sq, void* o,
+                        int64_t ldo, void* p, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d,
+                        float temperature, float drop_p, const int64_t* rng, int64_t site, b200st_stream_t stream) {
   if (B <= 0 || Lq <= 0) return 0;
   if (Lk <= 0) return set_error("mha_fwd: empty key sequence");
-  if (dtype == B200ST_BF16 && g_mha_backend == 0) {
+  if (drop_p > 0.f && (rng == nullptr || !(drop_p < 1.f))) return set_error("mha_fwd: dropout needs rng state and p < 1");
+  if (dtype == B200ST_BF16 && g_mha_backend == 0 && drop_p <= 0.f) {
     const int rc = mha_fwd_tc(q, ldq, k, ldk, v, ldv, mask, mask_sb, mask_sq, o, ldo, p, B, H, Lq, Lk, d, temperature,
                               (cudaStream_t)stream);
     if (rc <= 0) return rc;           // launched (0) or failed (-1); 1 = shape not covered, use the SIMT tiles
@@ -926,12 +953,13 @@ int b200st_mha_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t
           B200ST_CUDA(cudaFuncSetAttribute((const void*)mha_fwd_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
         B200ST_CUDA(launch_pdl(mha_fwd_tiled_kernel<T>, tg, dim3(MHA_T_THREADS), tsm, (cudaStream_t)stream,
                                (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, mask, mask_sb, mask_sq, (T*)o, ldo,
-                               (T*)p, (int)H, (int)Lq, (int)Lk, (int)d, temperature));
+                               (T*)p, (int)H, (int)Lq, (int)Lk, (int)d, temperature, drop_p, rng, site));
       });
       B200ST_LAUNCH_CHECK("mha_fwd_tiled");
       return 0;
     }
   }
+  if (drop_p > 0.f) return set_error("mha_fwd: attention dropout is implemented by the shared-memory tile kernel only (Lq=%lld Lk=%lld d=%lld does not fit)", (long long)Lq, (long long)Lk, (long long)d);
   const size_t smem = MHA_WARPS * (d + Lk) * sizeof(float);
   if (smem > 48 * 1024) return set_error("mha_fwd: Lk=%lld d=%lld exceeds the single-pass kernel", (long long)Lk, (long long)d);
   dim3 grid((unsigned)ceil_div(Lq, MHA_WARPS), (unsigned)H, (unsigned)B);
@@ -944,19 +972,37 @@ int b200st_mha_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t
   return 0;
 }
 
+int b200st_mha_fwd(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                   int64_t ldv, const uint8_t* mask, int64_t mask_sb, int64_t mask_sq, void* o,
+                   int64_t ldo, void* p, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d,
+                   float temperature, b200st_stream_t stream) {
+  return mha_fwd_impl(dtype, q, ldq, k, ldk, v, ldv, mask, mask_sb, mask_sq, o, ldo, p, B, H, Lq, Lk, d, temperature,
+                      0.f, nullptr, 0, stream);
+}
+
+int b200st_mha_fwd_dropout(int dtype, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                           int64_t ldv, const uint8_t* mask, int64_t mask_sb, int64_t mask_sq, void* o,
+                           int64_t ldo, void* p, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d,
+                           float temperature, float drop_p, const int64_t* rng, int64_t site,
+                           b200st_stream_t stream) {
+  return mha_fwd_impl(dtype, q, ldq, k, ldk, v, ldv, mask, mask_sb, mask_sq, o, ldo, p, B, H, Lq, Lk, d, temperature,
+                      drop_p, rng, site, stream);
+}
+
 int b200st_set_mha_backend(int mode) {
   const int old = g_mha_backend | (g_las_backend << 1);
   if (mode >= 0 && mode <= 3) { g_mha_backend = mode & 1; g_las_backend = (mode >> 1) & 1; }
   return old;
 }
 
-int b200st_mha_bwd(int dtype, const void* dout, int64_t ldo, const void* q, int64_t ldq,
-                   const void* k, int64_t ldk, const void* v, int64_t ldv, const void* p, void* ds,
-                   void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B,
-                   int64_t H, int64_t Lq, int64_t Lk, int64_t d, float temperature,
-                   b200st_stream_t stream) {
+static int mha_bwd_impl(int dtype, const void* dout, int64_t ldo, const void* q, int64_t ldq,
+                        const void* k, int64_t ldk, const void* v, int64_t ldv, const void* p, void* ds,
+                        void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B,
+                        int64_t H, int64_t Lq, int64_t Lk, int64_t d, float temperature, float drop_p,
+                        const int64_t* rng, int64_t site, b200st_stream_t stream) {
   if (B <= 0 || Lq <= 0 || Lk <= 0) return 0;
-  if (dtype == B200ST_BF16 && g_mha_backend == 0) {
+  if (drop_p > 0.f && (rng == nullptr || !(drop_p < 1.f))) return set_error("mha_bwd: dropout needs rng state and p < 1");
+  if (dtype == B200ST_BF16 && g_mha_backend == 0 && drop_p <= 0.f) {
     const int rc = mha_bwd_tc(dout, ldo, q, ldq, k, ldk, v, ldv, p, dq, lddq, dk, lddk, dv, lddv, B, H, Lq, Lk, d,
                               temperature, (cudaStream_t)stream);
     if (rc <= 0) return rc;
@@ -970,12 +1016,14 @@ int b200st_mha_bwd(int dtype, const void* dout, int64_t ldo, const void* q, int6
           B200ST_CUDA(cudaFuncSetAttribute((const void*)mha_bwd_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
         B200ST_CUDA(launch_pdl(mha_bwd_tiled_kernel<T>, tg, dim3(MHA_T_THREADS), tsm, (cudaStream_t)stream,
                                (const T*)dout, ldo, (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, (const T*)p,
-                               (T*)dq, lddq, (T*)dk, lddk, (T*)dv, lddv, (int)H, (int)Lq, (int)Lk, (int)d, temperature));
+                               (T*)dq, lddq, (T*)dk, lddk, (T*)dv, lddv, (int)H, (int)Lq, (int)Lk, (int)d, temperature,
+                               drop_p, rng, site));
       });
       B200ST_LAUNCH_CHECK("mha_bwd_tiled");
       return 0;
     }
   }
+  if (drop_p > 0.f) return set_error("mha_bwd: attention dropout is implemented by the shared-memory tile kernel only (Lq=%lld Lk=%lld d=%lld does not fit)", (long long)Lq, (long long)Lk, (long long)d);
   const size_t smem = MHA_WARPS * (d + Lk) * sizeof(float);
   if (smem > 48 * 1024) return set_error("mha_bwd: Lk=%lld d=%lld exceeds the single-pass kernel", (long long)Lk, (long long)d);
   dim3 gq((unsigned)ceil_div(Lq, MHA_WARPS), (unsigned)H, (unsigned)B);
@@ -991,6 +1039,24 @@ int b200st_mha_bwd(int dtype, const void* dout, int64_t ldo, const void* q, int6
   B200ST_LAUNCH_CHECK("mha_bwd");
   count_launch();
   return 0;
+}
+
+int b200st_mha_bwd(int dtype, const void* dout, int64_t ldo, const void* q, int64_t ldq,
+                   const void* k, int64_t ldk, const void* v, int64_t ldv, const void* p, void* ds,
+                   void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B,
+                   int64_t H, int64_t Lq, int64_t Lk, int64_t d, float temperature,
+                   b200st_stream_t stream) {
+  return mha_bwd_impl(dtype, dout, ldo, q, ldq, k, ldk, v, ldv, p, ds, dq, lddq, dk, lddk, dv, lddv, B, H, Lq, Lk, d,
+                      temperature, 0.f, nullptr, 0, stream);
+}
+
+int b200st_mha_bwd_dropout(int dtype, const void* dout, int64_t ldo, const void* q, int64_t ldq,
+                           const void* k, int64_t ldk, const void* v, int64_t ldv, const void* p, void* ds,
+                           void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B,
+                           int64_t H, int64_t Lq, int64_t Lk, int64_t d, float temperature, float drop_p,
+                           const int64_t* rng, int64_t site, b200st_stream_t stream) {
+  return mha_bwd_impl(dtype, dout, ldo, q, ldq, k, ldk, v, ldv, p, ds, dq, lddq, dk, lddk, dv, lddv, B, H, Lq, Lk, d,
+                      temperature, drop_p, rng, site, stream);
 }
 
 int b200st_las_attn_fwd(int dtype, const void* q, const void* wk, const void* vals,

@@ -344,3 +344,72 @@ int b200st_length_mask(const int32_t* lengths, uint8_t* mask, int64_t B, int64_t
 }
 
 }  // extern "C"
+
+// ---- dropout (nn.Dropout call sites: Enc.py:159-212, Dec.py:166,386-429, Seq2seq.py:195-209, layers.py:182-249) ----
+#include "philox.cuh"
+
+namespace b200st {
+
+// y[r, c] = x[r, c] * keep(r * ld_m + c_off + c) / (1 - p) (+ res[r, c]);  x, y, res row-strided 2-D views.
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ res, int64_t ldr, T* __restrict__ y,
+               int64_t ldy, int64_t rows, int64_t cols, int64_t ld_m, int64_t c_off, float p,
+               const int64_t* __restrict__ rng, int64_t site, int vec) {
+  pdl_wait();
+  pdl_launch_dependents();
+  DropRng d;
+  d.init(rng, site, p);
+  if (vec) {                         // dense, every extent a multiple of 4: one Philox call per 4 elements
+    const int64_t n4 = rows * cols / 4;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (int64_t)gridDim.x * blockDim.x) {
+      const Philox4 r = d.group((uint64_t)g);
+      float v[4], o[4];
+      load4(x + 4 * g, v);
+      if (res) load4(res + 4 * g, o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (r.v[j] >= d.thresh ? v[j] * d.scale : 0.f) + (res ? o[j] : 0.f);
+      store4(y + 4 * g, v);
+    }
+    return;
+  }
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    float v = to_f(x[r * ldx + c]) * d.factor((uint64_t)(r * ld_m + c_off + c));
+    if (res) v += to_f(res[r * ldr + c]);
+    y[r * ldy + c] = from_f<T>(v);
+  }
+}
+
+__global__ void rng_advance_kernel(int64_t* rng) { rng[1] += 1; }
+
+}  // namespace b200st
+
+extern "C" {
+
+int b200st_dropout(int dtype, const void* x, int64_t ldx, const void* residual, int64_t ldr, void* y, int64_t ldy,
+                   int64_t rows, int64_t cols, int64_t ld_mask, int64_t col_off, float p, const int64_t* rng,
+                   int64_t site, b200st_stream_t stream) {
+  if (rows * cols <= 0) return 0;
+  if (!(p >= 0.f && p < 1.f)) return set_error("dropout: p=%f outside [0, 1)", (double)p);
+  const bool dense = ldx == cols && ldy == cols && ld_mask == cols && col_off == 0 && (!residual || ldr == cols);
+  const int a = dtype == B200ST_F32 ? 15 : 7;
+  const int vec = dense && (rows * cols) % 4 == 0 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)residual) & a) == 0;
+  const int64_t work = vec ? rows * cols / 4 : rows * cols;
+  B200ST_DISPATCH(dtype, T, {
+    B200ST_CUDA(launch_pdl(dropout_kernel<T>, dim3(flat_grid(work, 256)), dim3(256), 0, (cudaStream_t)stream,
+                           (const T*)x, ldx, (const T*)residual, ldr, (T*)y, ldy, rows, cols, ld_mask, col_off, p, rng,
+                           site, vec));
+  });
+  B200ST_LAUNCH_CHECK("dropout");
+  return 0;
+}
+
+int b200st_rng_advance(int64_t* rng, b200st_stream_t stream) {
+  rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rng);
+  B200ST_LAUNCH_CHECK("rng_advance");
+  return 0;
+}
+
+}  // extern "C"

@@ -51,7 +51,7 @@ multi_sqnorm_kernel(const int64_t* __restrict__ table, const int* __restrict__ b
 // scal[0] = clip coefficient, scal[1] = lr / (1 - beta1^t), scal[2] = sqrt(1 - beta2^t), scal[3] = ||g||_2
 __global__ void __launch_bounds__(1024)
 adam_prepare_kernel(const float* __restrict__ partials, int64_t n_blocks, float max_grad_norm,
-                    const float* __restrict__ lr, float beta1, float beta2, float* __restrict__ step,
+                    const float* __restrict__ lr, double beta1, double beta2, float* __restrict__ step,
                     float* __restrict__ scal) {
   __shared__ double sh[1024];
   double acc = 0.0;
@@ -72,8 +72,8 @@ adam_prepare_kernel(const float* __restrict__ partials, int64_t n_blocks, float 
     }
     const float t = *step + 1.f;                               // fp32 scalar like torch's state['step']
     *step = t;
-    const double bc1 = 1.0 - pow((double)beta1, (double)t);
-    const double bc2 = 1.0 - pow((double)beta2, (double)t);
+    const double bc1 = 1.0 - pow(beta1, (double)t);
+    const double bc2 = 1.0 - pow(beta2, (double)t);
     scal[0] = clip;
     scal[1] = (float)((double)lr[0] / bc1);
     scal[2] = (float)sqrt(bc2);
@@ -82,18 +82,18 @@ adam_prepare_kernel(const float* __restrict__ partials, int64_t n_blocks, float 
 }
 
 __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float clip, float step_size,
-                                          float sqrt_bc2, float b1, float b2, float eps, float wd) {
+                                          float sqrt_bc2, float omb1, float b2, float omb2, float eps, float wd) {
   g *= clip;
   if (wd != 0.f) g = fmaf(wd, p, g);                            // Adam (not AdamW): L2 term joins the gradient
-  m = fmaf(1.f - b1, g - m, m);                                  // exp_avg.lerp_(grad, 1 - beta1)
-  v = fmaf(b2, v, (1.f - b2) * g * g);                          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  m = fmaf(omb1, g - m, m);                                      // exp_avg.lerp_(grad, 1 - beta1)
+  v = fmaf(b2, v, omb2 * g * g);                                // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
   const float denom = sqrtf(v) / sqrt_bc2 + eps;               // (sqrt(v) / sqrt(bc2)).add_(eps)
   p -= step_size * (m / denom);                                 // param.addcdiv_(exp_avg, denom, value=-lr/bc1)
 }
 
 __global__ void __launch_bounds__(OPT_THREADS)
 multi_adam_kernel(const int64_t* __restrict__ table, const int* __restrict__ blockmap,
-                  const float* __restrict__ scal, float b1, float b2, float eps, float wd) {
+                  const float* __restrict__ scal, float omb1, float b2, float omb2, float eps, float wd) {
   const int t = blockmap[2 * blockIdx.x], chunk = blockmap[2 * blockIdx.x + 1];
   float* p = reinterpret_cast<float*>(table[6 * t + 0]);
   const float* g = reinterpret_cast<const float*>(table[6 * t + 1]);
@@ -112,13 +112,13 @@ multi_adam_kernel(const int64_t* __restrict__ table, const int* __restrict__ blo
         float pp[4], gg[4], mm[4], vv[4];
         load4(p + i, pp); load4(g + i, gg); load4(m + i, mm); load4(v + i, vv);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) adam_elem(pp[j], gg[j], mm[j], vv[j], clip, step_size, isb2, b1, b2, eps, wd);
+        for (int j = 0; j < 4; ++j) adam_elem(pp[j], gg[j], mm[j], vv[j], clip, step_size, isb2, omb1, b2, omb2, eps, wd);
         store4(p + i, pp); store4(m + i, mm); store4(v + i, vv);
         if (sh) store4(sh + i, pp);
       } else {
         for (int64_t j = i; j < end; ++j) {
           float pp = p[j], mm = m[j], vv = v[j];
-          adam_elem(pp, g[j], mm, vv, clip, step_size, isb2, b1, b2, eps, wd);
+          adam_elem(pp, g[j], mm, vv, clip, step_size, isb2, omb1, b2, omb2, eps, wd);
           p[j] = pp; m[j] = mm; v[j] = vv;
           if (sh) sh[j] = __float2bfloat16_rn(pp);
         }
@@ -127,7 +127,7 @@ multi_adam_kernel(const int64_t* __restrict__ table, const int* __restrict__ blo
   } else {
     for (int64_t j = base + threadIdx.x; j < end; j += OPT_THREADS) {
       float pp = p[j], mm = m[j], vv = v[j];
-      adam_elem(pp, g[j], mm, vv, clip, step_size, isb2, b1, b2, eps, wd);
+      adam_elem(pp, g[j], mm, vv, clip, step_size, isb2, omb1, b2, omb2, eps, wd);
       p[j] = pp; m[j] = mm; v[j] = vv;
       if (sh) sh[j] = __float2bfloat16_rn(pp);
     }
@@ -150,19 +150,19 @@ int b200st_multi_sqnorm(const int64_t* table, const int32_t* blockmap, int64_t n
   return 0;
 }
 
-int b200st_adam_prepare(const float* partials, int64_t n_blocks, float max_grad_norm, const float* lr, float beta1,
-                        float beta2, float* step, float* scal, b200st_stream_t stream) {
+int b200st_adam_prepare(const float* partials, int64_t n_blocks, float max_grad_norm, const float* lr, double beta1,
+                        double beta2, float* step, float* scal, b200st_stream_t stream) {
   adam_prepare_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, n_blocks, max_grad_norm, lr, beta1, beta2, step,
                                                             scal);
   B200ST_LAUNCH_CHECK("adam_prepare");
   return 0;
 }
 
-int b200st_multi_adam(const int64_t* table, const int32_t* blockmap, int64_t n_blocks, const float* scal, float beta1,
-                      float beta2, float eps, float weight_decay, b200st_stream_t stream) {
+int b200st_multi_adam(const int64_t* table, const int32_t* blockmap, int64_t n_blocks, const float* scal, double beta1,
+                      double beta2, double eps, double weight_decay, b200st_stream_t stream) {
   if (n_blocks <= 0) return 0;
-  multi_adam_kernel<<<(unsigned)n_blocks, OPT_THREADS, 0, (cudaStream_t)stream>>>(table, blockmap, scal, beta1, beta2,
-                                                                                 eps, weight_decay);
+  multi_adam_kernel<<<(unsigned)n_blocks, OPT_THREADS, 0, (cudaStream_t)stream>>>(
+      table, blockmap, scal, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)weight_decay);
   B200ST_LAUNCH_CHECK("multi_adam");
   return 0;
 }

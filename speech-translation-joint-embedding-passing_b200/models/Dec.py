@@ -93,8 +93,6 @@ class Dec(nn.Module):
     def forward_device(self, acous_outputs, klens, tgt=None, teacher_forcing_ratio=0.0, need_logps=True):
         """Device-resident variant used by Seq2seq: klens int32[B] (valid keys) or None; returns
         (embs, logps|empty, symbols int64 [B,S,1], lengths int32 device tensor [B])."""
-        if self.training and (self.dropout.p > 0 or self.embedding_dropout.p > 0):
-            raise NotImplementedError('Dec dropout > 0 is not implemented by the b200st kernels yet')
         if tgt is None:
             n_steps = self.max_seq_len - 1                                  # Dec.py:158-162,205
         else:
@@ -108,7 +106,9 @@ class Dec(nn.Module):
         embs, logps, symbols, lengths = BF.las_decoder(
             acous_outputs, klens, ids_tf, n_steps, need_logps, self.embedder.weight,
             self.acous_att.linear_att_w.weight, self.acous_ffn.weight, self.acous_out.weight,
-            self.acous_out.bias, self._lstm_params())
+            self.acous_out.bias, self._lstm_params(),
+            p_emb=float(self.embedding_dropout.p) if self.training else 0.0,
+            p_drop=float(self.dropout.p) if self.training else 0.0)
         return embs, logps, symbols.unsqueeze(2), lengths
 
     def forward(self, acous_outputs, acous_lens=None, tgt=None, hidden=None, is_training=False,

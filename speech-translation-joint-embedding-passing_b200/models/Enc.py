@@ -84,8 +84,6 @@ class Enc(nn.Module):
 
     def forward(self, acous_feats, acous_lens=None, is_training=False, hidden=None, use_gpu=False,
                 lens_dev=None):
-        if self.training and self.dropout.p > 0:
-            raise NotImplementedError('Enc dropout > 0 is not implemented by the b200st kernels yet')
         batch_size, acous_len = acous_feats.size(0), acous_feats.size(1)
         assert acous_len % 8 == 0, 'feature length must be a multiple of 8 (trainer_st.py:252 pads it)'
         if is_training:
@@ -102,6 +100,9 @@ class Enc(nn.Module):
             last = li == len(layers) - 1
             x = BF.blstm_layer(x, lens, self._dir_weights(lstm, False), self._dir_weights(lstm, True),
                                pair=1 if last else 2, batch_first_out=last)
+            # Enc.py:159,178,195,212: dropout on the layer output (element-wise, so it commutes with the frame-pair
+            # concat that the recurrence kernel has already folded into its store addresses)
+            x = BF.dropout(x, float(self.dropout.p), self.training, tag=f'las.enc.l{li + 1}')
             if not last:
                 lens = lens // 2                                   # Enc.py:170,187,204
         return x                                                   # [B, T/8, 2H]

@@ -49,6 +49,9 @@ class LAS(nn.Module):
                 teacher_forcing_ratio=0.0, beam_width=1, use_gpu=False, lm_mode='null', lm_model=None):
         if lm_mode != 'null':
             raise NotImplementedError("LM fusion is out of scope; use lm_mode='null'")
+        if self.training:
+            from b200st import runtime as rt
+            rt.new_step()
         embs, logps, symbols, lengths = self.forward_device(
             acous_feats, acous_lens=acous_lens, tgt=tgt, is_training=is_training,
             teacher_forcing_ratio=teacher_forcing_ratio, need_logps=True)

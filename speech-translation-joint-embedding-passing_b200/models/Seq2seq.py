@@ -98,30 +98,30 @@ class Seq2seq(nn.Module):
             self.enc_src = Encoder(*enc_params)
             self.dec_tgt = Decoder(*dec_params)
             self.out_tgt = nn.Linear(dim_model, dec_vocab_size, bias=False)
+        for name, mod in self.named_modules():      # dropout sites are tagged by module path (test hook rt.site_log)
+            mod._b200st_tag = name
 
     # ------------------------------------------------------------------------------------------
     # building blocks (same names as the reference's private helpers)
     # ------------------------------------------------------------------------------------------
-    def _check_dropout(self):
-        if self.training and self.embedding_dropout.p > 0:
-            raise NotImplementedError('embedding_dropout > 0 is not implemented by the b200st kernels yet')
+    def _p_emb(self):
+        return float(self.embedding_dropout.p) if self.training else 0.0
 
     def _get_src_emb(self, src, emb_src_dyn, device):
         """The mix (Seq2seq.py:183-199).  Returns (src_mask, emb_src, src_mask_input) like the reference;
         both masks are uint8 device tensors."""
-        self._check_dropout()
         src = src.contiguous()
         src_mask_input = K().token_mask(src, PAD, causal=False)           # [B,1,S]
         src_mask = K().token_mask(src, PAD, causal=True)                  # [B,S,S]
-        emb_src = BF.mix(src, self.enc_embedder.weight, emb_src_dyn, self.enc_emb_proj.weight)
+        emb_src = BF.mix(src, self.enc_embedder.weight, emb_src_dyn, self.enc_emb_proj.weight, p=self._p_emb(),
+                         tag='mix')
         return src_mask, emb_src, src_mask_input
 
     def _get_tgt_emb(self, tgt, device):
         """Seq2seq.py:202-211: pad & causal mask [B,L,L] + (projected) target embeddings."""
-        self._check_dropout()
         tgt = tgt.contiguous()
         tgt_mask = K().token_mask(tgt, PAD, causal=True)
-        emb_tgt = BF.embedding(tgt, self.dec_embedder.weight, PAD)
+        emb_tgt = BF.dropout(BF.embedding(tgt, self.dec_embedder.weight, PAD), self._p_emb(), True, tag='tgt_emb')
         if self.dec_emb_proj_flag:
             emb_tgt = BF.linear(emb_tgt, self.dec_emb_proj.weight)
         return tgt_mask, emb_tgt
@@ -178,6 +178,8 @@ class Seq2seq(nn.Module):
         device = check_device(use_gpu)
         mode = mode.upper()
         assert src is not None
+        if self.training:
+            rt.new_step()           # dropout masks: fresh step seed, site numbering restarts
         if 'ST' in mode or 'ASR' in mode:
             assert acous_feats is not None
         if 'ST' in mode or 'MT' in mode:

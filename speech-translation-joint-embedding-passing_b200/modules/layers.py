@@ -15,11 +15,9 @@ from b200st.kernels import K
 from utils.config import PAD
 
 
-def _no_dropout(module, what):
-    if module.training and module.p > 0:
-        raise NotImplementedError(
-            f'{what}: dropout p={module.p} in training mode is not implemented by the b200st kernels yet; '
-            f'set it to 0 (parity runs do, SURVEY.md §8c-5)')
+def _p(module):
+    """Active dropout probability of an nn.Dropout: its p in training mode, 0 otherwise."""
+    return float(module.p) if module.training else 0.0
 
 
 class TransformerEncoderLayer(nn.Module):
@@ -71,21 +69,25 @@ class MultiheadAttention(nn.Module):
         if prior_weight is not None or decode_speedup:
             raise NotImplementedError('prior_weight / decode_speedup paths are unused by Seq2seq')
         assert self.d_k == self.d_v, 'the fused attention core assumes d_k == d_v (always true upstream)'
-        _no_dropout(self.dropout, 'MultiheadAttention')
-        _no_dropout(self.attention.dropout, 'ScaledDotProductAttention (hard-wired p=0.1, layers.py:207)')
+        # dropout on the fc output (layers.py:194) and the hard-wired p = 0.1 attention dropout (layers.py:207,226)
+        p_fc, p_attn = _p(self.dropout), _p(self.attention.dropout)
+        tag = getattr(self, '_b200st_tag', '')
         if mask is not None and mask.dtype == torch.bool:
             mask = mask.view(torch.uint8) if mask.is_contiguous() else mask.to(torch.uint8)
         if k is v:           # every call site of the reference (self- and cross-attention): one fused sub-layer node
             return BF.mha_block(q, k, mask, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps,
                                 self.w_qs.weight, self.w_ks.weight, self.w_vs.weight, self.fc.weight, self.n_head,
-                                self.attention.temperature)
+                                self.attention.temperature, p_attn=p_attn, p_fc=p_fc, tag=tag)
         residual = q
         qn = BF.layer_norm(q, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
         qp = BF.linear(qn, self.w_qs.weight)
         kp = BF.linear(k, self.w_ks.weight)
         vp = BF.linear(v, self.w_vs.weight)
-        o, attn = BF.mha_core(qp, kp, vp, mask, self.n_head, self.attention.temperature)
-        out = BF.linear(o, self.fc.weight, residual=residual)      # fc, dropout(p=0), += residual
+        o, attn = BF.mha_core(qp, kp, vp, mask, self.n_head, self.attention.temperature, p_attn=p_attn, tag=tag)
+        if p_fc > 0:
+            out = BF.dropout(BF.linear(o, self.fc.weight), p_fc, True, tag + '.fc', residual=residual)
+        else:
+            out = BF.linear(o, self.fc.weight, residual=residual)  # fc, += residual
         return out, attn
 
 
@@ -107,7 +109,8 @@ class ScaledDotProductAttention(nn.Module):
         kk = k.transpose(1, 2).reshape(B, k.size(2), H * d)
         vv = v.transpose(1, 2).reshape(B, v.size(2), H * d)
         m = None if mask is None else mask.reshape(B, -1, k.size(2)).to(torch.uint8)
-        o, attn = BF.mha_core(qq, kk, vv, m, H, self.temperature)
+        o, attn = BF.mha_core(qq, kk, vv, m, H, self.temperature, p_attn=_p(self.dropout),
+                              tag=getattr(self, '_b200st_tag', ''))
         return o.view(B, Lq, H, d).transpose(1, 2), attn
 
 
@@ -122,9 +125,9 @@ class PositionwiseFeedForward(nn.Module):
         self.dropout = nn.Dropout(dropout)
 
     def forward(self, x):
-        _no_dropout(self.dropout, 'PositionwiseFeedForward')
         return BF.ffn_block(x, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps,
-                            self.w_1.weight, self.w_1.bias, self.w_2.weight, self.w_2.bias)
+                            self.w_1.weight, self.w_1.bias, self.w_2.weight, self.w_2.bias, p=_p(self.dropout),
+                            tag=getattr(self, '_b200st_tag', ''))
 
 
 # ---- helpers (layers.py:260-309) ---------------------------------------------------------------

@@ -11,8 +11,36 @@ Each method restates the contract documented in include/b200st.h.
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.nn.functional as F
+
+
+def philox_factor(rng, site, idx, p):
+    """Dropout multiplier (0 or 1/(1-p)) of element indices `idx` (int64 tensor, any shape): Philox4x32-10 exactly as
+    include/b200st.h documents for b200st_dropout -- key {seed_lo, seed_hi ^ step_hi}, counter {idx/4 lo, idx/4 hi,
+    site, step_lo}, output word idx % 4, keep iff word >= p * 2^32.  numpy uint64 arithmetic."""
+    seed, step = (int(v) for v in rng.cpu().tolist())
+    M = np.uint64(0xffffffff)
+    i = idx.cpu().numpy().astype(np.uint64)
+    g, lane = i >> np.uint64(2), (i & np.uint64(3)).astype(np.int64)
+    c0, c1 = g & M, g >> np.uint64(32)
+    c2 = np.full_like(c0, np.uint64(site & 0xffffffff))
+    c3 = np.full_like(c0, np.uint64(step & 0xffffffff))
+    k0 = np.uint64(seed & 0xffffffff)
+    k1 = np.uint64(((seed >> 32) ^ (step >> 32)) & 0xffffffff)
+    for _ in range(10):
+        p0, p1 = np.uint64(0xD2511F53) * c0, np.uint64(0xCD9E8D57) * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & M, p1 >> np.uint64(32), p1 & M
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & M
+        k1 = (k1 + np.uint64(0xBB67AE85)) & M
+    words = np.stack([c0, c1, c2, c3], axis=-1)
+    r = np.take_along_axis(words, lane[..., None], axis=-1)[..., 0]
+    thresh = min(int(float(np.float32(p)) * 4294967296.0), 0xffffffff)
+    keep = r >= np.uint64(thresh)
+    scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    return torch.from_numpy(np.where(keep, scale, np.float32(0.0)).astype(np.float32)).to(idx.device)
 
 
 class FakeKernels:
@@ -59,6 +87,26 @@ class FakeKernels:
             return y.to(out_dtype or (residual.dtype if residual is not None else a.dtype))
         out.copy_(y.to(out.dtype))
         return out
+
+    # -- dropout ----------------------------------------------------------------------------------
+    def dropout(self, x, p, rng, site, residual=None, out=None, ld_mask=None, col_off=0):
+        self.launches += 1
+        x2 = x if x.dim() == 2 else x.reshape(-1, x.size(-1))
+        rows, cols = x2.shape
+        ld = cols if ld_mask is None else ld_mask
+        idx = torch.arange(rows, device=x.device)[:, None] * ld + col_off + torch.arange(cols, device=x.device)[None, :]
+        y = x2.float() * philox_factor(rng, site, idx, p)
+        if residual is not None:
+            y = y + residual.reshape(rows, cols).float()
+        y = y.to(x.dtype)
+        if out is None:
+            return y.view(x.shape) if x.dim() != 2 else y
+        (out if out.dim() == 2 else out.view(rows, cols)).copy_(y)
+        return out
+
+    def rng_advance(self, rng):
+        self.launches += 1
+        rng[1] += 1
 
     # -- fused clip + Adam ------------------------------------------------------------------------
     def opt_chunk(self):
@@ -109,7 +157,17 @@ class FakeKernels:
         return dx.to(x.dtype).view(x.shape)
 
     # -- attention --------------------------------------------------------------------------------
-    def mha_fwd(self, q, k, v, mask, n_head, temperature, want_probs=True):
+    @staticmethod
+    def _attn_drop(p_shape, dropout, device):
+        if dropout is None or dropout[0] <= 0:
+            return None
+        dp, rng, site = dropout
+        n = 1
+        for v in p_shape:
+            n *= v
+        return philox_factor(rng, site, torch.arange(n, device=device).view(p_shape), dp)
+
+    def mha_fwd(self, q, k, v, mask, n_head, temperature, want_probs=True, dropout=None):
         B, Lq, HD = q.shape
         Lk = k.size(1)
         d = HD // n_head
@@ -120,10 +178,11 @@ class FakeKernels:
         if mask is not None:
             s = s.masked_fill(mask.unsqueeze(1) == 0, -1e9)
         p = torch.softmax(s, dim=-1)
-        o = torch.matmul(p, vf).transpose(1, 2).reshape(B, Lq, HD)
+        m = self._attn_drop(p.shape, dropout, q.device)
+        o = torch.matmul(p if m is None else p * m, vf).transpose(1, 2).reshape(B, Lq, HD)
         return o.to(q.dtype), (p.to(q.dtype) if want_probs else None)
 
-    def mha_bwd(self, dout, q, k, v, p, n_head, temperature, dq=None, dk=None, dv=None):
+    def mha_bwd(self, dout, q, k, v, p, n_head, temperature, dq=None, dk=None, dv=None, dropout=None):
         outs = (dq, dk, dv)
         B, Lq, HD = q.shape
         Lk = k.size(1)
@@ -134,10 +193,14 @@ class FakeKernels:
         vf = v.float().reshape(B, Lk, n_head, d).transpose(1, 2)
         pf = p.float()
         dp = torch.matmul(do, vf.transpose(2, 3))
+        m = self._attn_drop(pf.shape, dropout, q.device)
+        pd = pf
+        if m is not None:
+            dp, pd = dp * m, pf * m
         ds = pf * (dp - (dp * pf).sum(-1, keepdim=True))
         dq = torch.matmul(ds, kf) / temperature
         dk = torch.matmul(ds.transpose(2, 3), qf)
-        dv = torch.matmul(pf.transpose(2, 3), do)
+        dv = torch.matmul(pd.transpose(2, 3), do)
         back = lambda t, L: t.transpose(1, 2).reshape(B, L, HD).to(q.dtype)
         res = [back(dq, Lq), back(dk, Lk), back(dv, Lk)]
         for i, o in enumerate(outs):
