@@ -117,6 +117,20 @@ int b200st_mha_bwd_dropout(int dtype, const void* dout, int64_t ldo, const void*
                            int64_t H, int64_t Lq, int64_t Lk, int64_t d, float temperature, float drop_p,
                            const int64_t* rng, int64_t site, b200st_stream_t stream);
 
+/* Single-query attention over a key/value cache: the decoder step of incremental decoding (forward_translate /
+ * forward_eval, Seq2seq.py:260-393, which upstream re-runs the whole decoder on the prefix every step).
+ * q: [n_hyp, H*d] (row stride ldq) = the newest position's queries; key t of hypothesis b is read at
+ * k_cache + slot*stride_b + t*stride_t + h*d with slot = anc[t*n_hyp + b] (int32 ancestry table: the cache slot that
+ * holds position t of b's history after beam re-ordering, Seq2seq.py:381-384) or, when anc is NULL, slot = b / bdiv
+ * (cross-attention: the bdiv beams of one utterance share its encoder keys).  mask: uint8 [*, Lk] rows of stride mask_sb,
+ * row b / mask_bdiv, nonzero = keep, NULL = none; masked scores are SET to -1e9 like b200st_mha_fwd.
+ * o: [n_hyp, H*d] (ldo).  Scores use (q / temperature) . k. */
+int b200st_mha_decode(int dtype, const void* q, int64_t ldq, const void* k_cache, const void* v_cache,
+                      int64_t stride_b, int64_t stride_t, const int32_t* anc, int64_t n_hyp, int64_t bdiv,
+                      const uint8_t* mask, int64_t mask_sb, int64_t mask_bdiv, void* o, int64_t ldo, int64_t H,
+                      int64_t Lk, int64_t d, float temperature, b200st_stream_t stream);
+
+
 
 /* ---- LSTM cell pointwise (one step of torch.nn.LSTM, Dec.py:393-419) ----------------------------
  * gates (+ gates_b + gates_c, NULLs skipped) [B,4H] = pre-activations x W_ih^T + h W_hh^T + b_ih + b_hh, possibly

@@ -225,6 +225,31 @@ class CudaKernels:
                                            float(temperature), self._stream()), 'mha_bwd')
         return dq, dk, dv
 
+    def mha_decode(self, q, k_cache, v_cache, Lk, n_head, temperature, anc=None, bdiv=1, mask=None, mask_bdiv=1):
+        """Attention of ONE new query per hypothesis over cached keys/values.  q [n_hyp, H*d]; k_cache / v_cache
+        [slots, Lmax, H*d] views (dense last dim, arbitrary slot / position strides, e.g. the two column halves of one
+        K|V cache); the first Lk positions are attended.  anc: int32 [>=Lk, n_hyp] ancestry table (slot holding
+        position t of hypothesis b) or None -> slot = b // bdiv.  mask: uint8 [rows, 1, >=Lk] or [rows, >=Lk], row
+        b // mask_bdiv."""
+        self._need_cuda(q, k_cache, v_cache, anc, mask)
+        n_hyp, HD = q.shape
+        d = HD // n_head
+        assert q.stride(1) == 1 and k_cache.dim() == 3 and k_cache.stride(2) == 1 and v_cache.stride(2) == 1
+        assert k_cache.stride(0) == v_cache.stride(0) and k_cache.stride(1) == v_cache.stride(1)
+        assert k_cache.dtype == q.dtype == v_cache.dtype and k_cache.size(1) >= Lk
+        if anc is not None:
+            assert anc.dtype == torch.int32 and anc.is_contiguous() and anc.size(1) == n_hyp and anc.size(0) >= Lk
+        msb = 0
+        if mask is not None:
+            assert mask.dtype in (torch.uint8, torch.bool) and mask.stride(-1) == 1 and mask.size(-1) >= Lk
+            msb = mask.stride(0)
+        o = torch.empty((n_hyp, HD), dtype=q.dtype, device=q.device)
+        _lib.check(self.lib.b200st_mha_decode(_dt(q), _p(q), q.stride(0), _p(k_cache), _p(v_cache), k_cache.stride(0),
+                                              k_cache.stride(1), _p(anc), n_hyp, int(bdiv), _p(mask), msb,
+                                              int(mask_bdiv), _p(o), HD, n_head, int(Lk), d, float(temperature),
+                                              self._stream()), 'mha_decode')
+        return o
+
     # -- LSTM -------------------------------------------------------------------------------------
     def lstm_cell_fwd(self, gates, c_prev, residual=None, save_acts=True, h_out=None, c_out=None,
                       acts_out=None, res_out=None, gates_b=None, gates_c=None):

@@ -380,6 +380,60 @@ int mha_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const voi
 int mha_bwd_tc(const void* dout, int64_t ldo, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                int64_t ldv, const void* p, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t d, float temperature, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// Single-query attention over a key/value CACHE (incremental decoding): the decoder step of
+// forward_translate / forward_eval (Seq2seq.py:260-393) only needs the newest position's output, whose keys and values
+// for positions < i were produced by earlier steps.  One CTA per (head, hypothesis); the hypothesis' history may live
+// in OTHER cache slots after a beam re-ordering, so key t of hypothesis b is read from slot anc[t * n_hyp + b]
+// (ancestry table, maintained by the host loop like the reference re-orders preds_exp, Seq2seq.py:381-384) -- the
+// cache itself is never moved.  Cross-attention passes anc = NULL and slot = b / bdiv (beams of one utterance share
+// the encoder keys).  Same score arithmetic as the full kernel: (q / temperature) . k, masked scores SET to -1e9.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128)
+mha_decode_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ kc, const T* __restrict__ vc,
+                  int64_t stride_b, int64_t stride_t, const int32_t* __restrict__ anc, int n_hyp, int bdiv,
+                  const uint8_t* __restrict__ mask, int64_t mask_sb, int mask_bdiv, T* __restrict__ o, int64_t ldo,
+                  int Lk, int d, float temperature) {
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ __align__(16) float sm[];
+  float* qs = sm;                      // [d]
+  float* sc = qs + d;                  // [Lk] scores -> probabilities
+  int* slot = reinterpret_cast<int*>(sc + Lk);   // [Lk] cache slot of every key
+  __shared__ float red[32];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) qs[c] = to_f(q[(int64_t)b * ldq + (int64_t)h * d + c]) / temperature;
+  for (int t = threadIdx.x; t < Lk; t += blockDim.x) slot[t] = anc ? anc[(int64_t)t * n_hyp + b] : b / bdiv;
+  __syncthreads();
+  const uint8_t* mr = mask ? mask + (int64_t)(b / mask_bdiv) * mask_sb : nullptr;
+  float mx = -INFINITY;
+  for (int t = w; t < Lk; t += nw) {
+    const T* kr = kc + (int64_t)slot[t] * stride_b + (int64_t)t * stride_t + (int64_t)h * d;
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) acc = fmaf(qs[c], to_f(kr[c]), acc);
+    acc = warp_sum(acc);
+    if (mr && mr[t] == 0) acc = -1e9f;
+    if (lane == 0) sc[t] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = block_max(mx, red);
+  __syncthreads();
+  float sum = 0.f;
+  for (int t = threadIdx.x; t < Lk; t += blockDim.x) { const float e = expf(sc[t] - mx); sc[t] = e; sum += e; }
+  sum = block_sum(sum, red);
+  __syncthreads();
+  const float inv = 1.f / sum;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float acc = 0.f;
+    for (int t = 0; t < Lk; ++t)
+      acc = fmaf(sc[t] * inv, to_f(vc[(int64_t)slot[t] * stride_b + (int64_t)t * stride_t + (int64_t)h * d + c]), acc);
+    o[(int64_t)b * ldo + (int64_t)h * d + c] = from_f<T>(acc);
+  }
+}
+
 static int g_las_backend = 0;     // 0 = auto (key-split cluster kernels for bf16), 1 = one CTA per sequence
 static int g_mha_backend = 0;     // 0 = auto (tensor cores for bf16 when the shape fits), 1 = SIMT tiles only
 
@@ -1057,6 +1111,27 @@ int b200st_mha_bwd_dropout(int dtype, const void* dout, int64_t ldo, const void*
                            const int64_t* rng, int64_t site, b200st_stream_t stream) {
   return mha_bwd_impl(dtype, dout, ldo, q, ldq, k, ldk, v, ldv, p, ds, dq, lddq, dk, lddk, dv, lddv, B, H, Lq, Lk, d,
                       temperature, drop_p, rng, site, stream);
+}
+
+int b200st_mha_decode(int dtype, const void* q, int64_t ldq, const void* k_cache, const void* v_cache,
+                      int64_t stride_b, int64_t stride_t, const int32_t* anc, int64_t n_hyp, int64_t bdiv,
+                      const uint8_t* mask, int64_t mask_sb, int64_t mask_bdiv, void* o, int64_t ldo, int64_t H,
+                      int64_t Lk, int64_t d, float temperature, b200st_stream_t stream) {
+  if (n_hyp <= 0) return 0;
+  if (Lk <= 0) return set_error("mha_decode: empty key cache");
+  if (bdiv <= 0 || mask_bdiv <= 0) return set_error("mha_decode: bdiv / mask_bdiv must be >= 1");
+  const size_t smem = (size_t)(d + 2 * Lk) * sizeof(float);
+  if (smem > 200 * 1024) return set_error("mha_decode: Lk=%lld exceeds the shared-memory score row", (long long)Lk);
+  dim3 grid((unsigned)H, (unsigned)n_hyp);
+  B200ST_DISPATCH(dtype, T, {
+    if (smem > 48 * 1024)
+      B200ST_CUDA(cudaFuncSetAttribute((const void*)mha_decode_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200ST_CUDA(launch_pdl(mha_decode_kernel<T>, grid, dim3(128), smem, (cudaStream_t)stream, (const T*)q, ldq,
+                           (const T*)k_cache, (const T*)v_cache, stride_b, stride_t, anc, (int)n_hyp, (int)bdiv, mask,
+                           mask_sb, (int)mask_bdiv, (T*)o, ldo, (int)Lk, (int)d, temperature));
+  });
+  B200ST_LAUNCH_CHECK("mha_decode");
+  return 0;
 }
 
 int b200st_las_attn_fwd(int dtype, const void* q, const void* wk, const void* vals,

@@ -248,9 +248,37 @@ class Seq2seq(nn.Module):
     # ------------------------------------------------------------------------------------------
     # greedy evaluation (Seq2seq.py:260-304, 512-638)
     # ------------------------------------------------------------------------------------------
+    # True: inference loops feed one token per step through b200st.decode.DecoderCache (cached keys/values);
+    # False: the reference's own loop, which re-runs the decoder on the whole prefix every step.  Same token ids.
+    decode_cache = True
+
+    def _greedy_decode_cached(self, enc_outputs, src_mask_input, batch, length_out, device):
+        """_greedy_decode with cached keys/values: identical bookkeeping (Seq2seq.py:260-304), O(L) decoder work."""
+        from b200st.decode import DecoderCache
+        dt = rt.compute_dtype()
+        cache = DecoderCache(self, enc_outputs, src_mask_input, 1, self.max_seq_len_tgt)
+        eos_mask = torch.zeros(batch, dtype=torch.bool, device=device)
+        logps = torch.full((batch, length_out, self.dec_vocab_size),
+                           float(torch.tensor(1.0 / self.dec_vocab_size).log()), dtype=dt, device=device)
+        preds = torch.full((batch, 1), BOS, dtype=torch.int64, device=device)
+        for i in range(1, self.max_seq_len_tgt):
+            logp, pred = cache.step_logps(preds[:, i - 1], i - 1)
+            eos_mask = eos_mask | (pred.squeeze(1) == EOS)
+            logps[:, i, :] = logp
+            preds = torch.cat((preds, pred), dim=1)
+            if int(eos_mask.sum()) == batch:
+                if length_out != preds.size(1):
+                    pad = torch.full((batch, length_out - preds.size(1)), PAD, dtype=torch.int64,
+                                     device=device)
+                    preds = torch.cat((preds, pad), dim=1)
+                break
+        return preds, logps
+
     def _greedy_decode(self, enc_outputs, src_mask_input, batch, length_out, device):
-        """The shared free-running loop of forward_eval (no KV cache: the reference re-runs the decoder on
-        the whole prefix each step; kept so that token ids are identical)."""
+        """The shared free-running loop of forward_eval.  With decode_cache off: no KV cache, the decoder is re-run
+        on the whole prefix each step exactly like the reference."""
+        if self.decode_cache:
+            return self._greedy_decode_cached(enc_outputs, src_mask_input, batch, length_out, device)
         dt = rt.compute_dtype()
         eos_mask = torch.zeros(batch, dtype=torch.bool, device=device)
         logps = torch.full((batch, length_out, self.dec_vocab_size),
@@ -334,18 +362,31 @@ class Seq2seq(nn.Module):
         S = enc_outputs.size(1)
         eos_mask = torch.zeros(batch * k, dtype=torch.bool, device=device)
         len_map = torch.ones(batch * k, device=device)
-        enc_exp = enc_outputs.repeat(1, k, 1).view(-1, S, self.dim_model)
         preds_exp = torch.full((batch * k, 1), BOS, dtype=torch.int64, device=device)
         scores_exp = torch.zeros(batch * k, device=device)
-        mask_exp = src_mask_input.repeat(1, k, 1).view(-1, 1, S).contiguous()
+        cache = None
+        if self.decode_cache:
+            # cached keys/values; the beams of an utterance share its encoder K/V (no beam_width-fold tiling)
+            from b200st.decode import DecoderCache
+            cache = DecoderCache(self, enc_outputs, src_mask_input, k, max_seq_len)
+        else:
+            enc_exp = enc_outputs.repeat(1, k, 1).view(-1, S, self.dim_model)
+            mask_exp = src_mask_input.repeat(1, k, 1).view(-1, 1, S).contiguous()
         for i in range(1, max_seq_len):
-            tgt_mask, emb_tgt = self._get_tgt_emb(preds_exp, device)
-            _, _, logp_all, pred_all, score_all = self._decoder_de(emb_tgt, enc_exp, tgt_mask=tgt_mask,
-                                                                   src_mask=mask_exp, beam_width=k)
-            if k == 1:
-                score_all = logp_all.data.float().gather(2, pred_all)
-            pred = pred_all[:, i - 1]
-            score = score_all[:, i - 1]
+            if cache is not None:
+                logp, pred = cache.step_logps(preds_exp[:, i - 1], i - 1)
+                if k == 1:
+                    score = logp.float().gather(1, pred)
+                else:
+                    score, pred = logp.float().topk(k)
+            else:
+                tgt_mask, emb_tgt = self._get_tgt_emb(preds_exp, device)
+                _, _, logp_all, pred_all, score_all = self._decoder_de(emb_tgt, enc_exp, tgt_mask=tgt_mask,
+                                                                       src_mask=mask_exp, beam_width=k)
+                if k == 1:
+                    score_all = logp_all.data.float().gather(2, pred_all)
+                pred = pred_all[:, i - 1]
+                score = score_all[:, i - 1]
             if i == 1:
                 scores_exp = scores_exp + score.reshape(batch, -1)[:, :k].contiguous().view(-1)
                 pred_select = pred.reshape(batch, -1)[:, :k].contiguous().view(-1)
@@ -363,6 +404,8 @@ class Seq2seq(nn.Module):
                 r_idxs, c_idxs = pos // k, pos % k
                 pred_select = pred[r_idxs, c_idxs].view(-1)
                 preds_exp[:, :i] = preds_exp[r_idxs.view(-1), :i]
+                if cache is not None:
+                    cache.reorder(r_idxs.view(-1), i)
                 preds_exp = torch.cat((preds_exp, pred_select.unsqueeze(-1)), dim=1)
             eos_mask = (pred_select == EOS) | eos_mask
             len_map = len_map + torch.ones(batch * k, device=device).masked_fill(eos_mask, 0)

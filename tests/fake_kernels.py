@@ -208,6 +208,23 @@ class FakeKernels:
                 o.copy_(res[i]); res[i] = o
         return tuple(res)
 
+    def mha_decode(self, q, k_cache, v_cache, Lk, n_head, temperature, anc=None, bdiv=1, mask=None, mask_bdiv=1):
+        self.launches += 1
+        n_hyp, HD = q.shape
+        d = HD // n_head
+        b = torch.arange(n_hyp, device=q.device)
+        t = torch.arange(Lk, device=q.device)
+        slot = anc[:Lk].long().t() if anc is not None else (b // bdiv)[:, None].expand(n_hyp, Lk)   # [n_hyp, Lk]
+        kk = k_cache[slot, t[None, :]].float().view(n_hyp, Lk, n_head, d)
+        vv = v_cache[slot, t[None, :]].float().view(n_hyp, Lk, n_head, d)
+        qq = (q.float() / temperature).view(n_hyp, n_head, d)
+        s = torch.einsum('bhd,bthd->bht', qq, kk)
+        if mask is not None:
+            m = mask.reshape(mask.size(0), -1)[:, :Lk][b // mask_bdiv]
+            s = s.masked_fill(m[:, None, :] == 0, -1e9)
+        p = torch.softmax(s, dim=-1)
+        return torch.einsum('bht,bthd->bhd', p, vv).reshape(n_hyp, HD).to(q.dtype)
+
     # -- LSTM cell --------------------------------------------------------------------------------
     def lstm_cell_fwd(self, gates, c_prev, residual=None, save_acts=True, h_out=None, c_out=None,
                       acts_out=None, res_out=None, gates_b=None, gates_c=None):

@@ -419,3 +419,33 @@ def test_gemm_tensor_core_views(ks):
     assert rel_err(y, a[:, 200:].float() @ w[:, 200:].float().t()) < 1e-2
     assert rel_err(out[:, 256:768], 2 * (a.float() @ w.float().t())) < 1e-2
     assert float(out[:, :256].abs().sum()) == 0 and float(out[:, 768:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('n_hyp,bdiv,H,d,Lk,Lmax', [(6, 1, 4, 16, 5, 9), (15, 5, 8, 64, 31, 31), (640, 5, 8, 64, 49, 50),
+                                                    (4, 1, 2, 8, 1, 3)])
+def test_mha_decode_cached_attention(ks, dtype, n_hyp, bdiv, H, d, Lk, Lmax):
+    """Single-query attention over a K|V cache: self-attention form (ancestry table, PAD-key mask) and cross-attention
+    form (beams share the utterance's keys: slot = b // bdiv, mask row b // bdiv)."""
+    c, f = ks
+    HD = H * d
+    g = torch.Generator().manual_seed(n_hyp + Lk)
+    q = torch.randn(n_hyp, HD, generator=g).cuda().to(dtype)
+    # self-attention: one [n_hyp, Lmax, 2*HD] cache, K and V are its column halves
+    cache = torch.randn(n_hyp, Lmax, 2 * HD, generator=g).cuda().to(dtype)
+    anc = torch.stack([torch.randperm(n_hyp, generator=g) for _ in range(Lmax)]).to(torch.int32).cuda()
+    mask = (torch.rand(n_hyp, Lmax, generator=g) > 0.3).to(torch.uint8).cuda()
+    mask[:, 0] = 1
+    for a, m in ((anc, mask), (None, None), (anc, None)):
+        got = c.mha_decode(q, cache[:, :, :HD], cache[:, :, HD:], Lk, H, d ** 0.5, anc=a, mask=m)
+        ref = f.mha_decode(q, cache[:, :, :HD], cache[:, :, HD:], Lk, H, d ** 0.5, anc=a, mask=m)
+        assert rel_err(got, ref) < TOL[dtype]
+    # cross-attention: n_hyp // bdiv utterances
+    if n_hyp % bdiv == 0:
+        nb = n_hyp // bdiv
+        kv = torch.randn(nb, Lk, 2 * HD, generator=g).cuda().to(dtype)
+        smask = (torch.rand(nb, 1, Lk, generator=g) > 0.3).to(torch.uint8).cuda()
+        smask[:, :, 0] = 1
+        got = c.mha_decode(q, kv[:, :, :HD], kv[:, :, HD:], Lk, H, d ** 0.5, bdiv=bdiv, mask=smask, mask_bdiv=bdiv)
+        ref = f.mha_decode(q, kv[:, :, :HD], kv[:, :, HD:], Lk, H, d ** 0.5, bdiv=bdiv, mask=smask, mask_bdiv=bdiv)
+        assert rel_err(got, ref) < TOL[dtype]

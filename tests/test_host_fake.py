@@ -97,13 +97,15 @@ def test_greedy_eval_and_translate_ids(golden, fake_backend):
     m.eval()
     I = golden.inputs()
     lens = [torch.tensor([n]) for n in I['acous_lens']]
-    ev = m.forward_eval(acous_feats=I['acous_feats'].clone(), acous_lens=lens, mode='ST', use_gpu=False)
-    assert torch.equal(ev['preds_st'], golden['eval/preds_st'])
-    for k in (1, 3):
-        tr = m.forward_translate(acous_feats=I['acous_feats'].clone(), acous_lens=lens, beam_width=k,
-                                 penalty_factor=1, use_gpu=False, max_seq_len=golden.cfg.max_seq_len_tgt,
-                                 mode='ST')
-        assert torch.equal(tr, golden[f'translate/beam{k}']), k
+    for cached in (True, False):       # KV-cached incremental decoder and the reference's recompute-the-prefix loop
+        m.decode_cache = cached
+        ev = m.forward_eval(acous_feats=I['acous_feats'].clone(), acous_lens=lens, mode='ST', use_gpu=False)
+        assert torch.equal(ev['preds_st'], golden['eval/preds_st']), cached
+        for k in (1, 3):
+            tr = m.forward_translate(acous_feats=I['acous_feats'].clone(), acous_lens=lens, beam_width=k,
+                                     penalty_factor=1, use_gpu=False, max_seq_len=golden.cfg.max_seq_len_tgt,
+                                     mode='ST')
+            assert torch.equal(tr, golden[f'translate/beam{k}']), (cached, k)
 
 
 def test_mt_mode(golden, fake_backend):
