@@ -62,6 +62,12 @@ int b200st_gemm2(int dtype_ab, int dtype_c, int trans_a, int trans_b, int64_t M,
                  void* C, int64_t ldc, const void* R, int64_t ldr, const float* bias, int relu,
                  b200st_stream_t stream);
 
+/* Persistent tensor-core GEMM (one CTA per SM walking the tile list, double-buffered TMEM accumulator) for problems
+ * with >= 4 tiles per SM.  Bit mask: bit 0 = persistent kernels, bit 1 = the CTA-pair (cta_group::2, 256 x 256 tile per
+ * two SMs) kernel for the largest shapes; default 3, 0 = always one tile per CTA.  Returns the previous mask (test /
+ * bench hook). */
+int b200st_set_gemm_persistent(int on);
+
 /* GEMM kernel selection: 0 = auto (bf16 operands that TMA can address -> tcgen05 tensor-core kernel, everything
  * else -> exact CUDA-core kernel), 1 = CUDA cores only, 2 = tensor cores required (error if not eligible).
  * Returns the previous mode.  Used by tests to compare the two kernels; the product leaves it at 0. */

@@ -10,7 +10,12 @@ shapes = [(64, 10000, 512, 0, 1), (64, 2048, 512, 0, 1), (64, 2048, 200, 0, 1), 
           (3200, 1024, 512, 0, 1), (3200, 10000, 512, 0, 1), (32256, 1024, 1024, 0, 1), (32256, 1024, 1024, 0, 0),
           (64512, 1024, 80, 0, 1), (1024, 1024, 32256, 1, 0), (1024, 256, 64512, 1, 0), (512, 512, 3200, 1, 0), (2048, 512, 3200, 1, 0), (512, 2048, 2048, 1, 0),
           (512, 512, 2048, 1, 0), (2048, 1024, 64, 1, 0), (2048, 512, 64, 1, 0)]
-for (M, N, K, ta, tb) in shapes:
+import itertools
+big = [(32256, 1024, 1024, 0, 1), (32256, 1024, 1024, 0, 0), (16128, 1024, 1024, 0, 1), (64512, 1024, 80, 0, 1), (3200, 10000, 512, 0, 1),
+       (3200, 512, 10000, 0, 0), (8064, 1024, 1024, 0, 1), (4032, 1024, 1024, 0, 1)]
+modes = [(s, 3) for s in shapes] + [(s, 1) for s in big] + [(s, 0) for s in big]
+for (M, N, K, ta, tb), persist in modes:
+    k.set_gemm_persistent(persist)
     a = torch.randn((K, M) if ta else (M, K), device='cuda').bfloat16()
     b = torch.randn((N, K) if tb else (K, N), device='cuda').bfloat16()
     od = torch.float32 if ta else torch.bfloat16
@@ -26,4 +31,4 @@ for (M, N, K, ta, tb) in shapes:
         k.gemm(a, b, trans_a=bool(ta), trans_b=bool(tb), out=out)
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / n * 1e3
-    print(f'M={M:6d} N={N:6d} K={K:6d} ta={ta} tb={tb}  {us:8.2f} us  {2.0*M*N*K/us/1e6:8.1f} TFLOP/s')
+    print(f'M={M:6d} N={N:6d} K={K:6d} ta={ta} tb={tb} persist={persist}  {us:8.2f} us  {2.0*M*N*K/us/1e6:8.1f} TFLOP/s', flush=True)

@@ -61,6 +61,10 @@ class CudaKernels:
         """0 auto, 1 CUDA cores only, 2 tensor cores required.  Returns the previous mode (test hook)."""
         return int(self.lib.b200st_set_gemm_backend(int(mode)))
 
+    def set_gemm_persistent(self, on: int) -> int:
+        """1 = persistent tcgen05 GEMM for the many-tile shapes (default), 0 = one tile per CTA.  Returns the old value."""
+        return int(self.lib.b200st_set_gemm_persistent(int(on)))
+
     def set_blstm_backend(self, mode: int) -> int:
         """0 auto (tcgen05 recurrence for bf16/H=256), 1 CUDA cores only.  Returns the previous mode."""
         return int(self.lib.b200st_set_blstm_backend(int(mode)))

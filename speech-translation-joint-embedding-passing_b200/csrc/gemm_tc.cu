@@ -253,6 +253,446 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
 }
 
+// ---- persistent variant for the throughput shapes (hundreds of output tiles) ------------------------------------
+// One CTA per SM walks a static list of 128 x BN output tiles (tile = blockIdx.x + j * gridDim.x, N fastest so the
+// CTAs of one wave share A rows through L2).  What the one-tile-per-CTA kernel pays per tile -- barrier init, TMEM
+// allocation, an empty pipeline at the start and an idle tensor pipe during the epilogue -- is paid once per CTA here:
+//   * the TMA producer runs ahead across tile boundaries (the smem ring never drains),
+//   * the accumulator is DOUBLE-BUFFERED in TMEM (2 x BN fp32 columns): the issuer starts tile j+1 into the other
+//     buffer while the four epilogue warps drain tile j (tmem_full / tmem_empty mbarrier pairs),
+//   * the epilogue stages 32-column chunks through a private 18 KB region (the pipeline buffers are never idle), so
+//     every global store still writes whole row segments.
+template <int BN, int STAGES>
+struct TcPersistSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STG_PITCH = 36;                                    // floats per staged row (32 + pad, 16 B aligned)
+  static constexpr int STG_OFF = STAGES * STAGE;
+  static constexpr int STG_BYTES = 4 * 32 * STG_PITCH * 4;
+  static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                       const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_b2,
+                       int kb_seg1, TC* __restrict__ C, int64_t ldc, const TC* R, int64_t ldr,
+                       const float* __restrict__ bias, int relu, float alpha, int M, int N, int K, int n_tiles_n,
+                       int n_tiles) {
+  using S = TcPersistSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;         // [2] accumulator buffer complete
+  uint64_t* tempty = tfull + 2;             // [2] accumulator buffer drained by the epilogue
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb_total = (K + TC_BK - 1) / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;                       // running k-block counter across tiles: ring slot and phase
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles_n) * TC_BM, n0 = (tile % n_tiles_n) * BN;
+        for (int kb = 0; kb < kb_total; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          uint8_t* sa = smem + s * S::STAGE;
+          uint8_t* sb = sa + S::A_BYTES;
+          mbar_expect_tx(&full[s], S::STAGE);
+          const bool seg2 = kb >= kb_seg1;
+          const CUtensorMap* pa = seg2 ? &tma_a2 : &tma_a;
+          const CUtensorMap* pb = seg2 ? &tma_b2 : &tma_b;
+          const int k0 = (kb - (seg2 ? kb_seg1 : 0)) * TC_BK;
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < TC_BM / 64; ++c) tma_load_2d(sa + c * (TC_BK * 128), pa, m0 + c * 64, k0, &full[s]);
+          } else {
+            tma_load_2d(sa, pa, k0, m0, &full[s]);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (TC_BK * 128), pb, n0 + c * 64, k0, &full[s]);
+          } else {
+            tma_load_2d(sb, pb, k0, n0, &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(TC_BM, BN, A_MN, B_MN);
+      uint32_t it = 0, j = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+        const uint32_t buf = j & 1;
+        mbar_wait(&tempty[buf], ((j >> 1) & 1) ^ 1);      // the epilogue has drained this buffer (free at first use)
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < kb_total; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * S::STAGE);
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t da = A_MN ? umma_desc(sa + k * 2048, TC_BK * 128, 1024) : umma_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc(sb + k * 2048, TC_BK * 128, 1024) : umma_desc(sb + k * 32, 16, 1024);
+            tc_mma_f16(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty[s]);
+        }
+        tc_commit(&tfull[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int wq = warp - 4;
+    constexpr int SP = S::STG_PITCH;
+    float* stg = reinterpret_cast<float*>(smem + S::STG_OFF) + wq * 32 * SP;
+    const int cc = (lane & 7) * 4;          // 8 lanes x 4 columns cover a 32-column chunk row
+    const int rl = lane >> 3;               // 4 rows per pass
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+      const int m0 = (tile / n_tiles_n) * TC_BM, n0 = (tile % n_tiles_n) * BN;
+      const uint32_t buf = j & 1;
+      mbar_wait(&tfull[buf], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + buf * BN + ((uint32_t)(wq * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(acc + (uint32_t)c0, r);
+        if (c0 + 32 >= BN) {                 // last TMEM read of this tile: hand the buffer back to the issuer
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+        __syncwarp();                        // the previous chunk's readers are done with the staging rows
+#pragma unroll
+        for (int q = 0; q < 32; q += 4)
+          *reinterpret_cast<float4*>(&stg[lane * SP + q]) =
+              make_float4(alpha * __uint_as_float(r[q]), alpha * __uint_as_float(r[q + 1]),
+                          alpha * __uint_as_float(r[q + 2]), alpha * __uint_as_float(r[q + 3]));
+        __syncwarp();
+        const int col = n0 + c0 + cc;
+        if (col >= N) continue;
+        const int nv = min(4, N - col);
+        // residual rows of the 8 passes are fetched 4 passes ahead of their use
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float radd[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            radd[u][0] = radd[u][1] = radd[u][2] = radd[u][3] = 0.f;
+            const int row = m0 + wq * 32 + (half * 4 + u) * 4 + rl;
+            if (R != nullptr && row < M) {
+              const TC* rp = R + (int64_t)row * ldr + col;
+              if constexpr (sizeof(TC) == 4) {
+                if (nv == 4 && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+                  const float4 v4 = *reinterpret_cast<const float4*>(rp);
+                  radd[u][0] = v4.x; radd[u][1] = v4.y; radd[u][2] = v4.z; radd[u][3] = v4.w;
+                } else {
+                  for (int e = 0; e < nv; ++e) radd[u][e] = to_f(rp[e]);
+                }
+              } else {
+                if (nv == 4 && (reinterpret_cast<uintptr_t>(rp) & 7) == 0) {
+                  const uint2 v2 = *reinterpret_cast<const uint2*>(rp);
+                  radd[u][0] = __uint_as_float(v2.x << 16); radd[u][1] = __uint_as_float(v2.x & 0xffff0000u);
+                  radd[u][2] = __uint_as_float(v2.y << 16); radd[u][3] = __uint_as_float(v2.y & 0xffff0000u);
+                } else {
+                  for (int e = 0; e < nv; ++e) radd[u][e] = to_f(rp[e]);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int rr = (half * 4 + u) * 4 + rl;
+            const int row = m0 + wq * 32 + rr;
+            if (row >= M) continue;
+            const float4 a4 = *reinterpret_cast<const float4*>(&stg[rr * SP + cc]);
+            float v[4] = {a4.x, a4.y, a4.z, a4.w};
+            if (bias) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (e < nv) v[e] += bias[col + e];
+            }
+            if (relu == 1) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            if (relu == 2) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = radd[u][e] > 0.f ? v[e] : 0.f;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] += radd[u][e];
+            }
+            TC* cp = C + (int64_t)row * ldc + col;
+            if constexpr (sizeof(TC) == 4) {
+              if (nv == 4 && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+                *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+              } else {
+                for (int e = 0; e < nv; ++e) reinterpret_cast<float*>(cp)[e] = v[e];
+              }
+            } else {
+              if (nv == 4 && (reinterpret_cast<uintptr_t>(cp) & 7) == 0) {
+                uint2 o2;
+                __nv_bfloat162* oo = reinterpret_cast<__nv_bfloat162*>(&o2);
+                oo[0] = __floats2bfloat162_rn(v[0], v[1]);
+                oo[1] = __floats2bfloat162_rn(v[2], v[3]);
+                *reinterpret_cast<uint2*>(cp) = o2;
+              } else {
+                for (int e = 0; e < nv; ++e) cp[e] = from_f<TC>(v[e]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+  }
+}
+
+// ---- CTA-pair variant (cta_group::2): the two CTAs of a cluster sit on the two SMs of one TPC and execute ONE
+// tcgen05.mma of M = 256, N = 256 per K step.  Each CTA stages only its own 128 A rows and HALF of the B tile
+// (128 of the 256 N rows), so shared-memory fill + operand-read traffic per FLOP is half that of the single-CTA kernel
+// -- a single SM streaming both operands of a 128-row MMA out of its own shared memory tops out near 50 % of the
+// tensor peak.  Pipeline = the persistent kernel's (smem ring across tiles, double-buffered TMEM accumulator), with the
+// cross-CTA plumbing: both CTAs' TMA bytes are credited to the LEADER's full barrier, the leader issues every MMA and
+// its tcgen05.commit arrives (multicast) on the empty / tmem_full barriers of BOTH CTAs, and both CTAs' epilogue warps
+// release an accumulator buffer by arriving on the leader's tmem_empty barrier.
+template <int STAGES, bool A_MN, bool B_MN, typename TC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                       const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_b2,
+                       int kb_seg1, TC* __restrict__ C, int64_t ldc, const TC* R, int64_t ldr,
+                       const float* __restrict__ bias, int relu, float alpha, int M, int N, int K, int n_tiles_n,
+                       int n_tiles) {
+  constexpr int BN = 256;                   // accumulator columns per CTA = N extent of the pair's tile
+  constexpr int BNH = 128;                  // B rows (N) staged by EACH CTA; the MMA reads both halves
+  using S = TcPersistSmem<BNH, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;         // [2] accumulator buffer complete
+  uint64_t* tempty = tfull + 2;             // [2] accumulator buffer drained by the epilogue
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb_total = (K + TC_BK - 1) / TC_BK;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }   // 4 epilogue warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {                           // the same warp of BOTH CTAs performs the pair allocation
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                        // both CTAs' barriers exist before any cross-CTA arrival
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;                       // running k-block counter across tiles: ring slot and phase
+      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+        // the pair's tile is 256 x 256: this CTA stages A rows [m0, m0+128) and B rows (N) [n0, n0+128)
+        const int m0 = (tile / n_tiles_n) * 256 + (int)rank * TC_BM, n0 = (tile % n_tiles_n) * BN + (int)rank * BNH;
+        for (int kb = 0; kb < kb_total; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          uint8_t* sa = smem + s * S::STAGE;
+          uint8_t* sb = sa + S::A_BYTES;
+          if (rank == 0) mbar_expect_tx(&full[s], 2 * S::STAGE);      // the leader's barrier counts both CTAs' bytes
+          const bool seg2 = kb >= kb_seg1;
+          const CUtensorMap* pa = seg2 ? &tma_a2 : &tma_a;
+          const CUtensorMap* pb = seg2 ? &tma_b2 : &tma_b;
+          const int k0 = (kb - (seg2 ? kb_seg1 : 0)) * TC_BK;
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < TC_BM / 64; ++c) tma_load_2d_pair(sa + c * (TC_BK * 128), pa, m0 + c * 64, k0, &full[s]);
+          } else {
+            tma_load_2d_pair(sa, pa, k0, m0, &full[s]);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BNH / 64; ++c) tma_load_2d_pair(sb + c * (TC_BK * 128), pb, n0 + c * 64, k0, &full[s]);
+          } else {
+            tma_load_2d_pair(sb, pb, k0, n0, &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc(256, BN, A_MN, B_MN);     // M = 256 across the pair
+      uint32_t it = 0, j = 0;
+      for (int tile = pair; tile < n_tiles; tile += n_pairs, ++j) {
+        const uint32_t buf = j & 1;
+        mbar_wait(&tempty[buf], ((j >> 1) & 1) ^ 1);      // the epilogue has drained this buffer (free at first use)
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < kb_total; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * S::STAGE);
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t da = A_MN ? umma_desc(sa + k * 2048, TC_BK * 128, 1024) : umma_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc(sb + k * 2048, TC_BK * 128, 1024) : umma_desc(sb + k * 32, 16, 1024);
+            tc_mma_f16_pair(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit_pair(&empty[s]);
+        }
+        tc_commit_pair(&tfull[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int wq = warp - 4;
+    constexpr int SP = S::STG_PITCH;
+    float* stg = reinterpret_cast<float*>(smem + S::STG_OFF) + wq * 32 * SP;
+    const int cc = (lane & 7) * 4;          // 8 lanes x 4 columns cover a 32-column chunk row
+    const int rl = lane >> 3;               // 4 rows per pass
+    uint32_t j = 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs, ++j) {
+      const int m0 = (tile / n_tiles_n) * 256 + (int)rank * TC_BM, n0 = (tile % n_tiles_n) * BN;
+      const uint32_t buf = j & 1;
+      mbar_wait(&tfull[buf], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + buf * BN + ((uint32_t)(wq * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(acc + (uint32_t)c0, r);
+        if (c0 + 32 >= BN) {                 // last TMEM read of this tile: hand the buffer back to the issuer
+          tc_fence_before();
+          if (lane == 0) mbar_arrive_leader(&tempty[buf]);
+        }
+        __syncwarp();                        // the previous chunk's readers are done with the staging rows
+#pragma unroll
+        for (int q = 0; q < 32; q += 4)
+          *reinterpret_cast<float4*>(&stg[lane * SP + q]) =
+              make_float4(alpha * __uint_as_float(r[q]), alpha * __uint_as_float(r[q + 1]),
+                          alpha * __uint_as_float(r[q + 2]), alpha * __uint_as_float(r[q + 3]));
+        __syncwarp();
+        const int col = n0 + c0 + cc;
+        if (col >= N) continue;
+        const int nv = min(4, N - col);
+        // residual rows of the 8 passes are fetched 4 passes ahead of their use
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float radd[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            radd[u][0] = radd[u][1] = radd[u][2] = radd[u][3] = 0.f;
+            const int row = m0 + wq * 32 + (half * 4 + u) * 4 + rl;
+            if (R != nullptr && row < M) {
+              const TC* rp = R + (int64_t)row * ldr + col;
+              if constexpr (sizeof(TC) == 4) {
+                if (nv == 4 && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+                  const float4 v4 = *reinterpret_cast<const float4*>(rp);
+                  radd[u][0] = v4.x; radd[u][1] = v4.y; radd[u][2] = v4.z; radd[u][3] = v4.w;
+                } else {
+                  for (int e = 0; e < nv; ++e) radd[u][e] = to_f(rp[e]);
+                }
+              } else {
+                if (nv == 4 && (reinterpret_cast<uintptr_t>(rp) & 7) == 0) {
+                  const uint2 v2 = *reinterpret_cast<const uint2*>(rp);
+                  radd[u][0] = __uint_as_float(v2.x << 16); radd[u][1] = __uint_as_float(v2.x & 0xffff0000u);
+                  radd[u][2] = __uint_as_float(v2.y << 16); radd[u][3] = __uint_as_float(v2.y & 0xffff0000u);
+                } else {
+                  for (int e = 0; e < nv; ++e) radd[u][e] = to_f(rp[e]);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int rr = (half * 4 + u) * 4 + rl;
+            const int row = m0 + wq * 32 + rr;
+            if (row >= M) continue;
+            const float4 a4 = *reinterpret_cast<const float4*>(&stg[rr * SP + cc]);
+            float v[4] = {a4.x, a4.y, a4.z, a4.w};
+            if (bias) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (e < nv) v[e] += bias[col + e];
+            }
+            if (relu == 1) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            if (relu == 2) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = radd[u][e] > 0.f ? v[e] : 0.f;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] += radd[u][e];
+            }
+            TC* cp = C + (int64_t)row * ldc + col;
+            if constexpr (sizeof(TC) == 4) {
+              if (nv == 4 && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+                *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+              } else {
+                for (int e = 0; e < nv; ++e) reinterpret_cast<float*>(cp)[e] = v[e];
+              }
+            } else {
+              if (nv == 4 && (reinterpret_cast<uintptr_t>(cp) & 7) == 0) {
+                uint2 o2;
+                __nv_bfloat162* oo = reinterpret_cast<__nv_bfloat162*>(&o2);
+                oo[0] = __floats2bfloat162_rn(v[0], v[1]);
+                oo[1] = __floats2bfloat162_rn(v[2], v[3]);
+                *reinterpret_cast<uint2*>(cp) = o2;
+              } else {
+                for (int e = 0; e < nv; ++e) cp[e] = from_f<TC>(v[e]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                        // neither CTA's shared memory / TMEM goes away while the other still uses it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+  }
+}
+
 // ---- cluster split-K for the decoder-step shapes (M <= 64, long K, few N tiles) ---------------------------------
 // A [64 x N] output with K = 2048 and N = 512 has 8 output tiles: 8 CTAs would each stream 256 KB of weights alone
 // (~12 us, latency-bound).  Here the K range of every tile is split over a cluster of CS CTAs along grid.z (CS x more
@@ -489,6 +929,77 @@ static int launch_tc_clk(int64_t M, int64_t N, int64_t K, float alpha, const CUt
   return 0;
 }
 
+static int g_persist_enabled = 1;
+int gemm_tc_set_persistent(int on) { const int old = g_persist_enabled; if (on == 0 || on == 1) g_persist_enabled = on; return old; }
+static int g_sm_count = 0;
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC>
+static int launch_tc_persist(int64_t M, int64_t N, int64_t K, float alpha, const CUtensorMap& ma, const CUtensorMap& mb,
+                             const CUtensorMap& ma2, const CUtensorMap& mb2, int kb_seg1, void* C, int64_t ldc,
+                             const void* R, int64_t ldr, const float* bias, int relu, cudaStream_t st) {
+  using S = TcPersistSmem<BN, STAGES>;
+  static_assert(S::TOTAL <= 227 * 1024, "persistent tile configuration exceeds shared memory");
+  if (g_sm_count == 0) {
+    int dev = 0;
+    B200ST_CUDA(cudaGetDevice(&dev));
+    B200ST_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int n_tiles_n = (int)ceil_div(N, BN);
+  const int n_tiles = (int)(ceil_div(M, TC_BM) * n_tiles_n);
+  auto kern = gemm_tc_persist_kernel<BN, STAGES, A_MN, B_MN, TC>;
+  B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  dim3 grid((unsigned)min(n_tiles, g_sm_count));
+  B200ST_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), S::TOTAL, st, ma, mb, ma2, mb2, kb_seg1, (TC*)C, ldc, (const TC*)R,
+                         ldr, bias, relu, alpha, (int)M, (int)N, (int)K, n_tiles_n, n_tiles));
+  B200ST_LAUNCH_CHECK("gemm_tc_persist");
+  return 0;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_pair(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                          Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+static int g_pair_enabled = 1;
+int gemm_tc_set_pair(int on) { const int old = g_pair_enabled; if (on == 0 || on == 1) g_pair_enabled = on; return old; }
+
+template <int STAGES, bool A_MN, bool B_MN, typename TC>
+static int launch_tc_pair(int64_t M, int64_t N, int64_t K, float alpha, const CUtensorMap& ma, const CUtensorMap& mb,
+                          const CUtensorMap& ma2, const CUtensorMap& mb2, int kb_seg1, void* C, int64_t ldc,
+                          const void* R, int64_t ldr, const float* bias, int relu, cudaStream_t st) {
+  using S = TcPersistSmem<128, STAGES>;
+  static_assert(S::TOTAL <= 227 * 1024, "pair tile configuration exceeds shared memory");
+  if (g_sm_count == 0) {
+    int dev = 0;
+    B200ST_CUDA(cudaGetDevice(&dev));
+    B200ST_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int n_tiles_n = (int)ceil_div(N, 256);
+  const int n_tiles = (int)(ceil_div(M, 256) * n_tiles_n);
+  auto kern = gemm_tc_pair_kernel<STAGES, A_MN, B_MN, TC>;
+  B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  dim3 grid((unsigned)(2 * min(n_tiles, g_sm_count / 2)));
+  B200ST_CUDA(launch_pdl_pair(kern, grid, dim3(TC_THREADS), S::TOTAL, st, ma, mb, ma2, mb2, kb_seg1, (TC*)C, ldc,
+                              (const TC*)R, ldr, bias, relu, alpha, (int)M, (int)N, (int)K, n_tiles_n, n_tiles));
+  B200ST_LAUNCH_CHECK("gemm_tc_pair");
+  return 0;
+}
+
 static int g_clk_enabled = 1;
 void gemm_tc_set_cluster_splitk(int on) { g_clk_enabled = on; }
 
@@ -521,7 +1032,14 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   // cfg 4: 128 x 64, 2 stages, 4 CTAs/SM -- many M tiles with a one- or two-block K (the first BLSTM layer's input
   // projection, K = acoustic dim): a tile is all prologue + epilogue latency, so what helps is more tiles in flight
   if (cfg != 2 && kb_total <= 2 && m_tiles >= 64) cfg = 4;
-  const int BN = (cfg == 0 || wide) ? 128 : (cfg == 2 ? 32 : 64);
+  // persistent kernel (one CTA per SM, double-buffered TMEM accumulator) for the throughput shapes: at least four
+  // tiles per SM, fp32-atomic split-K not involved.  128 x 256 tiles when N allows, else 128 x 128.
+  // CTA-pair kernel (256 x 256 tile per pair): the big throughput shapes
+  const bool pair = g_persist_enabled && g_pair_enabled && cfg == 0 && kb_total >= 4 && N >= 256 &&
+                    ceil_div(M, 256) * ceil_div(N, 256) >= 4 * 74;
+  const bool persist256 = !pair && g_persist_enabled && cfg == 0 && kb_total >= 4 && N >= 256 && m_tiles * ceil_div(N, 256) >= 4 * 148;
+  const bool persist128 = g_persist_enabled && cfg == 0 && !persist256 && kb_total >= 4 && m_tiles * ceil_div(N, 128) >= 4 * 148;
+  const int BN = persist256 ? 256 : ((cfg == 0 || wide || pair) ? 128 : (cfg == 2 ? 32 : 64));   // = B box rows
   const bool m64 = (cfg == 2 || cfg == 3) && M <= 64;       // half-height A tile for the decoder-step GEMMs
   CUtensorMap ma, mb;
   if (a_mn) { if (make_map(&ma, A, K1, M, lda, TC_BK)) return -1; }
@@ -563,6 +1081,38 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   int kb_per_split = (int)ceil_div(kb_total, splits);
   splits = (int)ceil_div(kb_total, kb_per_split);
   if (splits > 1) B200ST_CUDA(cudaMemset2DAsync(C, ldc * 4, 0, N * 4, M, st));
+#define TC_PERSIST(BN_, ST_, AMN, BMN)                                                                     \
+  do {                                                                                                     \
+    if (dtype_c == B200ST_F32)                                                                             \
+      return launch_tc_persist<BN_, ST_, AMN, BMN, float>(M, N, K, alpha, ma, mb, ma2, mb2, kb_seg1, C, ldc, R, ldr, bias, relu, st); \
+    return launch_tc_persist<BN_, ST_, AMN, BMN, __nv_bfloat16>(M, N, K, alpha, ma, mb, ma2, mb2, kb_seg1, C, ldc, R, ldr, bias, relu, st); \
+  } while (0)
+#define TC_PAIR(AMN, BMN)                                                                                  \
+  do {                                                                                                     \
+    if (dtype_c == B200ST_F32)                                                                             \
+      return launch_tc_pair<6, AMN, BMN, float>(M, N, K, alpha, ma, mb, ma2, mb2, kb_seg1, C, ldc, R, ldr, bias, relu, st); \
+    return launch_tc_pair<6, AMN, BMN, __nv_bfloat16>(M, N, K, alpha, ma, mb, ma2, mb2, kb_seg1, C, ldc, R, ldr, bias, relu, st); \
+  } while (0)
+  if (pair && splits == 1) {
+    if (!a_mn && !b_mn) TC_PAIR(false, false);
+    if (!a_mn && b_mn) TC_PAIR(false, true);
+    if (a_mn && !b_mn) TC_PAIR(true, false);
+    TC_PAIR(true, true);
+  }
+#undef TC_PAIR
+  if ((persist256 || persist128) && splits == 1) {
+    if (persist256) {
+      if (!a_mn && !b_mn) TC_PERSIST(256, 4, false, false);
+      if (!a_mn && b_mn) TC_PERSIST(256, 4, false, true);
+      if (a_mn && !b_mn) TC_PERSIST(256, 4, true, false);
+      TC_PERSIST(256, 4, true, true);
+    }
+    if (!a_mn && !b_mn) TC_PERSIST(128, 6, false, false);
+    if (!a_mn && b_mn) TC_PERSIST(128, 6, false, true);
+    if (a_mn && !b_mn) TC_PERSIST(128, 6, true, false);
+    TC_PERSIST(128, 6, true, true);
+  }
+#undef TC_PERSIST
 #define TC_GO(BN_, ST_, AMN, BMN)                                                                          \
   do {                                                                                                     \
     if (dtype_c == B200ST_F32)                                                                             \

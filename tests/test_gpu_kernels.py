@@ -43,6 +43,50 @@ def test_gemm(ks, dtype, ta, tb, M, N, K):
     assert rel_err(y, yr) < TOL[dtype]
 
 
+@pytest.mark.parametrize('out_dtype', [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize('ta,tb', [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize('M,N,K', [(20000, 1000, 328), (32256, 1024, 1024), (19001, 512, 264), (9472, 2048, 256),
+                                   (3200, 10000, 512)])
+def test_gemm_persistent_tiles(ks, out_dtype, ta, tb, M, N, K):
+    """The persistent tcgen05 kernel (>= 4 tiles per SM: 128 x 256 and 128 x 128 tiles, ragged M / N / K edges, every
+    transpose form, fused bias / residual / ReLU / ReLU-gate epilogues) against the torch restatement and against the
+    one-tile-per-CTA kernel."""
+    c, f = ks
+    dt = torch.bfloat16
+    a = rnd(K, M, dtype=dt) if ta else rnd(M, K, dtype=dt)
+    b = rnd(N, K, dtype=dt, seed=1) if tb else rnd(K, N, dtype=dt, seed=1)
+    bias = rnd(N, seed=2)
+    res = rnd(M, N, dtype=out_dtype, seed=3)
+    yr = f.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, residual=res, alpha=0.5, out_dtype=out_dtype)
+    y = c.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, residual=res, alpha=0.5, out_dtype=out_dtype)
+    assert rel_err(y, yr) < TOL[torch.bfloat16]
+    old = c.set_gemm_persistent(0)          # mask: bit 0 persistent kernels, bit 1 CTA-pair kernel; default 3
+    try:
+        y0 = c.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, residual=res, alpha=0.5, out_dtype=out_dtype)
+        c.set_gemm_persistent(1)
+        y1 = c.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, residual=res, alpha=0.5, out_dtype=out_dtype)
+    finally:
+        c.set_gemm_persistent(old)
+    assert old == 3
+    assert rel_err(y, y0) < 1e-6 and rel_err(y1, y0) < 1e-6        # same k order per output element: (near) identical
+    y = c.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, relu=True, out_dtype=out_dtype)
+    assert rel_err(y, f.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, relu=True, out_dtype=out_dtype)) < TOL[torch.bfloat16]
+    if not ta:
+        h = torch.relu(rnd(M, N, dtype=out_dtype, seed=4))
+        y = c.gemm(a, b, trans_b=tb, relu_gate=h)
+        assert rel_err(y, f.gemm(a, b, trans_b=tb, relu_gate=h)) < TOL[torch.bfloat16]
+        assert float(y[h == 0].abs().sum()) == 0.0
+
+
+def test_gemm2_persistent_two_segment(ks):
+    c, f = ks
+    dt = torch.bfloat16
+    M, N, K, K2 = 32256, 1024, 1024, 1024
+    a, a2 = rnd(M, K, dtype=dt), rnd(M, K2, dtype=dt, seed=1)
+    b, b2 = rnd(K, N, dtype=dt, seed=2), rnd(K2, N, dtype=dt, seed=3)
+    assert rel_err(c.gemm2(a, b, a2, b2), f.gemm2(a, b, a2, b2)) < TOL[dt]
+
+
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('M,N,K', [(3200, 2048, 512), (37, 29, 13), (64, 512, 2048)])
 def test_gemm_relu_gate_epilogue(ks, dtype, M, N, K):
