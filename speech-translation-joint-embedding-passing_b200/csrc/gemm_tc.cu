@@ -385,6 +385,58 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
           tc_fence_before();
           if (lane == 0) mbar_arrive(&tempty[buf]);
         }
+        if (R == nullptr) {
+          // No residual operand: registers -> global directly.  A thread owns 32 consecutive columns of its row (64 B of
+          // bf16 / 128 B of fp32): four / eight 16-byte stores, ~5x fewer instructions than the staged path below, which
+          // matters because the epilogue of a K = 1024 tile has to fit under that tile's 8k-cycle mainloop.
+          const int row = m0 + wq * 32 + lane;
+          const int colb = n0 + c0;
+          if (row < M && colb < N && !(false)) {
+            float v[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = alpha * __uint_as_float(r[q]);
+            const bool fullw = colb + 32 <= N;
+            if (bias) {
+              if (fullw && (reinterpret_cast<uintptr_t>(bias + colb) & 15) == 0) {
+#pragma unroll
+                for (int q = 0; q < 32; q += 4) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(bias + colb + q);
+                  v[q] += b4.x; v[q + 1] += b4.y; v[q + 2] += b4.z; v[q + 3] += b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) if (colb + q < N) v[q] += bias[colb + q];
+              }
+            }
+            if (relu == 1) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
+            }
+            TC* cp = C + (int64_t)row * ldc + colb;
+            if (fullw && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+              if constexpr (sizeof(TC) == 4) {
+#pragma unroll
+                for (int q = 0; q < 32; q += 4)
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(cp) + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 32; q += 8) {
+                  uint4 o4;
+                  __nv_bfloat162* oo = reinterpret_cast<__nv_bfloat162*>(&o4);
+                  oo[0] = __floats2bfloat162_rn(v[q], v[q + 1]);
+                  oo[1] = __floats2bfloat162_rn(v[q + 2], v[q + 3]);
+                  oo[2] = __floats2bfloat162_rn(v[q + 4], v[q + 5]);
+                  oo[3] = __floats2bfloat162_rn(v[q + 6], v[q + 7]);
+                  *reinterpret_cast<uint4*>(cp + q) = o4;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) if (colb + q < N) cp[q] = from_f<TC>(v[q]);
+            }
+          }
+          continue;
+        }
         __syncwarp();                        // the previous chunk's readers are done with the staging rows
 #pragma unroll
         for (int q = 0; q < 32; q += 4)
@@ -490,7 +542,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                        const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_b2,
                        int kb_seg1, TC* __restrict__ C, int64_t ldc, const TC* R, int64_t ldr,
                        const float* __restrict__ bias, int relu, float alpha, int M, int N, int K, int n_tiles_n,
-                       int n_tiles) {
+                       int n_tiles, int dbg) {
   constexpr int BN = 256;                   // accumulator columns per CTA = N extent of the pair's tile
   constexpr int BNH = 128;                  // B rows (N) staged by EACH CTA; the MMA reads both halves
   using S = TcPersistSmem<BNH, STAGES>;
@@ -524,7 +576,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   pdl_launch_dependents();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0 && !(dbg & 1)) {
       uint32_t it = 0;                       // running k-block counter across tiles: ring slot and phase
       for (int tile = pair; tile < n_tiles; tile += n_pairs) {
         // the pair's tile is 256 x 256: this CTA stages A rows [m0, m0+128) and B rows (N) [n0, n0+128)
@@ -565,7 +617,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const uint32_t acc = tmem_base + buf * BN;
         for (int kb = 0; kb < kb_total; ++kb, ++it) {
           const int s = it % STAGES;
-          mbar_wait(&full[s], (it / STAGES) & 1);
+          if (!(dbg & 1)) mbar_wait(&full[s], (it / STAGES) & 1);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * S::STAGE);
           const uint32_t sb = sa + S::A_BYTES;
@@ -601,6 +653,58 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           tc_fence_before();
           if (lane == 0) mbar_arrive_leader(&tempty[buf]);
         }
+        if (R == nullptr) {
+          // No residual operand: registers -> global directly.  A thread owns 32 consecutive columns of its row (64 B of
+          // bf16 / 128 B of fp32): four / eight 16-byte stores, ~5x fewer instructions than the staged path below, which
+          // matters because the epilogue of a K = 1024 tile has to fit under that tile's 8k-cycle mainloop.
+          const int row = m0 + wq * 32 + lane;
+          const int colb = n0 + c0;
+          if (row < M && colb < N && !(dbg & 2)) {
+            float v[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = alpha * __uint_as_float(r[q]);
+            const bool fullw = colb + 32 <= N;
+            if (bias) {
+              if (fullw && (reinterpret_cast<uintptr_t>(bias + colb) & 15) == 0) {
+#pragma unroll
+                for (int q = 0; q < 32; q += 4) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(bias + colb + q);
+                  v[q] += b4.x; v[q + 1] += b4.y; v[q + 2] += b4.z; v[q + 3] += b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) if (colb + q < N) v[q] += bias[colb + q];
+              }
+            }
+            if (relu == 1) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
+            }
+            TC* cp = C + (int64_t)row * ldc + colb;
+            if (fullw && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+              if constexpr (sizeof(TC) == 4) {
+#pragma unroll
+                for (int q = 0; q < 32; q += 4)
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(cp) + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 32; q += 8) {
+                  uint4 o4;
+                  __nv_bfloat162* oo = reinterpret_cast<__nv_bfloat162*>(&o4);
+                  oo[0] = __floats2bfloat162_rn(v[q], v[q + 1]);
+                  oo[1] = __floats2bfloat162_rn(v[q + 2], v[q + 3]);
+                  oo[2] = __floats2bfloat162_rn(v[q + 4], v[q + 5]);
+                  oo[3] = __floats2bfloat162_rn(v[q + 6], v[q + 7]);
+                  *reinterpret_cast<uint4*>(cp + q) = o4;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) if (colb + q < N) cp[q] = from_f<TC>(v[q]);
+            }
+          }
+          continue;
+        }
         __syncwarp();                        // the previous chunk's readers are done with the staging rows
 #pragma unroll
         for (int q = 0; q < 32; q += 4)
@@ -609,7 +713,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                           alpha * __uint_as_float(r[q + 2]), alpha * __uint_as_float(r[q + 3]));
         __syncwarp();
         const int col = n0 + c0 + cc;
-        if (col >= N) continue;
+        if (col >= N || (dbg & 2)) continue;
         const int nv = min(4, N - col);
         // residual rows of the 8 passes are fetched 4 passes ahead of their use
 #pragma unroll
@@ -976,6 +1080,8 @@ static inline cudaError_t launch_pdl_pair(void (*kernel)(KArgs...), dim3 grid, d
 }
 
 static int g_pair_enabled = 1;
+static int g_pair_dbg = 0;        // probe only: bit 0 = no TMA / no full-barrier wait, bit 1 = no epilogue stores
+int gemm_tc_set_pair_dbg(int v) { const int old = g_pair_dbg; g_pair_dbg = v; return old; }
 int gemm_tc_set_pair(int on) { const int old = g_pair_enabled; if (on == 0 || on == 1) g_pair_enabled = on; return old; }
 
 template <int STAGES, bool A_MN, bool B_MN, typename TC>
@@ -995,7 +1101,7 @@ static int launch_tc_pair(int64_t M, int64_t N, int64_t K, float alpha, const CU
   B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   dim3 grid((unsigned)(2 * min(n_tiles, g_sm_count / 2)));
   B200ST_CUDA(launch_pdl_pair(kern, grid, dim3(TC_THREADS), S::TOTAL, st, ma, mb, ma2, mb2, kb_seg1, (TC*)C, ldc,
-                              (const TC*)R, ldr, bias, relu, alpha, (int)M, (int)N, (int)K, n_tiles_n, n_tiles));
+                              (const TC*)R, ldr, bias, relu, alpha, (int)M, (int)N, (int)K, n_tiles_n, n_tiles, g_pair_dbg));
   B200ST_LAUNCH_CHECK("gemm_tc_pair");
   return 0;
 }
