@@ -15,6 +15,7 @@
 // transposed copies of activations or weights are ever made.  Out-of-range rows/cols/k are zero-filled by TMA.
 // Split-K (grid.z) with fp32 atomics covers the weight-gradient shapes (small M x N, K = T*B).
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -262,6 +263,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 //     buffer while the four epilogue warps drain tile j (tmem_full / tmem_empty mbarrier pairs),
 //   * the epilogue stages 32-column chunks through a private 18 KB region (the pipeline buffers are never idle), so
 //     every global store still writes whole row segments.
+constexpr int TCP_THREADS = 384;   // persistent kernels: warps 0-2 producer / issuer / allocator, warps 4-11 epilogue
+
 template <int BN, int STAGES>
 struct TcPersistSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
@@ -275,7 +278,7 @@ struct TcPersistSmem {
 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TCP_THREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                        const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_b2,
                        int kb_seg1, TC* __restrict__ C, int64_t ldc, const TC* R, int64_t ldr,
@@ -294,7 +297,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -365,7 +368,11 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       }
     }
   } else if (warp >= 4) {
-    const int wq = warp - 4;
+    // eight epilogue warps: warp w may touch TMEM lanes [32 (w % 4), +32); warps 4-7 take the even 32-column chunks,
+    // warps 8-11 the odd ones, so every scheduler has two warps whose TMEM-load / store latencies overlap.  The staged
+    // path (residual operand) is driven by warps 4-7 only: the staging region holds four warps' rows.
+    const int wq = warp & 3;
+    const int chalf = (warp - 4) >> 2;
     constexpr int SP = S::STG_PITCH;
     float* stg = reinterpret_cast<float*>(smem + S::STG_OFF) + wq * 32 * SP;
     const int cc = (lane & 7) * 4;          // 8 lanes x 4 columns cover a 32-column chunk row
@@ -377,11 +384,18 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       mbar_wait(&tfull[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + buf * BN + ((uint32_t)(wq * 32) << 16);
+      const bool staged = R != nullptr;
+      if (staged && chalf == 1) {            // nothing to read in staged mode: release immediately
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+        continue;
+      }
+      const int cstep = staged ? 32 : 64;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = staged ? 0 : chalf * 32; c0 < BN; c0 += cstep) {
         uint32_t r[32];
         tmem_ld32(acc + (uint32_t)c0, r);
-        if (c0 + 32 >= BN) {                 // last TMEM read of this tile: hand the buffer back to the issuer
+        if (c0 + cstep >= BN) {              // last TMEM read of this tile by this warp: hand the buffer back
           tc_fence_before();
           if (lane == 0) mbar_arrive(&tempty[buf]);
         }
@@ -413,7 +427,27 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
               for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
             }
             TC* cp = C + (int64_t)row * ldc + colb;
-            if (fullw && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+            if (fullw && (reinterpret_cast<uintptr_t>(cp) & 31) == 0) {
+              // 256-bit stores (sm_100): every instruction writes whole 32-byte sectors
+              if constexpr (sizeof(TC) == 4) {
+#pragma unroll
+                for (int q = 0; q < 32; q += 8)
+                  st_global_v8(reinterpret_cast<float*>(cp) + q, __float_as_uint(v[q]), __float_as_uint(v[q + 1]),
+                               __float_as_uint(v[q + 2]), __float_as_uint(v[q + 3]), __float_as_uint(v[q + 4]),
+                               __float_as_uint(v[q + 5]), __float_as_uint(v[q + 6]), __float_as_uint(v[q + 7]));
+              } else {
+#pragma unroll
+                for (int q = 0; q < 32; q += 16) {
+                  uint32_t w[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    __nv_bfloat162 b2 = __floats2bfloat162_rn(v[q + 2 * e], v[q + 2 * e + 1]);
+                    w[e] = *reinterpret_cast<uint32_t*>(&b2);
+                  }
+                  st_global_v8(cp + q, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+                }
+              }
+            } else if (fullw && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
               if constexpr (sizeof(TC) == 4) {
 #pragma unroll
                 for (int q = 0; q < 32; q += 4)
@@ -537,7 +571,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
 // its tcgen05.commit arrives (multicast) on the empty / tmem_full barriers of BOTH CTAs, and both CTAs' epilogue warps
 // release an accumulator buffer by arriving on the leader's tmem_empty barrier.
 template <int STAGES, bool A_MN, bool B_MN, typename TC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TCP_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                        const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_b2,
                        int kb_seg1, TC* __restrict__ C, int64_t ldc, const TC* R, int64_t ldr,
@@ -560,7 +594,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }   // 4 epilogue warps x 2 CTAs
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 16); }  // 8 epilogue warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {                           // the same warp of BOTH CTAs performs the pair allocation
@@ -633,7 +667,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   } else if (warp >= 4) {
-    const int wq = warp - 4;
+    // eight epilogue warps: warp w may touch TMEM lanes [32 (w % 4), +32); warps 4-7 take the even 32-column chunks,
+    // warps 8-11 the odd ones, so every scheduler has two warps whose TMEM-load / store latencies overlap.  The staged
+    // path (residual operand) is driven by warps 4-7 only: the staging region holds four warps' rows.
+    const int wq = warp & 3;
+    const int chalf = (warp - 4) >> 2;
     constexpr int SP = S::STG_PITCH;
     float* stg = reinterpret_cast<float*>(smem + S::STG_OFF) + wq * 32 * SP;
     const int cc = (lane & 7) * 4;          // 8 lanes x 4 columns cover a 32-column chunk row
@@ -645,11 +683,18 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_wait(&tfull[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + buf * BN + ((uint32_t)(wq * 32) << 16);
+      const bool staged = R != nullptr;
+      if (staged && chalf == 1) {            // nothing to read in staged mode: release immediately
+        tc_fence_before();
+        if (lane == 0) mbar_arrive_leader(&tempty[buf]);
+        continue;
+      }
+      const int cstep = staged ? 32 : 64;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = staged ? 0 : chalf * 32; c0 < BN; c0 += cstep) {
         uint32_t r[32];
         tmem_ld32(acc + (uint32_t)c0, r);
-        if (c0 + 32 >= BN) {                 // last TMEM read of this tile: hand the buffer back to the issuer
+        if (c0 + cstep >= BN) {              // last TMEM read of this tile by this warp: hand the buffer back
           tc_fence_before();
           if (lane == 0) mbar_arrive_leader(&tempty[buf]);
         }
@@ -681,7 +726,27 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
             }
             TC* cp = C + (int64_t)row * ldc + colb;
-            if (fullw && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+            if (fullw && (reinterpret_cast<uintptr_t>(cp) & 31) == 0) {
+              // 256-bit stores (sm_100): every instruction writes whole 32-byte sectors
+              if constexpr (sizeof(TC) == 4) {
+#pragma unroll
+                for (int q = 0; q < 32; q += 8)
+                  st_global_v8(reinterpret_cast<float*>(cp) + q, __float_as_uint(v[q]), __float_as_uint(v[q + 1]),
+                               __float_as_uint(v[q + 2]), __float_as_uint(v[q + 3]), __float_as_uint(v[q + 4]),
+                               __float_as_uint(v[q + 5]), __float_as_uint(v[q + 6]), __float_as_uint(v[q + 7]));
+              } else {
+#pragma unroll
+                for (int q = 0; q < 32; q += 16) {
+                  uint32_t w[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    __nv_bfloat162 b2 = __floats2bfloat162_rn(v[q + 2 * e], v[q + 2 * e + 1]);
+                    w[e] = *reinterpret_cast<uint32_t*>(&b2);
+                  }
+                  st_global_v8(cp + q, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+                }
+              }
+            } else if (fullw && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
               if constexpr (sizeof(TC) == 4) {
 #pragma unroll
                 for (int q = 0; q < 32; q += 4)
@@ -1053,7 +1118,7 @@ static int launch_tc_persist(int64_t M, int64_t N, int64_t K, float alpha, const
   auto kern = gemm_tc_persist_kernel<BN, STAGES, A_MN, B_MN, TC>;
   B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   dim3 grid((unsigned)min(n_tiles, g_sm_count));
-  B200ST_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), S::TOTAL, st, ma, mb, ma2, mb2, kb_seg1, (TC*)C, ldc, (const TC*)R,
+  B200ST_CUDA(launch_pdl(kern, grid, dim3(TCP_THREADS), S::TOTAL, st, ma, mb, ma2, mb2, kb_seg1, (TC*)C, ldc, (const TC*)R,
                          ldr, bias, relu, alpha, (int)M, (int)N, (int)K, n_tiles_n, n_tiles));
   B200ST_LAUNCH_CHECK("gemm_tc_persist");
   return 0;
@@ -1100,7 +1165,7 @@ static int launch_tc_pair(int64_t M, int64_t N, int64_t K, float alpha, const CU
   auto kern = gemm_tc_pair_kernel<STAGES, A_MN, B_MN, TC>;
   B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   dim3 grid((unsigned)(2 * min(n_tiles, g_sm_count / 2)));
-  B200ST_CUDA(launch_pdl_pair(kern, grid, dim3(TC_THREADS), S::TOTAL, st, ma, mb, ma2, mb2, kb_seg1, (TC*)C, ldc,
+  B200ST_CUDA(launch_pdl_pair(kern, grid, dim3(TCP_THREADS), S::TOTAL, st, ma, mb, ma2, mb2, kb_seg1, (TC*)C, ldc,
                               (const TC*)R, ldr, bias, relu, alpha, (int)M, (int)N, (int)K, n_tiles_n, n_tiles, g_pair_dbg));
   B200ST_LAUNCH_CHECK("gemm_tc_pair");
   return 0;
@@ -1140,11 +1205,19 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   if (cfg != 2 && kb_total <= 2 && m_tiles >= 64) cfg = 4;
   // persistent kernel (one CTA per SM, double-buffered TMEM accumulator) for the throughput shapes: at least four
   // tiles per SM, fp32-atomic split-K not involved.  128 x 256 tiles when N allows, else 128 x 128.
-  // CTA-pair kernel (256 x 256 tile per pair): the big throughput shapes
-  const bool pair = g_persist_enabled && g_pair_enabled && cfg == 0 && kb_total >= 4 && N >= 256 &&
-                    ceil_div(M, 256) * ceil_div(N, 256) >= 4 * 74;
-  const bool persist256 = !pair && g_persist_enabled && cfg == 0 && kb_total >= 4 && N >= 256 && m_tiles * ceil_div(N, 256) >= 4 * 148;
-  const bool persist128 = g_persist_enabled && cfg == 0 && !persist256 && kb_total >= 4 && m_tiles * ceil_div(N, 128) >= 4 * 148;
+  // Persistent kernels for the many-tile shapes (cfg 0, and cfg 4 = one/two-block K with many M tiles, which is bound by
+  // its output write): at least `min_rounds` tiles per CTA.  CTA-pair kernel (256 x 256 tile per pair of SMs) when it
+  // needs no more rounds than 128 x 256 single-CTA tiles would (wave quantisation; rows beyond M in the last 256-row
+  // tile are wasted work) -- it halves the L2 -> shared-memory traffic per FLOP.
+  static const int min_rounds = [] { const char* e = getenv("B200ST_GEMM_MIN_ROUNDS"); return e ? atoi(e) : 2; }();
+  const bool many = g_persist_enabled && (cfg == 0 || cfg == 4) && N >= 128;
+  const int64_t t_pair = ceil_div(M, 256) * ceil_div(N, 256), t_256 = m_tiles * ceil_div(N, 256), t_128 = m_tiles * ceil_div(N, 128);
+  const bool can256 = many && N >= 256 && t_256 >= (int64_t)min_rounds * 148;
+  const bool pair = many && g_pair_enabled && N >= 256 && kb_total >= 8 && t_pair >= 48 &&
+                    (!can256 || ceil_div(t_pair, 74) <= ceil_div(t_256, 148));
+  const bool persist256 = !pair && can256;
+  const bool persist128 = !pair && !persist256 && many && t_128 >= (int64_t)min_rounds * 148;
+  if (pair || persist256 || persist128) cfg = 0;
   const int BN = persist256 ? 256 : ((cfg == 0 || wide || pair) ? 128 : (cfg == 2 ? 32 : 64));   // = B box rows
   const bool m64 = (cfg == 2 || cfg == 3) && M <= 64;       // half-height A tile for the decoder-step GEMMs
   CUtensorMap ma, mb;
