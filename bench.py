@@ -154,6 +154,9 @@ class KernelTimer:
                     m, k = (x2.size(1), x2.size(0)) if ta else (x2.size(0), x2.size(1))
                     n_ = y2.size(0) if tb else y2.size(1)
                     self.meta[__n].append(2 * m * n_ * k * (x.size(0) if x.dim() == 3 else 1))
+                elif __n == 'gemm2':
+                    self.meta[__n].append(2 * a[0].size(0) * (a[1].size(0) if kw.get('trans_b') else a[1].size(1)) *
+                                          (a[0].size(1) + a[2].size(1)))
                 elif __n in ('blstm_fwd',):
                     _, T, B, H4 = a[0].shape
                     self.meta[__n].append(2 * 2 * T * B * (H4 // 4) * H4)
@@ -402,6 +405,11 @@ def run_b200(args):
             pass
         peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
         peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
+        # secondary roofline: the tensor-bound GEMMs proper -- every `gemm` / `gemm2` call of >= 5e10 FLOP in the eager
+        # pass (the BLSTM input projections and their input-gradient GEMMs: gemm_tc_pair_kernel, cta_group::2)
+        big = [(a.elapsed_time(b), f) for (a, b), f in zip(kt.records['gemm'], kt.meta['gemm']) if f >= 5e10]
+        big += [(a.elapsed_time(b), f) for (a, b), f in zip(kt.records['gemm2'], kt.meta['gemm2']) if f >= 5e10]
+        big_ms, big_fl = sum(t for t, _ in big), sum(f for _, f in big)
         r_calls = sum(roof[n]['calls'] for n in roof_names)
         r_ms = sum(roof[n]['ms'] for n in roof_names)
         r_flops = sum(roof[n]['flops'] or 0 for n in roof_names)
@@ -437,6 +445,16 @@ def run_b200(args):
                          'note': 'recurrent-GEMM FLOPs 2*2dirs*T*B*H*4H per launch; this kernel is bound by the '
                                  'serial time-step chain (latency), not by tensor throughput'},
         }
+        if big:
+            peak_b = peaks.get('bf16_tflops', 1650.0)
+            line['roofline_gemm'] = {
+                'kernel': 'gemm_tc_pair_kernel (tcgen05 cta_group::2, 256x256 tile per SM pair): BLSTM input projections '
+                          'and input-gradient GEMMs (>= 5e10 FLOP each)',
+                'bound': 'tensor', 'achieved': big_fl / max(big_ms, 1e-9) / 1e9, 'peak': peak_b, 'unit': 'TFLOP/s',
+                'frac': big_fl / max(big_ms, 1e-9) / 1e9 / peak_b, 'launches': len(big),
+                'avg_launch_ms': big_ms / len(big), 'peak_source': 'measured (MEASURED_PEAKS.json bf16_tflops, burst: '
+                'each launch is bracketed alone)' if peaks else 'fallback', 'traffic': None,
+                'timed': 'CUDA events around each launch on its stream, eager pass of the same step in this run'}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(args)
             line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}

@@ -15,7 +15,9 @@ model = bench.build_model(cfg, dev)
 host = O.synthetic_batch(cfg, 64, 1000, seed=333)
 items = {'srcid': [host['src'].to(dev)], 'tgtid': [host['tgt'].to(dev)], 'acous_feat': [host['acous_feat' + 's'].to(dev)],
          'acouslen': host['acous_lens']}
-tr = Trainer_ST(use_gpu=True, batch_size=64)
+from modules.optim import Optimizer
+opt = Optimizer(torch.optim.Adam(model.parameters(), lr=1e-5), max_grad_norm=1.0)     # trainer_base.py:422-426
+tr = Trainer_ST(use_gpu=True, batch_size=64, optimizer=opt)
 for i in range(warm + 1):
     if i == warm:
         torch.cuda.synchronize(); print('MARK step begins', flush=True)
