@@ -379,6 +379,8 @@ def run_b200(args):
             print(f'[bench] CUDA graph capture failed ({type(ex).__name__}: {ex}); timing the eager step', file=sys.stderr)
             graphed = None
             model.zero_grad(set_to_none=True)
+    probe_param = model.out_tgt.weight
+    probe_before = probe_param.detach().clone()
     sampler = ClockSampler(local)
     sampler.start()
     if graphed is not None:
@@ -396,6 +398,9 @@ def run_b200(args):
     launches = launches_per_step * args.steps
     live = False
     clocks = sampler.stop()
+    # the timed replays really stepped the weights (clip + Adam is inside the captured step)
+    optimizer_applied = bool((probe_param.detach() != probe_before).any())
+    opt_steps = float(optimizer._fused._step) if optimizer._fused is not None else 0.0
 
     if rank == 0:
         peaks = {}
@@ -435,6 +440,8 @@ def run_b200(args):
                 'what': 'the same graph without the optimizer step (forward + loss + backward' +
                         (' + grad all-reduce)' if world > 1 else ')')}),
             'eager_ms_per_step': ms_eager,
+            'optimizer': {'kind': 'fused grad-norm clip (1.0) + Adam (lr 1e-5), inside the timed step',
+                          'weights_changed_during_timed_region': optimizer_applied, 'adam_step_count': opt_steps},
             'clocks': clocks,
             'roofline': {'kernel': '+'.join(roof_names), 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
                          'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': _profile_traffic(args.frames + 8 - args.frames % 8, args.batch), 'peak_source': peak_src,
