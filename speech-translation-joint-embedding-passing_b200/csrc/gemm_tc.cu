@@ -142,6 +142,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     float* stg = reinterpret_cast<float*>(smem) + wq * 32 * SP;
     mbar_wait(tmem_full, 0);           // all MMAs retired: accumulator complete, smem stages no longer read
     tc_fence_after();
+    if (BM == 128 && !ATOMIC && R == nullptr && n_iter > 0) {
+      // no residual operand: registers -> global directly (a thread owns 32 consecutive columns of its row; 256-bit
+      // stores), skipping the staging round trip -- these tiles are latency-bound and the epilogue is their tail
+      const int row = m0 + wq * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, r);
+        const int colb = n0 + c0;
+        if (row >= M || colb >= N) continue;
+        float v[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = alpha * __uint_as_float(r[q]);
+        const bool fullw = colb + 32 <= N;
+        if (bias) {
+          if (fullw && (reinterpret_cast<uintptr_t>(bias + colb) & 15) == 0) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias + colb + q);
+              v[q] += b4.x; v[q + 1] += b4.y; v[q + 2] += b4.z; v[q + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) if (colb + q < N) v[q] += bias[colb + q];
+          }
+        }
+        if (relu == 1) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
+        }
+        TC* cp = C + (int64_t)row * ldc + colb;
+        if (fullw && (reinterpret_cast<uintptr_t>(cp) & 31) == 0) {
+          if constexpr (sizeof(TC) == 4) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 8)
+              st_global_v8(reinterpret_cast<float*>(cp) + q, __float_as_uint(v[q]), __float_as_uint(v[q + 1]),
+                           __float_as_uint(v[q + 2]), __float_as_uint(v[q + 3]), __float_as_uint(v[q + 4]),
+                           __float_as_uint(v[q + 5]), __float_as_uint(v[q + 6]), __float_as_uint(v[q + 7]));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; q += 16) {
+              uint32_t w[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(v[q + 2 * e], v[q + 2 * e + 1]);
+                w[e] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              st_global_v8(cp + q, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) if (colb + q < N) cp[q] = from_f<TC>(v[q]);
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -245,6 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
       }
     }
+    }   // staged epilogue
   }
   tc_fence_before();
   __syncthreads();
