@@ -43,20 +43,37 @@ class DecoderCache:
         if self.pe.dim() == 3:
             self.pe = self.pe[0]
         self.src_mask = src_mask.contiguous()                            # uint8 [B, 1, S]
-        enc2 = enc_outputs.contiguous().view(B * S, D)
+        self.enc = enc_outputs.contiguous()
         self.kv_cross, self.kv_self = [], []
         for layer in self.layers:
-            a = layer.encdec_attn
-            self.kv_cross.append(k.gemm(enc2, rt.operand_cat(a.w_ks.weight, a.w_vs.weight), trans_b=True)
-                                 .view(B, S, -1))
+            hd2c = 2 * layer.encdec_attn.w_ks.weight.size(0)
+            self.kv_cross.append(torch.empty((B, S, hd2c), dtype=dt, device=dev))
             hd2 = 2 * layer.decslf_attn.w_ks.weight.size(0)
             self.kv_self.append(torch.empty((self.n_hyp, max_len, hd2), dtype=dt, device=dev))
+        self.refresh_cross()
         # ancestry: slot holding position t of hypothesis b; identity until a beam re-ordering permutes it
         self.anc = None
         if beam_width > 1:
             self.anc = torch.arange(self.n_hyp, dtype=torch.int32, device=dev).expand(max_len, self.n_hyp).contiguous()
         # keys that are PAD tokens are masked (tgt_mask = pad & causal, Seq2seq.py:204-205)
         self.tokmask = torch.ones((self.n_hyp, max_len), dtype=torch.uint8, device=dev)
+
+    def refresh_cross(self):
+        """(Re)project the encoder output into every layer's cross-attention K|V buffer (in place)."""
+        k = K()
+        enc2 = self.enc.view(self.B * self.S, self.D)
+        for layer, kv in zip(self.layers, self.kv_cross):
+            a = layer.encdec_attn
+            k.gemm(enc2, rt.operand_cat(a.w_ks.weight, a.w_vs.weight), trans_b=True, out=kv.view(self.B * self.S, -1))
+
+    def reset(self, enc_outputs: torch.Tensor, src_mask: torch.Tensor):
+        """Re-use the buffers for a new batch of the same shape (everything a captured step graph points at stays put)."""
+        self.enc.copy_(enc_outputs)
+        self.src_mask.copy_(src_mask)
+        self.refresh_cross()
+        if self.anc is not None:
+            self.anc.copy_(torch.arange(self.n_hyp, dtype=torch.int32, device=self.anc.device).expand_as(self.anc))
+        self.tokmask.fill_(1)
 
     def reorder(self, rows: torch.Tensor, n_pos: int):
         """Hypothesis h continues hypothesis rows[h] (its first n_pos positions)."""
@@ -107,3 +124,97 @@ class DecoderCache:
         logits = k.gemm(x, rt.operand(self.model.out_tgt.weight), trans_b=True)
         logp, am = k.log_softmax_fwd(logits, want_argmax=True)
         return logp, am.view(-1, 1)
+
+
+BOS, EOS = 2, 3
+
+
+class BeamSearch:
+    """The step loop of forward_translate (`_prep_translate` + `_step_translate`, Seq2seq.py:307-393,720-739) over a
+    `DecoderCache`, with every piece of state in static device buffers so that a decode position is a fixed launch
+    sequence: positions >= 3 are captured once into one CUDA graph each and replayed (the eager loop is bound by host
+    launch overhead: ~90 launches per token).  Same arithmetic and selection rule as the reference, including the
+    length penalty `score / len^alpha`, the EOS masking and the final `reshape(batch, -1)[:, :max_seq_len]` slice quirk
+    (Seq2seq.py:738); one host read per step remains (the reference's all-EOS early exit, Seq2seq.py:388-393)."""
+
+    def __init__(self, model, enc_outputs, src_mask, beam_width, penalty_factor, max_len, graphs=True):
+        dev = enc_outputs.device
+        self.B, self.k, self.max_len, self.penalty = enc_outputs.size(0), beam_width, max_len, penalty_factor
+        self.n_hyp = self.B * beam_width
+        self.cache = DecoderCache(model, enc_outputs.clone(), src_mask.clone(), beam_width, max_len)
+        self.preds = torch.zeros((self.n_hyp, max_len), dtype=torch.int64, device=dev)
+        self.scores = torch.zeros(self.n_hyp, device=dev)
+        self.eos = torch.zeros(self.n_hyp, dtype=torch.bool, device=dev)
+        self.len_map = torch.ones(self.n_hyp, device=dev)
+        self.n_done = torch.zeros((), dtype=torch.int64, device=dev)
+        self.offs = torch.arange(0, self.n_hyp * beam_width, beam_width * beam_width, device=dev).float().reshape(self.B, 1)
+        self.graphs = {}
+        self.use_graphs = graphs and dev.type == 'cuda'
+        self.epoch = None
+        self.pool = None
+        self._fresh = True
+
+    def _reset(self, enc_outputs, src_mask):
+        if not self._fresh:
+            self.cache.reset(enc_outputs, src_mask)
+        self._fresh = False
+        self.preds.zero_()
+        self.preds[:, 0] = BOS
+        self.scores.zero_()
+        self.eos.zero_()
+        self.len_map.fill_(1.0)
+        self.n_done.zero_()
+
+    def _step(self, i: int):
+        B, k = self.B, self.k
+        logp, pred = self.cache.step_logps(self.preds[:, i - 1], i - 1)
+        if k == 1:
+            score = logp.float().gather(1, pred)
+        else:
+            score, pred = logp.float().topk(k)
+        if i == 1:      # all beams of an utterance are identical: take the first beam's top-k (Seq2seq.py:351-357)
+            self.scores.add_(score.reshape(B, -1)[:, :k].contiguous().view(-1))
+            pred_select = pred.reshape(B, -1)[:, :k].contiguous().view(-1)
+        else:
+            eos_exp = self.eos.reshape(-1, 1).repeat(1, k)
+            eos_exp[:, 0] = False
+            score_temp = self.scores.reshape(-1, 1) + score.masked_fill(self.eos.reshape(-1, 1), 0).masked_fill(eos_exp, -1e9)
+            lp = self.len_map.reshape(-1, 1) ** self.penalty
+            score_temp = score_temp / lp
+            score_select, pos = score_temp.reshape(B, -1).topk(k)
+            self.scores.copy_(score_select.view(-1) * lp.view(-1))
+            pos = (pos.float() + self.offs).long()
+            r_idxs, c_idxs = pos // k, pos % k
+            pred_select = pred[r_idxs, c_idxs].view(-1)
+            rows = r_idxs.view(-1)
+            self.preds[:, :i] = self.preds[rows, :i]
+            self.cache.reorder(rows, i)
+        self.preds[:, i] = pred_select
+        self.eos.copy_((pred_select == EOS) | self.eos)
+        self.len_map.add_(torch.ones_like(self.len_map).masked_fill(self.eos, 0))
+        self.n_done.copy_(self.eos.sum())
+
+    def run(self, enc_outputs, src_mask):
+        self._reset(enc_outputs, src_mask)
+        if self.use_graphs and self.epoch != rt.cache_epoch() and self.graphs:
+            self.graphs = {}                     # an operand copy baked into the graphs was re-created: recapture
+        width = 1
+        for i in range(1, self.max_len):
+            if not self.use_graphs or i < 3:
+                self._step(i)                    # eager: also creates every cached weight operand before any capture
+            else:
+                g = self.graphs.get(i)
+                if g is None:
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=self.pool):
+                        self._step(i)
+                    self.pool = self.pool or g.pool()
+                    self.graphs[i] = g
+                    self.epoch = rt.cache_epoch()
+                    # the capture itself did not execute the step: replay it below
+                g.replay()
+            width = i + 1
+            if int(self.n_done) == self.n_hyp:   # the reference's early exit, one host read per step
+                break
+        return self.preds[:, :width].reshape(self.B, -1)[:, :self.max_len].contiguous()

@@ -16,12 +16,19 @@ _DTYPES = {'fp32': torch.float32, 'float32': torch.float32, 'bf16': torch.bfloat
            'bfloat16': torch.bfloat16}
 _compute_dtype = _DTYPES[os.environ.get('B200ST_DTYPE', 'fp32').lower()]
 _cache = {}
+_epoch = [0]               # bumped whenever a cached operand copy is (re)created or dropped: captured CUDA graphs that
+                           # baked an operand pointer compare it to know when they are stale
+
+
+def cache_epoch() -> int:
+    return _epoch[0]
 
 
 def set_compute_dtype(d):
     global _compute_dtype
     _compute_dtype = _DTYPES[d.lower()] if isinstance(d, str) else d
     _cache.clear()
+    _epoch[0] += 1
 
 
 def compute_dtype() -> torch.dtype:
@@ -41,6 +48,7 @@ def operand(param: torch.Tensor) -> torch.Tensor:
     from .kernels import K
     shadow = K().cast(p.contiguous(), _compute_dtype)
     _cache[key] = (weakref.ref(param), ver, p.data_ptr(), shadow)
+    _epoch[0] += 1
     return shadow
 
 
@@ -65,11 +73,13 @@ def operand_cat(*params: torch.Tensor) -> torch.Tensor:
             K().cast(src, _compute_dtype, out=buf[r0:r0 + n])
         r0 += n
     _cache[key] = (tuple(weakref.ref(p) for p in params), vers, ptrs, buf)
+    _epoch[0] += 1
     return buf
 
 
 def clear_cache():
     _cache.clear()
+    _epoch[0] += 1
 
 
 # ------------------------------------------------------------------------------------------------

@@ -251,6 +251,8 @@ class Seq2seq(nn.Module):
     # True: inference loops feed one token per step through b200st.decode.DecoderCache (cached keys/values);
     # False: the reference's own loop, which re-runs the decoder on the whole prefix every step.  Same token ids.
     decode_cache = True
+    # with decode_cache: replay one CUDA graph per decode position in forward_translate (CUDA only)
+    decode_graphs = True
 
     def _greedy_decode_cached(self, enc_outputs, src_mask_input, batch, length_out, device):
         """_greedy_decode with cached keys/values: identical bookkeeping (Seq2seq.py:260-304), O(L) decoder work."""
@@ -360,18 +362,23 @@ class Seq2seq(nn.Module):
         final `reshape(batch, -1)[:, :max_seq_len]` slice quirk (Seq2seq.py:738)."""
         k = beam_width
         S = enc_outputs.size(1)
+        if self.decode_cache:
+            # cached keys/values, static state, one CUDA graph per decode position (b200st.decode.BeamSearch); the
+            # searcher (buffers + graphs) is kept per problem shape
+            from b200st.decode import BeamSearch
+            key = (batch, S, k, float(penalty_factor), max_seq_len, enc_outputs.dtype, str(enc_outputs.device),
+                   bool(self.decode_graphs))
+            if getattr(self, '_beam_key', None) != key:
+                self._beam_key, self._beam = key, BeamSearch(self, enc_outputs, src_mask_input, k, penalty_factor,
+                                                             max_seq_len, graphs=self.decode_graphs)
+            return self._beam.run(enc_outputs, src_mask_input)
         eos_mask = torch.zeros(batch * k, dtype=torch.bool, device=device)
         len_map = torch.ones(batch * k, device=device)
         preds_exp = torch.full((batch * k, 1), BOS, dtype=torch.int64, device=device)
         scores_exp = torch.zeros(batch * k, device=device)
         cache = None
-        if self.decode_cache:
-            # cached keys/values; the beams of an utterance share its encoder K/V (no beam_width-fold tiling)
-            from b200st.decode import DecoderCache
-            cache = DecoderCache(self, enc_outputs, src_mask_input, k, max_seq_len)
-        else:
-            enc_exp = enc_outputs.repeat(1, k, 1).view(-1, S, self.dim_model)
-            mask_exp = src_mask_input.repeat(1, k, 1).view(-1, 1, S).contiguous()
+        enc_exp = enc_outputs.repeat(1, k, 1).view(-1, S, self.dim_model)
+        mask_exp = src_mask_input.repeat(1, k, 1).view(-1, 1, S).contiguous()
         for i in range(1, max_seq_len):
             if cache is not None:
                 logp, pred = cache.step_logps(preds_exp[:, i - 1], i - 1)
@@ -464,6 +471,14 @@ class Seq2seq(nn.Module):
                                 lm_mode='null', lm_model=None):
         return self._translate(acous_feats, acous_lens, src, beam_width, penalty_factor, use_gpu,
                                max_seq_len, mode, lm_mode, lm_model, ref_en=True)
+
+    def __getstate__(self):
+        # checkpoints pickle whole modules (checkpoint.py:76): the inference searcher (device buffers + CUDA graphs) is a
+        # cache, not state
+        d = self.__dict__.copy()
+        d.pop('_beam', None)
+        d.pop('_beam_key', None)
+        return d
 
     def check_var(self, var_name, var_val_set=None):
         if not hasattr(self, var_name):
