@@ -420,6 +420,40 @@ class Seq2seq(nn.Module):
                 break
         return preds_exp.reshape(batch, -1)[:, :max_seq_len].contiguous()
 
+    def _frontend(self, acous_feats, lens_dev, mode):
+        """acoustic features -> (Transformer-encoder output, source mask) for ST / ST_BASE inference (Seq2seq.py:697-719),
+        free of host synchronisation (lengths stay on the device)."""
+        device = acous_feats.device
+        emb_src_dyn, _, preds_src, lengths = self._encoder_acous(acous_feats, lens_dev, device, True, is_training=False,
+                                                                 teacher_forcing_ratio=0.0, need_logps=False)
+        ids = preds_src.squeeze(2)
+        if mode == 'ST_BASE':
+            emb_src_dyn = self._dyn_ave(ids.size(0), ids.size(1), device)
+        _, emb_src, _ = self._get_src_emb(ids, emb_src_dyn, device)
+        src_mask_input = self._length_mask(self._as_device_lengths(lengths, device), emb_src.size(1))
+        return self._encoder_en(emb_src, src_mask=src_mask_input), src_mask_input
+
+    def _frontend_graphed(self, acous_feats, acous_lens, mode):
+        lens = [int(n) for n in acous_lens]
+        assert max(lens) + 8 - max(lens) % 8 == acous_feats.size(1), 'padded max length must equal the feature length'
+        key = (tuple(acous_feats.shape), acous_feats.dtype, str(acous_feats.device), mode, rt.compute_dtype())
+        fe = getattr(self, '_fe', None)
+        if fe is None or fe['key'] != key or fe['epoch'] != rt.cache_epoch():
+            feats = acous_feats.clone()
+            lens_dev = torch.zeros(len(lens), dtype=torch.int32, device=acous_feats.device)
+            lens_dev.copy_(torch.tensor(lens, dtype=torch.int32))
+            self._frontend(feats, lens_dev, mode)              # eager once: creates the cached weight operands
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._frontend(feats, lens_dev, mode)
+            fe = self._fe = {'key': key, 'epoch': rt.cache_epoch(), 'graph': g, 'feats': feats, 'lens': lens_dev,
+                             'out': out}
+        fe['feats'].copy_(acous_feats)
+        fe['lens'].copy_(torch.tensor(lens, dtype=torch.int32), non_blocking=True)
+        fe['graph'].replay()
+        return fe['out']
+
     def _translate(self, acous_feats, acous_lens, src, beam_width, penalty_factor, use_gpu, max_seq_len,
                    mode, lm_mode, lm_model, ref_en):
         device = check_device(use_gpu)
@@ -446,6 +480,12 @@ class Seq2seq(nn.Module):
                         teacher_forcing_ratio=1.0, need_logps=False)
                     ids = self._pre_proc_src(src, device)
                 else:
+                    if self.decode_cache and self.decode_graphs and acous_feats.is_cuda and acous_lens is not None:
+                        # the whole front end (acoustic encoder, free-running LAS decoder loop, mix, Transformer
+                        # encoder: ~1500 small launches) replayed as one CUDA graph per input shape
+                        enc_outputs, src_mask_input = self._frontend_graphed(acous_feats, acous_lens, mode)
+                        return self._beam_search(enc_outputs, src_mask_input, batch, beam_width, penalty_factor,
+                                                 max_seq_len, device)
                     emb_src_dyn, _, preds_src, lengths = self._encoder_acous(
                         acous_feats, acous_lens, device, use_gpu, is_training=False,
                         teacher_forcing_ratio=0.0, need_logps=False)
@@ -478,6 +518,7 @@ class Seq2seq(nn.Module):
         d = self.__dict__.copy()
         d.pop('_beam', None)
         d.pop('_beam_key', None)
+        d.pop('_fe', None)
         return d
 
     def check_var(self, var_name, var_val_set=None):
