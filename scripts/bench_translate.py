@@ -36,7 +36,8 @@ for k in (int(b) for b in args.beams.split(',')):
     def run():
         return model.forward_translate(acous_feats=feats, acous_lens=lens, beam_width=k, penalty_factor=1,
                                        use_gpu=True, max_seq_len=args.max_len, mode='ST')
-    out = run()
+    for _ in range(2):            # first call captures the graphs
+        out = run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

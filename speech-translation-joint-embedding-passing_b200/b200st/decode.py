@@ -195,9 +195,11 @@ class BeamSearch:
         self.n_done.copy_(self.eos.sum())
 
     def run(self, enc_outputs, src_mask):
+        if self.use_graphs:
+            rt.refresh_all()                     # the graphs read cached weight copies without re-casting them
+            if self.epoch != rt.cache_epoch() and self.graphs:
+                self.graphs = {}                 # the copies were re-allocated (compute dtype switch): recapture
         self._reset(enc_outputs, src_mask)
-        if self.use_graphs and self.epoch != rt.cache_epoch() and self.graphs:
-            self.graphs = {}                     # an operand copy baked into the graphs was re-created: recapture
         width = 1
         for i in range(1, self.max_len):
             if not self.use_graphs or i < 3:

@@ -36,34 +36,42 @@ def compute_dtype() -> torch.dtype:
 
 
 def operand(param: torch.Tensor) -> torch.Tensor:
-    """The tensor a GEMM should read for `param` in the current compute dtype."""
+    """The tensor a GEMM should read for `param` in the current compute dtype.  A cached copy is refreshed IN PLACE when
+    the parameter changed (same storage, so pointers baked into captured CUDA graphs stay valid; the epoch tells their
+    owners that the contents were stale until this refresh)."""
     p = param.detach()
     if p.dtype == _compute_dtype:
         return p
     key = id(param)
     hit = _cache.get(key)
     ver = param._version
-    if hit is not None and hit[0]() is param and hit[1] == ver and hit[2] == p.data_ptr():
-        return hit[3]
+    if hit is not None and hit[0]() is param and hit[2] == p.data_ptr():
+        if hit[1] == ver:
+            return hit[3]
+        if hit[3].shape == p.shape and hit[3].dtype == _compute_dtype:
+            from .kernels import K
+            K().cast(p.contiguous(), _compute_dtype, out=hit[3])
+            _cache[key] = (hit[0], ver, hit[2], hit[3])
+            return hit[3]
     from .kernels import K
     shadow = K().cast(p.contiguous(), _compute_dtype)
     _cache[key] = (weakref.ref(param), ver, p.data_ptr(), shadow)
-    _epoch[0] += 1
     return shadow
 
 
 def operand_cat(*params: torch.Tensor) -> torch.Tensor:
     """Row-wise concatenation [sum(out_i), in] of several weight matrices in the compute dtype (e.g. w_ks | w_vs so
-    that K and V are projected by ONE GEMM).  Cached like `operand`; rebuilt when any member's version changes."""
+    that K and V are projected by ONE GEMM).  Cached like `operand`; refreshed in place when any member changed."""
     key = ('cat',) + tuple(id(p) for p in params)
     vers = tuple(p._version for p in params)
     ptrs = tuple(p.data_ptr() for p in params)
     hit = _cache.get(key)
-    if hit is not None and all(r() is p for r, p in zip(hit[0], params)) and hit[1] == vers and hit[2] == ptrs:
+    same = hit is not None and all(r() is p for r, p in zip(hit[0], params)) and hit[2] == ptrs
+    if same and hit[1] == vers:
         return hit[3]
     from .kernels import K
     rows = [p.size(0) for p in params]
-    buf = torch.empty((sum(rows), params[0].size(1)), dtype=_compute_dtype, device=params[0].device)
+    buf = hit[3] if same else torch.empty((sum(rows), params[0].size(1)), dtype=_compute_dtype, device=params[0].device)
     r0 = 0
     for p, n in zip(params, rows):
         src = p.detach().contiguous()
@@ -73,13 +81,31 @@ def operand_cat(*params: torch.Tensor) -> torch.Tensor:
             K().cast(src, _compute_dtype, out=buf[r0:r0 + n])
         r0 += n
     _cache[key] = (tuple(weakref.ref(p) for p in params), vers, ptrs, buf)
-    _epoch[0] += 1
     return buf
 
 
+def refresh_all():
+    """Re-cast (in place) every cached operand copy whose parameter changed since it was made.  Owners of captured
+    graphs that read the copies WITHOUT re-casting them (the inference graphs) call this before a replay; it is a host
+    loop over the cache and launches nothing when the weights did not change."""
+    for key, hit in list(_cache.items()):
+        if isinstance(hit[1], tuple):
+            params = [r() for r in hit[0]]
+            if all(p is not None for p in params) and tuple(p._version for p in params) != hit[1]:
+                operand_cat(*params)
+        else:
+            p = hit[0]()
+            if p is not None and p._version != hit[1]:
+                operand(p)
+
+
 def clear_cache():
-    _cache.clear()
-    _epoch[0] += 1
+    """Marks every cached operand copy stale (parameters were written through raw pointers, e.g. by the fused optimizer
+    step): the next `operand()` re-casts into the SAME buffer.  Captured graphs that read those buffers without
+    re-casting (inference graphs) call `refresh_all()` before a replay."""
+    for key, hit in list(_cache.items()):
+        vers = -1 if not isinstance(hit[1], tuple) else tuple(-1 for _ in hit[1])
+        _cache[key] = (hit[0], vers, hit[2], hit[3])
 
 
 # ------------------------------------------------------------------------------------------------

@@ -438,6 +438,7 @@ class Seq2seq(nn.Module):
         assert max(lens) + 8 - max(lens) % 8 == acous_feats.size(1), 'padded max length must equal the feature length'
         key = (tuple(acous_feats.shape), acous_feats.dtype, str(acous_feats.device), mode, rt.compute_dtype())
         fe = getattr(self, '_fe', None)
+        rt.refresh_all()                    # the graph reads cached weight copies without re-casting them
         if fe is None or fe['key'] != key or fe['epoch'] != rt.cache_epoch():
             feats = acous_feats.clone()
             lens_dev = torch.zeros(len(lens), dtype=torch.int32, device=acous_feats.device)

@@ -256,3 +256,44 @@ def test_cached_decode_equals_recompute_midsize(dtype):
         assert outs[True].shape == outs[False].shape
         same = float((outs[True] == outs[False]).float().mean())
         assert same == 1.0 if dtype == 'fp32' else same >= 0.9, (k, same)
+
+
+def test_inference_graphs_follow_weight_updates():
+    """The inference graphs (front end + one graph per decode position) read cached bf16 weight copies: after the weights
+    change (here: load_state_dict of different values, and a fused-optimizer step that writes through raw pointers) a
+    replay must see the new weights -- same ids as a freshly built model."""
+    from b200st import runtime
+    from modules.optim import Optimizer
+    runtime.set_compute_dtype('bf16')
+    try:
+        cfg = O.STConfig(enc_vocab_size=300, dec_vocab_size=300, enc_embedding_size=40, dec_embedding_size=40,
+                         max_seq_len_src=10, max_seq_len_tgt=16, num_heads=2, dim_model=128, dim_feedforward=256,
+                         enc_layers=2, dec_layers=2, acous_dim=24, acous_hidden_size=256)
+        data = O.synthetic_batch(cfg, 8, 96, seed=2)
+        feats = data['acous_feats'].cuda()
+        lens = [torch.tensor([n]) for n in data['acous_lens']]
+
+        def translate(m):
+            return m.forward_translate(acous_feats=feats.clone(), acous_lens=lens, beam_width=3, penalty_factor=1,
+                                       use_gpu=True, max_seq_len=16, mode='ST')
+        P1, P2 = O.init_params(cfg, seed=1, scale=3.0), O.init_params(cfg, seed=2, scale=3.0)
+        m = build_model(cfg, P1, device='cuda').eval()
+        a1 = translate(m)
+        a1b = translate(m)                                    # replayed graphs
+        assert torch.equal(a1, a1b)
+        m.load_state_dict({k: v.float() for k, v in P2.items()}, strict=False)
+        a2 = translate(m)
+        ref2 = translate(build_model(cfg, P2, device='cuda').eval())
+        assert torch.equal(a2, ref2) and not torch.equal(a1, a2)
+        # raw-pointer update by the fused optimizer
+        m.train()
+        opt = Optimizer(torch.optim.Adam(m.parameters(), lr=5e-2), max_grad_norm=0)
+        loss, _ = train_step(m, data, 'cuda')
+        loss.backward()
+        opt.step()
+        m.eval()
+        a3 = translate(m)
+        fresh = build_model(cfg, {k: v.detach().cpu() for k, v in m.state_dict().items()}, device='cuda').eval()
+        assert torch.equal(a3, translate(fresh))
+    finally:
+        runtime.set_compute_dtype('fp32')
