@@ -269,7 +269,9 @@ int b200st_rng_advance(int64_t* rng, b200st_stream_t stream);
 /* ---- fused gradient-norm clip + Adam over all parameter tensors -----------------------
  * Replaces torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step() behind Optimizer.step()
  * (modules/optim.py:31-36; constructed at trainer/trainer_base.py:422-426).  `table` is a device array
- * int64 [n_tensors][6] = {param, grad, exp_avg, exp_avg_sq (fp32 device pointers), numel, bf16 shadow pointer or 0};
+ * int64 [n_tensors][b200st_opt_table_cols() = 7] = {param, grad, exp_avg, exp_avg_sq (fp32 device pointers), numel, and up
+ * to two bf16 destinations (or 0) that receive the updated parameter -- the operand copies the tensor-core GEMMs read, so
+ * no cast pass follows the step};
  * `blockmap` is int32 [n_blocks][2] = {tensor index, chunk index}, one CTA per chunk of b200st_opt_chunk() elements.
  * multi_sqnorm writes one partial sum of squares per block; adam_prepare (one CTA, fixed summation order) turns them
  * into scal[4] = {clip coefficient = min(1, max_grad_norm / (||g|| + 1e-6)), lr[0] / (1 - beta1^t), sqrt(1 - beta2^t),
@@ -277,6 +279,7 @@ int b200st_rng_advance(int64_t* rng, b200st_stream_t stream);
  * max_grad_norm <= 0 disables clipping.  multi_adam applies torch.optim.Adam's update (amsgrad off, L2 weight decay)
  * with the gradient scaled by the clip coefficient on the fly.  No host synchronisation: graph-capturable. */
 int b200st_opt_chunk(void);
+int b200st_opt_table_cols(void);
 int b200st_multi_sqnorm(const int64_t* table, const int32_t* blockmap, int64_t n_blocks, float* partials,
                         b200st_stream_t stream);
 int b200st_adam_prepare(const float* partials, int64_t n_blocks, float max_grad_norm, const float* lr, double beta1,

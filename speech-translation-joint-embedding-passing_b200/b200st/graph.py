@@ -50,7 +50,11 @@ class GraphedTrainStep:
         if with_optimizer:
             trainer.optimizer._engine().prepare()     # state + pointer tables for the parameters that got a gradient
         model.zero_grad(set_to_none=True)
-        rt.clear_cache()                      # weight shadows get (re)built inside the captured region
+        self.with_optimizer = with_optimizer
+        if with_optimizer:
+            rt.refresh_all()                  # the captured Adam kernel rewrites the bf16 operand copies itself: no casts
+        else:
+            rt.clear_cache()                  # weight copies get re-cast inside the captured region on every replay
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = trainer._train_batch_device(model, self.static)
@@ -68,8 +72,54 @@ class GraphedTrainStep:
             assert max(int(n) for n in lens) + 8 - max(int(n) for n in lens) % 8 == self.static['acous_feat'][0].size(1)
             self.static['acouslen'].copy_(torch.as_tensor([int(n) for n in lens], dtype=torch.int32), non_blocking=non_blocking)
 
+    # -- input pipelining: the next batch's host->device copy runs on a copy stream while the current step computes ----
+    def prefetch(self, items: Dict):
+        """Start copying `items` (pinned host tensors of the captured shapes) into a device staging set on a side stream;
+        returns immediately.  `step_prefetched()` swaps the staged batch in (three small device-to-device copies) and
+        replays the graph, so the PCIe transfer of batch i+1 is hidden under step i."""
+        if not hasattr(self, '_stage'):
+            self._stage = [{k: torch.empty_like(self.static[k][0]) for k in ('srcid', 'tgtid', 'acous_feat')} |
+                           {'acouslen': torch.empty_like(self.static['acouslen'])} for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream()
+            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._slot = 0
+            self._pending = None
+        slot = self._slot
+        self._slot ^= 1
+        st = self._stage[slot]
+        lens = items['acouslen']
+        if not torch.is_tensor(lens):
+            lens = torch.as_tensor([int(n) for n in lens], dtype=torch.int32)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._free[slot])        # the step that last read this slot has swapped it in
+            for k in ('srcid', 'tgtid', 'acous_feat'):
+                st[k].copy_(items[k][0], non_blocking=True)
+            st['acouslen'].copy_(lens.reshape(-1).to(torch.int32), non_blocking=True)
+            self._ready[slot].record(self._copy_stream)
+        self._pending = slot
+
+    def step_prefetched(self):
+        """Replay the step on the batch handed to the last `prefetch()`."""
+        slot = self._pending
+        assert slot is not None, 'call prefetch() first'
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ready[slot])
+        st = self._stage[slot]
+        for k in ('srcid', 'tgtid', 'acous_feat'):
+            self.static[k][0].copy_(st[k], non_blocking=True)
+        self.static['acouslen'].copy_(st['acouslen'], non_blocking=True)
+        self._free[slot].record(cur)
+        self._pending = None
+        self.graph.replay()
+        if self.with_optimizer:
+            rt.after_raw_update()             # copies the captured kernel does not maintain are stale now
+        return self.loss
+
     def __call__(self, items: Optional[Dict] = None):
         if items is not None:
             self.load(items)
         self.graph.replay()
+        if self.with_optimizer:
+            rt.after_raw_update()             # copies the captured kernel does not maintain are stale now
         return self.loss

@@ -572,6 +572,9 @@ class CudaKernels:
     def opt_chunk(self) -> int:
         return int(self.lib.b200st_opt_chunk())
 
+    def opt_table_cols(self) -> int:
+        return int(self.lib.b200st_opt_table_cols())
+
     def clip_adam_step(self, tensors, table, blockmap, partials, scal, step, lr, *, max_grad_norm, beta1, beta2,
                        eps, weight_decay):
         """One optimizer step over every tensor in `table` (device int64 [n][6], see include/b200st.h); `tensors`

@@ -72,15 +72,26 @@ class FusedClipAdam:
     def _build(self, params: List[torch.Tensor]):
         dev = params[0].device
         chunk = K().opt_chunk()
+        ncol = K().opt_table_cols()
         rows, bmap = [], []
+        keys_done, copies = {}, {}
+        index = rt.copies_index()
         for i, p in enumerate(params):
             g, st = p.grad, self.adam.state[p]
             for t, what in ((p, 'parameter'), (g, 'gradient'), (st['exp_avg'], 'exp_avg'), (st['exp_avg_sq'], 'exp_avg_sq')):
                 if t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
                     raise RuntimeError(f'fused Adam needs dense fp32 CUDA tensors on one device; {what} #{i} is '
                                        f'{t.dtype} {tuple(t.shape)} strides {t.stride()} on {t.device}')
+            # bf16 operand copies of this parameter (b200st.runtime cache): the kernel rewrites up to two of them with
+            # the updated value, so no cast pass follows the step; further copies (rare) are marked stale instead
+            dests = [(key, t) for key, t in index.get(id(p), []) if t.is_contiguous() and t.numel() == p.numel()][:2]
+            for key, _ in dests:
+                keys_done.setdefault(key, 0)
+                keys_done[key] += 1
+            d = [t.data_ptr() for _, t in dests] + [0, 0]
+            copies[p] = [t for _, t in dests]
             rows.append([p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
-                         p.numel(), 0])
+                         p.numel(), d[0], d[1]])
             bmap += [[i, c] for c in range((p.numel() + chunk - 1) // chunk)]
         b = self._bufs
         if b is None or b['table'].size(0) != len(rows) or b['blockmap'].size(0) != len(bmap):
@@ -90,8 +101,19 @@ class FusedClipAdam:
             blockmap = _pinned(torch.tensor(bmap, dtype=torch.int32), dev).to(dev, non_blocking=True)
             b = self._bufs = {'blockmap': blockmap, 'partials': torch.empty(len(bmap), dtype=torch.float32, device=dev),
                               'scal': torch.zeros(4, dtype=torch.float32, device=dev),
-                              'table_host': _pinned(torch.empty((len(rows), 6), dtype=torch.int64), dev),
-                              'table': torch.empty((len(rows), 6), dtype=torch.int64, device=dev)}
+                              'table_host': _pinned(torch.empty((len(rows), ncol), dtype=torch.int64), dev),
+                              'table': torch.empty((len(rows), ncol), dtype=torch.int64, device=dev)}
+        # a cached copy is "maintained" when every member parameter writes its block of it (a concatenated K|V copy needs
+        # both of its members in the table)
+        maintained = []
+        for key, n in keys_done.items():
+            need = len(key) - 1 if isinstance(key, tuple) else 1
+            if n >= need:
+                maintained.append(key)
+        rt.set_maintained(maintained)
+        self._copies = copies
+        if hasattr(K(), 'adam_copies'):
+            K().adam_copies = copies
         host = torch.tensor(rows, dtype=torch.int64)
         if _capturing(dev):
             # a capture records a copy NODE that re-reads its source on every replay: stage through the persistent
@@ -110,7 +132,7 @@ class FusedClipAdam:
         if params:
             self._ensure_state(params)
             self._build(params)
-            self._sig = (tuple(id(p) for p in params), tuple(p.grad.data_ptr() for p in params))
+            self._sig = (tuple(id(p) for p in params), tuple(p.grad.data_ptr() for p in params), rt.cache_len())
             self.set_lr(self.adam.param_groups[0]['lr'])
 
     # -- the step ---------------------------------------------------------------------------------------
@@ -125,7 +147,7 @@ class FusedClipAdam:
         params = [p for g in self.adam.param_groups for p in g['params'] if p.grad is not None]
         if not params:
             return
-        sig = (tuple(id(p) for p in params), tuple(p.grad.data_ptr() for p in params))
+        sig = (tuple(id(p) for p in params), tuple(p.grad.data_ptr() for p in params), rt.cache_len())
         if sig != self._sig:
             self._ensure_state(params)
             self._build(params)
@@ -141,9 +163,9 @@ class FusedClipAdam:
                            b['table'], b['blockmap'], b['partials'], b['scal'], self._step, self._lr,
                            max_grad_norm=self.max_grad_norm, beta1=g0['betas'][0], beta2=g0['betas'][1],
                            eps=g0['eps'], weight_decay=g0['weight_decay'])
-        # the kernels wrote through raw pointers: parameter version counters did not move, so drop the cached bf16
-        # operand copies (they are re-cast on next use; inside a captured step the re-cast is part of the graph)
-        rt.clear_cache()
+        # the kernels wrote through raw pointers: parameter version counters did not move.  Operand copies the kernel
+        # rewrote itself stay valid; any other cached copy is marked stale (re-cast in place on next use)
+        rt.after_raw_update()
 
     @property
     def grad_norm(self) -> torch.Tensor:

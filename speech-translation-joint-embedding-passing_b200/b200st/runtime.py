@@ -24,6 +24,10 @@ def cache_epoch() -> int:
     return _epoch[0]
 
 
+def cache_len() -> int:
+    return len(_cache) + (_epoch[0] << 20)
+
+
 def set_compute_dtype(d):
     global _compute_dtype
     _compute_dtype = _DTYPES[d.lower()] if isinstance(d, str) else d
@@ -82,6 +86,46 @@ def operand_cat(*params: torch.Tensor) -> torch.Tensor:
         r0 += n
     _cache[key] = (tuple(weakref.ref(p) for p in params), vers, ptrs, buf)
     return buf
+
+
+_maintained = set()        # cache keys whose copies the fused optimizer kernel rewrites itself (b200st/optim.py)
+
+
+def copies_index():
+    """{id(param): [(cache key, bf16 tensor view)]} over every cached operand copy (a parameter's own copy and its row
+    block inside concatenated copies) -- the destinations the fused Adam kernel can keep up to date."""
+    out = {}
+    for key, hit in _cache.items():
+        if hit[3].dtype != torch.bfloat16:
+            continue
+        if isinstance(key, tuple):
+            members = [r() for r in hit[0]]
+            if any(m is None for m in members):
+                continue
+            r0 = 0
+            for m in members:
+                out.setdefault(id(m), []).append((key, hit[3][r0:r0 + m.size(0)]))
+                r0 += m.size(0)
+        else:
+            p = hit[0]()
+            if p is not None:
+                out.setdefault(id(p), []).append((key, hit[3]))
+    return out
+
+
+def set_maintained(keys):
+    _maintained.clear()
+    _maintained.update(keys)
+
+
+def after_raw_update(updated=None):
+    """Parameters were written through raw pointers (fused optimizer step): every cached copy that the kernel did not
+    rewrite itself is marked stale.  A concatenated copy counts as maintained only if it was registered as such."""
+    for key, hit in list(_cache.items()):
+        if key in _maintained:
+            continue
+        vers = -1 if not isinstance(hit[1], tuple) else tuple(-1 for _ in hit[1])
+        _cache[key] = (hit[0], vers, hit[2], hit[3])
 
 
 def refresh_all():

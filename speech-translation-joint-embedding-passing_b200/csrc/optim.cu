@@ -5,7 +5,7 @@
 // elements at the benchmark config.  HBM-bound: the gradient is read once for the norm (278 MB) and once more,
 // with p, m, v, for the update (4 reads + 3 writes per element = 28 B/element, 1.95 GB per step).
 //
-// Multi-tensor layout: a device table of int64 [n_tensors][6] = {p, g, m, v, numel, shadow} and a block map
+// Multi-tensor layout: a device table of int64 [n_tensors][7] = {p, g, m, v, numel, bf16 copy, bf16 copy} and a block map
 // int32 [n_blocks][2] = {tensor, chunk} built once by the host (b200st/optim.py); one CTA handles one chunk of
 // OPT_CHUNK elements of one tensor, so a single launch covers every tensor regardless of size.
 // Three launches per step, no host synchronisation, CUDA-graph capturable:
@@ -20,15 +20,16 @@
 namespace b200st {
 
 constexpr int OPT_CHUNK = 8192;      // elements per CTA
-constexpr int OPT_THREADS = 256;     // 32 elements per thread = 8 x float4
+constexpr int OPT_THREADS = 256;
+constexpr int OPT_COLS = 7;          // table row: {p, g, m, v, numel, bf16 copy 1 or 0, bf16 copy 2 or 0}     // 32 elements per thread = 8 x float4
 
 __global__ void __launch_bounds__(OPT_THREADS)
 multi_sqnorm_kernel(const int64_t* __restrict__ table, const int* __restrict__ blockmap,
                     float* __restrict__ partials) {
   __shared__ float scratch[32];
   const int t = blockmap[2 * blockIdx.x], chunk = blockmap[2 * blockIdx.x + 1];
-  const float* g = reinterpret_cast<const float*>(table[6 * t + 1]);
-  const int64_t n = table[6 * t + 4];
+  const float* g = reinterpret_cast<const float*>(table[OPT_COLS * t + 1]);
+  const int64_t n = table[OPT_COLS * t + 4];
   const int64_t base = (int64_t)chunk * OPT_CHUNK;
   const int64_t end = min(base + OPT_CHUNK, n);
   float acc = 0.f;
@@ -95,17 +96,18 @@ __global__ void __launch_bounds__(OPT_THREADS)
 multi_adam_kernel(const int64_t* __restrict__ table, const int* __restrict__ blockmap,
                   const float* __restrict__ scal, float omb1, float b2, float omb2, float eps, float wd) {
   const int t = blockmap[2 * blockIdx.x], chunk = blockmap[2 * blockIdx.x + 1];
-  float* p = reinterpret_cast<float*>(table[6 * t + 0]);
-  const float* g = reinterpret_cast<const float*>(table[6 * t + 1]);
-  float* m = reinterpret_cast<float*>(table[6 * t + 2]);
-  float* v = reinterpret_cast<float*>(table[6 * t + 3]);
-  const int64_t n = table[6 * t + 4];
-  __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(table[6 * t + 5]);
+  float* p = reinterpret_cast<float*>(table[OPT_COLS * t + 0]);
+  const float* g = reinterpret_cast<const float*>(table[OPT_COLS * t + 1]);
+  float* m = reinterpret_cast<float*>(table[OPT_COLS * t + 2]);
+  float* v = reinterpret_cast<float*>(table[OPT_COLS * t + 3]);
+  const int64_t n = table[OPT_COLS * t + 4];
+  __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(table[OPT_COLS * t + 5]);
+  __nv_bfloat16* sh2 = reinterpret_cast<__nv_bfloat16*>(table[OPT_COLS * t + 6]);
   const float clip = scal[0], step_size = scal[1], isb2 = scal[2];
   const int64_t base = (int64_t)chunk * OPT_CHUNK;
   const int64_t end = min(base + OPT_CHUNK, n);
   const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
-                     reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(sh) & 7) == 0;
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0 && ((reinterpret_cast<uintptr_t>(sh) | reinterpret_cast<uintptr_t>(sh2)) & 7) == 0;
   if (vec) {
     for (int64_t i = base + threadIdx.x * 4; i < end; i += OPT_THREADS * 4) {
       if (i + 4 <= end) {
@@ -115,12 +117,14 @@ multi_adam_kernel(const int64_t* __restrict__ table, const int* __restrict__ blo
         for (int j = 0; j < 4; ++j) adam_elem(pp[j], gg[j], mm[j], vv[j], clip, step_size, isb2, omb1, b2, omb2, eps, wd);
         store4(p + i, pp); store4(m + i, mm); store4(v + i, vv);
         if (sh) store4(sh + i, pp);
+        if (sh2) store4(sh2 + i, pp);
       } else {
         for (int64_t j = i; j < end; ++j) {
           float pp = p[j], mm = m[j], vv = v[j];
           adam_elem(pp, g[j], mm, vv, clip, step_size, isb2, omb1, b2, omb2, eps, wd);
           p[j] = pp; m[j] = mm; v[j] = vv;
           if (sh) sh[j] = __float2bfloat16_rn(pp);
+          if (sh2) sh2[j] = __float2bfloat16_rn(pp);
         }
       }
     }
@@ -130,6 +134,7 @@ multi_adam_kernel(const int64_t* __restrict__ table, const int* __restrict__ blo
       adam_elem(pp, g[j], mm, vv, clip, step_size, isb2, omb1, b2, omb2, eps, wd);
       p[j] = pp; m[j] = mm; v[j] = vv;
       if (sh) sh[j] = __float2bfloat16_rn(pp);
+      if (sh2) sh2[j] = __float2bfloat16_rn(pp);
     }
   }
 }
@@ -141,6 +146,7 @@ using namespace b200st;
 extern "C" {
 
 int b200st_opt_chunk(void) { return OPT_CHUNK; }
+int b200st_opt_table_cols(void) { return OPT_COLS; }
 
 int b200st_multi_sqnorm(const int64_t* table, const int32_t* blockmap, int64_t n_blocks, float* partials,
                         b200st_stream_t stream) {

@@ -48,6 +48,7 @@ class FakeKernels:
 
     def __init__(self):
         self.launches = 0
+        self.adam_copies = {}
 
     def launch_count(self):
         return self.launches
@@ -112,6 +113,9 @@ class FakeKernels:
     def opt_chunk(self):
         return 8192
 
+    def opt_table_cols(self):
+        return 7
+
     def clip_adam_step(self, tensors, table, blockmap, partials, scal, step, lr, *, max_grad_norm, beta1, beta2,
                        eps, weight_decay):
         """torch.nn.utils.clip_grad_norm_ + torch.optim.Adam (amsgrad off) restated with torch ops on the tensors the
@@ -134,6 +138,9 @@ class FakeKernels:
             v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
             denom = (v.sqrt() / bc2 ** 0.5).add_(eps)
             p.data.addcdiv_(m, denom, value=-float(lr[0]) / bc1)
+        for p, dests in getattr(self, 'adam_copies', {}).items():      # bf16 operand copies kept by the real kernel
+            for d in dests:
+                d.copy_(p.data.reshape(d.shape))
 
     # -- LayerNorm --------------------------------------------------------------------------------
     def layernorm_fwd(self, x, gamma, beta, eps, save_stats=True):

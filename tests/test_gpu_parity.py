@@ -297,3 +297,59 @@ def test_inference_graphs_follow_weight_updates():
         assert torch.equal(a3, translate(fresh))
     finally:
         runtime.set_compute_dtype('fp32')
+
+
+def test_adam_maintains_bf16_operand_copies():
+    """bf16 mode: the fused Adam kernel rewrites the cached bf16 operand copies of the weights it updates (no cast pass
+    after the step).  Eager steps and whole-step graph replays must give the loss sequence of a run that re-casts every
+    copy from the fp32 weights after each step, and every cache entry that claims to be fresh must equal the cast of
+    its parameter(s)."""
+    from b200st import runtime
+    from b200st.graph import GraphedTrainStep
+    from modules.optim import Optimizer
+    from trainer.trainer_st import Trainer_ST
+    runtime.set_compute_dtype('bf16')
+    try:
+        cfg = O.STConfig(enc_vocab_size=300, dec_vocab_size=300, enc_embedding_size=40, dec_embedding_size=40,
+                         max_seq_len_src=10, max_seq_len_tgt=13, num_heads=2, dim_model=128, dim_feedforward=256,
+                         enc_layers=2, dec_layers=2, acous_dim=24, acous_hidden_size=256)
+        P = O.init_params(cfg, seed=11)
+        data = O.synthetic_batch(cfg, 16, 96, seed=21)
+        items = {'srcid': [data['src'].cuda()], 'tgtid': [data['tgt'].cuda()], 'acous_feat': [data['acous_feats'].cuda()],
+                 'acouslen': [int(n) for n in data['acous_lens']]}
+
+        def run(recast_every_step, graph):
+            m = build_model(cfg, P, device='cuda')
+            m.train()
+            opt = Optimizer(torch.optim.Adam(m.parameters(), lr=1e-2), max_grad_norm=1.0)
+            tr = Trainer_ST(use_gpu=True, batch_size=16, optimizer=opt)
+            losses = []
+            if graph:
+                g = GraphedTrainStep(m, tr, items, with_optimizer=True)
+                for _ in range(4):
+                    losses.append(float(g()))
+            else:
+                for _ in range(4):
+                    losses.append(tr._train_batch(m, items)['nll_loss_de'])
+                    if recast_every_step:
+                        runtime.clear_cache()
+            return losses, m
+        ref, _ = run(True, False)
+        eager, m = run(False, False)
+        assert eager == ref, (eager, ref)
+        n_fresh = 0
+        for key, hit in runtime._cache.items():
+            params = [r() for r in hit[0]] if isinstance(key, tuple) else [hit[0]()]
+            if any(p is None for p in params) or not any(p is q for p in params for q in m.parameters()):
+                continue
+            vers = tuple(p._version for p in params) if isinstance(key, tuple) else params[0]._version
+            if vers == hit[1]:
+                n_fresh += 1
+                want = torch.cat([p.detach().to(torch.bfloat16) for p in params], 0)
+                assert torch.equal(hit[3], want.view_as(hit[3])), key
+        assert n_fresh > 20
+        graphed, _ = run(False, True)
+        assert graphed == ref, (graphed, ref)
+        assert ref[-1] < ref[0]
+    finally:
+        runtime.set_compute_dtype('fp32')
