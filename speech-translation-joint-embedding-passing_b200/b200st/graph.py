@@ -52,7 +52,9 @@ class GraphedTrainStep:
         model.zero_grad(set_to_none=True)
         self.with_optimizer = with_optimizer
         if with_optimizer:
-            rt.refresh_all()                  # the captured Adam kernel rewrites the bf16 operand copies itself: no casts
+            # the captured Adam kernel rewrites the bf16 operand copies itself (no cast pass in the graph); every other
+            # cached copy (e.g. fp32 concatenations) is marked stale so that its refresh IS captured
+            rt.after_raw_update()
         else:
             rt.clear_cache()                  # weight copies get re-cast inside the captured region on every replay
         self.graph = torch.cuda.CUDAGraph()
