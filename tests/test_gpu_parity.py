@@ -336,7 +336,8 @@ def test_adam_maintains_bf16_operand_copies():
             return losses, m
         ref, _ = run(True, False)
         eager, m = run(False, False)
-        assert eager == ref, (eager, ref)
+        close = lambda a, b: all(abs(x - y) < 2e-4 * abs(y) for x, y in zip(a, b))   # split-K atomics: not bit-reproducible
+        assert close(eager, ref), (eager, ref)
         n_fresh = 0
         for key, hit in runtime._cache.items():
             params = [r() for r in hit[0]] if isinstance(key, tuple) else [hit[0]()]
@@ -349,7 +350,7 @@ def test_adam_maintains_bf16_operand_copies():
                 assert torch.equal(hit[3], want.view_as(hit[3])), key
         assert n_fresh > 20
         graphed, _ = run(False, True)
-        assert graphed == ref, (graphed, ref)
+        assert close(graphed, ref), (graphed, ref)
         assert ref[-1] < ref[0]
     finally:
         runtime.set_compute_dtype('fp32')
