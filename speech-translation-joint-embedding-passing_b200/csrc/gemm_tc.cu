@@ -633,7 +633,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                        const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_b2,
                        int kb_seg1, TC* __restrict__ C, int64_t ldc, const TC* R, int64_t ldr,
                        const float* __restrict__ bias, int relu, float alpha, int M, int N, int K, int n_tiles_n,
-                       int n_tiles, int dbg) {
+                       int n_tiles, int dbg, int splits, int kb_per_split) {
   constexpr int BN = 256;                   // accumulator columns per CTA = N extent of the pair's tile
   constexpr int BNH = 128;                  // B rows (N) staged by EACH CTA; the MMA reads both halves
   using S = TcPersistSmem<BNH, STAGES>;
@@ -669,10 +669,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 0) {
     if (lane == 0 && !(dbg & 1)) {
       uint32_t it = 0;                       // running k-block counter across tiles: ring slot and phase
-      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-        // the pair's tile is 256 x 256: this CTA stages A rows [m0, m0+128) and B rows (N) [n0, n0+128)
+      for (int unit = pair; unit < n_tiles * splits; unit += n_pairs) {
+        // work unit = (256 x 256 tile of the pair, K split); this CTA stages A rows [m0, m0+128) and B rows (N) [n0, n0+128)
+        const int tile = unit / splits, kb0 = (unit % splits) * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         const int m0 = (tile / n_tiles_n) * 256 + (int)rank * TC_BM, n0 = (tile % n_tiles_n) * BN + (int)rank * BNH;
-        for (int kb = 0; kb < kb_total; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
           uint8_t* sa = smem + s * S::STAGE;
@@ -701,12 +702,13 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = umma_idesc(256, BN, A_MN, B_MN);     // M = 256 across the pair
       uint32_t it = 0, j = 0;
-      for (int tile = pair; tile < n_tiles; tile += n_pairs, ++j) {
+      for (int unit = pair; unit < n_tiles * splits; unit += n_pairs, ++j) {
+        const int kb0 = (unit % splits) * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         const uint32_t buf = j & 1;
         mbar_wait(&tempty[buf], ((j >> 1) & 1) ^ 1);      // the epilogue has drained this buffer (free at first use)
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * BN;
-        for (int kb = 0; kb < kb_total; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           if (!(dbg & 1)) mbar_wait(&full[s], (it / STAGES) & 1);
           tc_fence_after();
@@ -716,7 +718,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint64_t da = A_MN ? umma_desc(sa + k * 2048, TC_BK * 128, 1024) : umma_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_desc(sb + k * 2048, TC_BK * 128, 1024) : umma_desc(sb + k * 32, 16, 1024);
-            tc_mma_f16_pair(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_mma_f16_pair(acc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tc_commit_pair(&empty[s]);
         }
@@ -734,7 +736,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int cc = (lane & 7) * 4;          // 8 lanes x 4 columns cover a 32-column chunk row
     const int rl = lane >> 3;               // 4 rows per pass
     uint32_t j = 0;
-    for (int tile = pair; tile < n_tiles; tile += n_pairs, ++j) {
+    for (int unit = pair; unit < n_tiles * splits; unit += n_pairs, ++j) {
+      const int tile = unit / splits;
       const int m0 = (tile / n_tiles_n) * 256 + (int)rank * TC_BM, n0 = (tile % n_tiles_n) * BN;
       const uint32_t buf = j & 1;
       mbar_wait(&tfull[buf], (j >> 1) & 1);
@@ -783,6 +786,20 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
             }
             TC* cp = C + (int64_t)row * ldc + colb;
+            if (splits > 1) {                  // split-K partial: fp32 reduction into the zero-filled output
+              if constexpr (sizeof(TC) == 4) {
+                float* fp = reinterpret_cast<float*>(cp);
+                if (fullw && (reinterpret_cast<uintptr_t>(fp) & 15) == 0) {
+#pragma unroll
+                  for (int q = 0; q < 32; q += 4)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(fp + q), "f"(v[q]), "f"(v[q + 1]), "f"(v[q + 2]), "f"(v[q + 3]) : "memory");
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 32; ++q) if (colb + q < N) atomicAdd(fp + q, v[q]);
+                }
+              }
+              continue;
+            }
             if (fullw && (reinterpret_cast<uintptr_t>(cp) & 31) == 0) {
               // 256-bit stores (sm_100): every instruction writes whole 32-byte sectors
               if constexpr (sizeof(TC) == 4) {
@@ -1209,9 +1226,11 @@ int gemm_tc_set_pair(int on) { const int old = g_pair_enabled; if (on == 0 || on
 template <int STAGES, bool A_MN, bool B_MN, typename TC>
 static int launch_tc_pair(int64_t M, int64_t N, int64_t K, float alpha, const CUtensorMap& ma, const CUtensorMap& mb,
                           const CUtensorMap& ma2, const CUtensorMap& mb2, int kb_seg1, void* C, int64_t ldc,
-                          const void* R, int64_t ldr, const float* bias, int relu, cudaStream_t st) {
+                          const void* R, int64_t ldr, const float* bias, int relu, cudaStream_t st, int splits = 1,
+                          int kb_per_split = 0x3fffffff) {
   using S = TcPersistSmem<128, STAGES>;
   static_assert(S::TOTAL <= 227 * 1024, "pair tile configuration exceeds shared memory");
+  if (splits > 1 && sizeof(TC) != 4) return set_error("gemm_tc_pair: split-K needs an fp32 output");
   if (g_sm_count == 0) {
     int dev = 0;
     B200ST_CUDA(cudaGetDevice(&dev));
@@ -1221,9 +1240,9 @@ static int launch_tc_pair(int64_t M, int64_t N, int64_t K, float alpha, const CU
   const int n_tiles = (int)(ceil_div(M, 256) * n_tiles_n);
   auto kern = gemm_tc_pair_kernel<STAGES, A_MN, B_MN, TC>;
   B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-  dim3 grid((unsigned)(2 * min(n_tiles, g_sm_count / 2)));
+  dim3 grid((unsigned)(2 * min(n_tiles * splits, g_sm_count / 2)));
   B200ST_CUDA(launch_pdl_pair(kern, grid, dim3(TCP_THREADS), S::TOTAL, st, ma, mb, ma2, mb2, kb_seg1, (TC*)C, ldc,
-                              (const TC*)R, ldr, bias, relu, alpha, (int)M, (int)N, (int)K, n_tiles_n, n_tiles, g_pair_dbg));
+                              (const TC*)R, ldr, bias, relu, alpha, (int)M, (int)N, (int)K, n_tiles_n, n_tiles, g_pair_dbg, splits, kb_per_split));
   B200ST_LAUNCH_CHECK("gemm_tc_pair");
   return 0;
 }
@@ -1272,10 +1291,13 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   const bool can256 = many && N >= 256 && t_256 >= (int64_t)min_rounds * 148;
   const bool pair = many && g_pair_enabled && N >= 256 && kb_total >= 8 && t_pair >= 48 &&
                     (!can256 || ceil_div(t_pair, 74) <= ceil_div(t_256, 148));
-  const bool persist256 = !pair && can256;
-  const bool persist128 = !pair && !persist256 && many && t_128 >= (int64_t)min_rounds * 148;
-  if (pair || persist256 || persist128) cfg = 0;
-  const int BN = persist256 ? 256 : ((cfg == 0 || wide || pair) ? 128 : (cfg == 2 ? 32 : 64));   // = B box rows
+  // split-K on the pair kernel: long-K weight gradients with few 256 x 256 tiles (fp32 output, plain sum)
+  const bool pair_splitk = g_persist_enabled && g_pair_enabled && !pair && dtype_c == B200ST_F32 && !dual && !bias && !relu &&
+                           !R && N >= 256 && M >= 256 && t_pair <= 37 && kb_total >= 64;
+  const bool persist256 = !pair && !pair_splitk && can256;
+  const bool persist128 = !pair && !pair_splitk && !persist256 && many && t_128 >= (int64_t)min_rounds * 148;
+  if (pair || pair_splitk || persist256 || persist128) cfg = 0;
+  const int BN = persist256 ? 256 : ((cfg == 0 || wide || pair || pair_splitk) ? 128 : (cfg == 2 ? 32 : 64));   // = B box rows
   const bool m64 = (cfg == 2 || cfg == 3) && M <= 64;       // half-height A tile for the decoder-step GEMMs
   CUtensorMap ma, mb;
   if (a_mn) { if (make_map(&ma, A, K1, M, lda, TC_BK)) return -1; }
@@ -1309,6 +1331,10 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
   // split-K when the output has few tiles and K is long (weight gradients): fp32 output, plain sum only.
   const int64_t tiles = m_tiles * ceil_div(N, BN);
   int splits = 1;
+  if (pair_splitk) {              // units = pair tiles x K splits fill the 74 SM pairs once
+    splits = (int)max((int64_t)1, 74 / t_pair);
+    if (splits > kb_total / 16) splits = max(1, kb_total / 16);
+  } else
   if (dtype_c == B200ST_F32 && !dual && !bias && !relu && !R && tiles < 96 && kb_total >= 16) {
     splits = (int)(296 / tiles);
     if (splits > kb_total / 4) splits = kb_total / 4;
@@ -1329,6 +1355,14 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
       return launch_tc_pair<6, AMN, BMN, float>(M, N, K, alpha, ma, mb, ma2, mb2, kb_seg1, C, ldc, R, ldr, bias, relu, st); \
     return launch_tc_pair<6, AMN, BMN, __nv_bfloat16>(M, N, K, alpha, ma, mb, ma2, mb2, kb_seg1, C, ldc, R, ldr, bias, relu, st); \
   } while (0)
+  if (pair_splitk) {
+#define TC_PAIRK(AMN, BMN) return launch_tc_pair<6, AMN, BMN, float>(M, N, K, alpha, ma, mb, ma2, mb2, kb_seg1, C, ldc, R, ldr, bias, relu, st, splits, kb_per_split)
+    if (!a_mn && !b_mn) TC_PAIRK(false, false);
+    if (!a_mn && b_mn) TC_PAIRK(false, true);
+    if (a_mn && !b_mn) TC_PAIRK(true, false);
+    TC_PAIRK(true, true);
+#undef TC_PAIRK
+  }
   if (pair && splits == 1) {
     if (!a_mn && !b_mn) TC_PAIR(false, false);
     if (!a_mn && b_mn) TC_PAIR(false, true);

@@ -78,6 +78,30 @@ def test_gemm_persistent_tiles(ks, out_dtype, ta, tb, M, N, K):
         assert float(y[h == 0].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize('ta,tb', [(True, False), (False, True), (True, True), (False, False)])
+@pytest.mark.parametrize('M,N,K', [(1024, 1024, 32256), (1024, 256, 64512), (512, 512, 8200), (1000, 700, 4100)])
+def test_gemm_pair_split_k_weight_gradients(ks, ta, tb, M, N, K):
+    """Long-K, few-tile products with fp32 output (the weight gradients dW = dG^T X): the CTA-pair kernel with the K
+    range split over the SM pairs and an fp32 reduction epilogue, against the torch restatement and the one-tile
+    split-K kernel."""
+    c, f = ks
+    dt = torch.bfloat16
+    a = rnd(K, M, dtype=dt, scale=0.1) if ta else rnd(M, K, dtype=dt, scale=0.1)
+    b = rnd(N, K, dtype=dt, seed=1) if tb else rnd(K, N, dtype=dt, seed=1)
+    y = c.gemm(a, b, trans_a=ta, trans_b=tb, out_dtype=torch.float32)
+    yr = f.gemm(a, b, trans_a=ta, trans_b=tb, out_dtype=torch.float32)
+    assert rel_err(y, yr) < 2e-3                                   # bf16 products, fp32 sums in a different order
+    old = c.set_gemm_persistent(0)
+    try:
+        y0 = c.gemm(a, b, trans_a=ta, trans_b=tb, out_dtype=torch.float32)
+    finally:
+        c.set_gemm_persistent(old)
+    assert rel_err(y, y0) < 1e-4                                   # fp32 partial sums in a different order
+    out = torch.full((M, N), 7.0, device='cuda')                   # a caller-provided output is overwritten, not added to
+    c.gemm(a, b, trans_a=ta, trans_b=tb, out=out)
+    assert rel_err(out, y) < 1e-4
+
+
 def test_gemm2_persistent_two_segment(ks):
     c, f = ks
     dt = torch.bfloat16
