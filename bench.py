@@ -430,6 +430,15 @@ def run_b200(args):
         ms_e2e = timed(lambda: eager_step(batch_items), args.steps)
     launches = launches_per_step * args.steps
     live = False
+    # nvidia-smi takes a moment to start and reports every 100 ms while K steps last ~70 ms: keep replaying the same step
+    # (untimed) until the sampler has seen the GPU under this load for a few periods
+    t_end = time.perf_counter() + 4.0
+    while len(sampler.lines) < 8 and time.perf_counter() < t_end and sampler.proc is not None:
+        if graphed is not None:
+            graphed()
+        else:
+            eager_step(dev_items)
+    torch.cuda.synchronize()
     clocks = sampler.stop()
     # the timed replays really stepped the weights (clip + Adam is inside the captured step)
     optimizer_applied = bool((probe_param.detach() != probe_before).any())
