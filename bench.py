@@ -432,8 +432,8 @@ def run_b200(args):
     live = False
     # nvidia-smi takes a moment to start and reports every 100 ms while K steps last ~70 ms: keep replaying the same step
     # (untimed) until the sampler has seen the GPU under this load for a few periods
-    t_end = time.perf_counter() + 4.0
-    while len(sampler.lines) < 8 and time.perf_counter() < t_end and sampler.proc is not None:
+    # (same count on every rank -- ms_dev is the all-reduced maximum -- because the step contains collectives)
+    for _ in range(int(min(300, max(20, 1200.0 / max(ms_dev, 1e-3))))):
         if graphed is not None:
             graphed()
         else:
