@@ -498,8 +498,9 @@ def run_b200(args):
         if big_n:
             peak_b = peaks.get('bf16_tflops', 1650.0)
             line['roofline_gemm'] = {
-                'kernel': 'gemm_tc_pair_kernel (tcgen05 cta_group::2, 256x256 tile per SM pair): BLSTM input projections '
-                          'and input-gradient GEMMs (>= 5e10 FLOP each)',
+                'kernel': 'gemm_tc_pair_kernel (tcgen05 cta_group::2, 256x256 tile per SM pair): every GEMM of the step with '
+                          '>= 5e10 FLOP -- BLSTM input projections, their input-gradient GEMMs and the largest weight '
+                          'gradient (split-K over the SM pairs)',
                 'bound': 'tensor', 'achieved': big_fl / max(big_ms, 1e-9) / 1e9, 'peak': peak_b, 'unit': 'TFLOP/s',
                 'frac': big_fl / max(big_ms, 1e-9) / 1e9 / peak_b, 'launches': big_n,
                 'avg_launch_ms': big_ms / big_n, 'shapes': big_shapes, 'peak_source': 'measured (MEASURED_PEAKS.json bf16_tflops, burst: '
