@@ -386,7 +386,7 @@ def test_embedding_and_mix(ks, dtype):
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize('rows,cols', [(5, 41), (64, 10000), (3, 33000)])
+@pytest.mark.parametrize('rows,cols', [(5, 41), (64, 10000), (3, 33000), (7, 2048), (9, 6000), (3136, 10000)])
 def test_softmax_family(ks, dtype, rows, cols):
     c, f = ks
     x = rnd(rows, cols, dtype=dtype, scale=3.0)
