@@ -32,6 +32,7 @@ def timed_graph(name, fn, reps=10):
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         fn()
+        runtime.join_deferred()        # weight-gradient GEMMs forked during backward
     for _ in range(3):
         g.replay()
     torch.cuda.synchronize()

@@ -56,6 +56,9 @@ class GradAllReducer:
             # tensors are reduced IN PLACE by one grouped (coalesced) launch with ReduceOp.AVG -- no flatten copy, no
             # divide pass, no unflatten copies at the end of backward (those used to be the serial tail of the step).
             self._stream.wait_stream(torch.cuda.current_stream())
+            from . import runtime as rt
+            for st in rt.deferred_streams():       # weight-gradient GEMMs still running on side streams (graph capture)
+                self._stream.wait_stream(st)
             with torch.cuda.stream(self._stream):
                 if dist.get_backend(self.group) == 'nccl':
                     with dist._coalescing_manager(self.group, device=grads[0].device, async_ops=True) as cm:

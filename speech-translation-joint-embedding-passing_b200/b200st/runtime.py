@@ -159,17 +159,17 @@ def clear_cache():
 _side = {}
 
 
-def side_streams(device, n):
-    """`n` persistent side streams for `device`.  Returns None entries (fork/join become no-ops, everything runs
+def side_streams(device, n, pool='main'):
+    """`n` persistent side streams for `device` (from the named pool).  Returns None entries (fork/join become no-ops, everything runs
     inline) on CPU and whenever no CUDA graph is being captured: eagerly, the event traffic of forking costs more
     host time than the overlap wins, while inside a capture the forks are free and become parallel graph branches."""
     if device.type != 'cuda' or not torch.cuda.is_current_stream_capturing():
         return [None] * n
-    key = (device.index if device.index is not None else torch.cuda.current_device())
-    pool = _side.setdefault(key, [])
-    while len(pool) < n:
-        pool.append(torch.cuda.Stream(device=device))
-    return pool[:n]
+    key = (device.index if device.index is not None else torch.cuda.current_device(), pool)
+    streams = _side.setdefault(key, [])
+    while len(streams) < n:
+        streams.append(torch.cuda.Stream(device=device))
+    return streams[:n]
 
 
 class fork:
@@ -197,6 +197,35 @@ def join(stream):
     """Make the current stream wait for everything enqueued so far on `stream`."""
     if stream is not None:
         torch.cuda.current_stream().wait_stream(stream)
+
+
+# Deferred joins: weight-gradient GEMMs of a backward node are forked onto side streams and NOT joined before the node
+# returns -- nothing downstream in backward reads a weight gradient, so they overlap the rest of the backward pass (the
+# next layer's latency-bound recurrence uses 64 of the 148 SMs).  Whoever consumes gradients (the trainer after
+# loss.backward(), the data-parallel reducer, the optimizer) calls join_deferred() / waits on deferred_streams() first.
+# The tensors those launches read are kept alive until then: a block freed at the end of the node could otherwise be
+# handed to a main-stream kernel that has no ordering against the side stream.
+_deferred = []
+_keepalive = []
+
+
+def defer(stream, *tensors):
+    if stream is None:
+        return
+    if stream not in _deferred:
+        _deferred.append(stream)
+    _keepalive.extend(t for t in tensors if t is not None)
+
+
+def deferred_streams():
+    return list(_deferred)
+
+
+def join_deferred():
+    for s in _deferred:
+        join(s)
+    _deferred.clear()
+    _keepalive.clear()
 
 
 # ------------------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@ data-parallel ranks before the optimizer step.
 """
 import torch
 
+from b200st import runtime as rt
 from modules.loss import NLLLoss
 from utils.config import PAD
 from utils.misc import check_device
@@ -98,6 +99,7 @@ class Trainer_ST(object):
             loss_de.acc_loss = loss_de.acc_loss / n_minibatch
             loss_de.backward()
             resloss_de = resloss_de + loss_de.acc_loss.detach()
+        rt.join_deferred()          # weight-gradient GEMMs forked onto side streams during backward
         if self.reducer is not None:
             self.reducer.finish()
         return resloss_de
