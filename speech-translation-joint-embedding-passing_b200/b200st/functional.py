@@ -50,13 +50,13 @@ class _Linear(Function):
         dx = dw = db = dres = None
         if ctx.needs_input_grad[0]:
             dx = K().gemm(dz, w).view(*dy.shape[:-1], weight.size(1))
-        side = rt.side_streams(dz.device, 1, pool='dw')
-        with rt.fork(side[0]):          # weight / bias gradients: off the dX chain, joined at the end of backward
-            if ctx.needs_input_grad[1]:
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = K().colsum(dz)
+        if ctx.needs_input_grad[1]:
+            side = rt.side_streams(dz.device, 1, pool='dw') if rt.can_defer(weight) else [None]
+            with rt.fork(side[0]):      # weight gradient: off the dX chain, joined at the end of backward
                 dw = K().gemm(dz, x2, trans_a=True, out_dtype=torch.float32)
-            if ctx.has_bias and ctx.needs_input_grad[2]:
-                db = K().colsum(dz)
-        rt.defer(side[0], dz, x2)
+            rt.defer(side[0], (dz, x2), [(weight, dw)])
         if ctx.has_res and ctx.needs_input_grad[4]:
             dres = dy
         return dx, dw, db, None, dres
@@ -207,10 +207,12 @@ class _MHABlock(Function):
         dout2 = _c(dout).reshape(-1, D)
         dfc = k.dropout(dout2, p_fc, rng, s_fc) if p_fc > 0 else dout2      # gradient of the fc output
         do = k.gemm(dfc, rt.operand(w_fc))
-        side = rt.side_streams(q2.device, 2, pool='dw')     # weight gradients: off the dX chain, joined at the end of backward
+        # weight gradients: off the dX chain on side streams, joined at the end of backward (rt.defer).  Every returned
+        # gradient is a whole fresh tensor so that autograd adopts it instead of copying it (hence two GEMMs for K | V)
+        side = rt.side_streams(q2.device, 2, pool='dw') if rt.can_defer(w_fc, w_q, w_k, w_v) else [None, None]
         with rt.fork(side[0]):
             dw_fc = k.gemm(dfc, o2, trans_a=True, out_dtype=torch.float32)
-        rt.defer(side[0], dfc, o2)
+        rt.defer(side[0], (dfc, o2), [(w_fc, dw_fc)])
         dqp = torch.empty_like(qp)
         dkvp = torch.empty_like(kvp)
         kv3, dkv3 = kvp.view(B, Lk, 2 * HD), dkvp.view(B, Lk, 2 * HD)
@@ -219,8 +221,9 @@ class _MHABlock(Function):
                   dropout=(p_attn, rng, s_attn))
         with rt.fork(side[1]):
             dw_q = k.gemm(dqp, qn, trans_a=True, out_dtype=torch.float32)
-            dw_kv = k.gemm(dkvp, kv2, trans_a=True, out_dtype=torch.float32)     # [2*HD, D]
-        rt.defer(side[1], dqp, qn, dkvp, kv2)
+            dw_k = k.gemm(dkvp[:, :HD], kv2, trans_a=True, out_dtype=torch.float32)
+            dw_v = k.gemm(dkvp[:, HD:], kv2, trans_a=True, out_dtype=torch.float32)
+        rt.defer(side[1], (dqp, qn, dkvp, kv2), [(w_q, dw_q), (w_k, dw_k), (w_v, dw_v)])
         dqn = k.gemm(dqp, rt.operand(w_q))
         dln = torch.zeros((2, D), dtype=torch.float32, device=q2.device)
         dq = k.layernorm_bwd(dqn, q2, ln_w, mean, rstd, dln[0], dln[1], add=dout2)   # + skip-connection gradient
@@ -230,7 +233,7 @@ class _MHABlock(Function):
             dkv = None
         else:
             dkv = k.gemm(dkvp, wkv).view(ctx.kv_shape)
-        return (dq.view(B, Lq, D), dkv, None, dln[0], dln[1], None, dw_q, dw_kv[:HD], dw_kv[HD:], dw_fc, None, None,
+        return (dq.view(B, Lq, D), dkv, None, dln[0], dln[1], None, dw_q, dw_k, dw_v, dw_fc, None, None,
                 None)
 
 
@@ -271,16 +274,16 @@ class _FFNBlock(Function):
         dout2 = _c(dout).reshape(-1, D)
         d2 = k.dropout(dout2, ctx.drop[0], rng, ctx.drop[1]) if ctx.drop[0] > 0 else dout2   # gradient of w_2's output
         dz = k.gemm(d2, rt.operand(w2), relu_gate=h)                              # ReLU backward in the epilogue
-        side = rt.side_streams(x2.device, 2, pool='dw')     # weight gradients: off the dX chain, joined at the end of backward
-        with rt.fork(side[0]):
+        side = rt.side_streams(x2.device, 2, pool='dw') if rt.can_defer(w1, w2) else [None, None]
+        with rt.fork(side[0]):              # weight gradients: off the dX chain, joined at the end of backward
             dw2 = k.gemm(d2, h, trans_a=True, out_dtype=torch.float32)
-            db2 = k.colsum(d2)
-        rt.defer(side[0], d2, h)
+        rt.defer(side[0], (d2, h), [(w2, dw2)])
+        db2 = k.colsum(d2)
         dy = k.gemm(dz, rt.operand(w1))
         with rt.fork(side[1]):
             dw1 = k.gemm(dz, y, trans_a=True, out_dtype=torch.float32)
-            db1 = k.colsum(dz)
-        rt.defer(side[1], dz, y)
+        rt.defer(side[1], (dz, y), [(w1, dw1)])
+        db1 = k.colsum(dz)
         dln = torch.zeros((2, D), dtype=torch.float32, device=x2.device)
         dx = k.layernorm_bwd(dy, x2, ln_w, mean, rstd, dln[0], dln[1], add=dout2)
         return dx.view(dout.shape), dln[0], dln[1], None, dw1, db1, dw2, db2, None, None
@@ -498,23 +501,29 @@ class _BLSTMLayer(Function):
         dw_hh_f, dw_hh_r = torch.empty_like(w_hh_f), torch.empty_like(w_hh_r)
         db_f = torch.empty(4 * H, dtype=f32, device=dev)
         db_r = torch.empty(4 * H, dtype=f32, device=dev)
-        side = rt.side_streams(dev, 2, pool='dw')
+        # bias gradients: b_ih and b_hh get the same values but need two tensors (autograd adopts a returned gradient
+        # only if nothing else references it)
+        db_f2 = torch.empty(4 * H, dtype=f32, device=dev)
+        db_r2 = torch.empty(4 * H, dtype=f32, device=dev)
+        side = rt.side_streams(dev, 2, pool='dw') if rt.can_defer(w_ih_f, w_hh_f, w_ih_r, w_hh_r) else [None, None]
         with rt.fork(side[0]):          # recurrent-weight gradients are split-K GEMMs over T*B rows: they leave SMs idle
             k.gemm(dgf, hs[0, :T].reshape(T * B, H), trans_a=True, out=dw_hh_f)
             k.gemm(dgr, hs[1, 1:].reshape(T * B, H), trans_a=True, out=dw_hh_r)
-            k.colsum(dgf, out=db_f)
-            k.colsum(dgr, out=db_r)
         with rt.fork(side[1]):
             k.gemm(dgf, x2, trans_a=True, out=dw_ih_f)
             k.gemm(dgr, x2, trans_a=True, out=dw_ih_r)
         # no join here: the weight gradients keep running under the NEXT layer's recurrence (rt.defer)
-        rt.defer(side[0], dg, hs)
-        rt.defer(side[1], dg, x2)
+        rt.defer(side[0], (dg, hs), [(w_hh_f, dw_hh_f), (w_hh_r, dw_hh_r)])
+        rt.defer(side[1], (dg, x2), [(w_ih_f, dw_ih_f), (w_ih_r, dw_ih_r)])
+        k.colsum(dgf, out=db_f)
+        k.colsum(dgr, out=db_r)
+        k.colsum(dgf, out=db_f2)
+        k.colsum(dgr, out=db_r2)
         dx = None
         if ctx.needs_input_grad[0]:
             # both directions' contributions in ONE launch (two-segment K loop into the same accumulator)
             dx = k.gemm2(dgf, rt.operand(w_ih_f), dgr, rt.operand(w_ih_r)).view(T, B, I)
-        return dx, None, dw_ih_f, dw_hh_f, db_f, db_f, dw_ih_r, dw_hh_r, db_r, db_r, None, None
+        return dx, None, dw_ih_f, dw_hh_f, db_f, db_f2, dw_ih_r, dw_hh_r, db_r, db_r2, None, None
 
 
 def blstm_layer(x_tm, lens, weights_f, weights_r, pair, batch_first_out=False):
