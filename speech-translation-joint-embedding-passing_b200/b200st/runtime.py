@@ -248,3 +248,67 @@ def join_deferred():
         raise RuntimeError(f'b200st: autograd copied {len(bad)} weight-gradient tensor(s) instead of adopting them while '
                            f'their GEMMs were still running on a side stream (shapes {bad[:4]}...); the copies are '
                            f'undefined.  This is a bug in the deferred-join bookkeeping, not in the caller.')
+
+
+
+# ------------------------------------------------------------------------------------------------
+# dropout randomness: counter-based (csrc/philox.cuh).  A mask is a pure function of
+# (seed, step, site, element index); seed and step live in a 2 x int64 DEVICE array so that a captured
+# CUDA graph draws fresh masks on every replay (`begin_step` is a captured launch that adds 1 to step).
+# `site` numbers the dropout calls inside one forward pass (host counter, deterministic call order);
+# backward passes the site it saved, so no mask tensor is ever stored.
+# ------------------------------------------------------------------------------------------------
+_rng = {}
+_site = [0]
+site_log = None            # TEST HOOK: set to a dict to record {tag: (site, p)} of every dropout call
+
+
+def rng_state(device) -> torch.Tensor:
+    key = (device.type, device.index)
+    st = _rng.get(key)
+    if st is None:
+        st = torch.tensor([torch.initial_seed() & 0x7fffffffffffffff, 0], dtype=torch.int64).to(device)
+        _rng[key] = st
+    return st
+
+
+def manual_seed(seed: int):
+    """Re-seed the dropout generator (all devices) and restart its step counter."""
+    for st in _rng.values():
+        st.copy_(torch.tensor([int(seed) & 0x7fffffffffffffff, 0], dtype=torch.int64))
+    _rng_step.clear()
+    new_step()
+
+
+_pending = [True]
+
+
+def new_step():
+    """Marks the start of a forward pass (Seq2seq.forward_train / LAS.forward in training mode): site numbering
+    restarts and the first dropout call of the pass advances the device step counter (fresh masks).  Costs nothing
+    when no dropout is active."""
+    _site[0] = 0
+    _pending[0] = True
+
+
+def next_site(tag: str = '', p: float = 0.0) -> int:
+    _site[0] += 1
+    if site_log is not None:
+        site_log[tag] = (_site[0], p)
+    return _site[0]
+
+
+_rng_step = {}
+
+
+def current_rng(device) -> torch.Tensor:
+    """The [seed, step] pair of THIS forward pass (a snapshot taken at its first dropout call): the forward launch and
+    the backward launch of a dropout site both read it, whatever happens to the live counter in between."""
+    key = (device.type, device.index)
+    if _pending[0] or key not in _rng_step:
+        from .kernels import K
+        st = rng_state(device)
+        K().rng_advance(st)
+        _rng_step[key] = st.clone()
+        _pending[0] = False
+    return _rng_step[key]
