@@ -86,6 +86,15 @@ int b200st_layernorm_bwd(int dtype, const void* dy, const void* x, const float* 
 int b200st_layernorm_bwd_add(int dtype, const void* dy, const void* x, const float* gamma,
                              const float* mean, const float* rstd, const void* add, void* dx,
                              float* dgamma, float* dbeta, int64_t rows, int64_t cols, b200st_stream_t stream);
+/* Same row work, but the dgamma / dbeta contributions of each CTA are STORED as one row of
+ * partials[b200st_layernorm_bwd_partial_blocks(rows, cols)][2 * cols] (fp32: cols sums for dgamma, then cols for dbeta)
+ * instead of being reduced with same-address atomics; the caller column-sums the partials (b200st_colsum) -- off the
+ * critical path, dgamma / dbeta being parameter gradients.  _blocks() returns 0 when the shape is not supported
+ * (needs cols % 128 == 0, cols <= 1024). */
+int64_t b200st_layernorm_bwd_partial_blocks(int64_t rows, int64_t cols);
+int b200st_layernorm_bwd_partial(int dtype, const void* dy, const void* x, const float* gamma,
+                                 const float* mean, const float* rstd, const void* add, void* dx, float* partials,
+                                 int64_t rows, int64_t cols, b200st_stream_t stream);
 
 /* ---- multi-head scaled-dot-product attention core (layers.py:162-170,213-229) -------------------
  * q,k,v are the projection outputs viewed as [B, L, H, d] with row strides ldq/ldk/ldv (elements);

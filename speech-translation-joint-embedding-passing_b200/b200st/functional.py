@@ -105,20 +105,37 @@ class _Add(Function):
 # ------------------------------------------------------------------------------------------------
 # LayerNorm: layers.py:139,153,240,245; TFEnc.py:61,89; TFDec.py:58,127
 # ------------------------------------------------------------------------------------------------
+def _ln_backward(k, dy, x, ln_w, ln_b, mean, rstd, add=None):
+    """LayerNorm backward -> (dx, dgamma, dbeta).  Inside a graph capture the per-CTA dgamma / dbeta partial sums are
+    stored instead of reduced with same-address atomics, and their column sums run on a side stream whose join is
+    deferred to the end of backward (they are parameter gradients: nothing in backward reads them)."""
+    D = x.size(-1)
+    side = rt.side_streams(x.device, 1, pool='dw') if rt.can_defer(ln_w, ln_b) else [None]
+    if side[0] is not None:
+        dx, part = k.layernorm_bwd_partial(dy, x, ln_w, mean, rstd, add=add)
+        if part is not None:
+            with rt.fork(side[0]):
+                dgamma = k.colsum(part[:, :D])
+                dbeta = k.colsum(part[:, D:])
+            rt.defer(side[0], (part,), [(ln_w, dgamma), (ln_b, dbeta)])
+            return dx, dgamma, dbeta
+    dln = torch.zeros((2, D), dtype=torch.float32, device=x.device)
+    dx = k.layernorm_bwd(dy, x, ln_w, mean, rstd, dln[0], dln[1], add=add)
+    return dx, dln[0], dln[1]
+
+
 class _LayerNorm(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, eps):
         xc = _c(x)
         y, mean, rstd = K().layernorm_fwd(xc, weight, bias, eps)
-        ctx.save_for_backward(xc, weight, mean, rstd)
+        ctx.save_for_backward(xc, weight, bias, mean, rstd)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, mean, rstd = ctx.saved_tensors
-        dgamma = torch.zeros_like(weight)
-        dbeta = torch.zeros_like(weight)
-        dx = K().layernorm_bwd(_c(dy), x, weight, mean, rstd, dgamma, dbeta)
+        x, weight, bias, mean, rstd = ctx.saved_tensors
+        dx, dgamma, dbeta = _ln_backward(K(), _c(dy), x, weight, bias, mean, rstd)
         return dx, dgamma, dbeta, None
 
 
@@ -192,14 +209,14 @@ class _MHABlock(Function):
         ctx.self_attn, ctx.n_head, ctx.temperature, ctx.dims = self_attn, n_head, temperature, (B, Lq, Lk, D, HD)
         ctx.kv_shape, ctx.drop = kv.shape, drop
         ctx.save_for_backward(q2, None if self_attn else kv2, qn, mean, rstd, qp, kvp, p, o2, ln_w, w_q, w_k, w_v, w_fc,
-                              rng)
+                              rng, ln_b)
         ctx.mark_non_differentiable(p)
         return out.view(B, Lq, D), p
 
     @staticmethod
     def backward(ctx, dout, _dp):
         k = K()
-        q2, kv2, qn, mean, rstd, qp, kvp, p, o2, ln_w, w_q, w_k, w_v, w_fc, rng = ctx.saved_tensors
+        q2, kv2, qn, mean, rstd, qp, kvp, p, o2, ln_w, w_q, w_k, w_v, w_fc, rng, ln_b = ctx.saved_tensors
         B, Lq, Lk, D, HD = ctx.dims
         p_attn, s_attn, p_fc, s_fc = ctx.drop
         if kv2 is None:
@@ -225,15 +242,14 @@ class _MHABlock(Function):
             dw_v = k.gemm(dkvp[:, HD:], kv2, trans_a=True, out_dtype=torch.float32)
         rt.defer(side[1], (dqp, qn, dkvp, kv2), [(w_q, dw_q), (w_k, dw_k), (w_v, dw_v)])
         dqn = k.gemm(dqp, rt.operand(w_q))
-        dln = torch.zeros((2, D), dtype=torch.float32, device=q2.device)
-        dq = k.layernorm_bwd(dqn, q2, ln_w, mean, rstd, dln[0], dln[1], add=dout2)   # + skip-connection gradient
+        dq, dgamma, dbeta = _ln_backward(k, dqn, q2, ln_w, ln_b, mean, rstd, add=dout2)   # + skip-connection gradient
         wkv = rt.operand_cat(w_k, w_v)
         if ctx.self_attn:
             dq = k.gemm(dkvp, wkv, residual=dq)
             dkv = None
         else:
             dkv = k.gemm(dkvp, wkv).view(ctx.kv_shape)
-        return (dq.view(B, Lq, D), dkv, None, dln[0], dln[1], None, dw_q, dw_k, dw_v, dw_fc, None, None,
+        return (dq.view(B, Lq, D), dkv, None, dgamma, dbeta, None, dw_q, dw_k, dw_v, dw_fc, None, None,
                 None)
 
 
@@ -263,30 +279,29 @@ class _FFNBlock(Function):
         else:
             out = k.gemm(h, rt.operand(w2), trans_b=True, bias=b2, residual=x2)
         ctx.drop = (p, site)
-        ctx.save_for_backward(x2, y, mean, rstd, h, ln_w, w1, w2, rng)
+        ctx.save_for_backward(x2, y, mean, rstd, h, ln_w, w1, w2, rng, ln_b, b1, b2)
         return out.view(x.shape)
 
     @staticmethod
     def backward(ctx, dout):
         k = K()
-        x2, y, mean, rstd, h, ln_w, w1, w2, rng = ctx.saved_tensors
+        x2, y, mean, rstd, h, ln_w, w1, w2, rng, ln_b, b1, b2 = ctx.saved_tensors
         D = x2.size(1)
         dout2 = _c(dout).reshape(-1, D)
         d2 = k.dropout(dout2, ctx.drop[0], rng, ctx.drop[1]) if ctx.drop[0] > 0 else dout2   # gradient of w_2's output
         dz = k.gemm(d2, rt.operand(w2), relu_gate=h)                              # ReLU backward in the epilogue
-        side = rt.side_streams(x2.device, 2, pool='dw') if rt.can_defer(w1, w2) else [None, None]
-        with rt.fork(side[0]):              # weight gradients: off the dX chain, joined at the end of backward
+        side = rt.side_streams(x2.device, 2, pool='dw') if rt.can_defer(w1, w2, b1, b2) else [None, None]
+        with rt.fork(side[0]):              # weight / bias gradients: off the dX chain, joined at the end of backward
             dw2 = k.gemm(d2, h, trans_a=True, out_dtype=torch.float32)
-        rt.defer(side[0], (d2, h), [(w2, dw2)])
-        db2 = k.colsum(d2)
+            db2 = k.colsum(d2)
+        rt.defer(side[0], (d2, h), [(w2, dw2), (b2, db2)])
         dy = k.gemm(dz, rt.operand(w1))
         with rt.fork(side[1]):
             dw1 = k.gemm(dz, y, trans_a=True, out_dtype=torch.float32)
-        rt.defer(side[1], (dz, y), [(w1, dw1)])
-        db1 = k.colsum(dz)
-        dln = torch.zeros((2, D), dtype=torch.float32, device=x2.device)
-        dx = k.layernorm_bwd(dy, x2, ln_w, mean, rstd, dln[0], dln[1], add=dout2)
-        return dx.view(dout.shape), dln[0], dln[1], None, dw1, db1, dw2, db2, None, None
+            db1 = k.colsum(dz)
+        rt.defer(side[1], (dz, y), [(w1, dw1), (b1, db1)])
+        dx, dgamma, dbeta = _ln_backward(k, dy, x2, ln_w, ln_b, mean, rstd, add=dout2)
+        return dx.view(dout.shape), dgamma, dbeta, None, dw1, db1, dw2, db2, None, None
 
 
 def ffn_block(x, ln_w, ln_b, eps, w1, b1, w2, b2, p=0.0, tag=''):

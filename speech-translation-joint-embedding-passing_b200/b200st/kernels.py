@@ -167,6 +167,21 @@ class CudaKernels:
                                                      self._stream()), 'layernorm_bwd')
         return dx
 
+    def layernorm_bwd_partial(self, dy, x, gamma, mean, rstd, add=None):
+        """(dx, partials) with partials fp32 [n_blocks, 2 * cols]: per-CTA dgamma | dbeta contributions, to be column-summed
+        by the caller (off the critical path); None for partials' shape support -> (None, None)."""
+        assert dy.is_contiguous() and x.is_contiguous() and (add is None or (add.is_contiguous() and add.dtype == x.dtype))
+        rows, cols = x.numel() // x.size(-1), x.size(-1)
+        nb = int(self.lib.b200st_layernorm_bwd_partial_blocks(rows, cols))
+        if nb == 0:
+            return None, None
+        dx = torch.empty_like(x)
+        partials = torch.empty((nb, 2 * cols), dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.b200st_layernorm_bwd_partial(_dt(x), _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(add),
+                                                         _p(dx), _p(partials), rows, cols, self._stream()),
+                   'layernorm_bwd_partial')
+        return dx, partials
+
     # -- multi-head attention core ----------------------------------------------------------------
     @staticmethod
     def _bld(t):

@@ -89,7 +89,7 @@ layernorm_bwd_reg_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
                          const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ add,
                          T* __restrict__ dx,
                          float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int cols,
-                         int rows_per_block) {
+                         int rows_per_block, float* __restrict__ partials) {
   pdl_wait();
   pdl_launch_dependents();
   extern __shared__ float sm[];   // [2][cols]
@@ -155,6 +155,14 @@ layernorm_bwd_reg_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
     }
   }
   __syncthreads();
+  if (partials != nullptr) {
+    // per-CTA partial sums [n_blocks][2 * cols], reduced by a separate (off-critical-path) column-sum launch: this
+    // kernel then ends with one coalesced store instead of a 200-deep chain of same-address L2 atomics
+    float* out = partials + (int64_t)blockIdx.x * 2 * cols;
+    for (int c = threadIdx.x * 4; c < 2 * cols; c += blockDim.x * 4)
+      *reinterpret_cast<float4*>(out + c) = *reinterpret_cast<const float4*>(sm + c);
+    return;
+  }
   // one 16-byte vector reduction per column quad: the per-address chain of same-location L2 atomics (one per CTA)
   // is what bounds this kernel once the row work is spread over many CTAs
   for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
@@ -412,30 +420,32 @@ int b200st_layernorm_fwd(int dtype, const void* x, const float* gamma, const flo
   return 0;
 }
 
-int b200st_layernorm_bwd_add(int dtype, const void* dy, const void* x, const float* gamma,
-                             const float* mean, const float* rstd, const void* add, void* dx, float* dgamma,
-                             float* dbeta, int64_t rows, int64_t cols, b200st_stream_t stream) {
+static int layernorm_bwd_impl(int dtype, const void* dy, const void* x, const float* gamma,
+                              const float* mean, const float* rstd, const void* add, void* dx, float* dgamma,
+                              float* dbeta, int64_t rows, int64_t cols, float* partials, b200st_stream_t stream) {
   if (rows <= 0) return 0;
   const size_t smem = 2 * cols * sizeof(float);
   if (smem > 48 * 1024) return set_error("layernorm_bwd: cols %lld too large", (long long)cols);
   // ~2 CTAs per SM worth of row strips keeps the final atomics few while filling the chip.
   if (cols % 128 == 0 && cols <= 1024 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dx & 15) == 0 &&
-      ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)add & 15) == 0 && ((uintptr_t)dgamma & 15) == 0 && ((uintptr_t)dbeta & 15) == 0) {
+      ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)add & 15) == 0 && ((uintptr_t)dgamma & 15) == 0 && ((uintptr_t)dbeta & 15) == 0 &&
+      ((uintptr_t)partials & 15) == 0) {
     const int rpb = 16;             // 8 warps x 2 rows (measured best: fewer rows per CTA lengthen the dgamma/dbeta atomic chains, more serialise the row loads)
     B200ST_DISPATCH(dtype, T, {
       if (cols <= 512) {
         B200ST_CUDA(launch_pdl(layernorm_bwd_reg_kernel<T, 4>, dim3((unsigned)ceil_div(rows, rpb)), dim3(256), smem,
                                (cudaStream_t)stream, (const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)add, (T*)dx, dgamma, dbeta,
-                               rows, (int)cols, rpb));
+                               rows, (int)cols, rpb, partials));
       } else {
         B200ST_CUDA(launch_pdl(layernorm_bwd_reg_kernel<T, 8>, dim3((unsigned)ceil_div(rows, rpb)), dim3(256), smem,
                                (cudaStream_t)stream, (const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)add, (T*)dx, dgamma, dbeta,
-                               rows, (int)cols, rpb));
+                               rows, (int)cols, rpb, partials));
       }
     });
     B200ST_LAUNCH_CHECK("layernorm_bwd_reg");
     return 0;
   }
+  if (partials != nullptr) return set_error("layernorm_bwd_partial: needs cols %% 128 == 0, cols <= 1024 and 16-byte aligned operands");
   int rpb = (int)ceil_div(rows, 296);
   if (rpb < 4) rpb = 4;
   B200ST_DISPATCH(dtype, T, {
@@ -445,6 +455,23 @@ int b200st_layernorm_bwd_add(int dtype, const void* dy, const void* x, const flo
   });
   B200ST_LAUNCH_CHECK("layernorm_bwd");
   return 0;
+}
+
+int b200st_layernorm_bwd_add(int dtype, const void* dy, const void* x, const float* gamma,
+                             const float* mean, const float* rstd, const void* add, void* dx, float* dgamma,
+                             float* dbeta, int64_t rows, int64_t cols, b200st_stream_t stream) {
+  return layernorm_bwd_impl(dtype, dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, rows, cols, nullptr, stream);
+}
+
+int64_t b200st_layernorm_bwd_partial_blocks(int64_t rows, int64_t cols) {
+  return (cols % 128 == 0 && cols <= 1024) ? ceil_div(rows, 16) : 0;
+}
+
+int b200st_layernorm_bwd_partial(int dtype, const void* dy, const void* x, const float* gamma,
+                                 const float* mean, const float* rstd, const void* add, void* dx, float* partials,
+                                 int64_t rows, int64_t cols, b200st_stream_t stream) {
+  if (partials == nullptr) return set_error("layernorm_bwd_partial: partials buffer required");
+  return layernorm_bwd_impl(dtype, dy, x, gamma, mean, rstd, add, dx, partials, partials, rows, cols, partials, stream);
 }
 
 int b200st_layernorm_bwd(int dtype, const void* dy, const void* x, const float* gamma,

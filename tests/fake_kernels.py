@@ -163,6 +163,12 @@ class FakeKernels:
             dx = dx + add.float().reshape(-1, cols)
         return dx.to(x.dtype).view(x.shape)
 
+    def layernorm_bwd_partial(self, dy, x, gamma, mean, rstd, add=None):
+        cols = x.size(-1)
+        part = torch.zeros((1, 2 * cols), dtype=torch.float32, device=x.device)
+        dx = self.layernorm_bwd(dy, x, gamma, mean, rstd, part[0, :cols], part[0, cols:], add=add)
+        return dx, part
+
     # -- attention --------------------------------------------------------------------------------
     @staticmethod
     def _attn_drop(p_shape, dropout, device):

@@ -517,3 +517,20 @@ def test_mha_decode_cached_attention(ks, dtype, n_hyp, bdiv, H, d, Lk, Lmax):
         got = c.mha_decode(q, kv[:, :, :HD], kv[:, :, HD:], Lk, H, d ** 0.5, bdiv=bdiv, mask=smask, mask_bdiv=bdiv)
         ref = f.mha_decode(q, kv[:, :, :HD], kv[:, :, HD:], Lk, H, d ** 0.5, bdiv=bdiv, mask=smask, mask_bdiv=bdiv)
         assert rel_err(got, ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('rows,cols', [(3200, 512), (37, 128), (1984, 1024)])
+def test_layernorm_bwd_partial_sums(ks, dtype, rows, cols):
+    """LayerNorm backward with per-CTA dgamma / dbeta partial sums (column-summed by the caller) == the atomics version."""
+    c, f = ks
+    x, dy, add = rnd(rows, cols, dtype=dtype), rnd(rows, cols, dtype=dtype, seed=1), rnd(rows, cols, dtype=dtype, seed=2)
+    gamma = rnd(cols, seed=3)
+    _, mean, rstd = c.layernorm_fwd(x, gamma, rnd(cols, seed=4), 1e-6)
+    dx, part = c.layernorm_bwd_partial(dy, x, gamma, mean, rstd, add=add)
+    dg, db = torch.zeros(cols, device='cuda'), torch.zeros(cols, device='cuda')
+    dx_ref = f.layernorm_bwd(dy, x, gamma, mean, rstd, dg, db, add=add)
+    assert part.shape == ((rows + 15) // 16, 2 * cols)
+    assert rel_err(dx, dx_ref) < TOL[dtype]
+    assert rel_err(c.colsum(part[:, :cols]), dg) < 1e-4 and rel_err(c.colsum(part[:, cols:]), db) < 1e-4
+    assert c.layernorm_bwd_partial(dy[:, :100].contiguous(), x[:, :100].contiguous(), gamma[:100], mean, rstd) == (None, None)
