@@ -194,10 +194,13 @@ class _MHABlock(Function):
         self_attn = kv is q
         q2 = _c(q).reshape(-1, D)
         kv2 = q2 if self_attn else _c(kv).reshape(-1, D)
-        qn, mean, rstd = k.layernorm_fwd(q2, ln_w, ln_b, eps)
         HD = w_q.size(0)
+        side = rt.side_streams(q.device, 1, pool='fwd')
+        with rt.fork(side[0]):          # K | V come from the RAW input: independent of the LayerNorm -> Q chain
+            kvp = k.gemm(kv2, rt.operand_cat(w_k, w_v), trans_b=True)             # [B*Lk, 2*HD] = K | V
+        qn, mean, rstd = k.layernorm_fwd(q2, ln_w, ln_b, eps)
         qp = k.gemm(qn, rt.operand(w_q), trans_b=True)
-        kvp = k.gemm(kv2, rt.operand_cat(w_k, w_v), trans_b=True)                 # [B*Lk, 2*HD] = K | V
+        rt.join(side[0])
         kv3 = kvp.view(B, Lk, 2 * HD)
         o, p = k.mha_fwd(qp.view(B, Lq, HD), kv3[:, :, :HD], kv3[:, :, HD:], mask, n_head, temperature,
                          dropout=(p_attn, rng, s_attn))
@@ -788,39 +791,49 @@ class _LASDecoder(Function):
             rt.join(st)
 
         SB = S * B
-        grads_lstm = []
-        for i in range(n_layers):
-            dg2 = DG[i].view(SB, 4 * D)
-            if i == 0:
-                dw_ih = torch.empty_like(lp[0][0])
-                k.gemm(dg2, EMB.view(SB, E), trans_a=True, out=dw_ih[:, :E])
-                k.gemm(dg2, CV[:S].reshape(SB, D), trans_a=True, out=dw_ih[:, E:])
-            else:
-                below = XD[i - 1] if XD is not None else (RES[i - 1] if RES[i - 1] is not None else Hst[i - 1][1:])
-                dw_ih = k.gemm(dg2, below.reshape(SB, D), trans_a=True, out_dtype=f32)
-            dw_hh = k.gemm(dg2, Hst[i][:S].reshape(SB, D), trans_a=True, out_dtype=f32)
-            db = k.colsum(dg2)
-            grads_lstm += [dw_ih, dw_hh, db, db]
         dec_out_stack = RES[n_layers - 1] if RES[n_layers - 1] is not None else Hst[n_layers - 1][1:]
         if XD is not None:
             dec_out_stack = XD[n_layers - 1]
-        dcv2 = DCV.view(SB, D)
-        dw_ffn = torch.empty_like(w_ffn)
-        k.gemm(dcv2, (CTXD if CTXD is not None else CTX).view(SB, H2), trans_a=True, out=dw_ffn[:, :H2])
-        k.gemm(dcv2, dec_out_stack.reshape(SB, D), trans_a=True, out=dw_ffn[:, H2:])
-        if p_emb > 0:
-            d_e = DEMB[0] if fused_feed else DEMB.view(SB, E)
-            k.dropout(d_e, p_emb, rng, site_emb, out=d_e)
-        d_table = torch.zeros_like(emb_table)
-        k.embedding_bwd(ids_in.reshape(-1), DEMB.view(SB, E), d_table, PAD)      # Dec.py:80-81 padding_idx
-        # keys / values: d wk[b] = dscore[:, b]^T dec_out[:, b];  d vals[b] = probs[:, b]^T dctx[:, b]
+        # keys / values first -- d_enc is what the BLSTM backward is waiting for:
+        # d wk[b] = dscore[:, b]^T dec_out[:, b];  d vals[b] = probs[:, b]^T dctx[:, b]
         dsc = k.cast(DSC, dt).permute(1, 0, 2)                                   # [B][S,Tk]
         prb = k.cast(PROBS, dt).permute(1, 0, 2)
         d_wk = k.gemm(dsc, dec_out_stack.permute(1, 0, 2), trans_a=True)         # [B,Tk,D]
         d_enc = k.gemm(prb, DCTX.permute(1, 0, 2), trans_a=True)                 # [B,Tk,2H]
         k.gemm(d_wk.view(B * Tk, D), rt.operand(w_att), residual=d_enc.view(B * Tk, H2),
                out=d_enc.view(B * Tk, H2))
-        dw_att = k.gemm(d_wk.view(B * Tk, D), enc.view(B * Tk, H2), trans_a=True, out_dtype=f32)
+        # every weight gradient of the loop is ONE GEMM over S*B rows; none of them is read again in backward: side
+        # stream, joined at the end of backward (rt.defer).  Each returned gradient is its own whole tensor.
+        flat_params = [q for layer in lp for q in layer]
+        side = rt.side_streams(dev, 1, pool='dw') if rt.can_defer(emb_table, w_att, w_ffn, *flat_params) else [None]
+        expect = []
+        with rt.fork(side[0]):
+            grads_lstm = []
+            for i in range(n_layers):
+                dg2 = DG[i].view(SB, 4 * D)
+                if i == 0:
+                    dw_ih = torch.empty_like(lp[0][0])
+                    k.gemm(dg2, EMB.view(SB, E), trans_a=True, out=dw_ih[:, :E])
+                    k.gemm(dg2, CV[:S].reshape(SB, D), trans_a=True, out=dw_ih[:, E:])
+                else:
+                    below = XD[i - 1] if XD is not None else (RES[i - 1] if RES[i - 1] is not None else Hst[i - 1][1:])
+                    dw_ih = k.gemm(dg2, below.reshape(SB, D), trans_a=True, out_dtype=f32)
+                dw_hh = k.gemm(dg2, Hst[i][:S].reshape(SB, D), trans_a=True, out_dtype=f32)
+                db_i, db_h = k.colsum(dg2), k.colsum(dg2)
+                grads_lstm += [dw_ih, dw_hh, db_i, db_h]
+                expect += list(zip(lp[i], (dw_ih, dw_hh, db_i, db_h)))
+            dcv2 = DCV.view(SB, D)
+            dw_ffn = torch.empty_like(w_ffn)
+            k.gemm(dcv2, (CTXD if CTXD is not None else CTX).view(SB, H2), trans_a=True, out=dw_ffn[:, :H2])
+            k.gemm(dcv2, dec_out_stack.reshape(SB, D), trans_a=True, out=dw_ffn[:, H2:])
+            if p_emb > 0:
+                d_e = DEMB[0] if fused_feed else DEMB.view(SB, E)
+                k.dropout(d_e, p_emb, rng, site_emb, out=d_e)
+            d_table = torch.zeros_like(emb_table)
+            k.embedding_bwd(ids_in.reshape(-1), DEMB.view(SB, E), d_table, PAD)  # Dec.py:80-81 padding_idx
+            dw_att = k.gemm(d_wk.view(B * Tk, D), enc.view(B * Tk, H2), trans_a=True, out_dtype=f32)
+            expect += [(w_ffn, dw_ffn), (emb_table, d_table), (w_att, dw_att)]
+        rt.defer(side[0], (DG, EMB, CV, Hst, RES, XD, DCV, CTX, CTXD, DEMB, ids_in, d_wk, enc, dec_out_stack), expect)
         return (d_enc, None, None, None, None, None, d_table, dw_att, dw_ffn, dw_out, db_out, *grads_lstm)
 
 

@@ -223,7 +223,7 @@ def defer(stream, tensors=(), grads=()):
         return
     if stream not in _deferred:
         _deferred.append(stream)
-    _keepalive.extend(t for t in tensors if t is not None)
+    _keepalive.extend(t for t in tensors if t is not None)      # (lists of tensors are kept as they are)
     for prm, g in grads:
         if prm is not None and g is not None:
             _expect.append((weakref.ref(prm), g.data_ptr()))
