@@ -429,7 +429,6 @@ def run_b200(args):
         ms_dev = ms_eager
         ms_e2e = timed(lambda: eager_step(batch_items), args.steps)
     launches = launches_per_step * args.steps
-    live = False
     # nvidia-smi takes a moment to start and reports every 100 ms while K steps last ~70 ms: keep replaying the same step
     # (untimed) until the sampler has seen the GPU under this load for a few periods
     # (same count on every rank -- ms_dev is the all-reduced maximum -- because the step contains collectives)
