@@ -275,6 +275,16 @@ int b200st_dropout(int dtype, const void* x, int64_t ldx, const void* residual, 
                    int64_t site, b200st_stream_t stream);
 int b200st_rng_advance(int64_t* rng, b200st_stream_t stream);
 
+/* ---- input stage: Dataset.load_acous_from_flis (utils/dataset.py:155-184) on the device -----------------------------
+ * packed: fp32 [sum(lens), F], the batch's utterances back to back (no padding crosses PCIe); offsets int64 [B] = first
+ * frame of utterance i in `packed`; lens int32 [B]; mu, sd: fp32 [B, F] per-UTTERANCE rows of the speaker statistics
+ * (dataset.py:134-153) or both NULL (acous_norm off).  out fp32 [B, T_pad, F]:
+ *   out[i, t, :] = (packed[offsets[i] + t, :] - mu[i]) / sd[i]   for t < lens[i]     (IEEE division, dataset.py:173)
+ *   out[i, t, :] = 0                                             otherwise            (pad_sequence, dataset.py:178-182)
+ * with T_pad = max(lens) + 8 - max(lens) % 8 chosen by the caller (dataset.py:179). */
+int b200st_fbank_norm_pad(const float* packed, const int64_t* offsets, const int32_t* lens, const float* mu,
+                          const float* sd, float* out, int64_t B, int64_t T_pad, int64_t F, b200st_stream_t stream);
+
 /* ---- fused gradient-norm clip + Adam over all parameter tensors -----------------------
  * Replaces torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step() behind Optimizer.step()
  * (modules/optim.py:31-36; constructed at trainer/trainer_base.py:422-426).  `table` is a device array

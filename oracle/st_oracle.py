@@ -619,3 +619,33 @@ def synthetic_batch(cfg: STConfig, batch: int, frames: int, seed: int = 333, rag
     src = tokens(cfg.max_seq_len_src, cfg.enc_vocab_size)
     tgt = tokens(tgt_len or cfg.max_seq_len_tgt, cfg.dec_vocab_size)
     return {'src': src, 'tgt': tgt, 'acous_feats': feats, 'acous_lens': lens}
+
+
+# --------------------------------------------------------------------------------------------
+# Input stage (utils/dataset.py:121-184), SURVEY.md 8 f-3
+# --------------------------------------------------------------------------------------------
+def load_acous_from_flis(flis, spkids=None, norm_path=None):
+    """Dataset.load_mu_std + Dataset.load_acous_from_flis: `.npy` fbank matrices, optional per-speaker (x - mu) / std
+    (statistics truncated to the feature width, dataset.py:168-171), zero padding to max_len + 8 - max_len % 8 frames
+    through the reference's own trick of padding against a dummy of that length (dataset.py:178-182)."""
+    import os
+    import numpy as np
+    feat_lis, max_len, cache = [], 0, {}
+    for i, f in enumerate(flis):
+        featarr = np.load(f)
+        acous_dim = featarr.shape[1]
+        if spkids is not None and norm_path is not None:
+            spk = spkids[i]
+            if spk not in cache:                                              # dataset.py:141-151
+                cache[spk] = [np.load(os.path.join(norm_path, spk + '.mu.npy')),
+                              np.load(os.path.join(norm_path, spk + '.std.npy'))]
+            mu, std = cache[spk]
+            if mu.shape[0] != acous_dim:                                      # dataset.py:168-171
+                mu, std = mu[:acous_dim], std[:acous_dim]
+            featarr = 1. * (featarr - mu) / std                               # dataset.py:173
+        feat = torch.FloatTensor(featarr)
+        max_len = max(max_len, feat.size(0))
+        feat_lis.append(feat)
+    divisible_eight = max_len + 8 - max_len % 8                               # dataset.py:179
+    feat_lis.append(torch.ones(divisible_eight, acous_dim))
+    return torch.nn.utils.rnn.pad_sequence(feat_lis, batch_first=True)[:-1]

@@ -583,6 +583,24 @@ class CudaKernels:
         assert rng.dtype == torch.int64 and rng.numel() == 2
         _lib.check(self.lib.b200st_rng_advance(_p(rng), self._stream()), 'rng_advance')
 
+    # -- input stage ------------------------------------------------------------------------------------
+    def fbank_norm_pad(self, packed, offsets, lens, mu, sd, T_pad, out=None):
+        """packed fp32 [N, F] (utterances back to back), offsets int64 [B], lens int32 [B], mu / sd fp32 [B, F] or None
+        -> normalised, zero-padded fp32 [B, T_pad, F] (utils/dataset.py:155-184)."""
+        self._need_cuda(packed, offsets, lens, mu, sd, out)
+        B, F = lens.numel(), packed.size(1)
+        assert packed.dtype == torch.float32 and packed.is_contiguous() and offsets.dtype == torch.int64
+        assert lens.dtype == torch.int32 and (mu is None) == (sd is None)
+        if mu is not None:
+            assert mu.shape == (B, F) and sd.shape == (B, F) and mu.is_contiguous() and sd.is_contiguous()
+            assert mu.dtype == torch.float32 and sd.dtype == torch.float32
+        if out is None:
+            out = torch.empty((B, T_pad, F), dtype=torch.float32, device=packed.device)
+        assert out.shape == (B, T_pad, F) and out.is_contiguous() and out.dtype == torch.float32
+        _lib.check(self.lib.b200st_fbank_norm_pad(_p(packed), _p(offsets), _p(lens), _p(mu), _p(sd), _p(out), B, T_pad, F,
+                                                  self._stream()), 'fbank_norm_pad')
+        return out
+
     # -- fused clip + Adam (modules/optim.py:31-36) -------------------------------------------------
     def opt_chunk(self) -> int:
         return int(self.lib.b200st_opt_chunk())

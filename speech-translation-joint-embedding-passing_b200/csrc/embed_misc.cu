@@ -413,3 +413,44 @@ int b200st_rng_advance(int64_t* rng, b200st_stream_t stream) {
 }
 
 }  // extern "C"
+
+// ---- input stage: batch assembly of Dataset.load_acous_from_flis (utils/dataset.py:155-184) on the device -----------
+// The host ships the utterances of a batch back to back (no padding over PCIe); this kernel applies the per-speaker
+// mean / std normalisation (dataset.py:169-173) and writes the zero-padded [B, T_pad, F] batch (dataset.py:178-182).
+namespace b200st {
+
+__global__ void __launch_bounds__(256)
+fbank_norm_pad_kernel(const float* __restrict__ packed, const int64_t* __restrict__ offsets,
+                      const int32_t* __restrict__ lens, const float* __restrict__ mu, const float* __restrict__ sd,
+                      float* __restrict__ out, int64_t T_pad, int F) {
+  const int b = blockIdx.y;
+  const int64_t n = T_pad * F;
+  const int len = lens[b];
+  const float* src = packed + offsets[b] * F;
+  float* dst = out + (int64_t)b * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / F;
+    const int c = (int)(i - t * F);
+    float v = 0.f;
+    if (t < len) {
+      v = src[i];
+      if (mu != nullptr) v = __fdiv_rn(v - mu[(int64_t)b * F + c], sd[(int64_t)b * F + c]);   // 1. * (x - mu) / std
+    }
+    dst[i] = v;
+  }
+}
+
+}  // namespace b200st
+
+extern "C" int b200st_fbank_norm_pad(const float* packed, const int64_t* offsets, const int32_t* lens, const float* mu,
+                                     const float* sd, float* out, int64_t B, int64_t T_pad, int64_t F,
+                                     b200st_stream_t stream) {
+  if (B <= 0 || T_pad <= 0 || F <= 0) return 0;
+  if ((mu == nullptr) != (sd == nullptr)) return set_error("fbank_norm_pad: mu and sd must both be given or both be NULL");
+  const int64_t n = T_pad * F;
+  const int64_t gx = ceil_div(n, 256 * 4);
+  dim3 grid((unsigned)(gx < 1024 ? gx : 1024), (unsigned)B);
+  fbank_norm_pad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(packed, offsets, lens, mu, sd, out, T_pad, (int)F);
+  B200ST_LAUNCH_CHECK("fbank_norm_pad");
+  return 0;
+}

@@ -109,6 +109,22 @@ class FakeKernels:
         self.launches += 1
         rng[1] += 1
 
+    # -- input stage --------------------------------------------------------------------------------
+    def fbank_norm_pad(self, packed, offsets, lens, mu, sd, T_pad, out=None):
+        self.launches += 1
+        B, F = lens.numel(), packed.size(1)
+        res = torch.zeros((B, T_pad, F), dtype=torch.float32, device=packed.device)
+        for i in range(B):
+            o, n = int(offsets[i]), int(lens[i])
+            x = packed[o:o + n]
+            if mu is not None:
+                x = (x - mu[i]) / sd[i]
+            res[i, :n] = x
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
     # -- fused clip + Adam ------------------------------------------------------------------------
     def opt_chunk(self):
         return 8192
