@@ -57,6 +57,7 @@ class GraphedTrainStep:
             rt.after_raw_update()
         else:
             rt.clear_cache()                  # weight copies get re-cast inside the captured region on every replay
+        rt.reset_deferred()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = trainer._train_batch_device(model, self.static)

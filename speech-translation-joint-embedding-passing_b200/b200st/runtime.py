@@ -233,6 +233,14 @@ def deferred_streams():
     return list(_deferred)
 
 
+def reset_deferred():
+    """Forget bookkeeping left behind by a backward pass that did not reach join_deferred() (an exception inside a
+    capture); called before a new capture starts."""
+    _deferred.clear()
+    _keepalive.clear()
+    _expect.clear()
+
+
 def join_deferred():
     for s in _deferred:
         join(s)
