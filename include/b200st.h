@@ -204,6 +204,13 @@ int b200st_argmax_rows_lengths(int dtype, const void* x, int64_t ld, int64_t row
 int b200st_argmax_rows_embed(int dtype, const void* x, int64_t ld, int64_t rows, int64_t cols, int64_t* idx,
                              int64_t idx_stride, int32_t* lengths, int step, const float* table, void* emb,
                              int64_t ld_emb, int64_t dim, b200st_stream_t stream);
+/* Same, plus a second gather in the activation dtype: out2[r * ld_out2 ..] = table2[idx[r]] ([cols, dim2], `dtype`).  The
+ * LAS decoder passes table2 = E W_ih0[:, :E]^T + b (made once per forward): the next step's first-layer gate
+ * contribution of the fed-back token (Dec.py:383,393-401) becomes a row gather instead of a GEMM on the step's chain. */
+int b200st_argmax_rows_embed2(int dtype, const void* x, int64_t ld, int64_t rows, int64_t cols, int64_t* idx,
+                              int64_t idx_stride, int32_t* lengths, int step, const float* table, void* emb,
+                              int64_t ld_emb, int64_t dim, const void* table2, void* out2, int64_t ld_out2,
+                              int64_t dim2, b200st_stream_t stream);
 /* Dec.decode lengths rule (Dec.py:334-340) kept on device: if sym in {EOS,PAD} and lengths[b] > step
  * then lengths[b] = step + 1. */
 int b200st_las_update_lengths(const int64_t* sym, int64_t sym_stride, int32_t* lengths, int step,

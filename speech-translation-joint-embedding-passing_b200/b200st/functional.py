@@ -632,11 +632,21 @@ class _LASDecoder(Function):
         CTXD = e(S, B, H2) if p_drop > 0 else None                               # dropped attention contexts
         site_l = [[0] * n_layers for _ in range(S)]
         site_att = [0] * S
+        # Free running: the fed-back token's first-layer gate contribution emb W_ih0[:, :E]^T + b is a row of the table
+        # TOK = E W_ih0[:, :E]^T + b ([V, 4D], one GEMM per forward, on a side branch): the arg-max kernel gathers that
+        # row for the next step, which takes one GEMM off every step's dependent chain.  (Gated on the vocabulary size:
+        # the table costs V / (S B) times the FLOPs of the per-step products it replaces.)
+        TOK = None
+        if fused_feed and S > 1 and V * 4 * D * 2 <= (256 << 20) and V % 8 == 0:
+            with rt.fork(side[0]):      # joined by the first `rt.join(side[0])` of step 1
+                TOK = k.gemm(rt.operand(emb_table), wih[0][:, :E], trans_b=True, bias=bias[0])
         for s in range(S):
             x = EMB[s]
             for i in range(n_layers):
                 # gates = x W_ih^T + b_ih + b_hh + h W_hh^T   (torch.nn.LSTM step, Dec.py:393-415)
-                if i == 0:      # x = cat(emb, prev cell_value) (Dec.py:383) without materialising the concat
+                if i == 0 and TOK is not None and s > 0:
+                    pass            # Gx[0] was gathered from TOK by the previous step's arg-max kernel
+                elif i == 0:    # x = cat(emb, prev cell_value) (Dec.py:383) without materialising the concat
                     k.gemm(x, wih[0][:, :E], trans_b=True, bias=bias[0], out=Gx[0])
                 else:
                     k.gemm(x, wih[i], trans_b=True, bias=bias[i], out=Gx[i])
@@ -671,7 +681,10 @@ class _LASDecoder(Function):
                     k.gemm(CV[s + 1], wih[0][:, E:], trans_b=True, out=Gcv)
             k.gemm(CV[s + 1], wo, trans_b=True, bias=b_out, out=LOGITS[s])       # Dec.py:434
             feed = (emb_table, EMB[s + 1]) if (fused_feed and s + 1 < S) else None
-            k.argmax_rows(LOGITS[s], sym_dst[s], lengths=lengths, step=s, embed=feed)   # Dec.py:331 + 334-341
+            feed2 = (TOK, Gx[0]) if (TOK is not None and s + 1 < S) else None
+            if s == 0 and feed2 is not None:
+                rt.join(side[0])        # the table GEMM was forked before the loop
+            k.argmax_rows(LOGITS[s], sym_dst[s], lengths=lengths, step=s, embed=feed, embed2=feed2)   # Dec.py:331 + 334-341
         for st in side:
             rt.join(st)
         if ids_tf is None:

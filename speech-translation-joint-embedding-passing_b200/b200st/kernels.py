@@ -356,10 +356,11 @@ class CudaKernels:
                    'las_attn_bwd')
         return dscore, dq
 
-    def argmax_rows(self, x, idx_out, lengths=None, step=0, embed=None):
+    def argmax_rows(self, x, idx_out, lengths=None, step=0, embed=None, embed2=None):
         """x [rows, cols] (row-strided); idx_out: int64 1-D view (any stride) of length rows.  With `lengths`
         (int32 [rows]) the LAS decode-length rule (Dec.py:334-340) is applied in the same launch; with
-        `embed = (table fp32 [cols, dim], out [rows, dim])` the chosen token's embedding row is written too."""
+        `embed = (table fp32 [cols, dim], out [rows, dim])` the chosen token's embedding row is written too, and with
+        `embed2 = (table2 [cols, dim2] in x's dtype, out2 [rows, dim2])` its row of a second table."""
         self._need_cuda(x, idx_out, lengths)
         _rows(x)
         assert idx_out.dtype == torch.int64 and idx_out.dim() == 1 and idx_out.numel() == x.size(0)
@@ -373,10 +374,18 @@ class CudaKernels:
             assert table.dtype == torch.float32 and table.is_contiguous() and table.size(0) == x.size(1)
             assert emb.dtype == x.dtype and emb.dim() == 2 and emb.stride(1) == 1 and emb.shape == (x.size(0), table.size(1))
             ld_emb, dim = emb.stride(0), table.size(1)
-        _lib.check(self.lib.b200st_argmax_rows_embed(
+        table2 = out2 = None
+        ld2 = dim2 = 0
+        if embed2 is not None:
+            table2, out2 = embed2
+            self._need_cuda(table2, out2)
+            assert table2.dtype == x.dtype == out2.dtype and table2.is_contiguous() and table2.size(0) == x.size(1)
+            assert out2.dim() == 2 and out2.stride(1) == 1 and out2.shape == (x.size(0), table2.size(1))
+            ld2, dim2 = out2.stride(0), table2.size(1)
+        _lib.check(self.lib.b200st_argmax_rows_embed2(
             _dt(x), _p(x), x.stride(0), x.size(0), x.size(1), _p(idx_out),
             idx_out.stride(0) if idx_out.numel() > 1 else 1, _p(lengths), int(step), _p(table), _p(emb), ld_emb, dim,
-            self._stream()), 'argmax_rows')
+            _p(table2), _p(out2), ld2, dim2, self._stream()), 'argmax_rows')
         return idx_out
 
     def las_update_lengths(self, sym, lengths, step):

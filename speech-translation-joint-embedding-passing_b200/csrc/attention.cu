@@ -922,7 +922,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 argmax_rows_vec_kernel(const T* __restrict__ x, int64_t ld, int cols, int64_t* __restrict__ idx, int64_t idx_stride,
                        int32_t* __restrict__ lengths, int step, const float* __restrict__ table, T* __restrict__ emb,
-                       int64_t ld_emb, int dim) {
+                       int64_t ld_emb, int dim, const T* __restrict__ table2, T* __restrict__ out2, int64_t ld_out2,
+                       int dim2) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ float sv[32];
@@ -969,6 +970,12 @@ argmax_rows_vec_kernel(const T* __restrict__ x, int64_t ld, int cols, int64_t* _
     const float* src = table + (int64_t)s_sym * dim;
     T* dst = emb + r * ld_emb;
     for (int c = threadIdx.x; c < dim; c += 256) dst[c] = from_f<T>(src[c]);
+  }
+  if (table2) {       // ... and the token's row of a second table in the activation dtype (the pre-multiplied first-layer
+    __syncthreads();  // gate contribution E W_ih^T + b of the next decoder step: a gather instead of a GEMM on the chain)
+    const T* src = table2 + (int64_t)s_sym * dim2;
+    T* dst = out2 + r * ld_out2;
+    for (int c = threadIdx.x; c < dim2; c += 256) dst[c] = src[c];
   }
 }
 
@@ -1225,18 +1232,28 @@ int b200st_argmax_rows_lengths(int dtype, const void* x, int64_t ld, int64_t row
 int b200st_argmax_rows_embed(int dtype, const void* x, int64_t ld, int64_t rows, int64_t cols, int64_t* idx,
                              int64_t idx_stride, int32_t* lengths, int step, const float* table, void* emb,
                              int64_t ld_emb, int64_t dim, b200st_stream_t stream) {
+  return b200st_argmax_rows_embed2(dtype, x, ld, rows, cols, idx, idx_stride, lengths, step, table, emb, ld_emb, dim,
+                                   nullptr, nullptr, 0, 0, stream);
+}
+
+int b200st_argmax_rows_embed2(int dtype, const void* x, int64_t ld, int64_t rows, int64_t cols, int64_t* idx,
+                              int64_t idx_stride, int32_t* lengths, int step, const float* table, void* emb,
+                              int64_t ld_emb, int64_t dim, const void* table2, void* out2, int64_t ld_out2,
+                              int64_t dim2, b200st_stream_t stream) {
   if (rows <= 0) return 0;
   const bool vec = cols % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x & 15) == 0;
   if (vec) {
     B200ST_DISPATCH(dtype, T, {
       B200ST_CUDA(launch_pdl(argmax_rows_vec_kernel<T>, dim3((unsigned)rows), dim3(256), 0, (cudaStream_t)stream,
-                             (const T*)x, ld, (int)cols, idx, idx_stride, lengths, step, table, (T*)emb, ld_emb, (int)dim));
+                             (const T*)x, ld, (int)cols, idx, idx_stride, lengths, step, table, (T*)emb, ld_emb, (int)dim,
+                             (const T*)table2, (T*)out2, ld_out2, (int)dim2));
     });
     B200ST_LAUNCH_CHECK("argmax_rows_vec");
     return 0;
   }
   if (b200st_argmax_rows(dtype, x, ld, rows, cols, idx, idx_stride, stream)) return -1;
   if (lengths && b200st_las_update_lengths(idx, idx_stride, lengths, step, rows, stream)) return -1;
+  if (table2) return set_error("argmax_rows_embed2: the second gather needs the vectorised route (cols %% 8 == 0, aligned rows)");
   if (table) {
     if (idx_stride != 1) return set_error("argmax_rows_embed: the unfused route needs dense ids");
     return b200st_embedding_fwd(dtype, idx, table, emb, ld_emb, rows, dim, cols, stream);

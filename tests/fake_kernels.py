@@ -382,13 +382,16 @@ class FakeKernels:
             dscore_out.copy_(ds); ds = dscore_out
         return ds, dq
 
-    def argmax_rows(self, x, idx_out, lengths=None, step=0, embed=None):
+    def argmax_rows(self, x, idx_out, lengths=None, step=0, embed=None, embed2=None):
         idx_out.copy_(x.float().argmax(dim=1))
         if lengths is not None:
             self.las_update_lengths(idx_out, lengths, step)
         if embed is not None:
             table, out = embed
             out.copy_(table[idx_out].to(out.dtype))
+        if embed2 is not None:
+            table2, out2 = embed2
+            out2.copy_(table2[idx_out])
         return idx_out
 
     def las_update_lengths(self, sym, lengths, step):
