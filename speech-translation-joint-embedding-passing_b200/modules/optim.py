@@ -39,23 +39,27 @@ class Optimizer(object):
         self._engine().set_lr(lr)
 
     def update(self, loss, epoch):
-        if self.scheduler is None:
-            pass
-        elif isinstance(self.scheduler, torch.optim.lr_scheduler.ReduceLROnPlateau):
-            self.scheduler.step(loss)
-        else:
-            self.scheduler.step()
+        """Scheduler hook of the reference (modules/optim.py:38-52): plateau schedulers are fed the loss, any other
+        scheduler is simply stepped; no scheduler, no effect.  `epoch` is accepted for signature compatibility."""
+        sched = self.scheduler
+        if sched is not None:
+            args = (loss,) if isinstance(sched, torch.optim.lr_scheduler.ReduceLROnPlateau) else ()
+            sched.step(*args)
+
+
+def lr_at(step, init_lr=0.00001, peak_lr=0.0005, warmup_steps=16000):
+    """The reference's learning-rate rule (trainer_base.py:145-149): linear warm-up from init_lr to peak_lr over
+    warmup_steps, then peak_lr * step^-0.5 * warmup_steps^0.5 (same floating-point expression order as upstream)."""
+    if step <= warmup_steps:
+        return step * 1. * (peak_lr - init_lr) / warmup_steps + init_lr
+    return peak_lr * (step ** (-0.5)) * (warmup_steps ** 0.5)
 
 
 def lr_scheduler(optimizer, step, init_lr=0.00001, peak_lr=0.0005, warmup_steps=16000):
-    """Linear warm-up from init_lr to peak_lr over warmup_steps, then peak_lr * sqrt(warmup_steps / step)
-    (trainer_base.py:135-154).  `optimizer` is the wrapped torch optimizer; returns it, like the reference."""
-    if warmup_steps <= 0:
-        return optimizer
-    if step <= warmup_steps:
-        lr = step * 1. * (peak_lr - init_lr) / warmup_steps + init_lr
-    else:
-        lr = peak_lr * (step ** (-0.5)) * (warmup_steps ** 0.5)
-    for param_group in optimizer.param_groups:
-        param_group['lr'] = lr
+    """`Trainer.lr_scheduler` (trainer_base.py:135-154): writes lr_at(step) into every parameter group of the wrapped
+    torch optimizer and returns it; warmup_steps <= 0 switches the rule off."""
+    if warmup_steps > 0:
+        lr = lr_at(step, init_lr, peak_lr, warmup_steps)
+        for group in optimizer.param_groups:
+            group['lr'] = lr
     return optimizer
