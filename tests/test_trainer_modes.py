@@ -110,11 +110,23 @@ def test_asr_st_trainer_step_gpu():
 
 @pytest.mark.parametrize('boost', [0.0, 1.5, 4.0, 40.0])
 def test_beam_search_early_exit_and_width_cpu(fake_backend, boost):
+    _early_exit_case('cpu', boost)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('boost', [0.0, 4.0, 40.0])
+def test_beam_search_early_exit_and_width_gpu_graphs(boost):
+    from b200st import runtime
+    runtime.set_compute_dtype('fp32')
+    _early_exit_case('cuda', boost)
+
+
+def _early_exit_case(device, boost):
     """The static-buffer, KV-cached search loop against the reference-shaped recompute loop when hypotheses hit EOS:
     `boost` pushes the EOS logit (through the decoder's final LayerNorm bias) so that the all-EOS early exit
     (Seq2seq.py:388-393) fires after 0 .. max steps; output shape (the `reshape(batch, -1)[:, :max_seq_len]` quirk) and
     every token id must agree for greedy and beam search."""
-    cfg, P, data, m, _ = _case('cpu')
+    cfg, P, data, m, _ = _case(device)
     m.eval()
     with torch.no_grad():
         w = m.out_tgt.weight[3]                                  # EOS row
@@ -125,8 +137,10 @@ def test_beam_search_early_exit_and_width_cpu(fake_backend, boost):
         outs = {}
         for cached in (True, False):
             m.decode_cache = cached
-            outs[cached] = m.forward_translate(acous_feats=data['acous_feats'].clone(), acous_lens=lens, beam_width=k,
-                                               penalty_factor=1, use_gpu=False, max_seq_len=9, mode='ST')
+            for _ in range(2 if cached else 1):      # on the GPU the second call replays the captured graphs
+                outs[cached] = m.forward_translate(acous_feats=data['acous_feats'].clone().to(device), acous_lens=lens,
+                                                   beam_width=k, penalty_factor=1, use_gpu=device != 'cpu', max_seq_len=9,
+                                                   mode='ST')
         assert outs[True].shape == outs[False].shape, (k, outs[True].shape, outs[False].shape)
         assert torch.equal(outs[True], outs[False]), (k, boost)
         widths.add(outs[True].size(1))
