@@ -298,7 +298,7 @@ def run_b200(args):
     from b200st import runtime
     from b200st.dp import GradAllReducer
     from b200st.kernels import K
-    from trainer.trainer_st import Trainer_ST
+    from b200st.train_step import Trainer_ST
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))

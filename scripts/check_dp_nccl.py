@@ -11,7 +11,7 @@ import torch.distributed as dist
 from b200st import runtime
 from b200st.dp import GradAllReducer
 from b200st.graph import GraphedTrainStep
-from trainer.trainer_st import Trainer_ST
+from b200st.train_step import Trainer_ST
 from oracle import st_oracle as O
 from helpers import build_model
 

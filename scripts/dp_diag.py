@@ -50,7 +50,7 @@ for mb in (8, 32, 64):
 from b200st import runtime
 from b200st.dp import GradAllReducer
 from b200st.graph import GraphedTrainStep
-from trainer.trainer_st import Trainer_ST
+from b200st.train_step import Trainer_ST
 from oracle import st_oracle as O
 import bench
 

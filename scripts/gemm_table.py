@@ -7,7 +7,7 @@ import bench
 from b200st import runtime
 from b200st.kernels import K
 from oracle import st_oracle as O
-from trainer.trainer_st import Trainer_ST
+from b200st.train_step import Trainer_ST
 dt = sys.argv[1] if len(sys.argv) > 1 else 'bf16'
 runtime.set_compute_dtype(dt)
 cfg = bench.st_config()

@@ -6,7 +6,7 @@ import torch
 import bench
 from b200st import runtime
 from oracle import st_oracle as O
-from trainer.trainer_st import Trainer_ST
+from b200st.train_step import Trainer_ST
 warm = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 runtime.set_compute_dtype(sys.argv[2] if len(sys.argv) > 2 else 'bf16')
 cfg = bench.st_config()

@@ -8,7 +8,7 @@ import torch
 import bench
 from b200st import runtime, functional as BF
 from oracle import st_oracle as O
-from trainer.trainer_st import Trainer_ST
+from b200st.train_step import Trainer_ST
 from models.Enc import padded_lengths
 
 runtime.set_compute_dtype(sys.argv[1] if len(sys.argv) > 1 else 'bf16')

@@ -31,14 +31,22 @@ class GradAllReducer:
         self._inflight = []                          # (work, flat, [grads])
         self._hooks = []
         self._stream = None
+        self._armed = True
         if self.world > 1:
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
     # -- hook path --------------------------------------------------------------------------------
+    def arm(self, on: bool = True):
+        """Gradient accumulation over `minibatch_partition` slices (trainer_st.py:225-290): the trainers arm the hooks
+        for the LAST slice's backward only, so that every parameter's ACCUMULATED gradient is queued and reduced exactly
+        once.  (Reducing in place while a later slice's AccumulateGrad adds into the same tensor on the compute stream
+        would race, and would multiply the traffic by n_minibatch.)"""
+        self._armed = bool(on)
+
     def _on_grad(self, p: torch.Tensor):
         g = p.grad
-        if g is None:
+        if g is None or not self._armed:
             return
         self._pending.append(g)
         self._pending_bytes += g.numel() * g.element_size()

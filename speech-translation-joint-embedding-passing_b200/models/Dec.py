@@ -22,8 +22,8 @@ import torch.nn as nn
 from b200st import functional as BF
 from b200st import runtime as rt
 from modules.attention import AttentionLayer
-from utils.config import PAD, EOS, BOS
-from utils.misc import check_device
+from b200st.hostutil import PAD, EOS, BOS
+from b200st.hostutil import check_device
 
 KEY_ATTN_SCORE = 'attention_score'
 KEY_ATTN_OUT = 'attention_out'

@@ -19,7 +19,7 @@ import torch.nn as nn
 from b200st import functional as BF
 from b200st import runtime as rt
 from b200st.kernels import K
-from utils.misc import check_device
+from b200st.hostutil import check_device
 
 
 def padded_lengths(acous_lens, batch_size, acous_len, device):

@@ -20,8 +20,8 @@ import torch.nn as nn
 from b200st import functional as BF
 from b200st import runtime as rt
 from b200st.kernels import K
-from utils.config import PAD, EOS, BOS, UNK
-from utils.misc import check_device
+from b200st.hostutil import PAD, EOS, BOS, UNK
+from b200st.hostutil import check_device
 
 from .Las import LAS
 from .TFDec import Decoder

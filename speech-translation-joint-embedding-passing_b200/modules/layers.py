@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from b200st import functional as BF
 from b200st.kernels import K
-from utils.config import PAD
+from b200st.hostutil import PAD
 
 
 def _p(module):

@@ -36,7 +36,7 @@ def _worker(rank, world, port, name, out):
     from fake_kernels import FakeKernels
     from b200st.dp import GradAllReducer
     from helpers import build_model
-    from trainer.trainer_st import Trainer_ST
+    from b200st.train_step import Trainer_ST
     kernels.set_backend(FakeKernels())
     g = Golden(name)
     m = build_model(g.cfg, g.params())
@@ -60,7 +60,7 @@ def test_dp2_equals_minibatch_partition(tmp_path, name):
     from b200st import kernels
     from fake_kernels import FakeKernels
     from helpers import build_model
-    from trainer.trainer_st import Trainer_ST
+    from b200st.train_step import Trainer_ST
     g = Golden(name)
     I = g.inputs()
     B = (I['src'].size(0) // 2) * 2

@@ -258,7 +258,7 @@ def test_dropout_train_step_bf16_graph_replays_draw_new_masks():
     """bf16 + whole-step CUDA graph with the reference's default dropouts: replays give different (fresh-mask) losses
     that stay close to the no-dropout loss, and gradients are finite."""
     from b200st.graph import GraphedTrainStep
-    from trainer.trainer_st import Trainer_ST
+    from b200st.train_step import Trainer_ST
     rt.set_compute_dtype('bf16')
     try:
         cfg = O.STConfig(enc_vocab_size=300, dec_vocab_size=300, enc_embedding_size=40, dec_embedding_size=40,

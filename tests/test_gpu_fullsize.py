@@ -21,7 +21,7 @@ def _items(batch, frames, seed=333):
 
 
 def _step(dtype, items, cfg):
-    from trainer.trainer_st import Trainer_ST
+    from b200st.train_step import Trainer_ST
     runtime.set_compute_dtype(dtype)
     model = bench.build_model(cfg, torch.device('cuda'))
     loss = float(Trainer_ST(use_gpu=True, batch_size=64)._train_batch_device(model, items))
@@ -45,7 +45,7 @@ def test_full_size_bf16_step_agrees_with_fp32_step():
 
 def test_full_size_graph_replay_equals_eager_step_bf16():
     from b200st.graph import GraphedTrainStep
-    from trainer.trainer_st import Trainer_ST
+    from b200st.train_step import Trainer_ST
     try:
         cfg, _, items = _items(64, 1000)
         le, ne, ge, model = _step('bf16', items, cfg)

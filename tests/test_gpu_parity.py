@@ -54,7 +54,7 @@ def test_golden_forward_backward_fp32(golden):
 
 def _trainer_step(golden, dtype, fused):
     from b200st import runtime
-    from trainer.trainer_st import Trainer_ST
+    from b200st.train_step import Trainer_ST
     runtime.set_compute_dtype(dtype)
     m = build_model(golden.cfg, golden.params(), device='cuda')
     m.train()
@@ -189,7 +189,7 @@ def test_graphed_train_step_with_optimizer_matches_oracle_adam():
     fp32: losses of every step and the final weights agree."""
     from b200st.graph import GraphedTrainStep
     from modules.optim import Optimizer
-    from trainer.trainer_st import Trainer_ST
+    from b200st.train_step import Trainer_ST
     cfg = O.STConfig(enc_vocab_size=200, dec_vocab_size=200, enc_embedding_size=24, dec_embedding_size=24,
                      max_seq_len_src=8, max_seq_len_tgt=11, num_heads=4, dim_model=64, dim_feedforward=96,
                      enc_layers=2, dec_layers=2, acous_dim=16, acous_hidden_size=32)
@@ -307,7 +307,7 @@ def test_adam_maintains_bf16_operand_copies():
     from b200st import runtime
     from b200st.graph import GraphedTrainStep
     from modules.optim import Optimizer
-    from trainer.trainer_st import Trainer_ST
+    from b200st.train_step import Trainer_ST
     runtime.set_compute_dtype('bf16')
     try:
         cfg = O.STConfig(enc_vocab_size=300, dec_vocab_size=300, enc_embedding_size=40, dec_embedding_size=40,

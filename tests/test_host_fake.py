@@ -61,7 +61,7 @@ def test_backward_st_matches_reference(golden, fake_backend):
 def test_trainer_step_matches_reference_grads(golden, fake_backend, fused):
     """Trainer_ST._train_batch_device (fused softmax+NLL from the logits, or the reference's logps -> NLLLoss
     route) reproduces the reference loss and gradients (trainer_st.py:253-288)."""
-    from trainer.trainer_st import Trainer_ST
+    from b200st.train_step import Trainer_ST
     m = build_model(golden.cfg, golden.params())
     m.train()
     b = golden.inputs()

@@ -51,7 +51,7 @@ def _manual(m, data, coeff, device):
 
 
 def _check_trainer(device):
-    from trainer.trainer_asr_st import Trainer_ASR_ST
+    from b200st.train_step import Trainer_ASR_ST
     coeff = {'nll_asr': 0.3, 'nll_st': 1.0}
     cfg, P, data, m, items = _case(device)
     m.train()
