@@ -201,6 +201,70 @@ def case_st(Seq2seq, patched_load, name, cfg, lens, seed):
           f'-> {path} ({os.path.getsize(path) / 1024:.0f} KiB)')
 
 
+def case_st_seeded(Seq2seq, patched_load, name, cfg, lens, seed, wscale=1.0):
+    """A fixture at the benchmark's kernel shapes (H = 256 per direction, d_k = 64) without shipping its ~20 M weights:
+    the weights are `oracle.st_oracle.init_params(cfg, seed, scale)` (a seeded CPU torch.Generator, reproducible wherever
+    the same torch runs) loaded into the UNMODIFIED reference model; the fixture stores the inputs, every output, the full
+    gradient of each small parameter and, for the large ones, the gradient norm plus a fixed strided sample."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+    from oracle import st_oracle as O
+    ocfg = O.STConfig(enc_vocab_size=cfg['V'], dec_vocab_size=cfg['V'], enc_embedding_size=cfg['E'],
+                      dec_embedding_size=cfg['E'], max_seq_len_src=cfg['S'], max_seq_len_tgt=cfg['L'],
+                      num_heads=cfg['heads'], dim_model=cfg['dim_model'], dim_feedforward=cfg['FF'],
+                      enc_layers=cfg['layers'], dec_layers=cfg['layers'], acous_dim=cfg['F'], acous_hidden_size=cfg['H'])
+    P = O.init_params(ocfg, seed=seed, scale=wscale)
+    m = build(Seq2seq, patched_load, dict(cfg, wscale=1.0, eos_bias=0.0), 'ST', seed)
+    missing, unexpected = m.load_state_dict(P, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    g = torch.Generator().manual_seed(seed + 1)
+    B = len(lens)
+    T = max(n + 8 - n % 8 for n in lens)
+    feats = torch.randn(B, T, cfg['F'], generator=g)
+    for b, n in enumerate(lens):
+        feats[b, n:] = 0
+    src = tokens(g, B, cfg['S'], cfg['V'], 2)
+    tgt = tokens(g, B, cfg['L'], cfg['V'], 3)
+    acous_lens = [torch.tensor([n]) for n in lens]
+    d = {}
+    pack(d, 'cfg/', {k: np.int64(v) for k, v in cfg.items()})
+    d['seed'], d['wscale'] = np.int64(seed), np.float64(wscale)
+    pack(d, 'param_abssum/', {k: v.double().abs().sum() for k, v in P.items()})      # detects RNG drift
+    pack(d, 'in/', {'src': src, 'tgt': tgt, 'acous_feats': feats, 'acous_lens': np.array(lens)})
+    m.train()
+    seed_all(seed + 2)
+    out = m.forward_train(src, tgt=tgt, acous_feats=feats.clone(), acous_lens=acous_lens, mode='ST', use_gpu=False)
+    loss = masked_nll_ref(out['logps_st'], tgt)
+    loss.backward()
+    pack(d, 'st/', {'loss': loss.acc_loss, 'logps_st': out['logps_st'], 'emb_st': out['emb_st'], 'preds_st': out['preds_st']})
+    for n, p in m.named_parameters():
+        if p.grad is None or float(p.grad.abs().sum()) == 0:
+            continue
+        gflat = p.grad.reshape(-1)
+        d['st_gradnorm/' + n] = gflat.double().norm().numpy()
+        stride = max(1, gflat.numel() // 4096)
+        d['st_gradsample/' + n] = gflat[::stride][:4096].numpy().copy()
+    m.zero_grad()
+    with torch.no_grad():
+        embs, logps, syms, lengths = m.las(feats.clone(), acous_lens=acous_lens, use_gpu=False)
+    pack(d, 'las/', {'embs': embs, 'symbols': syms, 'lengths': np.array(lengths),
+                     'margin': (lambda t: t[..., 0] - t[..., 1])(logps.topk(2, dim=-1)[0])})
+    m.eval()
+    with torch.no_grad():
+        for k in (1, 5):
+            tr = m.forward_translate(acous_feats=feats.clone(), acous_lens=acous_lens, beam_width=k, penalty_factor=1,
+                                     use_gpu=False, max_seq_len=cfg['L'], mode='ST')
+            pack(d, 'translate/', {f'beam{k}': tr})
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + '.npz')
+    np.savez_compressed(path, **d)
+    print(f'{name}: loss_st={float(d["st/loss"]):.9f} las_lengths={list(d["las/lengths"])} min LAS margin '
+          f'{float(d["las/margin"].min()):.3e} -> {path} ({os.path.getsize(path) / 1024:.0f} KiB)')
+
+
+H256_CFG = dict(V=304, E=24, dim_model=512, heads=8, FF=128, layers=1, F=16, H=256, S=10, L=12)
+H256_LENS = [120, 97, 128, 66, 101, 115, 80, 124, 90, 73, 111, 128, 64, 85, 99, 107]
+
+
 def main():
     Seq2seq, patched_load = import_reference()
     tiny = dict(V=41, E=12, dim_model=32, heads=4, FF=48, layers=2, F=8, H=16, S=7, L=9)
@@ -208,6 +272,8 @@ def main():
     case_st(Seq2seq, patched_load, 'st_tiny_aligned', tiny, lens=[16, 16], seed=13)   # 16 -> 24: the +8 quirk
     small = dict(V=67, E=20, dim_model=48, heads=8, FF=64, layers=2, F=16, H=24, S=10, L=12)
     case_st(Seq2seq, patched_load, 'st_small', small, lens=[61, 50, 64, 33, 47], seed=6)
+    # the benchmark's kernel shapes: H = 256 per direction (blstm_*_tc_kernel), 8 heads x d_k = 64 (mha_*_tc_kernel), B = 16
+    case_st_seeded(Seq2seq, patched_load, 'st_h256', H256_CFG, lens=H256_LENS, seed=17, wscale=1.5)
 
 
 if __name__ == '__main__':

@@ -73,6 +73,45 @@ class Golden:
         return i
 
 
+class SeededGolden(Golden):
+    """A fixture whose weights are not stored: they are `oracle.st_oracle.init_params(cfg, seed, scale)` (seeded CPU
+    generator; make_golden.case_st_seeded loaded exactly those into the real reference).  Gradients are stored as a norm
+    plus a strided sample of <= 4096 entries per parameter."""
+
+    def params(self, requires_grad=False, dtype=torch.float32):
+        from oracle.st_oracle import init_params
+        P = init_params(self.cfg, seed=int(self.z['seed']), scale=float(self.z['wscale']), dtype=dtype)
+        for k, v in self.group('param_abssum').items():       # the seeded generator must reproduce the fixture's weights
+            got = float(P[k].double().abs().sum())
+            assert abs(got - float(v)) <= 1e-9 * max(1.0, float(v)), f'seeded init drifted for {k}: regenerate the fixture'
+        if requires_grad:
+            for v in P.values():
+                v.requires_grad_(True)
+        return P
+
+    def grad_check(self, named_grads, tol):
+        """Every stored parameter: |norm - ref| and the error on the stored sample, both relative to the parameter's
+        reference norm floored at 1e-3 of the global norm (the metric of test_gpu_parity._grad_check).  Returns the
+        worst error / bound."""
+        norms = self.group('st_gradnorm')
+        gn = sum(float(v) ** 2 for v in norms.values()) ** 0.5
+        worst = 0.0
+        for name, ref_norm in norms.items():
+            g = named_grads[name]
+            assert g is not None, name
+            g = g.detach().double().cpu().reshape(-1)
+            sample = self['st_gradsample/' + name].double()
+            stride = max(1, g.numel() // 4096)
+            got = g[::stride][:4096]
+            frac = (sample.numel() / g.numel()) ** 0.5          # a sample carries ~sqrt(fraction) of the norm
+            bound = tol * max(float(ref_norm), 1e-3 * gn)
+            e1 = abs(float(g.norm()) - float(ref_norm)) / bound
+            e2 = float((got - sample).norm()) / max(bound * frac, 1e-30)
+            worst = max(worst, e1, e2 / 2)                       # sampling noise: allow 2x on the sample
+            assert e1 <= 1 and e2 <= 2, (name, e1, e2, float(ref_norm), gn)
+        return worst
+
+
 @pytest.fixture(params=GOLDEN_CASES)
 def golden(request):
     return Golden(request.param)

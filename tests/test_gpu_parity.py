@@ -354,3 +354,55 @@ def test_adam_maintains_bf16_operand_copies():
         assert ref[-1] < ref[0]
     finally:
         runtime.set_compute_dtype('fp32')
+
+
+# ---- golden from the REAL reference at the benchmark's kernel shapes: H = 256 per direction (blstm_*_tc_kernel),
+#      8 heads x d_k = 64 (mha_*_tc_kernel), B = 16 ragged utterances (oracle/make_golden.py: case_st_seeded)
+def test_golden_h256_fp32_and_beam5_ids():
+    from conftest import SeededGolden
+    g = SeededGolden('st_h256')
+    m = build_model(g.cfg, g.params(), device='cuda')
+    m.train()
+    loss, out = train_step(m, g.inputs(), 'cuda')
+    loss.backward()
+    assert rel_err(out['logps_st'].cpu(), g['st/logps_st']) < 1e-4
+    assert rel_err(out['emb_st'].cpu(), g['st/emb_st']) < 1e-4
+    assert torch.equal(out['preds_st'].cpu(), g['st/preds_st'])
+    assert abs(loss.get_loss() - float(g['st/loss'])) < 1e-4 * abs(float(g['st/loss']))
+    g.grad_check({k: v.grad for k, v in m.named_parameters()}, 1e-4)
+    m.eval()
+    I = g.inputs()
+    lens = [torch.tensor([n]) for n in I['acous_lens']]
+    feats = I['acous_feats'].cuda()
+    with torch.no_grad():
+        _, _, syms, lengths = m.las(feats.clone(), acous_lens=lens, use_gpu=True)
+    assert torch.equal(syms.cpu(), g['las/symbols']) and list(lengths) == [int(v) for v in g['las/lengths']]
+    for cached in (True, False):
+        m.decode_cache = cached
+        for k in (1, 5):
+            tr = m.forward_translate(acous_feats=feats.clone(), acous_lens=lens, beam_width=k, penalty_factor=1,
+                                     use_gpu=True, max_seq_len=g.cfg.max_seq_len_tgt, mode='ST')
+            assert torch.equal(tr.cpu(), g[f'translate/beam{k}']), (cached, k)
+
+
+def test_golden_h256_bf16_tensor_core_kernels():
+    """bf16: blstm_*_tc_kernel (H 256), mha_*_tc_kernel (d_k 64) and the tcgen05 GEMMs against the REAL reference's loss and
+    gradients at the 2e-2 contract, LAS symbols pinned to the reference's (see test_gpu_oracle_fullsize.py for why)."""
+    from b200st import runtime
+    from b200st.kernels import K
+    from conftest import SeededGolden
+    from test_gpu_oracle_fullsize import _force_las_symbols
+    g = SeededGolden('st_h256')
+    runtime.set_compute_dtype('bf16')
+    old = (K().set_gemm_backend(0), K().set_blstm_backend(0), K().set_mha_backend(0))      # auto = tcgen05 where eligible
+    try:
+        m = build_model(g.cfg, g.params(), device='cuda')
+        m.train()
+        _force_las_symbols(m, g['las/symbols'].squeeze(-1))
+        loss, out = train_step(m, g.inputs(), 'cuda')
+        loss.backward()
+        assert abs(loss.get_loss() - float(g['st/loss'])) < 2e-2 * abs(float(g['st/loss']))
+        assert rel_err(out['logps_st'].float().cpu(), g['st/logps_st']) < 2e-2
+        g.grad_check({k: v.grad for k, v in m.named_parameters()}, 2e-2)
+    finally:
+        K().set_gemm_backend(old[0]); K().set_blstm_backend(old[1]); K().set_mha_backend(old[2])

@@ -106,3 +106,24 @@ def test_asr_mode_teacher_forced(golden):
     assert list(out['lengths_asr']) == [int(v) for v in golden['asr/lengths']]
     for name, n in golden.group('asr_gradnorm').items():
         assert abs(float(P[name].grad.norm()) - float(n)) < 1e-4 * float(n) + 1e-7, name
+
+
+# ---- the fixture at the benchmark's kernel shapes (H = 256 per direction, 8 heads x d_k = 64, B = 16; seeded weights)
+def test_h256_oracle_matches_reference_fixture():
+    from conftest import SeededGolden
+    g = SeededGolden('st_h256')
+    P, cfg, I = g.params(requires_grad=True), g.cfg, g.inputs()
+    loss, out = O.train_step_st(P, cfg, I['src'], I['tgt'], I['acous_feats'], I['acous_lens'])
+    loss.backward()
+    assert rel_err(out['logps_st'], g['st/logps_st']) < TOL
+    assert rel_err(out['emb_st'], g['st/emb_st']) < TOL
+    assert abs(float(loss) - float(g['st/loss'])) < TOL * abs(float(g['st/loss']))
+    assert torch.equal(out['preds_st'], g['st/preds_st'])
+    assert torch.equal(out['preds_asr'], g['las/symbols'])
+    assert list(out['lengths_asr']) == [int(v) for v in g['las/lengths']]
+    g.grad_check({k: v.grad for k, v in P.items()}, 1e-4)
+    Pn = {k: v.detach() for k, v in P.items()}
+    for beam in (1, 5):
+        ids = O.forward_translate_st(Pn, cfg, I['acous_feats'], I['acous_lens'], beam_width=beam, penalty_factor=1,
+                                     max_seq_len=cfg.max_seq_len_tgt)
+        assert torch.equal(ids, g[f'translate/beam{beam}']), beam
