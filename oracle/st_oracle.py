@@ -449,11 +449,14 @@ def translation_decoder(P: Params, cfg: STConfig, emb_tgt, enc_out, tgt_mask, sr
 
 
 def forward_train_st(P: Params, cfg: STConfig, src, tgt, acous_feats, acous_lens,
-                     hoist_keys: bool = False, loops: bool = False):
-    """Seq2seq.forward_train(mode='ST') (Seq2seq.py:468-507)."""
+                     hoist_keys: bool = False, loops: bool = False, las_tgt=None):
+    """Seq2seq.forward_train(mode='ST') (Seq2seq.py:468-507).  `las_tgt` [B, S+1] (BOS first): feed these tokens to the
+    LAS decoder instead of its own arg-max (Dec.py:196-221 teacher forcing) -- with las_tgt = BOS | the free-running
+    symbols this is the same computation, which is how tests pin the symbol path when comparing reduced precision."""
     tgt_mask, emb_tgt = target_embeddings(P, cfg, tgt)
     enc_ac = las_encoder(P, cfg, acous_feats, acous_lens, loops=loops)
-    emb_dyn, logps_src, preds_src, lengths = las_decoder(P, cfg, enc_ac, acous_lens,
+    emb_dyn, logps_src, preds_src, lengths = las_decoder(P, cfg, enc_ac, acous_lens, tgt=las_tgt,
+                                                         teacher_forcing=las_tgt is not None,
                                                          hoist_keys=hoist_keys)
     src_trim = src[:, 1:]                                                   # Seq2seq.py:214-219
     emb_src = mix_embeddings(P, src_trim, emb_dyn)

@@ -1,7 +1,7 @@
-"""BASELINE.json's FULL sizes (configs[2]: B 64, 1000 frames, V 10k, 6+6 layers) — too large for the CPU oracle inside a
-test, so the CUDA path is checked through size-independent properties: the two numerical modes agree with each other
-within the bf16 contract, the whole-step CUDA graph reproduces the eager step, and the KV-cached / graphed inference
-loop returns the token ids of the reference-shaped recompute loop."""
+"""BASELINE.json's FULL sizes (configs[2]: B 64, 1000 frames, V 10k, 6+6 layers): size-independent properties of the CUDA
+path -- the two numerical modes agree with each other within the bf16 contract, the whole-step CUDA graph reproduces the
+eager step, and the KV-cached / graphed inference loop returns the token ids of the reference-shaped recompute loop.
+Parity with the ORACLE at these sizes is tests/test_gpu_oracle_fullsize.py."""
 import pytest
 import torch
 
@@ -36,8 +36,8 @@ def test_full_size_bf16_step_agrees_with_fp32_step():
         l32, n32, g32, _ = _step('fp32', items, cfg)
         l16, n16, g16, _ = _step('bf16', items, cfg)
         assert abs(l16 - l32) < 2e-2 * abs(l32), (l16, l32)                      # north-star bf16 tolerance
-        assert abs(n16 - n32) < 5e-2 * n32, (n16, n32)
-        assert float((g16 - g32).norm() / g32.norm()) < 5e-2
+        assert abs(n16 - n32) < 2e-2 * n32, (n16, n32)
+        assert float((g16 - g32).norm() / g32.norm()) < 2e-2
         assert abs(l32 - 9.21) < 0.5                                             # ~ log(10000): random-init weights
     finally:
         runtime.set_compute_dtype('fp32')

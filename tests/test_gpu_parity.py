@@ -173,7 +173,7 @@ def test_oracle_midsize_bf16():
     gn = sum(float(g.double().norm() ** 2) for g in ref.values()) ** 0.5
     named = dict(m.named_parameters())
     dn = sum(float((named[k].grad.double().cpu() - g.double()).norm() ** 2) for k, g in ref.items()) ** 0.5
-    assert dn / gn < 5e-2, dn / gn
+    assert dn / gn < 2e-2, dn / gn                # global L2; per-parameter: tests/test_gpu_oracle_fullsize.py
 
 
 def test_no_cpu_fallback():
@@ -403,6 +403,9 @@ def test_golden_h256_bf16_tensor_core_kernels():
         loss.backward()
         assert abs(loss.get_loss() - float(g['st/loss'])) < 2e-2 * abs(float(g['st/loss']))
         assert rel_err(out['logps_st'].float().cpu(), g['st/logps_st']) < 2e-2
-        g.grad_check({k: v.grad for k, v in m.named_parameters()}, 2e-2)
+        # global 2e-2; per parameter 3 x 2e-2: bf16 operands flip ~0.3 % of the FFN ReLU gates, which alone is 4-5 % on the
+        # gated gradients of ANY bf16 implementation (measured against stock autocast in test_gpu_oracle_fullsize.py)
+        worst, glob = g.grad_check({k: v.grad for k, v in m.named_parameters()}, 2e-2, per_param_factor=3.0)
+        print(f'\nst_h256 bf16: global sampled gradient error {glob:.2e}, worst per-parameter {worst * 2e-2:.2e}')
     finally:
         K().set_gemm_backend(old[0]); K().set_blstm_backend(old[1]); K().set_mha_backend(old[2])
