@@ -199,60 +199,131 @@ ALL_FAMILIES = ['gemm', 'gemm2', 'layernorm_fwd', 'layernorm_bwd', 'mha_fwd', 'm
 # ------------------------------------------------------------------------------------------------
 # the CPU arm: the reference's algorithm (oracle port, plain PyTorch fp32) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_step(P, cfg, data, adam=None):
+REF_STAGED = os.path.join(ROOT, 'oracle', '_ref')
+
+
+def _reference_root():
+    """The UNMODIFIED reference tree: staged by oracle/build_ref.sh (travels to the GPU box), else the build container's."""
+    for cand in (REF_STAGED, '/root/reference'):
+        if os.path.isfile(os.path.join(cand, 'trainer', 'trainer_st.py')):
+            return cand
+    return None
+
+
+def _reference_step_fn(ref_root, cfg, batch, frames):
+    """step() = the reference's OWN `Trainer_ST._train_batch` (trainer/trainer_st.py:211-299: forward_train('ST') + NLLLoss
+    + backward + Optimizer.step() = clip_grad_norm_ + Adam) on the reference's own `models.Seq2seq.Seq2seq`, CPU, fp32.
+    Import shims of SURVEY.md 8c only (absent third-party packages, the hard-coded .npy); none touches arithmetic."""
+    import tempfile
+    import types
+    import numpy as np
+    from oracle import st_oracle as O                      # synthetic_batch only: the same seeded inputs as the GPU arm
+    sys.dont_write_bytecode = True
+    for p in (PKG, os.path.join(ROOT, 'tests')):           # this repo's models/ modules/ must NOT shadow the reference's
+        while p in sys.path:
+            sys.path.remove(p)
+    assert 'models' not in sys.modules and 'modules' not in sys.modules
+    sys.path.insert(0, ref_root)
+    for name in ['bpemb', 'matplotlib', 'matplotlib.pyplot', 'torchtext']:
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules['bpemb'].BPEmb = object
+    sys.modules['matplotlib'].use = lambda *a, **k: None
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    np_load = np.load
+    np.load = lambda p, *a, **k: (np.zeros(cfg.dim_model, np.float32) if str(p).endswith('dyn_emb_ave.npy')
+                                  else np_load(p, *a, **k))
+    from models.Seq2seq import Seq2seq
+    from modules.optim import Optimizer
+    from trainer.trainer_st import Trainer_ST
+    assert os.path.realpath(sys.modules['models.Seq2seq'].__file__).startswith(os.path.realpath(ref_root))
+    torch.manual_seed(333)
+    model = Seq2seq(cfg.enc_vocab_size, cfg.dec_vocab_size, share_embedder=False,
+                    enc_embedding_size=cfg.enc_embedding_size, dec_embedding_size=cfg.dec_embedding_size,
+                    max_seq_len_src=cfg.max_seq_len_src, max_seq_len_tgt=cfg.max_seq_len_tgt, num_heads=cfg.num_heads,
+                    dim_model=cfg.dim_model, dim_feedforward=cfg.dim_feedforward, enc_layers=cfg.enc_layers,
+                    dec_layers=cfg.dec_layers, embedding_dropout=0.0, dropout=0.0, acous_dim=cfg.acous_dim,
+                    acous_hidden_size=cfg.acous_hidden_size, mode='ST', load_mode='null')
+    for mod in model.modules():                            # the hidden attention dropout (layers.py:207), like the GPU arm
+        if type(mod).__name__ == 'ScaledDotProductAttention':
+            mod.dropout.p = 0.0
+    model.train()
+    t = Trainer_ST(expt_dir=tempfile.mkdtemp(prefix='b200st_ref_'), load_dir=None, load_mode='null', batch_size=batch,
+                   use_gpu=False, learning_rate=1e-5, learning_rate_init=1e-5, lr_warmup_steps=0, max_grad_norm=1.0,
+                   loss_coeff={'nll_asr': 1.0, 'nll_mt': 1.0, 'nll_st': 1.0}, minibatch_partition=1)
+    t.optimizer = Optimizer(torch.optim.Adam(model.parameters(), lr=1e-5), max_grad_norm=1.0)   # trainer_base.py:420-426
+
+    def make_items(b, seed):
+        d = O.synthetic_batch(cfg, b, frames, seed=seed)
+        return {'srcid': [d['src']], 'srclen': [cfg.max_seq_len_src] * b, 'tgtid': [d['tgt']],
+                'tgtlen': [cfg.max_seq_len_tgt] * b, 'acous_feat': [d['acous_feats']],
+                'acouslen': [torch.tensor([n]) for n in d['acous_lens']]}
+
+    def step(items):
+        t.minibatch_size = items['srcid'][0].size(0)
+        return float(t._train_batch(model, items, None, 0, 1)['nll_loss_de'])
+    return step, make_items
+
+
+def _port_step_fn(cfg, frames):
+    """Fallback when no reference tree is at hand: the oracle restatement (same torch primitives at the same call sites)."""
     from oracle import st_oracle as O
-    for v in P.values():
-        v.grad = None
-    loss, _ = O.train_step_st(P, cfg, data['src'], data['tgt'], data['acous_feats'], data['acous_lens'])
-    loss.backward()
-    if adam is not None:                     # Optimizer.step(): modules/optim.py:31-36
-        torch.nn.utils.clip_grad_norm_([v for v in P.values() if v.grad is not None], 1.0)
+    P = {k: v.requires_grad_(True) for k, v in O.init_params(cfg, seed=333).items()}
+    adam = torch.optim.Adam(list(P.values()), lr=1e-5)
+
+    def step(data):
+        for v in P.values():
+            v.grad = None
+        loss, _ = O.train_step_st(P, cfg, data['src'], data['tgt'], data['acous_feats'], data['acous_lens'])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([v for v in P.values() if v.grad is not None], 1.0)   # modules/optim.py:31-36
         adam.step()
-    return float(loss.detach())
+        return float(loss.detach())
+    return step, (lambda b, seed: O.synthetic_batch(cfg, b, frames, seed=seed))
 
 
-def cpu_baseline(args, budget_s=25.0, steps=1, warmup=0):
-    """Times `steps` oracle steps on a bounded sample of the workload (same shapes, smaller batch).
-    The batch is chosen from a one-utterance probe so that the whole call stays within ~budget_s seconds."""
-    from oracle import st_oracle as O
+def cpu_reference(args, batch, steps, warmup, budget_s):
+    """Times the reference's CPU implementation of the step at `batch` utterances per step, all host cores.  As many of
+    the requested warm-up + timed steps as fit into ~budget_s seconds are run (at least one timed step; a one-utterance
+    probe warms the thread pool and sizes the plan)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = st_config()
-    P = {k: v.requires_grad_(True) for k, v in O.init_params(cfg, seed=333).items()}
-    adam = torch.optim.Adam(list(P.values()), lr=1e-5)
-    probe = O.synthetic_batch(cfg, 1, args.frames, seed=1)
-    t0 = time.perf_counter(); cpu_step(P, cfg, probe, adam); t_probe = time.perf_counter() - t0   # also warms the threads
-    total_steps = steps + warmup
-    # cost model: t(b) ~ t_probe * (0.5 + 0.5 * b)  (the 1890 serial LSTM steps have a large batch-independent part)
-    b = 1
-    while b < min(args.batch, 8) and t_probe * (0.5 + 0.5 * (b * 2)) * total_steps <= budget_s - t_probe:
-        b *= 2
-    if t_probe * total_steps > budget_s:        # even batch 1 blows the budget: the probe IS the measurement
-        dt, b, steps_done = t_probe, 1, 1
+    ref_root = _reference_root()
+    if ref_root is not None:
+        step, make = _reference_step_fn(ref_root, cfg, batch, args.frames)
+        kind, what = 'reference', (f"the UNMODIFIED reference ({'oracle/_ref' if ref_root == REF_STAGED else ref_root}): its own "
+                                   f"Trainer_ST._train_batch on its own models.Seq2seq")
     else:
-        data = O.synthetic_batch(cfg, b, args.frames, seed=333)
-        for _ in range(warmup):
-            cpu_step(P, cfg, data, adam)
+        step, make = _port_step_fn(cfg, args.frames)
+        kind, what = 'port', 'oracle/st_oracle.py (no reference tree staged: run oracle/build_ref.sh in the build container)'
+    t0 = time.perf_counter(); step(make(1, 1)); t_probe = time.perf_counter() - t0
+    items = make(batch, 333)
+    t0 = time.perf_counter(); step(items); t_first = time.perf_counter() - t0       # doubles as warm-up when one is requested
+    remaining = budget_s - t_probe - t_first
+    if warmup >= 1 and remaining >= t_first:       # the first full step was the warm-up; time what still fits
+        n = int(max(1, min(steps, remaining // max(t_first, 1e-9))))
         t0 = time.perf_counter()
-        for _ in range(steps):
-            cpu_step(P, cfg, data, adam)
-        dt = (time.perf_counter() - t0) / steps
-        steps_done = steps
-    return {'value': b / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': f'configs[2] shapes ({args.frames} frames, V=10k, 6+6 layers), batch {b} of {args.batch}, '
-                      f'{steps_done} timed step(s) of fwd+bwd+clip+Adam, fp32, torch.set_num_threads({cores}); the reference is '
-                      f'pure Python/PyTorch and cannot travel to the GPU box, so its algorithm is timed through '
-                      f'oracle/st_oracle.py (same torch primitives at the same call sites)',
-            'ms_per_step': dt * 1e3, 'batch': b}
+        for _ in range(n):
+            step(items)
+        dt, timed, warmed = (time.perf_counter() - t0) / n, n, 1
+    else:                                          # budget allows ONE full-size step: it is the measurement (cold)
+        dt, timed, warmed = t_first, 1, 0
+    return {'value': batch / dt, 'unit': UNIT, 'cores': cores, 'kind': kind, 'ms_per_step': dt * 1e3, 'batch': batch,
+            'timed_steps': timed, 'warmup_steps': warmed,
+            'sample': f'configs[2] shapes ({args.frames} frames, V=10k, 6+6 layers), batch {batch} of {args.batch} per step, '
+                      f'{timed} timed step(s) after {warmed} warm-up step(s) (requested {steps}+{warmup}; bounded to ~{budget_s:.0f} s '
+                      f'of CPU work), fwd + loss + bwd + clip_grad_norm_ + Adam, fp32, torch.set_num_threads({cores}); {what}'}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cb = cpu_baseline(args, budget_s=120.0, steps=max(1, args.steps), warmup=max(0, args.warmup))
+    cb = cpu_reference(args, args.batch, max(1, args.steps), max(0, args.warmup), args.ref_budget)
     line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': cb['ms_per_step'],
+            'steps': cb['timed_steps'], 'warmup': cb['warmup_steps'], 'requested': {'steps': args.steps, 'warmup': args.warmup},
+            'ms_per_step': cb['ms_per_step'],
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic', 'config': workload(args), 'cpu_baseline': {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
             'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -260,21 +331,99 @@ def run_reference(args):
     emit(line)
 
 
+def cpu_baseline_subprocess(args, batch=16, budget_s=30.0):
+    """The `cpu_baseline` object of the GPU arm's line: the reference arm at a bounded batch in a fresh process (the
+    reference's `models` / `modules` packages cannot share a process with this repo's)."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--batch', str(batch), '--frames', str(args.frames),
+           '--steps', '1', '--warmup', '0', '--ref-budget', str(budget_s)]
+    env = dict(os.environ)
+    for k in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT'):
+        env.pop(k, None)
+    env['CUDA_VISIBLE_DEVICES'] = ''
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    cb = line['cpu_baseline']
+    cb['sample'] = cb['sample'].replace(f'batch {batch} of {batch}', f'batch {batch} of {args.batch}')
+    return cb
+
+
+def stock_torch_cuda(args):
+    """The reference's algorithm on STOCK PyTorch CUDA kernels (cuDNN LSTM, cuBLAS, ATen) on this GPU, same shapes, fp32
+    with TF32 off: scripts/bench_torch_cuda.py in a fresh process.  Context for the GPU-vs-GPU comparison; None on failure."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'bench_torch_cuda.py'), '--batch', str(args.batch),
+                            '--frames', str(args.frames), '--steps', '3'], capture_output=True, text=True, timeout=600)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        return {'value': d['value'], 'unit': UNIT, 'ms_per_step': d['ms_per_step'], 'what': d['impl'] + ', fp32 (TF32 off), eager, '
+                'fwd + loss + bwd + clip_grad_norm_ + Adam, 3 timed steps after 2 warm-ups, wall clock around a synchronize'}
+    except Exception as ex:
+        return {'value': None, 'error': f'{type(ex).__name__}: {ex}'[:200]}
+
+
 # ------------------------------------------------------------------------------------------------
 # the GPU arm
 # ------------------------------------------------------------------------------------------------
-def _profile_traffic(frames_padded, batch):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the recurrence kernels from the committed
-    `ncu --set full` capture (profiles/r01_blstm_ncu.json: one fwd + one bwd launch at T=1008, B=64), averaged over
-    fwd+bwd and scaled to the AVERAGE launch of this run (the four pyramid layers run T, T/2, T/4, T/8 steps; the
-    kernels' traffic is linear in T*B), like `achieved`; None if not captured."""
+def hbm_kernels(device, B, cfg, reps=10):
+    """Achieved HBM GB/s of the bandwidth-bound kernels north_star names (loss, LayerNorm, the mix), each launched ALONE at
+    its configs[2] shape with the L2 flushed before every launch (a 512 MB memset), CUDA events around the launch, median
+    of `reps`.  `achieved` = algorithmic bytes / that time; the small kernels (a few MB) are launch-latency bound, which
+    is exactly what the figure shows."""
+    from b200st.kernels import K
+    k = K()
+    peaks = {}
     try:
-        d = json.load(open(os.path.join(ROOT, 'profiles', 'r01_blstm_ncu.json')))
-        ref = d['blstm_fwd_tc']
-        mean_t = sum(frames_padded // 2 ** l for l in range(4)) / 4.0
-        return d['dram_bytes_per_launch_avg'] * (mean_t * batch) / (ref['T'] * ref['B'])
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except Exception:
-        return None
+        pass
+    peak = peaks.get('hbm_gbs', 6550.0)
+    dt = torch.bfloat16 if runtime_dtype() == 'bf16' else torch.float32
+    es = 2 if dt == torch.bfloat16 else 4
+    L, S, D, V, E = cfg.max_seq_len_tgt, cfg.max_seq_len_src - 1, cfg.dim_model, cfg.dec_vocab_size, cfg.enc_embedding_size
+    rows = B * L
+    g = torch.Generator(device='cpu').manual_seed(1)
+    logits = torch.randn(rows, V, generator=g).to(device, dt)
+    target = torch.randint(5, V, (rows,), generator=g).to(device)
+    mask = torch.ones(rows, dtype=torch.uint8, device=device)
+    scale = torch.full((1,), 1.0 / rows, device=device)
+    x = torch.randn(rows, D, generator=g).to(device, dt)
+    dy = torch.randn(rows, D, generator=g).to(device, dt)
+    gamma, beta = torch.ones(D, device=device), torch.zeros(D, device=device)
+    _, mean, rstd = k.layernorm_fwd(x, gamma, beta, 1e-6)
+    ids = torch.randint(5, V, (B * S,), generator=g).to(device)
+    table = torch.randn(V, E, generator=g).to(device)
+    dyn = torch.randn(B * S, D, generator=g).to(device, dt)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)
+    cases = {
+        'loss': ('softmax_nll_fused_vec_kernel (fused softmax + masked NLL + dlogits)', 2 * rows * V * es,
+                 lambda: k.softmax_nll_fused(logits, target, mask, scale)),
+        'layernorm_fwd': ('layernorm_fwd_kernel', 2 * rows * D * es, lambda: k.layernorm_fwd(x, gamma, beta, 1e-6)),
+        'layernorm_bwd': ('layernorm_bwd_reg_kernel (dx + per-CTA dgamma/dbeta partial sums)', 3 * rows * D * es,
+                          lambda: k.layernorm_bwd_partial(dy, x, gamma, mean, rstd)),
+        'mix': ('mix_gather_concat_kernel (static rows gathered next to the dynamic embedding)',
+                B * S * (E * 4 + D * es + (E + D) * es), lambda: k.mix_gather_concat(ids, table, dyn)),
+    }
+    out = {}
+    for name, (kern, nbytes, fn) in cases.items():
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        ms = ts[len(ts) // 2]
+        out[name] = {'kernel': kern, 'bound': 'hbm', 'achieved': nbytes / ms / 1e6, 'peak': peak, 'unit': 'GB/s',
+                     'frac': nbytes / ms / 1e6 / peak, 'algorithmic_bytes': nbytes, 'us': round(ms * 1e3, 2)}
+    out['how'] = ('each kernel launched alone at its configs[2] shape, L2 flushed (512 MB memset) before every launch, CUDA '
+                  f'events around the launch, median of {reps}; peak = MEASURED_PEAKS.json hbm_gbs')
+    return out
+
+
+def runtime_dtype():
+    from b200st import runtime
+    return 'bf16' if runtime.compute_dtype() == torch.bfloat16 else 'fp32'
 
 
 def build_model(cfg, device):
@@ -386,6 +535,7 @@ def run_b200(args):
         b_shapes.append({'call': list(key), 'us': round(t * 1e3, 2), 'tflops': round(fl / t / 1e9, 1)})
     big_gemm = (b_ms, b_fl, b_n, b_shapes)
     del kt
+    hbm = hbm_kernels(device, args.batch, cfg) if rank == 0 else None
     ms_eager = timed(lambda: eager_step(dev_items), args.steps)
 
     # ---- the measured step: one CUDA graph of forward_train + loss + backward (+ all-reduce)
@@ -486,7 +636,7 @@ def run_b200(args):
                           'weights_changed_during_timed_region': optimizer_applied, 'adam_step_count': opt_steps},
             'clocks': clocks,
             'roofline': {'kernel': '+'.join(roof_names), 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
-                         'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': _profile_traffic(args.frames + 8 - args.frames % 8, args.batch), 'peak_source': peak_src,
+                         'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None, 'traffic_note': 'not measured in this run (ncu cannot run inside the bench); the per-launch dram__bytes of one `ncu --set full` capture are in profiles/', 'peak_source': peak_src,
                          'us_per_time_step': 1e3 * r_ms / (2 * sum((args.frames + 8 - args.frames % 8) // 2 ** l for l in range(4))),
                          'launches': r_calls, 'avg_launch_ms': r_ms / max(r_calls, 1),
                          'timed': 'CUDA events around every launch of this kernel family on its stream, eager pass of the '
@@ -506,9 +656,12 @@ def run_b200(args):
                 'each launch is bracketed alone)' if peaks else 'fallback', 'traffic': None,
                 'timed': 'every distinct >= 5e10-FLOP GEMM call of the step re-issued 20x back to back on its own operands, CUDA '
                          'events around the batch (an eager bracket would include host launch gaps)'}
+        line['hbm'] = hbm
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_baseline(args)
-            line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+            del graphed
+            torch.cuda.empty_cache()
+            line['stock_torch_cuda'] = stock_torch_cuda(args)
+            line['cpu_baseline'] = cpu_baseline_subprocess(args)
         emit(line)
     if world > 1:
         # A process group whose collectives were captured into a CUDA graph can block in teardown; results are
@@ -548,6 +701,7 @@ def main():
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--frames', type=int, default=1000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ref-budget', type=float, default=150.0, help='--impl reference: seconds of CPU work to spend')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA graph replay')
     args = ap.parse_args()
     _capture_stdout()
