@@ -24,6 +24,11 @@ import torch
 from . import runtime as rt
 from .kernels import K
 
+
+def position_signal(module):
+    from modules.layers import position_signal as f
+    return f(module)
+
 PAD = 0
 
 
@@ -37,9 +42,10 @@ class DecoderCache:
         self.B, self.S, self.D, self.k = B, S, D, beam_width
         self.n_hyp = B * beam_width
         self.max_len = max_len
-        assert max_len <= dec.time_signal.shape[1], 'call expand_time() for longer sequences'
+        if max_len > dec.time_signal.shape[1]:       # the API default max_seq_len = 900 exceeds the 500-row table the
+            dec.expand_time(max_len)                 # constructor builds; rows < 500 are unchanged (layers.py:293-309)
         dev, dt = enc_outputs.device, enc_outputs.dtype
-        self.pe = dec._pe.on(dec.time_signal, dev)                       # fp32 [max_len, D] on the device
+        self.pe = position_signal(dec).on(dec.time_signal, dev)                       # fp32 [max_len, D] on the device
         if self.pe.dim() == 3:
             self.pe = self.pe[0]
         self.src_mask = src_mask.contiguous()                            # uint8 [B, 1, S]

@@ -63,6 +63,13 @@ class GraphedTrainStep:
             self.loss = trainer._train_batch_device(model, self.static)
             if with_optimizer:
                 trainer.optimizer.step()
+        self._epoch = rt.cache_epoch()
+
+    def _check_epoch(self):
+        if rt.cache_epoch() != self._epoch:
+            raise RuntimeError('b200st: a cached low-precision weight copy was re-allocated after this step was captured '
+                               '(compute dtype switched, model.to(), load_state_dict(assign=True) or a parameter .data swap): '
+                               'the graph holds stale pointers; build a new GraphedTrainStep')
 
     def load(self, items: Dict, non_blocking: bool = True):
         """Copy a new batch (host pinned or device tensors of the captured shapes) into the static buffers."""
@@ -114,6 +121,7 @@ class GraphedTrainStep:
         self.static['acouslen'].copy_(st['acouslen'], non_blocking=True)
         self._free[slot].record(cur)
         self._pending = None
+        self._check_epoch()
         self.graph.replay()
         if self.with_optimizer:
             rt.after_raw_update()             # copies the captured kernel does not maintain are stale now
@@ -122,6 +130,7 @@ class GraphedTrainStep:
     def __call__(self, items: Optional[Dict] = None):
         if items is not None:
             self.load(items)
+        self._check_epoch()
         self.graph.replay()
         if self.with_optimizer:
             rt.after_raw_update()             # copies the captured kernel does not maintain are stale now

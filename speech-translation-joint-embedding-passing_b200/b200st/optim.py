@@ -31,7 +31,11 @@ def _pinned(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
 
 
 class FusedClipAdam:
-    """Drives csrc/optim.cu for one `torch.optim.Adam` instance (one hyper-parameter set for all groups)."""
+    """Drives csrc/optim.cu for one `torch.optim.Adam` instance (one hyper-parameter set for all groups).
+    Limitation: ONE step counter is shared by every parameter (seeded from the largest existing per-parameter step), so the
+    bias correction of a parameter that receives its first gradient later than the others follows the shared count --
+    identical to torch.optim.Adam whenever all trained parameters get a gradient from the first step on, which is the case
+    for every trainer mode of the reference (parameters without a gradient are never touched)."""
 
     def __init__(self, adam: torch.optim.Adam, max_grad_norm: float = 0.0):
         if type(adam) is not torch.optim.Adam:
@@ -41,8 +45,9 @@ class FusedClipAdam:
         for g in adam.param_groups:
             if g.get('amsgrad') or g.get('maximize'):
                 raise NotImplementedError('amsgrad / maximize are not implemented by the fused Adam kernel')
-            if any(g[k] != g0[k] for k in ('betas', 'eps', 'weight_decay')):
-                raise NotImplementedError('parameter groups with different betas/eps/weight_decay')
+            if any(g[k] != g0[k] for k in ('lr', 'betas', 'eps', 'weight_decay')):
+                raise NotImplementedError('parameter groups with different lr/betas/eps/weight_decay (the reference builds '
+                                          'ONE group, trainer_base.py:423; the fused kernel applies one set to every tensor)')
         self.adam = adam
         self.max_grad_norm = float(max_grad_norm or 0.0)
         self._sig = None            # (param ids, grad pointers) the device table was built for

@@ -59,6 +59,8 @@ def operand(param: torch.Tensor) -> torch.Tensor:
             return hit[3]
     from .kernels import K
     shadow = K().cast(p.contiguous(), _compute_dtype)
+    if hit is not None:
+        _epoch[0] += 1         # a NEW buffer replaces one that captured graphs may have baked in (model.to, p.data swap)
     _cache[key] = (weakref.ref(param), ver, p.data_ptr(), shadow)
     return shadow
 
@@ -76,6 +78,8 @@ def operand_cat(*params: torch.Tensor) -> torch.Tensor:
     from .kernels import K
     rows = [p.size(0) for p in params]
     buf = hit[3] if same else torch.empty((sum(rows), params[0].size(1)), dtype=_compute_dtype, device=params[0].device)
+    if hit is not None and not same:
+        _epoch[0] += 1         # re-allocated: stale pointers in captured graphs
     r0 = 0
     for p, n in zip(params, rows):
         src = p.detach().contiguous()

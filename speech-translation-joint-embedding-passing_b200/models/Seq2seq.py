@@ -46,7 +46,9 @@ class Seq2seq(nn.Module):
         if os.path.exists(self.EMB_DYN_AVE_PATH):
             self.EMB_DYN_AVE = torch.from_numpy(np.load(self.EMB_DYN_AVE_PATH))
         else:
-            self.EMB_DYN_AVE = torch.zeros(dim_model)
+            # the reference crashes here; ST / ASR modes never read the vector, so construction goes on and the MT /
+            # ST_BASE paths raise when they would need it (assign model.EMB_DYN_AVE = <float32[dim_model]> to provide it)
+            self.EMB_DYN_AVE = None
         if load_embedding_src or load_embedding_tgt:
             raise NotImplementedError('pre-trained embedding files are host I/O outside the hot path; '
                                       'load them into enc_embedder/dec_embedder.weight after construction')
@@ -162,6 +164,9 @@ class Seq2seq(nn.Module):
         return K().length_mask(lengths, max_len)
 
     def _dyn_ave(self, batch, length, device):
+        if self.EMB_DYN_AVE is None:
+            raise FileNotFoundError(f'MT / ST_BASE modes need the average dynamic embedding: {self.EMB_DYN_AVE_PATH} was not '
+                                    f'found at construction (Seq2seq.py:64-66); set model.EMB_DYN_AVE to a float32[dim_model] tensor')
         ave = self.EMB_DYN_AVE.to(device=device, dtype=rt.compute_dtype())
         return ave.repeat(batch, length, 1)
 
@@ -433,9 +438,14 @@ class Seq2seq(nn.Module):
         src_mask_input = self._length_mask(self._as_device_lengths(lengths, device), emb_src.size(1))
         return self._encoder_en(emb_src, src_mask=src_mask_input), src_mask_input
 
+    @staticmethod
+    def _padded_to_rule(acous_feats, acous_lens):
+        """The graphed front end bakes the padded length in; other inputs take the eager front end."""
+        m = max(int(n) for n in acous_lens)
+        return m + 8 - m % 8 == acous_feats.size(1)
+
     def _frontend_graphed(self, acous_feats, acous_lens, mode):
         lens = [int(n) for n in acous_lens]
-        assert max(lens) + 8 - max(lens) % 8 == acous_feats.size(1), 'padded max length must equal the feature length'
         key = (tuple(acous_feats.shape), acous_feats.dtype, str(acous_feats.device), mode, rt.compute_dtype())
         fe = getattr(self, '_fe', None)
         rt.refresh_all()                    # the graph reads cached weight copies without re-casting them
@@ -481,7 +491,8 @@ class Seq2seq(nn.Module):
                         teacher_forcing_ratio=1.0, need_logps=False)
                     ids = self._pre_proc_src(src, device)
                 else:
-                    if self.decode_cache and self.decode_graphs and acous_feats.is_cuda and acous_lens is not None:
+                    if (self.decode_cache and self.decode_graphs and acous_feats.is_cuda and acous_lens is not None
+                            and self._padded_to_rule(acous_feats, acous_lens)):
                         # the whole front end (acoustic encoder, free-running LAS decoder loop, mix, Transformer
                         # encoder: ~1500 small launches) replayed as one CUDA graph per input shape
                         enc_outputs, src_mask_input = self._frontend_graphed(acous_feats, acous_lens, mode)
@@ -521,6 +532,13 @@ class Seq2seq(nn.Module):
         d.pop('_beam_key', None)
         d.pop('_fe', None)
         return d
+
+    def __setstate__(self, state):
+        # also the path a pickle written by the REFERENCE's classes takes (checkpoint.py:76,160-164): attributes this
+        # class adds on top of the reference's are class-level defaults or created on first use
+        self.__dict__.update(state)
+        if not hasattr(self, 'EMB_DYN_AVE_PATH'):
+            self.EMB_DYN_AVE_PATH = 'models/base/ted-asr-v001/eval_ted_train_STATS/2020_09_02_04_10_44/dyn_emb_ave.npy'
 
     def check_var(self, var_name, var_val_set=None):
         if not hasattr(self, var_name):

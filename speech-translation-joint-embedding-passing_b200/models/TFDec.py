@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from b200st import functional as BF
-from modules.layers import TransformerDecoderLayer, _gen_position_signal, PositionSignal
+from modules.layers import TransformerDecoderLayer, _gen_position_signal, PositionSignal, position_signal
 
 
 class Decoder(nn.Module):
@@ -42,7 +42,7 @@ class Decoder(nn.Module):
         if decode_speedup:
             raise NotImplementedError('decode_speedup is never used by Seq2seq (SURVEY.md §2.1 #6)')
         assert tgt.shape[1] <= self.time_signal.shape[1], 'call expand_time() for longer sequences'
-        x = BF.add_posenc(tgt, self._pe.on(self.time_signal, tgt.device))     # TFDec.py:85-86
+        x = BF.add_posenc(tgt, position_signal(self).on(self.time_signal, tgt.device))     # TFDec.py:85-86
         att_decslf = att_encdec = None
         for layer in self.dec_layers:
             x, att_decslf, att_encdec = layer(x, memory, decslf_attn_mask=tgt_mask,

@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from b200st import functional as BF
-from modules.layers import TransformerEncoderLayer, _gen_position_signal, PositionSignal
+from modules.layers import TransformerEncoderLayer, _gen_position_signal, PositionSignal, position_signal
 
 
 class Encoder(nn.Module):
@@ -40,7 +40,7 @@ class Encoder(nn.Module):
 
     def forward(self, src, src_mask=None):
         assert src.shape[1] <= self.time_signal.shape[1], 'call expand_time() for longer sequences'
-        x = BF.add_posenc(src, self._pe.on(self.time_signal, src.device))     # TFEnc.py:82-83
+        x = BF.add_posenc(src, position_signal(self).on(self.time_signal, src.device))     # TFEnc.py:82-83
         att = None
         for layer in self.enc_layers:
             x, att = layer(x, slf_attn_mask=src_mask)

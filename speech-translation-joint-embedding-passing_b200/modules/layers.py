@@ -154,12 +154,24 @@ def _gen_position_signal(max_len, d_model):
     return pe.unsqueeze(0).clone().detach()
 
 
+def position_signal(module):
+    """The PositionSignal cache of an Encoder / Decoder; created on first use for instances that never ran this
+    package's constructor (whole-module pickles written by the reference's classes, checkpoint.py:76)."""
+    pe = module.__dict__.get('_pe')
+    if pe is None:
+        pe = module.__dict__['_pe'] = PositionSignal()
+    return pe
+
+
 class PositionSignal:
     """Device-resident copy of a time-signal table: the reference re-uploads it on every call
     (`.type_as`, TFEnc.py:82-83); here it is uploaded once per device and fused into one add kernel."""
 
     def __init__(self):
         self._dev = {}
+
+    def __getstate__(self):          # whole-module pickles (checkpoint.py:76) must not carry device tensors of a cache
+        return {'_dev': {}}
 
     def on(self, table, device):
         key = (str(device), table.data_ptr(), table.size(1))

@@ -12,6 +12,7 @@ from b200st.optim import FusedClipAdam
 class Optimizer(object):
 
     _ARG_MAX_GRAD_NORM = 'max_grad_norm'
+    _fused = None          # class default: instances unpickled from a checkpoint the REFERENCE wrote have no such attribute
 
     def __init__(self, optim, max_grad_norm=0):
         self.optimizer = optim

@@ -409,3 +409,47 @@ def test_golden_h256_bf16_tensor_core_kernels():
         print(f'\nst_h256 bf16: global sampled gradient error {glob:.2e}, worst per-parameter {worst * 2e-2:.2e}')
     finally:
         K().set_gemm_backend(old[0]); K().set_blstm_backend(old[1]); K().set_mha_backend(old[2])
+
+
+@pytest.mark.parametrize('penalty', [0.6, 1.0, 1.5])
+def test_beam5_length_penalty_and_early_eos_vs_oracle(penalty):
+    """Seq2seq.py:337-393 edge cases against the CPU oracle, fp32, ids exact: beam 5 (the configs[4] width), length penalty
+    score / len^alpha with alpha != 1 (Seq2seq.py:367-371), hypotheses that hit EOS early (their scores are frozen and
+    their length stops growing, Seq2seq.py:361-365,384-387) next to ones that do not, ragged utterances; through the
+    KV-cached graph-replayed loop AND the reference-shaped recompute loop."""
+    cfg = O.STConfig(enc_vocab_size=48, dec_vocab_size=48, enc_embedding_size=24, dec_embedding_size=24,
+                     max_seq_len_src=10, max_seq_len_tgt=20, num_heads=4, dim_model=64, dim_feedforward=128,
+                     enc_layers=2, dec_layers=2, acous_dim=16, acous_hidden_size=32)
+    P = O.init_params(cfg, seed=12, scale=3.0)
+    data = O.synthetic_batch(cfg, 10, 88, seed=6, ragged=True)
+    ref = O.forward_translate_st(P, cfg, data['acous_feats'], data['acous_lens'], beam_width=5, penalty_factor=penalty,
+                                 max_seq_len=20)
+    assert (ref == 3).any(), 'the case must contain EOS tokens to exercise the masking'
+    m = build_model(cfg, P, device='cuda').eval()
+    lens = [torch.tensor([n]) for n in data['acous_lens']]
+    for cached in (True, False):
+        m.decode_cache = cached
+        for _ in range(2 if cached else 1):          # second call replays the captured per-position graphs
+            got = m.forward_translate(acous_feats=data['acous_feats'].cuda(), acous_lens=lens, beam_width=5,
+                                      penalty_factor=penalty, use_gpu=True, max_seq_len=20, mode='ST')
+        assert got.shape == ref.shape and torch.equal(got.cpu(), ref), (cached, penalty)
+
+
+def test_translate_default_max_seq_len_and_unpadded_features():
+    """API defaults: forward_translate's default max_seq_len = 900 exceeds the decoder's 500-row time signal
+    (the KV cache expands it instead of asserting).  ids == the recompute loop."""
+    cfg = O.STConfig(enc_vocab_size=48, dec_vocab_size=48, enc_embedding_size=24, dec_embedding_size=24,
+                     max_seq_len_src=8, max_seq_len_tgt=12, num_heads=4, dim_model=64, dim_feedforward=128,
+                     enc_layers=1, dec_layers=1, acous_dim=16, acous_hidden_size=32)
+    P = O.init_params(cfg, seed=12, scale=3.0)
+    P['out_tgt.weight'][3] += 0.5 * P['out_tgt.weight'].abs().max()       # make EOS likely: the 900-step loop exits early
+    data = O.synthetic_batch(cfg, 4, 40, seed=6, ragged=True)
+    m = build_model(cfg, P, device='cuda').eval()
+    lens = [torch.tensor([n]) for n in data['acous_lens']]
+    feats = data['acous_feats'].cuda()
+    outs = {}
+    for cached in (True, False):
+        m.decode_cache = cached
+        outs[cached] = m.forward_translate(acous_feats=feats.clone(), acous_lens=lens, beam_width=2, use_gpu=True, mode='ST')
+    assert torch.equal(outs[True], outs[False])
+    assert m.dec_tgt.time_signal.shape[1] >= 900

@@ -146,3 +146,112 @@ def _early_exit_case(device, boost):
         widths.add(outs[True].size(1))
     if boost >= 40.0:
         assert min(widths) < 9          # greedy: every hypothesis ended at once, the loop stopped early
+
+
+# ------------------------------------------------------------------------------------------------
+# MT and ASR trainer steps (trainer_mt.py:199-282, trainer_asr.py:199-283) against the REAL reference's goldens
+# ------------------------------------------------------------------------------------------------
+def test_mt_and_asr_trainer_steps_match_reference_goldens(golden, fake_backend):
+    from b200st.train_step import Trainer_ASR, Trainer_MT
+    I = golden.inputs()
+    m = build_model(golden.cfg, golden.params())
+    m.EMB_DYN_AVE = golden['in/emb_dyn_ave']
+    m.train()
+    res = Trainer_MT(use_gpu=False, batch_size=I['src'].size(0))._train_batch(
+        m, {'srcid': [I['src']], 'tgtid': [I['tgt']], 'srclen': None, 'tgtlen': None})
+    assert set(res) == {'nll_loss_de'}
+    assert abs(res['nll_loss_de'] - float(golden['mt/loss'])) < 2e-5 * abs(float(golden['mt/loss']))
+    named = dict(m.named_parameters())
+    for name, n in golden.group('mt_gradnorm').items():
+        assert abs(float(named[name].grad.norm()) - float(n)) < 2e-4 * float(n) + 1e-7, name
+    m.zero_grad()
+    m.las.encoder.spec_aug = False          # the golden's features are the already-augmented copy (make_golden.py)
+    res = Trainer_ASR(use_gpu=False, batch_size=I['src'].size(0))._train_batch(
+        m, {'srcid': [I['src']], 'acous_feat': [golden['asr/aug_feats']], 'acouslen': I['acous_lens']})
+    assert res['nll_loss_de'] == 0 and abs(res['nll_loss_en'] - float(golden['asr/loss'])) < 2e-5 * abs(float(golden['asr/loss']))
+    for name, n in golden.group('asr_gradnorm').items():
+        assert abs(float(named[name].grad.norm()) - float(n)) < 2e-4 * float(n) + 1e-7, name
+
+
+# ------------------------------------------------------------------------------------------------
+# a checkpoint WRITTEN BY THE REFERENCE loads into this repo's classes (checkpoint.py:54-180), and Trainer.train's
+# load_mode / load_freeze path (trainer_base.py:244-313, trainer_st.py:30) trains with las.* frozen
+# ------------------------------------------------------------------------------------------------
+def test_reference_written_checkpoint_loads_translates_and_fine_tunes_frozen(tmp_path):
+    import json
+    import os
+    import subprocess
+    import sys
+    ref = '/root/reference'
+    if not os.path.isdir(os.path.join(ref, 'models')):
+        pytest.skip('build container only: needs the reference to write the checkpoint')
+    drv = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'ckpt_driver.py')
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1')
+    w = subprocess.run([sys.executable, drv, '--write', str(tmp_path)], capture_output=True, text=True, env=env, timeout=600)
+    assert w.returncode == 0, w.stderr[-3000:]
+    assert '/root/reference/models/Seq2seq.py' in json.loads(w.stdout.strip().splitlines()[-1])['cls']
+    r = subprocess.run([sys.executable, drv, '--load', str(tmp_path)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert 'speech-translation-joint-embedding-passing_b200/models/Seq2seq.py' in res['cls_file']
+    assert 'speech-translation-joint-embedding-passing_b200/modules/optim.py' in res['optimizer_cls_file']
+    assert (res['epoch'], res['step']) == (3, 77)
+    assert res['beam1_equal_golden'] and res['beam3_equal_golden']
+    assert abs(res['loss'] - res['golden_loss']) < 2e-5 * abs(res['golden_loss'])
+    assert res['frozen_with_grad'] == [] and res['worst_unfrozen_grad_err'] < 5e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_frozen_las_step_launches_no_lstm_backward_and_matches_oracle(dtype):
+    """The fine-tuning recipe (trainer_st.py:30 load_freeze=True): las.* has requires_grad=False.  No recurrence / LAS-decoder
+    backward kernel may be launched, and the loss and every remaining gradient equal the oracle's."""
+    from b200st import runtime
+    from b200st.kernels import K
+    from b200st.train_step import Trainer_ST
+    from test_gpu_parity import _grad_check
+    runtime.set_compute_dtype(dtype)
+    try:
+        cfg = O.STConfig(enc_vocab_size=304, dec_vocab_size=304, enc_embedding_size=24, dec_embedding_size=24,
+                         max_seq_len_src=8, max_seq_len_tgt=11, num_heads=2, dim_model=128, dim_feedforward=96,
+                         enc_layers=2, dec_layers=2, acous_dim=16, acous_hidden_size=256)
+        P = O.init_params(cfg, seed=3)
+        data = O.synthetic_batch(cfg, batch=16, frames=61, seed=4, ragged=True)
+        Pg = {k: v.clone().requires_grad_(not k.startswith('las.')) for k, v in P.items()}
+        loss_ref, _ = O.train_step_st(Pg, cfg, data['src'], data['tgt'], data['acous_feats'], data['acous_lens'])
+        loss_ref.backward()
+        m = build_model(cfg, P, device='cuda')
+        m.train()
+        for n, p in m.named_parameters():
+            if n.startswith('las.'):
+                p.requires_grad = False
+        calls = {'blstm_bwd': 0, 'lstm_cell_bwd': 0, 'las_attn_bwd': 0}
+        k = K()
+        orig = {n: getattr(k, n) for n in calls}
+        for n in calls:
+            def wrapped(*a, __n=n, **kw):
+                calls[__n] += 1
+                return orig[__n](*a, **kw)
+            setattr(k, n, wrapped)
+        try:
+            items = {'srcid': [data['src'].cuda()], 'tgtid': [data['tgt'].cuda()], 'acous_feat': [data['acous_feats'].cuda()],
+                     'acouslen': data['acous_lens']}
+            loss = float(Trainer_ST(use_gpu=True, batch_size=16)._train_batch_device(m, items))
+        finally:
+            for n in calls:
+                delattr(k, n)
+        assert calls == {'blstm_bwd': 0, 'lstm_cell_bwd': 0, 'las_attn_bwd': 0}, calls
+        tol = 1e-4 if dtype == 'fp32' else 2e-2
+        assert abs(loss - float(loss_ref)) < tol * abs(float(loss_ref))
+        named = dict(m.named_parameters())
+        assert all(named[n].grad is None for n in named if n.startswith('las.'))
+        ref = {n: v.grad for n, v in Pg.items() if v.grad is not None and float(v.grad.abs().sum()) > 0}
+        assert ref and not any(n.startswith('las.') for n in ref)
+        if dtype == 'fp32':
+            _grad_check(named, ref, 1e-4)
+        else:       # bf16: free-running LAS symbols may flip on near ties (nothing is pinned here): global bound only
+            gn = sum(float(g.double().norm() ** 2) for g in ref.values()) ** 0.5
+            dn = sum(float((named[n].grad.double().cpu() - g.double()).norm() ** 2) for n, g in ref.items()) ** 0.5
+            assert dn / gn < 5e-2, dn / gn
+    finally:
+        runtime.set_compute_dtype('fp32')
