@@ -184,6 +184,22 @@ int b200st_blstm_bwd(int dtype, const void* dout, int64_t out_ld_t, int64_t out_
                      const int32_t* lens, void* dgates, int64_t T, int64_t B, int64_t H,
                      b200st_stream_t stream);
 
+/* ---- Persistent LAS decoder loop, forward (Dec.forward / forward_step / decode, Dec.py:130-233,320-438) ------------
+ * ONE launch runs all S decode steps (3 uni-LSTM layers -> bilinear attention -> acous_ffn -> vocabulary projection ->
+ * arg-max feedback and the EOS/PAD length rule) for bf16 activations with decoder width 512 and 512-wide keys/values;
+ * replaces S x ~9 dependent launches of b200st_gemm / lstm_cell_fwd / las_attn_fwd / argmax_rows.  `args` is a HOST array
+ * of `n_args` = 42 int64 slots holding device pointers and sizes, in this order:
+ *   0 wk bf16[B,Tk,512] projected keys   1 enc bf16[B,Tk,512] values   2 klens int32[B]|0
+ *   3 gx0 bf16: free running [V,2048] = E W_ih0[:, :E]^T + b0 (row gathered by the fed-back token), teacher forced [S,B,2048]
+ *   4..15 per layer i = 0,1,2: wx_i bf16 (layer 0: W_ih0[:, E:]), row stride of wx_i, whh_i bf16[2048,512], bias_i f32[2048]|0
+ *   16 w_ffn bf16[512,1024]   17 w_out bf16[V,512]   18 b_out f32[V]
+ *   19 CV bf16[S+1,B,512] (row 0 zero)   20..28 per layer: H_i bf16[S+1,B,512] (row 0 zero), C_i f32[S+1,B,512] (row 0 zero),
+ *   ACT_i f32[S,B,2048]   29 RES1 bf16[S,B,512]   30 CTX bf16[S,B,512]   31 PROBS f32[S,B,Tk]   32 LOGITS bf16[S,B,V]|0
+ *   33 SYM int64[S,B]   34 lengths int32[B] (pre-set to S+1)   35 best u64[2,B] scratch   36 barrier u32[1] scratch
+ *   37 B   38 Tk   39 S   40 V   41 teacher forcing (0 | 1)
+ * Needs 128 co-resident CTAs (one per SM). */
+int b200st_las_decoder_fwd(const int64_t* args, int64_t n_args, b200st_stream_t stream);
+
 /* ---- LAS bilinear attention step (attention.py:190-193,250-273; Dec.py:423-425) ------------------
  * score[b,j] = q[b] . wk[b,j]; j >= klens[b] -> -1e12; softmax; ctx[b] = sum_j p[b,j] vals[b,j]. */
 int b200st_las_attn_fwd(int dtype, const void* q, const void* wk, const void* vals,

@@ -590,6 +590,11 @@ class _LASDecoder(Function):
 
         z = lambda *s, dtype=dt: torch.zeros(s, dtype=dtype, device=dev)
         e = lambda *s, dtype=dt: torch.empty(s, dtype=dtype, device=dev)
+        if (rt.las_persistent() and dt == torch.bfloat16 and D == 512 and H2 == 512 and n_layers == 3 and p_emb == 0 and
+                p_drop == 0 and 1 <= Tk <= 512 and B <= 1024 and V <= 128 * 80 and hasattr(k, 'las_decoder_fwd')
+                and enc.is_cuda and torch.cuda.get_device_properties(dev).multi_processor_count >= 128):
+            return _LASDecoder._forward_persistent(ctx, k, enc, klens, ids_tf, S, need_logps, drop, emb_table, w_att, w_ffn,
+                                                   w_out, b_out, lstm_params, lp, wih, whh, bias, wf, wo, wk)
         CV = z(S + 1, B, D)                                   # CV[s+1] = cell_value of step s; CV[0] = 0
         Hst = [z(S + 1, B, D) for _ in range(n_layers)]
         Cst = [z(S + 1, B, D, dtype=torch.float32) for _ in range(n_layers)]
@@ -710,6 +715,64 @@ class _LASDecoder(Function):
         saved.append(rng)
         saved += list(lstm_params)
         ctx.res_layers = [i for i in range(n_layers) if RES[i] is not None]
+        ctx.save_for_backward(*saved)
+        ctx.mark_non_differentiable(symbols, lengths)
+        return embs, logps, symbols, lengths
+
+    @staticmethod
+    def _forward_persistent(ctx, k, enc, klens, ids_tf, S, need_logps, drop, emb_table, w_att, w_ffn, w_out, b_out,
+                            lstm_params, lp, wih, whh, bias, wf, wo, wk):
+        """Same outputs and saved buffers as the step-by-step path below, produced by ONE persistent launch
+        (csrc/las_decoder.cu): bf16, D = 512, 3 layers, no dropout."""
+        dt, dev, f32 = enc.dtype, enc.device, torch.float32
+        B, Tk, H2 = enc.shape
+        E, D, V, n_layers = emb_table.size(1), w_ffn.size(0), w_out.size(0), 3
+        z = lambda *s, dtype=dt: torch.zeros(s, dtype=dtype, device=dev)
+        e = lambda *s, dtype=dt: torch.empty(s, dtype=dtype, device=dev)
+        CV = e(S + 1, B, D); CV[0].zero_()
+        Hst = [e(S + 1, B, D) for _ in range(3)]
+        Cst = [e(S + 1, B, D, dtype=f32) for _ in range(3)]
+        for t in Hst + Cst:
+            t[0].zero_()
+        ACT = [e(S, B, 4 * D, dtype=f32) for _ in range(3)]
+        RES = [None, e(S, B, D), None]
+        CTX, PROBS = e(S, B, H2), e(S, B, Tk, dtype=f32)
+        LOGITS = e(S, B, V) if need_logps else None
+        lengths = torch.full((B,), S + 1, dtype=torch.int32, device=dev)       # Dec.py:163
+        teacher = ids_tf is not None
+        if teacher:      # every input token is known: its first-layer gate contribution for all steps is ONE GEMM
+            ids_in = ids_tf.t()[:S].contiguous()
+            SYM = e(S, B, dtype=torch.int64)
+            EMB = k.embedding_fwd(ids_in.reshape(-1), emb_table, dt).view(S, B, E)
+            gx0 = k.gemm(EMB.view(S * B, E), wih[0][:, :E], trans_b=True, bias=bias[0])
+        else:            # free running: row of E W_ih0[:, :E]^T + b gathered by the fed-back token (Dec.py:199,223,383)
+            IDS = e(S + 1, B, dtype=torch.int64)
+            IDS[0].fill_(BOS)                                                  # Dec.py:158-160,199
+            SYM = IDS[1:]
+            gx0 = k.gemm(rt.operand(emb_table), wih[0][:, :E], trans_b=True, bias=bias[0])
+        k.las_decoder_fwd(wk, enc, klens, gx0, [wih[0][:, E:], wih[1], wih[2]], whh, [None, bias[1], bias[2]], wf, wo, b_out,
+                          CV, Hst, Cst, ACT, RES[1], CTX, PROBS, LOGITS, SYM, lengths, teacher)
+        if not teacher:
+            ids_in = IDS[:S]
+            EMB = k.embedding_fwd(ids_in.reshape(-1), emb_table, dt).view(S, B, E)     # what backward multiplies dG0 with
+        embs = k.transpose01(CV[1:])                                             # [B,S,D]
+        if need_logps:
+            logp_tm, _ = k.log_softmax_fwd(LOGITS.view(S * B, V))
+            logps = k.transpose01(logp_tm.view(S, B, V))
+        else:
+            logp_tm = None
+            logps = torch.empty(0, dtype=dt, device=dev)
+        symbols = SYM.t().contiguous()
+        ctx.geom = (B, Tk, H2, S, E, D, V, n_layers)
+        ctx.need_logps = need_logps
+        ctx.has_klens = klens is not None
+        ctx.n_fixed = 10
+        ctx.drop = (0.0, 0.0, 0, [[0] * n_layers for _ in range(S)], [0] * S, not teacher)
+        saved = [enc, klens, ids_in.contiguous(), wk, CV, CTX, PROBS, EMB, logp_tm, emb_table, w_att, w_ffn, w_out]
+        saved += Hst + Cst + ACT + [RES[1]]
+        saved.append(None)
+        saved += list(lstm_params)
+        ctx.res_layers = [1]
         ctx.save_for_backward(*saved)
         ctx.mark_non_differentiable(symbols, lengths)
         return embs, logps, symbols, lengths

@@ -356,6 +356,37 @@ class CudaKernels:
                    'las_attn_bwd')
         return dscore, dq
 
+    def las_decoder_fwd(self, wk, enc, klens, gx0, wx, whh, bias, wffn, wout, bout, CV, H, C, ACT, RES1, CTX, PROBS, LOGITS,
+                        SYM, lengths, teacher):
+        """The whole S-step LAS decoder loop in ONE persistent launch (csrc/las_decoder.cu; slot list in include/b200st.h).
+        bf16, decoder width 512, 3 layers.  wx / whh / bias / H / C / ACT are 3-element lists; SYM int64 [S, B] contiguous."""
+        tensors = [wk, enc, klens, gx0] + [t for i in range(3) for t in (wx[i], whh[i], bias[i])] + \
+                  [wffn, wout, bout, CV] + [t for i in range(3) for t in (H[i], C[i], ACT[i])] + [RES1, CTX, PROBS, LOGITS, SYM, lengths]
+        self._need_cuda(*tensors)
+        B, Tk, D = wk.shape
+        S = SYM.size(0)
+        V = wout.size(0)
+        bf = torch.bfloat16
+        assert D == 512 and enc.shape == (B, Tk, 512) and wk.dtype == bf and enc.dtype == bf and wk.is_contiguous() and enc.is_contiguous()
+        assert all(w.dtype == bf and w.stride(1) == 1 and w.shape == (2048, 512) for w in wx + whh) and all(w.is_contiguous() for w in whh)
+        assert wffn.shape == (512, 1024) and wffn.is_contiguous() and wout.shape == (V, 512) and wout.is_contiguous()
+        assert gx0.dtype == bf and gx0.is_contiguous() and gx0.size(-1) == 2048
+        assert CV.shape == (S + 1, B, 512) and all(h.shape == (S + 1, B, 512) and h.is_contiguous() for h in H + C)
+        assert SYM.dtype == torch.int64 and SYM.is_contiguous() and SYM.shape == (S, B) and lengths.dtype == torch.int32
+        scratch = torch.empty(2 * B + 2, dtype=torch.int64, device=wk.device)      # best[2][B] | barrier
+        ptr = lambda t: 0 if t is None else t.data_ptr()
+        vals = [ptr(wk), ptr(enc), ptr(klens), ptr(gx0)]
+        for i in range(3):
+            vals += [ptr(wx[i]), wx[i].stride(0), ptr(whh[i]), ptr(bias[i])]
+        vals += [ptr(wffn), ptr(wout), ptr(bout), ptr(CV)]
+        for i in range(3):
+            vals += [ptr(H[i]), ptr(C[i]), ptr(ACT[i])]
+        vals += [ptr(RES1), ptr(CTX), ptr(PROBS), ptr(LOGITS), ptr(SYM), ptr(lengths), scratch.data_ptr(),
+                 scratch.data_ptr() + 16 * B, B, Tk, S, V, int(bool(teacher))]
+        arr = (ctypes.c_int64 * len(vals))(*vals)
+        _lib.check(self.lib.b200st_las_decoder_fwd(arr, len(vals), self._stream()), 'las_decoder_fwd')
+        return scratch           # keep alive until the launch is enqueued (stream-ordered allocator: safe to drop after)
+
     def argmax_rows(self, x, idx_out, lengths=None, step=0, embed=None, embed2=None):
         """x [rows, cols] (row-strided); idx_out: int64 1-D view (any stride) of length rows.  With `lengths`
         (int32 [rows]) the LAS decode-length rule (Dec.py:334-340) is applied in the same launch; with

@@ -20,6 +20,19 @@ _epoch = [0]               # bumped whenever a cached operand copy is (re)create
                            # baked an operand pointer compare it to know when they are stale
 
 
+_las_persistent = [os.environ.get('B200ST_LAS_PERSISTENT', '1') != '0']
+
+
+def las_persistent(on=None) -> bool:
+    """The persistent one-launch LAS decoder loop (csrc/las_decoder.cu) is used where its shape constraints hold (bf16,
+    decoder width 512, 3 layers, no dropout); `las_persistent(False)` forces the step-by-step kernels (test hook).
+    Returns the previous / current setting."""
+    old = _las_persistent[0]
+    if on is not None:
+        _las_persistent[0] = bool(on)
+    return old
+
+
 def cache_epoch() -> int:
     return _epoch[0]
 
