@@ -199,6 +199,10 @@ int b200st_blstm_bwd(int dtype, const void* dout, int64_t out_ld_t, int64_t out_
  *   37 B   38 Tk   39 S   40 V   41 teacher forcing (0 | 1)
  * Needs 128 co-resident CTAs (one per SM). */
 int b200st_las_decoder_fwd(const int64_t* args, int64_t n_args, b200st_stream_t stream);
+/* Debug aid: register an int64 [S * 16 + 1] device buffer; CTA 0 then records %globaltimer (ns) at the phase boundaries of
+ * every decode step ([s][0] start, [1..3] after LSTM layer 0..2 + barrier, [7] end of attention, [4] after its barrier,
+ * [5] after acous_ffn + barrier, [6] after the vocabulary phase + barrier; [8..11] inside the layer-1/2 hand-over: after the fresh-half GEMM, the cell, the barrier arrive, the recurrent-half GEMM; [S*16] kernel start).  NULL switches it off. */
+int b200st_las_decoder_timeline(void* buf);
 
 /* ---- LAS bilinear attention step (attention.py:190-193,250-273; Dec.py:423-425) ------------------
  * score[b,j] = q[b] . wk[b,j]; j >= klens[b] -> -1e12; softmax; ctx[b] = sum_j p[b,j] vals[b,j]. */

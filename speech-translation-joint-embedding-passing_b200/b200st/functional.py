@@ -591,7 +591,7 @@ class _LASDecoder(Function):
         z = lambda *s, dtype=dt: torch.zeros(s, dtype=dtype, device=dev)
         e = lambda *s, dtype=dt: torch.empty(s, dtype=dtype, device=dev)
         if (rt.las_persistent() and dt == torch.bfloat16 and D == 512 and H2 == 512 and n_layers == 3 and p_emb == 0 and
-                p_drop == 0 and 1 <= Tk <= 512 and B <= 1024 and V <= 128 * 80 and hasattr(k, 'las_decoder_fwd')
+                p_drop == 0 and 1 <= Tk <= 512 and B <= 128 and V <= 128 * 80 and hasattr(k, 'las_decoder_fwd')
                 and enc.is_cuda and torch.cuda.get_device_properties(dev).multi_processor_count >= 128):
             return _LASDecoder._forward_persistent(ctx, k, enc, klens, ids_tf, S, need_logps, drop, emb_table, w_att, w_ffn,
                                                    w_out, b_out, lstm_params, lp, wih, whh, bias, wf, wo, wk)
