@@ -184,6 +184,25 @@ int b200st_blstm_bwd(int dtype, const void* dout, int64_t out_ld_t, int64_t out_
                      const int32_t* lens, void* dgates, int64_t T, int64_t B, int64_t H,
                      b200st_stream_t stream);
 
+/* ---- On-device beam search of Seq2seq._step_translate (Seq2seq.py:337-393) --------------------------------------------
+ * topk_logsoftmax: score[r, 0..k) = the k largest log_softmax(x[r, :]) values (fp32, descending; ties: lower index first),
+ * pred[r, 0..k) their column indices; one pass for the log-sum-exp, k <= 8.  Replaces log_softmax + topk (Seq2seq.py:254-257). */
+int b200st_topk_logsoftmax(int dtype, const void* x, int64_t ld, int64_t rows, int64_t cols, int64_t k, float* score,
+                           int64_t* pred, b200st_stream_t stream);
+/* beam_select: one decode position of the beam bookkeeping for n_utt utterances x k hypotheses (hypothesis h = u * k + m):
+ *   first != 0 (position 1): scores[h] += cand_score[u*k, m]; token = cand_pred[u*k, m]           (Seq2seq.py:349-356)
+ *   else: candidates (r, j): (scores[u*k+r] + (eos[u*k+r] ? (j == 0 ? 0 : -1e9) : cand_score[u*k+r, j])) / len_map[u*k+r]^penalty;
+ *         the k best (ties: lower r*k+j first) become the new hypotheses: scores[h] = value * len_map[h]^penalty (slot h's own
+ *         length: the reference's rule), token = cand_pred[u*k+r, j], and positions [0, pos) of preds / anc / tokmask of slot h
+ *         are copied from slot u*k+r                                                               (Seq2seq.py:358-383)
+ *   then preds[h, pos] = token; eos[h] |= token == EOS; len_map[h] += !eos[h]; *n_done = number of finished hypotheses.
+ * preds int64 [n_hyp, ld_preds]; anc int32 [>= pos, n_hyp] KV-cache ancestry table or NULL; tokmask uint8 [n_hyp, ld_tok];
+ * done_u int32 [n_utt] and ticket u32 [1] (zero once) are scratch. */
+int b200st_beam_select(float* scores, const float* cand_score, const int64_t* cand_pred, uint8_t* eos, float* len_map,
+                       float penalty, int64_t pos, int first, int64_t* preds, int64_t ld_preds, int32_t* anc,
+                       uint8_t* tokmask, int64_t ld_tok, int64_t k, int64_t n_utt, int32_t* done_u, void* ticket,
+                       int64_t* n_done, b200st_stream_t stream);
+
 /* ---- Persistent LAS decoder loop, forward (Dec.forward / forward_step / decode, Dec.py:130-233,320-438) ------------
  * ONE launch runs all S decode steps (3 uni-LSTM layers -> bilinear attention -> acous_ffn -> vocabulary projection ->
  * arg-max feedback and the EOS/PAD length rule) for bf16 activations with decoder width 512 and 512-wide keys/values;

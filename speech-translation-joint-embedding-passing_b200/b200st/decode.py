@@ -153,6 +153,8 @@ class BeamSearch:
         self.eos = torch.zeros(self.n_hyp, dtype=torch.bool, device=dev)
         self.len_map = torch.ones(self.n_hyp, device=dev)
         self.n_done = torch.zeros((), dtype=torch.int64, device=dev)
+        self.done_u = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         self.offs = torch.arange(0, self.n_hyp * beam_width, beam_width * beam_width, device=dev).float().reshape(self.B, 1)
         self.graphs = {}
         self.use_graphs = graphs and dev.type == 'cuda'
@@ -170,35 +172,17 @@ class BeamSearch:
         self.eos.zero_()
         self.len_map.fill_(1.0)
         self.n_done.zero_()
+        self.ticket.zero_()
 
     def _step(self, i: int):
-        B, k = self.B, self.k
-        logp, pred = self.cache.step_logps(self.preds[:, i - 1], i - 1)
-        if k == 1:
-            score = logp.float().gather(1, pred)
-        else:
-            score, pred = logp.float().topk(k)
-        if i == 1:      # all beams of an utterance are identical: take the first beam's top-k (Seq2seq.py:351-357)
-            self.scores.add_(score.reshape(B, -1)[:, :k].contiguous().view(-1))
-            pred_select = pred.reshape(B, -1)[:, :k].contiguous().view(-1)
-        else:
-            eos_exp = self.eos.reshape(-1, 1).repeat(1, k)
-            eos_exp[:, 0] = False
-            score_temp = self.scores.reshape(-1, 1) + score.masked_fill(self.eos.reshape(-1, 1), 0).masked_fill(eos_exp, -1e9)
-            lp = self.len_map.reshape(-1, 1) ** self.penalty
-            score_temp = score_temp / lp
-            score_select, pos = score_temp.reshape(B, -1).topk(k)
-            self.scores.copy_(score_select.view(-1) * lp.view(-1))
-            pos = (pos.float() + self.offs).long()
-            r_idxs, c_idxs = pos // k, pos % k
-            pred_select = pred[r_idxs, c_idxs].view(-1)
-            rows = r_idxs.view(-1)
-            self.preds[:, :i] = self.preds[rows, :i]
-            self.cache.reorder(rows, i)
-        self.preds[:, i] = pred_select
-        self.eos.copy_((pred_select == EOS) | self.eos)
-        self.len_map.add_(torch.ones_like(self.len_map).masked_fill(self.eos, 0))
-        self.n_done.copy_(self.eos.sum())
+        """One decode position: incremental decoder -> vocabulary projection -> top-k log-probabilities -> the reference's
+        selection rule and re-ordering (Seq2seq.py:337-393), the last two as ONE kernel each (csrc/beam.cu)."""
+        k = K()
+        x = self.cache.step(self.preds[:, i - 1], i - 1)
+        logits = k.gemm(x, rt.operand(self.cache.model.out_tgt.weight), trans_b=True)
+        score, pred = k.topk_logsoftmax(logits, self.k)
+        k.beam_select(self.scores, score, pred, self.eos, self.len_map, self.penalty, i, i == 1, self.preds, self.cache.anc,
+                      self.cache.tokmask, self.k, self.done_u, self.ticket, self.n_done)
 
     def run(self, enc_outputs, src_mask):
         if self.use_graphs:

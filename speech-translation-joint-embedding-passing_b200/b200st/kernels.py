@@ -419,6 +419,35 @@ class CudaKernels:
             _p(table2), _p(out2), ld2, dim2, self._stream()), 'argmax_rows')
         return idx_out
 
+    def topk_logsoftmax(self, x, k):
+        """(score fp32 [rows, k], pred int64 [rows, k]): the k largest log_softmax(x, -1) values per row and their indices
+        (Seq2seq.py:254-257: log_softmax + topk in one pass); k <= 8."""
+        self._need_cuda(x)
+        _rows(x)
+        rows, cols = x.shape
+        score = torch.empty((rows, k), dtype=torch.float32, device=x.device)
+        pred = torch.empty((rows, k), dtype=torch.int64, device=x.device)
+        _lib.check(self.lib.b200st_topk_logsoftmax(_dt(x), _p(x), x.stride(0), rows, cols, int(k), _p(score), _p(pred),
+                                                   self._stream()), 'topk_logsoftmax')
+        return score, pred
+
+    def beam_select(self, scores, cand_score, cand_pred, eos, len_map, penalty, pos, first, preds, anc, tokmask, k, done_u,
+                    ticket, n_done):
+        """One decode position of the beam bookkeeping, in place (Seq2seq.py:337-393; include/b200st.h)."""
+        self._need_cuda(scores, cand_score, cand_pred, eos, len_map, preds, anc, tokmask, done_u, ticket, n_done)
+        n_hyp = scores.numel()
+        assert n_hyp % k == 0 and cand_score.shape == (n_hyp, k) and cand_pred.shape == (n_hyp, k)
+        assert scores.dtype == torch.float32 and cand_score.dtype == torch.float32 and cand_pred.dtype == torch.int64
+        assert cand_score.is_contiguous() and cand_pred.is_contiguous() and len_map.dtype == torch.float32
+        assert eos.dtype in (torch.bool, torch.uint8) and eos.numel() == n_hyp and n_done.dtype == torch.int64
+        assert preds.dtype == torch.int64 and preds.stride(1) == 1 and tokmask.dtype == torch.uint8 and tokmask.stride(1) == 1
+        assert anc is None or (anc.dtype == torch.int32 and anc.is_contiguous() and anc.size(1) == n_hyp)
+        assert done_u.dtype == torch.int32 and done_u.numel() >= n_hyp // k and ticket.dtype == torch.int32
+        _lib.check(self.lib.b200st_beam_select(_p(scores), _p(cand_score), _p(cand_pred), _p(eos), _p(len_map), float(penalty),
+                                               int(pos), int(bool(first)), _p(preds), preds.stride(0), _p(anc), _p(tokmask),
+                                               tokmask.stride(0), int(k), n_hyp // k, _p(done_u), _p(ticket), _p(n_done),
+                                               self._stream()), 'beam_select')
+
     def las_update_lengths(self, sym, lengths, step):
         assert sym.dtype == torch.int64 and sym.dim() == 1 and lengths.dtype == torch.int32
         _lib.check(self.lib.b200st_las_update_lengths(_p(sym), sym.stride(0) if sym.numel() > 1 else 1,

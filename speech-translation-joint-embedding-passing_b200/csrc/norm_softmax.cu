@@ -34,6 +34,74 @@ __global__ void layernorm_fwd_kernel(const T* __restrict__ x, const float* __res
   }
 }
 
+// Vectorised variant for cols = 256 * NV (16-byte aligned rows): the row is read ONCE with 16-byte loads and stays in
+// registers for both statistics passes and the normalisation (the scalar kernel above re-reads it three times with 2-byte
+// loads).  Warp per row.
+__device__ __forceinline__ void ln_load8(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ln_load8(const __nv_bfloat16* p, float* v) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void ln_store8(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void ln_store8(__nv_bfloat16* p, const float* v) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, T* __restrict__ y,
+                                                                float* __restrict__ mean, float* __restrict__ rstd,
+                                                                int64_t rows, float eps) {
+  constexpr int cols = 256 * NV;
+  const int lane = threadIdx.x & 31;
+  // gamma / beta do not depend on the predecessor kernel: fetched before the dependency wait
+  float g[NV][8], b[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { ln_load8(gamma + (lane + 32 * i) * 8, g[i]); ln_load8(beta + (lane + 32 * i) * 8, b[i]); }
+  pdl_wait();
+  pdl_launch_dependents();
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[NV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    ln_load8(x + row * cols + (lane + 32 * i) * 8, v[i]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += v[i][e];
+  }
+  const float mu = warp_sum(s) / cols;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mu; q += d * d; }
+  const float rs = rsqrtf(warp_sum(q) / cols + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[i][e] = (v[i][e] - mu) * rs * g[i][e] + b[i][e];
+    ln_store8(y + row * cols + (lane + 32 * i) * 8, v[i]);
+  }
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+}
+
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += dy * xhat; dbeta += dy.
 // Each CTA walks a strip of rows; column partials live in shared memory and are flushed once.
 template <typename T>
@@ -411,6 +479,23 @@ int b200st_layernorm_fwd(int dtype, const void* x, const float* gamma, const flo
                          float* mean, float* rstd, int64_t rows, int64_t cols, float eps,
                          b200st_stream_t stream) {
   if (rows <= 0) return 0;
+  if ((cols == 256 || cols == 512 || cols == 1024) && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 &&
+      ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)beta & 15) == 0) {
+    const int wv = 8;
+    B200ST_DISPATCH(dtype, T, {
+      if (cols == 256)
+        B200ST_CUDA(launch_pdl(layernorm_fwd_vec_kernel<T, 1>, dim3((unsigned)ceil_div(rows, wv)), dim3(wv * 32), 0,
+                               (cudaStream_t)stream, (const T*)x, gamma, beta, (T*)y, mean, rstd, rows, eps));
+      else if (cols == 512)
+        B200ST_CUDA(launch_pdl(layernorm_fwd_vec_kernel<T, 2>, dim3((unsigned)ceil_div(rows, wv)), dim3(wv * 32), 0,
+                               (cudaStream_t)stream, (const T*)x, gamma, beta, (T*)y, mean, rstd, rows, eps));
+      else
+        B200ST_CUDA(launch_pdl(layernorm_fwd_vec_kernel<T, 4>, dim3((unsigned)ceil_div(rows, wv)), dim3(wv * 32), 0,
+                               (cudaStream_t)stream, (const T*)x, gamma, beta, (T*)y, mean, rstd, rows, eps));
+    });
+    B200ST_LAUNCH_CHECK("layernorm_fwd_vec");
+    return 0;
+  }
   const int wpb = 4;
   B200ST_DISPATCH(dtype, T, {
     B200ST_CUDA(launch_pdl(layernorm_fwd_kernel<T>, dim3((unsigned)ceil_div(rows, wpb)), dim3(wpb * 32), 0,

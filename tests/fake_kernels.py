@@ -254,6 +254,43 @@ class FakeKernels:
         p = torch.softmax(s, dim=-1)
         return torch.einsum('bht,bthd->bhd', p, vv).reshape(n_hyp, HD).to(q.dtype)
 
+    # -- beam search bookkeeping (csrc/beam.cu), written with the reference's own op sequence (Seq2seq.py:337-393) --------
+    def topk_logsoftmax(self, x, k):
+        self.launches += 1
+        score, pred = torch.log_softmax(x.float(), dim=-1).topk(k)
+        return score.contiguous(), pred.contiguous()
+
+    def beam_select(self, scores, cand_score, cand_pred, eos, len_map, penalty, pos, first, preds, anc, tokmask, k, done_u,
+                    ticket, n_done):
+        self.launches += 1
+        n_hyp = scores.numel()
+        B = n_hyp // k
+        if first:
+            scores.add_(cand_score.reshape(B, -1)[:, :k].contiguous().view(-1))
+            pred_select = cand_pred.reshape(B, -1)[:, :k].contiguous().view(-1)
+        else:
+            eos_b = eos.bool()
+            eos_exp = eos_b.reshape(-1, 1).repeat(1, k)
+            eos_exp[:, 0] = False
+            score_temp = scores.reshape(-1, 1) + cand_score.masked_fill(eos_b.reshape(-1, 1), 0).masked_fill(eos_exp, -1e9)
+            lp = len_map.reshape(-1, 1) ** penalty
+            score_temp = score_temp / lp
+            score_select, sel = score_temp.reshape(B, -1).topk(k)
+            scores.copy_(score_select.view(-1) * lp.view(-1))
+            sel = sel + torch.arange(0, n_hyp * k, k * k, device=sel.device).reshape(B, 1)
+            r_idxs, c_idxs = sel // k, sel % k
+            pred_select = cand_pred[r_idxs, c_idxs].view(-1)
+            rows = r_idxs.view(-1)
+            preds[:, :pos] = preds[rows, :pos]
+            if anc is not None:
+                anc[:pos] = anc[:pos][:, rows]
+            tokmask[:, :pos] = tokmask[rows, :pos]
+        preds[:, pos] = pred_select
+        new_eos = (pred_select == 3) | eos.bool()
+        eos.copy_(new_eos.to(eos.dtype))
+        len_map.add_(torch.ones_like(len_map).masked_fill(new_eos, 0))
+        n_done.copy_(new_eos.sum())
+
     # -- LSTM cell --------------------------------------------------------------------------------
     def lstm_cell_fwd(self, gates, c_prev, residual=None, save_acts=True, h_out=None, c_out=None,
                       acts_out=None, res_out=None, gates_b=None, gates_c=None):

@@ -421,10 +421,13 @@ def test_beam5_length_penalty_and_early_eos_vs_oracle(penalty):
                      max_seq_len_src=10, max_seq_len_tgt=20, num_heads=4, dim_model=64, dim_feedforward=128,
                      enc_layers=2, dec_layers=2, acous_dim=16, acous_hidden_size=32)
     P = O.init_params(cfg, seed=12, scale=3.0)
+    # make EOS competitive so that some hypotheses finish early and others never do (checked below)
+    P['out_tgt.weight'][3] += 0.8 * P['out_tgt.weight'].abs().max() * torch.sign(P['out_tgt.weight'].sum(0))
     data = O.synthetic_batch(cfg, 10, 88, seed=6, ragged=True)
     ref = O.forward_translate_st(P, cfg, data['acous_feats'], data['acous_lens'], beam_width=5, penalty_factor=penalty,
                                  max_seq_len=20)
-    assert (ref == 3).any(), 'the case must contain EOS tokens to exercise the masking'
+    has_eos = (ref == 3).any(dim=1)
+    assert has_eos.any() and not has_eos.all(), 'the case must mix finished and unfinished hypotheses'
     m = build_model(cfg, P, device='cuda').eval()
     lens = [torch.tensor([n]) for n in data['acous_lens']]
     for cached in (True, False):
