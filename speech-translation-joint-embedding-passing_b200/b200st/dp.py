@@ -32,6 +32,7 @@ class GradAllReducer:
         self._hooks = []
         self._stream = None
         self._armed = True
+        self.trace = None              # set to [] to record (start event, end event, bytes, n tensors) per bucket (diagnostics)
         if self.world > 1:
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
@@ -69,9 +70,17 @@ class GradAllReducer:
                 self._stream.wait_stream(st)
             with torch.cuda.stream(self._stream):
                 if dist.get_backend(self.group) == 'nccl':
+                    ev = None
+                    if self.trace is not None:
+                        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                        ev[0].record(self._stream)
                     with dist._coalescing_manager(self.group, device=grads[0].device, async_ops=True) as cm:
                         for g in grads:
                             dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+                    if ev is not None:
+                        cm.wait()                         # stream-level wait (the NCCL kernels run on the group's own stream)
+                        ev[1].record(self._stream)
+                        self.trace.append((ev[0], ev[1], sum(g.numel() * g.element_size() for g in grads), len(grads)))
                     self._inflight.append((cm, None, grads))
                     return
                 flat = torch._utils._flatten_dense_tensors(grads)
