@@ -2,18 +2,30 @@
 // Specialised for the reference's acoustic encoder: H = 256 hidden units per direction (Seq2seq.py:57).
 //
 // Layout of the work (forward):
-//   grid = (8, ceil(B/16), 2): one thread-block CLUSTER of 8 CTAs per (direction, group of 16 sequences).
-//   CTA `rank` owns hidden units [32*rank, 32*rank+32): the 128 matching rows of W_hh (4 gates x 32 units) are
-//   converted to bf16 once and stay resident in shared memory in the 128B-swizzled K-major layout UMMA reads.
-//   Every time step:  D[128 gate rows, 16 seqs] = W_slice[128,256] . h_{t-1}^T   (16 tcgen05.mma, K=16 each,
-//   accumulator in TMEM) -> tcgen05.ld -> + x-projection -> sigmoid/tanh -> cell update (state in registers)
-//   -> the CTA's 32x16 slice of h_t is written as bf16 straight into the *next-step B operand* of all 8 CTAs
-//   (16-byte st.shared::cluster stores into the swizzled layout) -> barrier.cluster.arrive; the matching
-//   barrier.cluster.wait sits right before the next step's MMA so global stores/prefetch overlap the barrier.
+//   grid = (8, ceil(B/16), 2): one thread-block CLUSTER of 8 CTAs per (direction, group of 16 sequences); 4 epilogue warps
+//   + 1 issuer warp per CTA.  CTA `rank` owns hidden units [32*rank, 32*rank+32): the 128 matching rows of W_hh (4 gates x
+//   32 units) are converted to bf16 once and stay resident in TENSOR MEMORY as the A operand of TS-form tcgen05.mma
+//   (A from TMEM, B = h_{t-1} tile from shared memory: an SS-form N=16 MMA spends ~110 cycles streaming the 4 KB A tile
+//   out of shared memory, the TS form ~22).
+//   Every time step:  D[128 gate rows, 16 seqs] = W_slice[128,256] . h_{t-1}^T  (16 MMAs of K=16 into 4 independent TMEM
+//   accumulators, one commit) -> tcgen05.ld -> + x-projection -> sigmoid/tanh (tanh.approx) -> smem transpose -> cell update
+//   (c in registers) -> the CTA's 32x16 slice of h_t goes as bf16 straight into the NEXT-STEP B operand of all 8 CTAs:
+//   16-byte `st.async ... mbarrier::complete_tx` stores into the peers' swizzled K-major tile; data and signal travel together,
+//   there is no cluster barrier in the loop, and the issuer's wait on the local `hfull` mbarrier (8 KB expected) is the only
+//   synchronisation.  Global stores of the saved state and the two-step-ahead x-projection prefetch sit behind the send.
 //
-// Backward keeps W_hh^T[256 units, own 128 gate rows] resident instead: each CTA multiplies its own gate
-// gradients (no all-gather) into partial dh for all 256 units, and the partials are reduce-scattered to the
-// owning CTAs through distributed shared memory.
+// Backward keeps W_hh^T[256 units, own 128 gate rows] resident in TMEM instead: each CTA multiplies its own gate gradients
+// (no all-gather) into partial dh for all 256 units, and the bf16 partials are reduce-scattered to the owning CTAs through
+// distributed shared memory with the same st.async + complete_tx mechanism.
+//
+// What bounds a step (profiles/r02_blstm_experiments.txt; ~1880 cycles): MMA issue + completion ~630, epilogue ~830, and the
+// h exchange: every CTA must receive the other 7 slices = 7 KB per step, and the SM-to-SM network moves ~21 B/clk per SM
+// (B300_MICROARCH.md: "DSMEM BW 17-21 B/cyc, producer pays") -> ~340 cycles of pure transfer + ~215 latency that nothing in
+// this decomposition can overlap.  Two restructurings were built and measured in round 2 and are NOT kept:
+//   * 8 epilogue warps (two per TMEM lane quarter, 8 sequence columns each; every thread sends to 2 peers instead of 8):
+//     tcgen05.ld + activation phase 450 -> 340 cycles, but the scattered sends land later (470 -> 800): 2370 cycles/step;
+//   * per-source operand barriers (the two MMAs of source r issued as soon as r's 1 KB lands): each extra wait costs a
+//     ~90-cycle mbarrier.try_wait + a 33-cycle proxy fence on the single issuer thread: 2620 cycles/step.
 #include "common.cuh"
 
 namespace b200st {
