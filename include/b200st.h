@@ -175,9 +175,17 @@ int b200st_blstm_fwd(int dtype, const void* xproj, const float* w_hh_f, const fl
 /* Debug aid: register (or clear with NULL) a device buffer of >= 128 int64; the tensor-core recurrence kernels then
  * record clock64() at fixed points of time steps 64..71 (16 slots per step) for the first CTA. */
 int b200st_debug_timeline(void* buf);
-/* Recurrence kernel selection: 0 = auto (bf16 activations with H = 256 -> tcgen05 kernel), 1 = CUDA cores only.
- * Returns the previous mode (test hook). */
+/* Recurrence kernel selection: 0 = auto (bf16 activations with H = 256 -> tcgen05 kernels, lstm_tc.cu), 1 = CUDA cores
+ * only, 2 = same as 0, 3 = register-resident warp-MMA kernels (lstm_rg.cu: measured on a par with the tcgen05 kernels,
+ * profiles/r02_blstm_experiments.txt; kept selectable, not the default).  Returns the previous mode (test / profiling hook). */
 int b200st_set_blstm_backend(int mode);
+/* Layout of the saved state (`acts`, `cs`) that b200st_blstm_fwd writes and b200st_blstm_bwd reads for this dtype / H
+ * under the current backend: 0 = plain acts [2, T, B, 4H], cs [2, T, B, H] (fp32);  1 = kernel-private blocked layout
+ * of the register-resident kernels, sized for B rounded up to a multiple of 16:
+ *   acts [2][T][B/16][rank 8][thread 256][gate 4][seq 2], cs [2][T][B/16][rank 8][thread 256][seq 2]   (fp32)
+ * thread = (n-tile nt * 4 + unit block ub) * 32 + r * 4 + c  <->  unit 32 rank + 8 ub + r, sequence 16 grp + 8 nt + 2 c + seq.
+ * The saved state is opaque to callers (Enc.py keeps nothing comparable); the layout is documented for the tests. */
+int b200st_blstm_saved_layout(int dtype, int64_t H);
 /* dout in the same layout as out; dgates [2][T][B][4H] dtype written (zeros for t>=len). */
 int b200st_blstm_bwd(int dtype, const void* dout, int64_t out_ld_t, int64_t out_ld_b, int pair,
                      const float* acts, const float* cs, const float* w_hh_f, const float* w_hh_r,

@@ -8,6 +8,7 @@ the host-side orchestration on a machine without a GPU; nothing in the product d
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -41,6 +42,9 @@ class CudaKernels:
 
     def __init__(self):
         self.lib = _lib.load()
+        mode = os.environ.get('B200ST_BLSTM_BACKEND')      # profiling hook: see b200st_set_blstm_backend in include/b200st.h
+        if mode is not None:
+            self.lib.b200st_set_blstm_backend(int(mode))
 
     # -- plumbing ---------------------------------------------------------------------------------
     @staticmethod
@@ -314,16 +318,49 @@ class CudaKernels:
         assert lens.dtype == torch.int32 and out.dtype == xproj.dtype
         dev = xproj.device
         hs = torch.empty((2, T + 1, B, H), dtype=xproj.dtype, device=dev) if save else None
-        acts = torch.empty((2, T, B, H4), dtype=torch.float32, device=dev) if save else None
-        cs = torch.empty((2, T, B, H), dtype=torch.float32, device=dev) if save else None
+        # saved gates / cell states: opaque to the caller; the register-resident kernels use a blocked layout sized for
+        # B rounded up to whole groups of 16 sequences (b200st_blstm_saved_layout)
+        Bs = -(-B // 16) * 16 if self.blstm_saved_blocked(xproj.dtype, H) else B
+        acts = torch.empty((2, T, Bs, H4), dtype=torch.float32, device=dev) if save else None
+        cs = torch.empty((2, T, Bs, H), dtype=torch.float32, device=dev) if save else None
         _lib.check(self.lib.b200st_blstm_fwd(_dt(xproj), _p(xproj), _p(w_hh_f), _p(w_hh_r), _p(lens),
                                              _p(out), out_ld_t, out_ld_b, pair, _p(hs), _p(acts),
                                              _p(cs), T, B, H, self._stream()), 'blstm_fwd')
         return hs, acts, cs
 
+    def blstm_saved_blocked(self, dtype, H) -> bool:
+        return bool(self.lib.b200st_blstm_saved_layout(_dt(dtype), int(H)))
+
+    @staticmethod
+    def blstm_unblock(acts, cs, B):
+        """Blocked saved state (b200st_blstm_saved_layout == 1) -> plain acts [2, T, B, 4H], cs [2, T, B, H] (tests)."""
+        two, T, Bs, H4 = acts.shape
+        G = Bs // 16
+        # dims: dir, T, grp, rank, nt, ub, r, c, gate, seq
+        a = acts.view(2, T, G, 8, 2, 4, 8, 4, 4, 2).permute(0, 1, 2, 4, 7, 9, 8, 3, 5, 6).reshape(2, T, Bs, H4)
+        c = cs.view(2, T, G, 8, 2, 4, 8, 4, 2).permute(0, 1, 2, 4, 7, 8, 3, 5, 6).reshape(2, T, Bs, H4 // 4)
+        return a[:, :, :B].contiguous(), c[:, :, :B].contiguous()
+
+    @staticmethod
+    def blstm_block(acts, cs):
+        """Plain saved state -> the blocked layout (inverse of blstm_unblock; pads B to a multiple of 16 with zeros)."""
+        two, T, B, H4 = acts.shape
+        Bs = -(-B // 16) * 16
+        G = Bs // 16
+        a = torch.zeros((2, T, Bs, H4), dtype=acts.dtype, device=acts.device)
+        c = torch.zeros((2, T, Bs, H4 // 4), dtype=cs.dtype, device=cs.device)
+        a[:, :, :B] = acts
+        c[:, :, :B] = cs
+        # plain dims: dir, T, (grp, nt, c, seq), (gate, rank, ub, r)
+        a = a.view(2, T, G, 2, 4, 2, 4, 8, 4, 8).permute(0, 1, 2, 7, 3, 8, 9, 4, 6, 5).reshape(2, T, Bs, H4)
+        c = c.view(2, T, G, 2, 4, 2, 8, 4, 8).permute(0, 1, 2, 6, 3, 7, 8, 4, 5).reshape(2, T, Bs, H4 // 4)
+        return a.contiguous(), c.contiguous()
+
     def blstm_bwd(self, dout, out_ld_t, out_ld_b, pair, acts, cs, w_hh_f, w_hh_r, lens, dtype):
-        _, T, B, H = cs.shape
-        assert dout.is_contiguous()
+        _, T, _, H = cs.shape
+        B = lens.numel()
+        assert dout.is_contiguous() and acts.is_contiguous() and cs.is_contiguous()
+        assert cs.shape[2] == (-(-B // 16) * 16 if self.blstm_saved_blocked(dtype, H) else B), 'saved-state layout mismatch'
         dgates = torch.empty((2, T, B, 4 * H), dtype=dtype, device=cs.device)
         _lib.check(self.lib.b200st_blstm_bwd(_dt(dtype), _p(dout), out_ld_t, out_ld_b, pair, _p(acts),
                                              _p(cs), _p(w_hh_f), _p(w_hh_r), _p(lens), _p(dgates), T, B,

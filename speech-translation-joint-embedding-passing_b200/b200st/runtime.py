@@ -284,6 +284,7 @@ def join_deferred():
 # backward passes the site it saved, so no mask tensor is ever stored.
 # ------------------------------------------------------------------------------------------------
 _rng = {}
+_seed = [None]             # set by manual_seed(); devices that create their state later start from it too
 _site = [0]
 site_log = None            # TEST HOOK: set to a dict to record {tag: (site, p)} of every dropout call
 
@@ -292,13 +293,16 @@ def rng_state(device) -> torch.Tensor:
     key = (device.type, device.index)
     st = _rng.get(key)
     if st is None:
-        st = torch.tensor([torch.initial_seed() & 0x7fffffffffffffff, 0], dtype=torch.int64).to(device)
+        seed = _seed[0] if _seed[0] is not None else torch.initial_seed() & 0x7fffffffffffffff
+        st = torch.tensor([seed, 0], dtype=torch.int64).to(device)
         _rng[key] = st
     return st
 
 
 def manual_seed(seed: int):
-    """Re-seed the dropout generator (all devices) and restart its step counter."""
+    """Re-seed the dropout generator (all devices, including those whose state is created later) and restart its step
+    counter."""
+    _seed[0] = int(seed) & 0x7fffffffffffffff
     for st in _rng.values():
         st.copy_(torch.tensor([int(seed) & 0x7fffffffffffffff, 0], dtype=torch.int64))
     _rng_step.clear()

@@ -325,7 +325,16 @@ int blstm_bwd_tc(const void* dout, int64_t out_ld_t, int64_t out_ld_b, int pair,
                  const float* w_hh_f, const float* w_hh_r, const int32_t* lens, void* dgates, int64_t T_, int64_t B,
                  cudaStream_t st);
 int set_timeline(void* buf);
-static int g_blstm_backend = 0;   // 0 auto, 1 CUDA cores only
+// lstm_rg.cu: register-resident weights + warp-level MMA, two independent sub-chains per CTA
+bool blstm_rg_eligible(int dtype, int64_t H);
+int blstm_fwd_rg(const void* xproj, const float* w_hh_f, const float* w_hh_r, const int32_t* lens, void* out,
+                 int64_t out_ld_t, int64_t out_ld_b, int pair, void* hs, float* acts, float* cs, int64_t T_, int64_t B,
+                 cudaStream_t st);
+int blstm_bwd_rg(const void* dout, int64_t out_ld_t, int64_t out_ld_b, int pair, const float* acts, const float* cs,
+                 const float* w_hh_f, const float* w_hh_r, const int32_t* lens, void* dgates, int64_t T_, int64_t B,
+                 cudaStream_t st);
+int set_timeline_rg(void* buf);
+static int g_blstm_backend = 0;   // 0 auto (tcgen05 kernels where eligible), 1 CUDA cores only, 2 = 0, 3 register-resident warp-MMA kernels
 
 }  // namespace b200st
 
@@ -333,12 +342,16 @@ using namespace b200st;
 
 extern "C" {
 
-int b200st_debug_timeline(void* buf) { return set_timeline(buf); }
+int b200st_debug_timeline(void* buf) { const int a = set_timeline(buf), b = set_timeline_rg(buf); return a ? a : b; }
 
 int b200st_set_blstm_backend(int mode) {
   const int old = g_blstm_backend;
-  if (mode == 0 || mode == 1) g_blstm_backend = mode;
+  if (mode >= 0 && mode <= 3) g_blstm_backend = mode;
   return old;
+}
+
+int b200st_blstm_saved_layout(int dtype, int64_t H) {
+  return (g_blstm_backend == 3 && blstm_rg_eligible(dtype, H)) ? 1 : 0;
 }
 
 int b200st_lstm_cell_fwd(int dtype, const void* gates, const void* gates_b, const void* gates_c,
@@ -374,12 +387,17 @@ int b200st_blstm_fwd(int dtype, const void* xproj, const float* w_hh_f, const fl
   if (T_ <= 0 || B <= 0) return 0;
   if (H % 4 != 0) return set_error("blstm_fwd: hidden size %lld must be a multiple of 4", (long long)H);
   if (pair != 1 && pair != 2) return set_error("blstm_fwd: pair must be 1 or 2");
-  if (g_blstm_backend == 0 && blstm_tc_eligible(dtype, H, out_ld_t, out_ld_b)) {
+  const bool use_rg = g_blstm_backend == 3 && blstm_rg_eligible(dtype, H);
+  const bool use_tc = !use_rg && g_blstm_backend != 1 && blstm_tc_eligible(dtype, H, out_ld_t, out_ld_b);
+  if (use_rg || use_tc) {
     if (hs) {
       const size_t plane = (size_t)B * H * 2;
       B200ST_CUDA(cudaMemsetAsync(hs, 0, plane, (cudaStream_t)stream));
       B200ST_CUDA(cudaMemsetAsync((char*)hs + ((size_t)(T_ + 1) + T_) * plane, 0, plane, (cudaStream_t)stream));
     }
+    if (use_rg)
+      return blstm_fwd_rg(xproj, w_hh_f, w_hh_r, lens, out, out_ld_t, out_ld_b, pair, hs, acts, cs, T_, B,
+                          (cudaStream_t)stream);
     return blstm_fwd_tc(xproj, w_hh_f, w_hh_r, lens, out, out_ld_t, out_ld_b, pair, hs, acts, cs, T_, B,
                         (cudaStream_t)stream);
   }
@@ -409,7 +427,10 @@ int b200st_blstm_bwd(int dtype, const void* dout, int64_t out_ld_t, int64_t out_
                      b200st_stream_t stream) {
   if (T_ <= 0 || B <= 0) return 0;
   if (H % 4 != 0) return set_error("blstm_bwd: hidden size %lld must be a multiple of 4", (long long)H);
-  if (g_blstm_backend == 0 && blstm_tc_eligible(dtype, H, out_ld_t, out_ld_b))
+  if (g_blstm_backend == 3 && blstm_rg_eligible(dtype, H))
+    return blstm_bwd_rg(dout, out_ld_t, out_ld_b, pair, acts, cs, w_hh_f, w_hh_r, lens, dgates, T_, B,
+                        (cudaStream_t)stream);
+  if (g_blstm_backend != 1 && blstm_tc_eligible(dtype, H, out_ld_t, out_ld_b))
     return blstm_bwd_tc(dout, out_ld_t, out_ld_b, pair, acts, cs, w_hh_f, w_hh_r, lens, dgates, T_, B,
                         (cudaStream_t)stream);
   constexpr int NB = 8;

@@ -266,11 +266,22 @@ def test_lstm_cell(ks, dtype):
     assert rel_err(dg, dgr) < TOL[dtype] and rel_err(dcp, dcpr) < 1e-5
 
 
+@pytest.fixture(params=[0, 3], ids=['default', 'warp-mma'])
+def blstm_backend(request, ks):
+    """0 = the default kernels (tcgen05 for bf16 / H = 256, CUDA cores otherwise), 3 = the register-resident warp-MMA
+    kernels of csrc/lstm_rg.cu (bf16 / H = 256; other shapes fall through to the same kernels as 0)."""
+    old = ks[0].set_blstm_backend(request.param)
+    yield request.param
+    ks[0].set_blstm_backend(old)
+
+
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('T,B,H,pair', [(8, 3, 16, 2), (24, 5, 24, 2), (6, 11, 16, 1), (40, 9, 32, 2),
-                                        (16, 8, 256, 2), (64, 40, 256, 2), (24, 16, 256, 1), (2, 1, 256, 2)])
-def test_blstm_recurrence(ks, dtype, T, B, H, pair):
+                                        (16, 8, 256, 2), (64, 40, 256, 2), (24, 16, 256, 1), (2, 1, 256, 2), (1, 19, 256, 1)])
+def test_blstm_recurrence(ks, blstm_backend, dtype, T, B, H, pair):
     c, f = ks
+    if blstm_backend == 3 and not (dtype == torch.bfloat16 and H == 256):
+        pytest.skip('the warp-MMA kernels take bf16 / H = 256 only')
     xproj = rnd(2, T, B, 4 * H, dtype=dtype)
     wf, wr = rnd(4 * H, H, seed=1, scale=H ** -0.5), rnd(4 * H, H, seed=2, scale=H ** -0.5)
     lens = torch.randint(1, T + 1, (B,), device='cuda', dtype=torch.int32)
@@ -287,9 +298,16 @@ def test_blstm_recurrence(ks, dtype, T, B, H, pair):
     assert rel_err(out, outr) < tol
     assert rel_err(hs, hsr) < tol
     valid = (torch.arange(T, device='cuda')[:, None] < lens[None, :]).float()[None, :, :, None]
+    blocked = c.blstm_saved_blocked(dtype, H)       # the saved state is kernel-private: compare / feed it through the documented layout
+    if blocked:
+        acts, cs = c.blstm_unblock(acts, cs, B)
     assert rel_err(acts * valid, actsr * valid) < tol and rel_err(cs * valid, csr * valid) < tol
     dout = rnd(*shape, dtype=dtype, seed=7)
-    dg = c.blstm_bwd(dout, ld_t, ld_b, pair, actsr, csr, wf, wr, lens, dtype)
+    a_in, c_in = c.blstm_block(actsr, csr) if blocked else (actsr, csr)
+    if blocked:
+        ra, rc = c.blstm_unblock(a_in, c_in, B)
+        assert torch.equal(ra, actsr) and torch.equal(rc, csr)
+    dg = c.blstm_bwd(dout, ld_t, ld_b, pair, a_in, c_in, wf, wr, lens, dtype)
     dgr = f.blstm_bwd(dout, ld_t, ld_b, pair, actsr, csr, wf, wr, lens, dtype)
     assert rel_err(dg, dgr) < tol
 
