@@ -611,6 +611,26 @@ def run_b200(args):
         t_pad = args.frames + 8 - args.frames % 8
         alg = algorithmic_flops(args.batch, t_pad)
         total_units = args.batch * world
+        # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the recurrence kernels from ONE `ncu --set full` capture
+        # (ncu cannot run inside the bench): the committed round-2 capture at T = 1008 (profiles/r02_blstm_ncu.json), scaled by
+        # T to the four pyramid layers and averaged per launch exactly like `achieved` (forward + backward launches).
+        traffic, traffic_note = None, 'no ncu capture found under profiles/'
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'r02_blstm_ncu.json')) as fh:
+                cap = json.load(fh)
+            t_pad = args.frames + 8 - args.frames % 8
+            if cap['blstm_fwd_tc']['T'] == t_pad and cap['blstm_fwd_tc']['B'] == args.batch:
+                t_mean = sum(t_pad // 2 ** l for l in range(4)) / 4.0
+                traffic = cap['dram_bytes_per_launch_T1008_avg'] * t_mean / t_pad
+                traffic_note = ('DRAM bytes per launch averaged over the 8 recurrence launches of a step (4 layers x fwd/bwd): ncu --set full '
+                                'capture of the T = %d launches (fwd %.0f MB, bwd %.0f MB; profiles/r02_blstm_ncu.json, r02_ncu_summary.txt) '
+                                'scaled by T per layer; the algorithmic bytes of the same launches are 990 / 957 MB, i.e. no wasted re-reads'
+                                % (t_pad, (cap['blstm_fwd_tc']['dram_bytes_read'] + cap['blstm_fwd_tc']['dram_bytes_write']) / 1e6,
+                                   (cap['blstm_bwd_tc']['dram_bytes_read'] + cap['blstm_bwd_tc']['dram_bytes_write']) / 1e6))
+            else:
+                traffic_note = 'the committed ncu capture is for another shape'
+        except (OSError, KeyError, ValueError):
+            pass
         line = {
             'metric': METRIC, 'value': total_units / (ms_dev / 1e3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev,
@@ -636,7 +656,7 @@ def run_b200(args):
                           'weights_changed_during_timed_region': optimizer_applied, 'adam_step_count': opt_steps},
             'clocks': clocks,
             'roofline': {'kernel': '+'.join(roof_names), 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
-                         'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None, 'traffic_note': 'not measured in this run (ncu cannot run inside the bench); the per-launch dram__bytes of one `ncu --set full` capture are in profiles/', 'peak_source': peak_src,
+                         'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': peak_src,
                          'us_per_time_step': 1e3 * r_ms / (2 * sum((args.frames + 8 - args.frames % 8) // 2 ** l for l in range(4))),
                          'launches': r_calls, 'avg_launch_ms': r_ms / max(r_calls, 1),
                          'timed': 'CUDA events around every launch of this kernel family on its stream, eager pass of the '

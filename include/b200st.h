@@ -73,6 +73,23 @@ int b200st_set_gemm_persistent(int on);
  * Returns the previous mode.  Used by tests to compare the two kernels; the product leaves it at 0. */
 int b200st_set_gemm_backend(int mode);
 
+/* GEMM with a fused residual + LayerNorm epilogue (csrc/gemm_ln.cu; bf16, N = 512 = d_model):
+ *   Y[M, N]  = A[M, K] . W[N, K]^T (+ bias[N]) + R[M, N]        -- a sub-layer's output: fc + skip (layers.py:190-197),
+ *                                                                  w_2 + bias + skip (layers.py:247-252)
+ *   YN[M, N] = LayerNorm(Y; gamma, beta, eps), mean[M], rstd[M]  -- the NEXT sub-layer's pre-norm (layers.py:153, 245;
+ *                                                                  TFEnc.py:89, TFDec.py:127 for the final norm)
+ * replaces b200st_gemm(+residual) followed by b200st_layernorm_fwd.  Four CTAs (a cluster) cover a 128-row block; row
+ * statistics are exchanged through distributed shared memory.  b200st_gemm_ln_eligible returns 1 when the shapes /
+ * alignments are served (bf16, N == 512, K % 8 == 0, 16-byte aligned rows; Y / YN rows 32-byte aligned); callers use
+ * the two separate kernels otherwise.  bias and R may be NULL. */
+int b200st_gemm_ln_eligible(int dtype, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* W,
+                            int64_t ldw, const void* R, int64_t ldr, const void* Y, int64_t ldy, const void* YN,
+                            int64_t ldyn, const float* bias, const float* gamma, const float* beta);
+int b200st_gemm_ln(int dtype, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* W, int64_t ldw,
+                   const float* bias, const void* R, int64_t ldr, void* Y, int64_t ldy, const float* gamma,
+                   const float* beta, float eps, void* YN, int64_t ldyn, float* mean, float* rstd,
+                   b200st_stream_t stream);
+
 /* ---- LayerNorm (layers.py:139,153,240,245; TFEnc.py:61,89; TFDec.py:58,127) -------------------- */
 int b200st_layernorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y,
                          float* mean, float* rstd, int64_t rows, int64_t cols, float eps,

@@ -20,6 +20,9 @@ ap.add_argument('--dtype', default='bf16')
 ap.add_argument('--reps', type=int, default=3)
 ap.add_argument('--beams', default='1,5')
 ap.add_argument('--no-cache', action='store_true', help="the reference's recompute-every-step decoder loop")
+ap.add_argument('--las-max-len', type=int, default=0,
+                help='LAS decoder steps: 0 = the model default (max_seq_len_src = 32 -> 31 steps), 150 = what the reference CLI '
+                     'sets before translating (translate.py:70-77: model.las.decoder.max_seq_len = 150)')
 args = ap.parse_args()
 
 dev = torch.device('cuda', 0)
@@ -29,6 +32,10 @@ cfg = bench.st_config()
 model = bench.build_model(cfg, dev).eval()
 if args.no_cache and hasattr(model, 'decode_cache'):
     model.decode_cache = False
+if args.las_max_len:
+    model.las.decoder.max_seq_len = args.las_max_len          # translate.py:73
+    model.enc_src.expand_time(args.las_max_len)                # translate.py:75-77 (sinusoid tables long enough)
+    model.dec_tgt.expand_time(max(args.las_max_len, args.max_len))
 data = O.synthetic_batch(cfg, args.batch, args.frames, seed=5)
 feats = data['acous_feats'].to(dev)
 lens = data['acous_lens']
@@ -48,5 +55,5 @@ for k in (int(b) for b in args.beams.split(',')):
     ms = e0.elapsed_time(e1) / args.reps
     print(json.dumps({'metric': 'st_translate_utt_per_s', 'beam_width': k, 'value': args.batch / (ms / 1e3), 'unit': 'utt/s',
                       'ms_per_batch': ms, 'batch': args.batch, 'frames': args.frames, 'max_seq_len': args.max_len,
-                      'dtype': args.dtype, 'decoder': 'recompute' if args.no_cache else 'kv-cache',
+                      'las_decoder_steps': int(model.las.decoder.max_seq_len) - 1, 'dtype': args.dtype, 'decoder': 'recompute' if args.no_cache else 'kv-cache',
                       'out_shape': list(out.shape), 'checksum': int(out.sum())}), flush=True)

@@ -128,9 +128,10 @@ class _LayerNorm(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, eps):
         xc = _c(x)
-        y, mean, rstd = K().layernorm_fwd(xc, weight, bias, eps)
+        pre = rt.take_prenorm(xc, weight, bias, eps)          # the producing GEMM's epilogue may already have normalised x
+        y, mean, rstd = pre if pre is not None else K().layernorm_fwd(xc, weight, bias, eps)
         ctx.save_for_backward(xc, weight, bias, mean, rstd)
-        return y
+        return y.view(x.shape)
 
     @staticmethod
     def backward(ctx, dy):
@@ -183,7 +184,7 @@ class _MHABlock(Function):
     (LayerNorm on the query input only, K/V from the raw input, no biases, dropout p = 0)."""
 
     @staticmethod
-    def forward(ctx, q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature, drop):
+    def forward(ctx, q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature, drop, next_ln=None):
         # drop = (p_attn, site_attn, p_fc, site_fc): attention dropout on the probabilities (layers.py:226) and
         # dropout on the fc output before the residual add (layers.py:194-195); all zeros = the fused fast path
         k = K()
@@ -198,17 +199,23 @@ class _MHABlock(Function):
         side = rt.side_streams(q.device, 1, pool='fwd')
         with rt.fork(side[0]):          # K | V come from the RAW input: independent of the LayerNorm -> Q chain
             kvp = k.gemm(kv2, rt.operand_cat(w_k, w_v), trans_b=True)             # [B*Lk, 2*HD] = K | V
-        qn, mean, rstd = k.layernorm_fwd(q2, ln_w, ln_b, eps)
+        pre = rt.take_prenorm(q2, ln_w, ln_b, eps)           # LayerNorm(q) from the previous sub-layer's GEMM epilogue
+        qn, mean, rstd = pre if pre is not None else k.layernorm_fwd(q2, ln_w, ln_b, eps)
         qp = k.gemm(qn, rt.operand(w_q), trans_b=True)
         rt.join(side[0])
         kv3 = kvp.view(B, Lk, 2 * HD)
         o, p = k.mha_fwd(qp.view(B, Lq, HD), kv3[:, :, :HD], kv3[:, :, HD:], mask, n_head, temperature,
                          dropout=(p_attn, rng, s_attn))
         o2 = o.view(-1, HD)
+        wfc = rt.operand(w_fc)
         if p_fc > 0:
-            out = k.dropout(k.gemm(o2, rt.operand(w_fc), trans_b=True), p_fc, rng, s_fc, residual=q2)
+            out = k.dropout(k.gemm(o2, wfc, trans_b=True), p_fc, rng, s_fc, residual=q2)
+        elif next_ln is not None and k.gemm_ln_ok(o2, wfc, q2):
+            # fc + skip connection + the NEXT sub-layer's LayerNorm in one launch; the result is handed over through rt
+            out, yn, mean_n, rstd_n = k.gemm_ln(o2, wfc, None, q2, next_ln[0], next_ln[1], next_ln[2])
+            rt.offer_prenorm(out, next_ln[0], next_ln[1], next_ln[2], yn, mean_n, rstd_n)
         else:
-            out = k.gemm(o2, rt.operand(w_fc), trans_b=True, residual=q2)
+            out = k.gemm(o2, wfc, trans_b=True, residual=q2)
         ctx.self_attn, ctx.n_head, ctx.temperature, ctx.dims = self_attn, n_head, temperature, (B, Lq, Lk, D, HD)
         ctx.kv_shape, ctx.drop = kv.shape, drop
         ctx.save_for_backward(q2, None if self_attn else kv2, qn, mean, rstd, qp, kvp, p, o2, ln_w, w_q, w_k, w_v, w_fc,
@@ -244,41 +251,55 @@ class _MHABlock(Function):
             dw_k = k.gemm(dkvp[:, :HD], kv2, trans_a=True, out_dtype=torch.float32)
             dw_v = k.gemm(dkvp[:, HD:], kv2, trans_a=True, out_dtype=torch.float32)
         rt.defer(side[1], (dqp, qn, dkvp, kv2), [(w_q, dw_q), (w_k, dw_k), (w_v, dw_v)])
-        dqn = k.gemm(dqp, rt.operand(w_q))
-        dq, dgamma, dbeta = _ln_backward(k, dqn, q2, ln_w, ln_b, mean, rstd, add=dout2)   # + skip-connection gradient
+        # dX of the K | V projections runs on a parallel branch beside the dQ GEMM; for self-attention its epilogue also
+        # adds the skip-connection gradient, and the LayerNorm-backward kernel adds that sum to its own dx: the chain is
+        # fc-dX -> attention backward -> max(dQ, dK|V GEMM) -> LayerNorm backward (4 dependent kernels, not 5)
         wkv = rt.operand_cat(w_k, w_v)
+        side_x = rt.side_streams(q2.device, 1, pool='fwd')
+        with rt.fork(side_x[0]):
+            dkv = k.gemm(dkvp, wkv, residual=dout2 if ctx.self_attn else None)
+        dqn = k.gemm(dqp, rt.operand(w_q))
+        rt.join(side_x[0])
         if ctx.self_attn:
-            dq = k.gemm(dkvp, wkv, residual=dq)
+            dq, dgamma, dbeta = _ln_backward(k, dqn, q2, ln_w, ln_b, mean, rstd, add=dkv)
             dkv = None
         else:
-            dkv = k.gemm(dkvp, wkv).view(ctx.kv_shape)
+            dq, dgamma, dbeta = _ln_backward(k, dqn, q2, ln_w, ln_b, mean, rstd, add=dout2)   # + skip-connection gradient
+            dkv = dkv.view(ctx.kv_shape)
         return (dq.view(B, Lq, D), dkv, None, dgamma, dbeta, None, dw_q, dw_k, dw_v, dw_fc, None, None,
-                None)
+                None, None)
 
 
-def mha_block(q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature, p_attn=0.0, p_fc=0.0, tag=''):
+def mha_block(q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature, p_attn=0.0, p_fc=0.0, tag='',
+              next_ln=None):
     """Returns (out [B, Lq, D], attention probabilities [B, H, Lq, Lk]).  Pass the SAME tensor object as q and kv
     for self-attention: its two gradient contributions are then merged inside the GEMM epilogue.
-    p_attn / p_fc: dropout on the attention probabilities / on the fc output (training mode values, 0 otherwise)."""
+    p_attn / p_fc: dropout on the attention probabilities / on the fc output (training mode values, 0 otherwise).
+    next_ln = (weight, bias, eps) of the LayerNorm that will normalise the OUTPUT of this sub-layer next (the following
+    sub-layer's pre-norm): when given (and dropout is off, bf16, d_model = 512) it is computed in the fc GEMM's epilogue."""
     drop = (p_attn, rt.next_site(tag + '.attn', p_attn) if p_attn > 0 else 0,
             p_fc, rt.next_site(tag + '.fc', p_fc) if p_fc > 0 else 0)
-    return _MHABlock.apply(q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature, drop)
+    return _MHABlock.apply(q, kv, mask, ln_w, ln_b, eps, w_q, w_k, w_v, w_fc, n_head, temperature, drop, next_ln)
 
 
 class _FFNBlock(Function):
     """x + w_2(relu(w_1(LN(x))));  PositionwiseFeedForward.forward, layers.py:232-252."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, eps, w1, b1, w2, b2, p, site):
+    def forward(ctx, x, ln_w, ln_b, eps, w1, b1, w2, b2, p, site, next_ln=None):
         k = K()
         D = x.size(-1)
         x2 = _c(x).reshape(-1, D)
-        y, mean, rstd = k.layernorm_fwd(x2, ln_w, ln_b, eps)
+        pre = rt.take_prenorm(x2, ln_w, ln_b, eps)           # LayerNorm(x) from the previous sub-layer's GEMM epilogue
+        y, mean, rstd = pre if pre is not None else k.layernorm_fwd(x2, ln_w, ln_b, eps)
         h = k.gemm(y, rt.operand(w1), trans_b=True, bias=b1, relu=True)
         rng = None
         if p > 0:            # x + dropout(w_2(.)) (layers.py:248-250)
             rng = rt.current_rng(x.device)
             out = k.dropout(k.gemm(h, rt.operand(w2), trans_b=True, bias=b2), p, rng, site, residual=x2)
+        elif next_ln is not None and k.gemm_ln_ok(h, rt.operand(w2), x2):
+            out, yn, mean_n, rstd_n = k.gemm_ln(h, rt.operand(w2), b2, x2, next_ln[0], next_ln[1], next_ln[2])
+            rt.offer_prenorm(out, next_ln[0], next_ln[1], next_ln[2], yn, mean_n, rstd_n)
         else:
             out = k.gemm(h, rt.operand(w2), trans_b=True, bias=b2, residual=x2)
         ctx.drop = (p, site)
@@ -304,11 +325,12 @@ class _FFNBlock(Function):
             db1 = k.colsum(dz)
         rt.defer(side[1], (dz, y), [(w1, dw1), (b1, db1)])
         dx, dgamma, dbeta = _ln_backward(k, dy, x2, ln_w, ln_b, mean, rstd, add=dout2)
-        return dx.view(dout.shape), dgamma, dbeta, None, dw1, db1, dw2, db2, None, None
+        return dx.view(dout.shape), dgamma, dbeta, None, dw1, db1, dw2, db2, None, None, None
 
 
-def ffn_block(x, ln_w, ln_b, eps, w1, b1, w2, b2, p=0.0, tag=''):
-    return _FFNBlock.apply(x, ln_w, ln_b, eps, w1, b1, w2, b2, p, rt.next_site(tag + '.ffn', p) if p > 0 else 0)
+def ffn_block(x, ln_w, ln_b, eps, w1, b1, w2, b2, p=0.0, tag='', next_ln=None):
+    """next_ln: see mha_block."""
+    return _FFNBlock.apply(x, ln_w, ln_b, eps, w1, b1, w2, b2, p, rt.next_site(tag + '.ffn', p) if p > 0 else 0, next_ln)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -449,6 +471,9 @@ def masked_nll_sum(logp, target, mask):
     return _MaskedNLL.apply(logp, target, mask)
 
 
+_unit_upstream = [False]     # did the last eager backward of the fused loss see an upstream gradient of exactly 1?
+
+
 class _FusedSoftmaxNLL(Function):
     """K17: softmax + masked NLL + gradient in one pass; gradient is formed in forward."""
 
@@ -464,9 +489,18 @@ class _FusedSoftmaxNLL(Function):
     @staticmethod
     def backward(ctx, g):
         (d,) = ctx.saved_tensors
-        # g is 1 in the training step; anything else is a (rare) scalar rescale of the stored gradient
+        # The upstream gradient g is 1 in the training step (loss.backward() on the already normalised loss); anything
+        # else is a scalar rescale of the stored gradient.  Multiplying regardless costs a full pass over [rows, V]
+        # (128 MB at configs[2], ~60 us on the critical path), and g is a device value: an eager pass reads it (one
+        # sync, eager only) and remembers whether it was exactly 1; a graph capture -- which replays the same Python
+        # path its eager warm-up ran -- skips the multiply only if that check passed.
         dl = d.view(ctx.shape)
-        if g.numel() == 1:
+        if torch.cuda.is_available() and g.is_cuda and torch.cuda.is_current_stream_capturing():
+            unit = _unit_upstream[0]
+        else:
+            unit = bool((g == 1).all())
+            _unit_upstream[0] = unit
+        if not unit:
             dl = dl * g.to(dl.dtype)
         return dl, None, None, None, None
 

@@ -148,6 +148,32 @@ class CudaKernels:
                                          out.stride(0), _p(residual), ldr, _p(bias), 0, self._stream()), 'gemm2')
         return out
 
+    def gemm_ln_ok(self, a, w, residual=None, bias=None) -> bool:
+        """Can `gemm_ln` serve  a @ w^T (+ bias) + residual  followed by a LayerNorm over the 512 output columns?"""
+        if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or a.dim() != 2 or w.dim() != 2 or not a.is_cuda:
+            return False
+        if w.size(0) != 512 or a.size(1) != w.size(1) or a.size(1) % 8 or a.size(1) < 64:
+            return False
+        ts = [a, w] + ([residual] if residual is not None else [])
+        if any(t.stride(1) != 1 or t.stride(0) % 8 or t.data_ptr() % 16 for t in ts):
+            return False
+        return residual is None or (residual.dtype == torch.bfloat16 and tuple(residual.shape) == (a.size(0), 512))
+
+    def gemm_ln(self, a, w, bias, residual, gamma, beta, eps):
+        """y = a @ w^T (+ bias) + residual;  yn, mean, rstd = LayerNorm(y; gamma, beta, eps)  in ONE launch
+        (csrc/gemm_ln.cu).  a [M, K], w [512, K] bf16.  Returns (y, yn, mean, rstd)."""
+        self._need_cuda(a, w, bias, residual, gamma, beta)
+        M, K = a.shape
+        N = w.size(0)
+        y = torch.empty((M, N), dtype=a.dtype, device=a.device)
+        yn = torch.empty((M, N), dtype=a.dtype, device=a.device)
+        mean = torch.empty(M, dtype=torch.float32, device=a.device)
+        rstd = torch.empty(M, dtype=torch.float32, device=a.device)
+        _lib.check(self.lib.b200st_gemm_ln(_dt(a), M, N, K, _p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(residual),
+                                           residual.stride(0) if residual is not None else 0, _p(y), N, _p(gamma), _p(beta),
+                                           float(eps), _p(yn), N, _p(mean), _p(rstd), self._stream()), 'gemm_ln')
+        return y, yn, mean, rstd
+
     # -- LayerNorm --------------------------------------------------------------------------------
     def layernorm_fwd(self, x, gamma, beta, eps, save_stats=True):
         self._need_cuda(x, gamma, beta)

@@ -277,6 +277,30 @@ def join_deferred():
 
 
 # ------------------------------------------------------------------------------------------------
+# Pre-norm hand-over: a sub-layer whose last GEMM ran with the fused residual + LayerNorm epilogue
+# (b200st_gemm_ln) has already produced LayerNorm(out) for the sub-layer that consumes `out` next.  The
+# producer offers it here; the very next LayerNorm on the path takes it if it is about to normalise
+# exactly that tensor with exactly those parameters, and launches nothing.  One slot, strictly
+# producer -> next consumer: any other LayerNorm call in between discards the offer.
+# ------------------------------------------------------------------------------------------------
+_prenorm = [None]
+
+
+def offer_prenorm(out, ln_w, ln_b, eps, yn, mean, rstd):
+    _prenorm[0] = (out.data_ptr(), out.numel(), out.dtype, ln_w.data_ptr(), ln_b.data_ptr(), float(eps), yn, mean, rstd)
+
+
+def take_prenorm(x, ln_w, ln_b, eps):
+    """(LayerNorm(x), mean, rstd) computed by the producer of `x`, or None."""
+    e, _prenorm[0] = _prenorm[0], None
+    if e is None:
+        return None
+    if (x.data_ptr(), x.numel(), x.dtype, ln_w.data_ptr(), ln_b.data_ptr(), float(eps)) != e[:6]:
+        return None
+    return e[6], e[7], e[8]
+
+
+# ------------------------------------------------------------------------------------------------
 # dropout randomness: counter-based (csrc/philox.cuh).  A mask is a pure function of
 # (seed, step, site, element index); seed and step live in a 2 x int64 DEVICE array so that a captured
 # CUDA graph draws fresh masks on every replay (`begin_step` is a captured launch that adds 1 to step).

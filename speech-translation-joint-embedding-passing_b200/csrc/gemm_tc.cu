@@ -1106,7 +1106,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // Tensor map over a row-major bf16 matrix [rows, cols] (cols contiguous, leading dim ld), box = 64 cols x box_rows.
-static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error("gemm_tc: cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};

@@ -8,7 +8,8 @@ import torch
 import torch.nn as nn
 
 from b200st import functional as BF
-from modules.layers import TransformerDecoderLayer, _gen_position_signal, PositionSignal, position_signal
+from modules.layers import (TransformerDecoderLayer, _gen_position_signal, PositionSignal, position_signal, _next_ln,
+                            _ln_args)
 
 
 class Decoder(nn.Module):
@@ -44,9 +45,12 @@ class Decoder(nn.Module):
         assert tgt.shape[1] <= self.time_signal.shape[1], 'call expand_time() for longer sequences'
         x = BF.add_posenc(tgt, position_signal(self).on(self.time_signal, tgt.device))     # TFDec.py:85-86
         att_decslf = att_encdec = None
-        for layer in self.dec_layers:
-            x, att_decslf, att_encdec = layer(x, memory, decslf_attn_mask=tgt_mask,
-                                              encdec_attn_mask=src_mask)
+        n = len(self.dec_layers)
+        for i, layer in enumerate(self.dec_layers):
+            nxt = self.dec_layers[i + 1].decslf_attn.layer_norm if i + 1 < n else self.norm     # see TFEnc.Encoder.forward
+            with _next_ln(layer, _ln_args(nxt)):
+                x, att_decslf, att_encdec = layer(x, memory, decslf_attn_mask=tgt_mask,
+                                                  encdec_attn_mask=src_mask)
         x = BF.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)
         return x, att_decslf, att_encdec
 

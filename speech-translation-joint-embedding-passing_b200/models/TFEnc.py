@@ -9,7 +9,8 @@ import torch
 import torch.nn as nn
 
 from b200st import functional as BF
-from modules.layers import TransformerEncoderLayer, _gen_position_signal, PositionSignal, position_signal
+from modules.layers import (TransformerEncoderLayer, _gen_position_signal, PositionSignal, position_signal, _next_ln,
+                            _ln_args)
 
 
 class Encoder(nn.Module):
@@ -42,8 +43,12 @@ class Encoder(nn.Module):
         assert src.shape[1] <= self.time_signal.shape[1], 'call expand_time() for longer sequences'
         x = BF.add_posenc(src, position_signal(self).on(self.time_signal, src.device))     # TFEnc.py:82-83
         att = None
-        for layer in self.enc_layers:
-            x, att = layer(x, slf_attn_mask=src_mask)
+        n = len(self.enc_layers)
+        for i, layer in enumerate(self.enc_layers):
+            # the LayerNorm that normalises this layer's output next: the following layer's pre-norm, or the final norm
+            nxt = self.enc_layers[i + 1].slf_attn.layer_norm if i + 1 < n else self.norm
+            with _next_ln(layer, _ln_args(nxt)):
+                x, att = layer(x, slf_attn_mask=src_mask)
         x = BF.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)
         return x, att
 

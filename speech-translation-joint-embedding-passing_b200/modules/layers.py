@@ -20,6 +20,29 @@ def _p(module):
     return float(module.p) if module.training else 0.0
 
 
+# Which LayerNorm normalises a sub-layer's OUTPUT next (the following sub-layer's pre-norm, or the stack's final norm)?
+# The stack / layer forward passes note it on the sub-layer module for the duration of the call (a plain __dict__ entry, not
+# a registered sub-module: state_dicts and pickles are unaffected), so that the sub-layer's last GEMM can normalise in its
+# epilogue (b200st.functional.mha_block / ffn_block, csrc/gemm_ln.cu).  Forward signatures stay the reference's.
+_NEXT_LN = '_b200st_next_ln'
+
+
+def _ln_args(ln):
+    return None if ln is None else (ln.weight, ln.bias, ln.eps)
+
+
+class _next_ln:
+    def __init__(self, module, ln_args):
+        self.module, self.ln_args = module, ln_args
+
+    def __enter__(self):
+        self.module.__dict__[_NEXT_LN] = self.ln_args
+
+    def __exit__(self, *exc):
+        self.module.__dict__.pop(_NEXT_LN, None)
+        return False
+
+
 class TransformerEncoderLayer(nn.Module):
     """layers.py:23-63"""
 
@@ -29,8 +52,10 @@ class TransformerEncoderLayer(nn.Module):
         self.pos_ffn = PositionwiseFeedForward(dim_model, dim_feedforward, dropout=dropout)
 
     def forward(self, src, slf_attn_mask=None, prior_weight=None):
-        y, att = self.slf_attn(src, src, src, mask=slf_attn_mask, prior_weight=prior_weight)
-        return self.pos_ffn(y), att
+        with _next_ln(self.slf_attn, _ln_args(self.pos_ffn.layer_norm)):
+            y, att = self.slf_attn(src, src, src, mask=slf_attn_mask, prior_weight=prior_weight)
+        with _next_ln(self.pos_ffn, self.__dict__.get(_NEXT_LN)):
+            return self.pos_ffn(y), att
 
 
 class TransformerDecoderLayer(nn.Module):
@@ -46,9 +71,12 @@ class TransformerDecoderLayer(nn.Module):
                 decode_speedup=False, cache_decslf=None, cache_encdec=None):
         if decode_speedup:
             raise NotImplementedError('decode_speedup is never used by Seq2seq (SURVEY.md §2.1 #6)')
-        y, att_decslf = self.decslf_attn(dec_input, dec_input, dec_input, mask=decslf_attn_mask)
-        y, att_encdec = self.encdec_attn(y, enc_output, enc_output, mask=encdec_attn_mask)
-        return self.pos_ffn(y), att_decslf, att_encdec
+        with _next_ln(self.decslf_attn, _ln_args(self.encdec_attn.layer_norm)):
+            y, att_decslf = self.decslf_attn(dec_input, dec_input, dec_input, mask=decslf_attn_mask)
+        with _next_ln(self.encdec_attn, _ln_args(self.pos_ffn.layer_norm)):
+            y, att_encdec = self.encdec_attn(y, enc_output, enc_output, mask=encdec_attn_mask)
+        with _next_ln(self.pos_ffn, self.__dict__.get(_NEXT_LN)):
+            return self.pos_ffn(y), att_decslf, att_encdec
 
 
 class MultiheadAttention(nn.Module):
@@ -77,7 +105,8 @@ class MultiheadAttention(nn.Module):
         if k is v:           # every call site of the reference (self- and cross-attention): one fused sub-layer node
             return BF.mha_block(q, k, mask, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps,
                                 self.w_qs.weight, self.w_ks.weight, self.w_vs.weight, self.fc.weight, self.n_head,
-                                self.attention.temperature, p_attn=p_attn, p_fc=p_fc, tag=tag)
+                                self.attention.temperature, p_attn=p_attn, p_fc=p_fc, tag=tag,
+                                next_ln=self.__dict__.get(_NEXT_LN))
         residual = q
         qn = BF.layer_norm(q, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
         qp = BF.linear(qn, self.w_qs.weight)
@@ -127,7 +156,7 @@ class PositionwiseFeedForward(nn.Module):
     def forward(self, x):
         return BF.ffn_block(x, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps,
                             self.w_1.weight, self.w_1.bias, self.w_2.weight, self.w_2.bias, p=_p(self.dropout),
-                            tag=getattr(self, '_b200st_tag', ''))
+                            tag=getattr(self, '_b200st_tag', ''), next_ln=self.__dict__.get(_NEXT_LN))
 
 
 # ---- helpers (layers.py:260-309) ---------------------------------------------------------------

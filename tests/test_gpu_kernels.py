@@ -552,3 +552,27 @@ def test_layernorm_bwd_partial_sums(ks, dtype, rows, cols):
     assert rel_err(dx, dx_ref) < TOL[dtype]
     assert rel_err(c.colsum(part[:, :cols]), dg) < 1e-4 and rel_err(c.colsum(part[:, cols:]), db) < 1e-4
     assert c.layernorm_bwd_partial(dy[:, :100].contiguous(), x[:, :100].contiguous(), gamma[:100], mean, rstd) == (None, None)
+
+
+@pytest.mark.parametrize('M,K,with_bias,with_res', [(3200, 512, False, True), (2048, 1024, True, True), (50, 512, True, False),
+                                                   (129, 72, False, True), (1, 64, True, True), (300, 1024, False, False)])
+def test_gemm_ln_fused_epilogue(ks, M, K, with_bias, with_res):
+    """b200st_gemm_ln == b200st_gemm(+bias, +residual) followed by b200st_layernorm_fwd (layers.py:190-197,245-252 + 153)."""
+    c, f = ks
+    a = rnd(M, K, dtype=torch.bfloat16, seed=1)
+    w = rnd(512, K, dtype=torch.bfloat16, seed=2, scale=K ** -0.5)
+    bias = rnd(512, seed=3) if with_bias else None
+    res = rnd(M, 512, dtype=torch.bfloat16, seed=4, scale=2.0) if with_res else None
+    gamma, beta = 1 + 0.2 * rnd(512, seed=5), 0.1 * rnd(512, seed=6)
+    assert c.gemm_ln_ok(a, w, res)
+    y, yn, mean, rstd = c.gemm_ln(a, w, bias, res, gamma, beta, 1e-6)
+    y0 = c.gemm(a, w, trans_b=True, bias=bias, residual=res)
+    yn0, mean0, rstd0 = c.layernorm_fwd(y0, gamma, beta, 1e-6)
+    assert rel_err(y, y0) < 1e-2                       # same fp32 accumulator, bf16 rounding of the sum may differ in the last bit
+    # the statistics are those of the fused kernel's OWN rounded y: compare against the LayerNorm of exactly that tensor
+    yn1, mean1, rstd1 = c.layernorm_fwd(y, gamma, beta, 1e-6)
+    assert rel_err(mean, mean1) < 1e-5 and rel_err(rstd, rstd1) < 1e-5
+    assert rel_err(yn, yn1) < 4e-3
+    ynr, meanr, rstdr = f.layernorm_fwd(y, gamma, beta, 1e-6)
+    assert rel_err(yn, ynr) < 4e-3 and rel_err(mean, meanr) < 1e-5 and rel_err(rstd, rstdr) < 1e-5
+    assert rel_err(yn, yn0) < 2e-2

@@ -159,3 +159,47 @@ def test_specaug_draw_order_matches_reference(fake_backend):
         t0 = random.randint(0, 40 - t - 1); f0 = random.randint(0, 8 - f - 1)
         ref[:, t0:t0 + t, :] = 0; ref[:, :, f0:f0 + f] = 0
     assert torch.equal(y, ref)
+
+
+def test_prenorm_handover_between_sublayers_fake():
+    """A sub-layer that is told which LayerNorm consumes its output computes it in its last GEMM (gemm_ln) and hands it
+    over: the next sub-layer launches no LayerNorm of its own and produces the same result (layers.py:153,245)."""
+    from b200st import functional as BF, kernels
+    from fake_kernels import FakeKernels
+    fk = FakeKernels()
+    calls = {'ln': 0, 'gemm_ln': 0}
+    ln0, gl0 = fk.layernorm_fwd, fk.gemm_ln
+    fk.layernorm_fwd = lambda *a, **k: (calls.__setitem__('ln', calls['ln'] + 1), ln0(*a, **k))[1]
+    fk.gemm_ln = lambda *a, **k: (calls.__setitem__('gemm_ln', calls['gemm_ln'] + 1), gl0(*a, **k))[1]
+    old = kernels.set_backend(fk)
+    try:
+        g = torch.Generator().manual_seed(0)
+        B, L, D, FF, H = 2, 5, 512, 64, 8
+        bf = torch.bfloat16
+        x = torch.randn(B, L, D, generator=g).to(bf)
+        mk = lambda *s, sc=0.05: (sc * torch.randn(*s, generator=g)).requires_grad_(True)
+        ln1, ln2, ln3 = [(1 + mk(D, sc=0.1).detach(), mk(D, sc=0.1).detach(), 1e-6) for _ in range(3)]
+        wq, wk, wv, wfc = mk(D, D), mk(D, D), mk(D, D), mk(D, D)
+        w1, b1, w2, b2 = mk(FF, D), mk(FF), mk(D, FF), mk(D)
+
+        def chain(handover):
+            xin = x.clone().requires_grad_(True)
+            y, _ = BF.mha_block(xin, xin, None, ln1[0], ln1[1], ln1[2], wq, wk, wv, wfc, H, 8.0, next_ln=ln2 if handover else None)
+            z = BF.ffn_block(y, ln2[0], ln2[1], ln2[2], w1, b1, w2, b2, next_ln=ln3 if handover else None)
+            out = BF.layer_norm(z, ln3[0], ln3[1], ln3[2])
+            out.float().sum().backward()
+            return out.detach().float(), xin.grad.float()
+        from b200st import runtime as rt
+        rt.set_compute_dtype('bf16')
+        try:
+            calls.update(ln=0, gemm_ln=0)
+            o0, g0 = chain(False)
+            assert calls == {'ln': 3, 'gemm_ln': 0}
+            calls.update(ln=0, gemm_ln=0)
+            o1, g1 = chain(True)
+            assert calls['gemm_ln'] == 2 and calls['ln'] == 1 + 2       # only the first pre-norm is a launch of its own (+ the 2 inside the fake gemm_ln)
+        finally:
+            rt.set_compute_dtype('fp32')
+        assert rel_err(o1, o0) < 1e-2 and rel_err(g1, g0) < 2e-2
+    finally:
+        kernels.set_backend(old)
