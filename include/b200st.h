@@ -90,6 +90,20 @@ int b200st_gemm_ln(int dtype, int64_t M, int64_t N, int64_t K, const void* A, in
                    const float* beta, float eps, void* YN, int64_t ldyn, float* mean, float* rstd,
                    b200st_stream_t stream);
 
+/* The backward twin (csrc/gemm_ln.cu): the input-gradient GEMM that feeds a LayerNorm backward, with that backward as
+ * its epilogue (replaces b200st_gemm followed by b200st_layernorm_bwd_partial):
+ *   G[M, N]  = A[M, K] . W[K, N]                              -- dqn = dqp . w_qs, dy = dz . w_1 (N = 512 = d_model)
+ *   DX[M, N] = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)) + ADD,  g = G * gamma, xhat = (X - mean) * rstd
+ *   partials[row block, 0:N] = sum_rows G * xhat (dgamma), partials[row block, N:2N] = sum_rows G (dbeta): fp32
+ *   [b200st_gemm_lnbwd_blocks(M), 2N], column-summed by the caller off the critical path.
+ * X, ADD (may be NULL), DX are dense [M, N] bf16.  *_eligible as for b200st_gemm_ln. */
+int b200st_gemm_lnbwd_eligible(int dtype, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* W,
+                               int64_t ldw, const void* X, const void* ADD, const void* DX, const float* gamma);
+int64_t b200st_gemm_lnbwd_blocks(int64_t M);
+int b200st_gemm_lnbwd(int dtype, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* W, int64_t ldw,
+                      const void* X, const float* gamma, const float* mean, const float* rstd, const void* ADD, void* DX,
+                      float* partials, b200st_stream_t stream);
+
 /* ---- LayerNorm (layers.py:139,153,240,245; TFEnc.py:61,89; TFDec.py:58,127) -------------------- */
 int b200st_layernorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y,
                          float* mean, float* rstd, int64_t rows, int64_t cols, float eps,

@@ -124,6 +124,23 @@ def _ln_backward(k, dy, x, ln_w, ln_b, mean, rstd, add=None):
     return dx, dln[0], dln[1]
 
 
+def _dx_ln_backward(k, dyp, w, x, ln_w, ln_b, mean, rstd, add=None):
+    """LayerNorm backward of  dy = dyp @ w  (the input-gradient GEMM in front of a pre-norm) -> (dx [+ add], dgamma, dbeta).
+    One launch (b200st_gemm_lnbwd: the LayerNorm backward is the GEMM's epilogue) where the shapes allow, the GEMM and the
+    LayerNorm-backward kernel otherwise.  The dgamma / dbeta column sums of the per-row-block partials run on a side stream
+    whose join is deferred to the end of backward when the gradients can be adopted (graph capture)."""
+    if not k.gemm_lnbwd_ok(dyp, w, x, add):
+        return _ln_backward(k, k.gemm(dyp, w), x, ln_w, ln_b, mean, rstd, add=add)
+    D = x.size(-1)
+    dx, part = k.gemm_lnbwd(dyp, w, x, ln_w, mean, rstd, add=add)
+    side = rt.side_streams(x.device, 1, pool='dw') if rt.can_defer(ln_w, ln_b) else [None]
+    with rt.fork(side[0]):
+        dgamma = k.colsum(part[:, :D])
+        dbeta = k.colsum(part[:, D:])
+    rt.defer(side[0], (part,), [(ln_w, dgamma), (ln_b, dbeta)])
+    return dx, dgamma, dbeta
+
+
 class _LayerNorm(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, eps):
@@ -258,13 +275,13 @@ class _MHABlock(Function):
         side_x = rt.side_streams(q2.device, 1, pool='fwd')
         with rt.fork(side_x[0]):
             dkv = k.gemm(dkvp, wkv, residual=dout2 if ctx.self_attn else None)
-        dqn = k.gemm(dqp, rt.operand(w_q))
         rt.join(side_x[0])
+        # dQ GEMM with the LayerNorm backward (+ the skip-connection / K|V gradient) as its epilogue
         if ctx.self_attn:
-            dq, dgamma, dbeta = _ln_backward(k, dqn, q2, ln_w, ln_b, mean, rstd, add=dkv)
+            dq, dgamma, dbeta = _dx_ln_backward(k, dqp, rt.operand(w_q), q2, ln_w, ln_b, mean, rstd, add=dkv)
             dkv = None
         else:
-            dq, dgamma, dbeta = _ln_backward(k, dqn, q2, ln_w, ln_b, mean, rstd, add=dout2)   # + skip-connection gradient
+            dq, dgamma, dbeta = _dx_ln_backward(k, dqp, rt.operand(w_q), q2, ln_w, ln_b, mean, rstd, add=dout2)
             dkv = dkv.view(ctx.kv_shape)
         return (dq.view(B, Lq, D), dkv, None, dgamma, dbeta, None, dw_q, dw_k, dw_v, dw_fc, None, None,
                 None, None)
@@ -319,12 +336,11 @@ class _FFNBlock(Function):
             dw2 = k.gemm(d2, h, trans_a=True, out_dtype=torch.float32)
             db2 = k.colsum(d2)
         rt.defer(side[0], (d2, h), [(w2, dw2), (b2, db2)])
-        dy = k.gemm(dz, rt.operand(w1))
         with rt.fork(side[1]):
             dw1 = k.gemm(dz, y, trans_a=True, out_dtype=torch.float32)
             db1 = k.colsum(dz)
         rt.defer(side[1], (dz, y), [(w1, dw1), (b1, db1)])
-        dx, dgamma, dbeta = _ln_backward(k, dy, x2, ln_w, ln_b, mean, rstd, add=dout2)
+        dx, dgamma, dbeta = _dx_ln_backward(k, dz, rt.operand(w1), x2, ln_w, ln_b, mean, rstd, add=dout2)
         return dx.view(dout.shape), dgamma, dbeta, None, dw1, db1, dw2, db2, None, None, None
 
 

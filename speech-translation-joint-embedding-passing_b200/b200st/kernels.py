@@ -174,6 +174,32 @@ class CudaKernels:
                                            float(eps), _p(yn), N, _p(mean), _p(rstd), self._stream()), 'gemm_ln')
         return y, yn, mean, rstd
 
+    def gemm_lnbwd_ok(self, a, w, x, add=None) -> bool:
+        """Can `gemm_lnbwd` serve  LayerNorm-backward(a @ w; x, ...) + add  (w [K, 512], x / add dense [M, 512] bf16)?"""
+        if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or a.dim() != 2 or w.dim() != 2 or not a.is_cuda:
+            return False
+        if w.size(1) != 512 or a.size(1) != w.size(0) or a.size(1) % 8 or a.size(1) < 64:
+            return False
+        if any(t.stride(1) != 1 or t.stride(0) % 8 or t.data_ptr() % 16 for t in (a, w)):
+            return False
+        for t in (x, add):
+            if t is not None and not (t.dtype == torch.bfloat16 and t.is_contiguous() and t.numel() == a.size(0) * 512
+                                      and t.data_ptr() % 16 == 0):
+                return False
+        return True
+
+    def gemm_lnbwd(self, a, w, x, gamma, mean, rstd, add=None):
+        """dx = LayerNorm-backward(dy = a @ w; x, gamma, mean, rstd) [+ add] in ONE launch (csrc/gemm_ln.cu).
+        Returns (dx [M, 512], partials fp32 [row blocks, 1024] = dgamma | dbeta contributions to be column-summed)."""
+        self._need_cuda(a, w, x, gamma, mean, rstd, add)
+        M, K = a.shape
+        N = w.size(1)
+        dx = torch.empty((M, N), dtype=a.dtype, device=a.device)
+        partials = torch.empty((int(self.lib.b200st_gemm_lnbwd_blocks(M)), 2 * N), dtype=torch.float32, device=a.device)
+        _lib.check(self.lib.b200st_gemm_lnbwd(_dt(a), M, N, K, _p(a), a.stride(0), _p(w), w.stride(0), _p(x), _p(gamma),
+                                              _p(mean), _p(rstd), _p(add), _p(dx), _p(partials), self._stream()), 'gemm_lnbwd')
+        return dx, partials
+
     # -- LayerNorm --------------------------------------------------------------------------------
     def layernorm_fwd(self, x, gamma, beta, eps, save_stats=True):
         self._need_cuda(x, gamma, beta)

@@ -159,6 +159,21 @@ class FakeKernels:
                 d.copy_(p.data.reshape(d.shape))
 
     # -- LayerNorm --------------------------------------------------------------------------------
+    def gemm_lnbwd_ok(self, a, w, x, add=None):
+        return a.dim() == 2 and w.dim() == 2 and w.size(1) == 512 and a.dtype == torch.bfloat16
+
+    def gemm_lnbwd(self, a, w, x, gamma, mean, rstd, add=None):
+        dy = a.float() @ w.float()                       # fp32 gradient of the LayerNorm output (not rounded to bf16)
+        cols = x.size(-1)
+        xf = x.float().reshape(-1, cols)
+        xh = (xf - mean[:, None]) * rstd[:, None]
+        g = dy * gamma
+        dx = rstd[:, None] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+        if add is not None:
+            dx = dx + add.float().reshape(-1, cols)
+        part = torch.cat([(dy * xh).sum(0), dy.sum(0)])[None, :]
+        return dx.to(x.dtype), part
+
     def gemm_ln_ok(self, a, w, residual=None, bias=None):
         return a.dim() == 2 and w.dim() == 2 and w.size(0) == 512 and a.dtype == torch.bfloat16
 

@@ -576,3 +576,26 @@ def test_gemm_ln_fused_epilogue(ks, M, K, with_bias, with_res):
     ynr, meanr, rstdr = f.layernorm_fwd(y, gamma, beta, 1e-6)
     assert rel_err(yn, ynr) < 4e-3 and rel_err(mean, meanr) < 1e-5 and rel_err(rstd, rstdr) < 1e-5
     assert rel_err(yn, yn0) < 2e-2
+
+
+@pytest.mark.parametrize('M,K,with_add', [(3200, 512, True), (2048, 1024, True), (50, 512, False), (129, 72, True), (1, 64, True)])
+def test_gemm_lnbwd_fused_epilogue(ks, M, K, with_add):
+    """b200st_gemm_lnbwd == b200st_gemm followed by the LayerNorm backward (+ skip gradient) and its dgamma / dbeta sums."""
+    c, f = ks
+    a = rnd(M, K, dtype=torch.bfloat16, seed=1)
+    w = rnd(K, 512, dtype=torch.bfloat16, seed=2, scale=K ** -0.5)
+    x = rnd(M, 512, dtype=torch.bfloat16, seed=3, scale=2.0)
+    add = rnd(M, 512, dtype=torch.bfloat16, seed=4) if with_add else None
+    gamma, beta = 1 + 0.2 * rnd(512, seed=5), 0.1 * rnd(512, seed=6)
+    _, mean, rstd = c.layernorm_fwd(x, gamma, beta, 1e-6)
+    assert c.gemm_lnbwd_ok(a, w, x, add)
+    dx, part = c.gemm_lnbwd(a, w, x, gamma, mean, rstd, add=add)
+    dxr, partr = f.gemm_lnbwd(a, w, x, gamma, mean, rstd, add=add)
+    assert part.shape == ((M + 127) // 128, 1024)
+    assert rel_err(dx, dxr) < 1e-2
+    assert rel_err(part.sum(0), partr.sum(0)) < 2e-3
+    # and against the two separate kernels it replaces (their dy is rounded to bf16 in between)
+    dy = c.gemm(a, w)
+    dln = torch.zeros(2, 512, device='cuda')
+    dx0 = c.layernorm_bwd(dy, x, gamma, mean, rstd, dln[0], dln[1], add=add)
+    assert rel_err(dx, dx0) < 2e-2 and rel_err(part.sum(0), dln.reshape(-1)) < 1e-2

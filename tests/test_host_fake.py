@@ -167,8 +167,9 @@ def test_prenorm_handover_between_sublayers_fake():
     from b200st import functional as BF, kernels
     from fake_kernels import FakeKernels
     fk = FakeKernels()
-    calls = {'ln': 0, 'gemm_ln': 0}
-    ln0, gl0 = fk.layernorm_fwd, fk.gemm_ln
+    calls = {'ln': 0, 'gemm_ln': 0, 'lnbwd': 0}
+    ln0, gl0, lb0 = fk.layernorm_fwd, fk.gemm_ln, fk.gemm_lnbwd
+    fk.gemm_lnbwd = lambda *a, **k: (calls.__setitem__('lnbwd', calls['lnbwd'] + 1), lb0(*a, **k))[1]
     fk.layernorm_fwd = lambda *a, **k: (calls.__setitem__('ln', calls['ln'] + 1), ln0(*a, **k))[1]
     fk.gemm_ln = lambda *a, **k: (calls.__setitem__('gemm_ln', calls['gemm_ln'] + 1), gl0(*a, **k))[1]
     old = kernels.set_backend(fk)
@@ -192,10 +193,10 @@ def test_prenorm_handover_between_sublayers_fake():
         from b200st import runtime as rt
         rt.set_compute_dtype('bf16')
         try:
-            calls.update(ln=0, gemm_ln=0)
+            calls.update(ln=0, gemm_ln=0, lnbwd=0)
             o0, g0 = chain(False)
-            assert calls == {'ln': 3, 'gemm_ln': 0}
-            calls.update(ln=0, gemm_ln=0)
+            assert calls == {'ln': 3, 'gemm_ln': 0, 'lnbwd': 2}      # the two sub-layers' dX GEMM + LayerNorm backward
+            calls.update(ln=0, gemm_ln=0, lnbwd=0)
             o1, g1 = chain(True)
             assert calls['gemm_ln'] == 2 and calls['ln'] == 1 + 2       # only the first pre-norm is a launch of its own (+ the 2 inside the fake gemm_ln)
         finally:
