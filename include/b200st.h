@@ -271,6 +271,11 @@ int b200st_las_attn_fwd(int dtype, const void* q, const void* wk, const void* va
 int b200st_las_attn_bwd(int dtype, const void* dctx, const void* wk, const void* vals,
                         const float* probs, float* dscore, void* dq, int64_t B, int64_t Tk,
                         int64_t D, int64_t Dv, b200st_stream_t stream);
+/* Key / value gradients of the attention over all S decode steps in one launch (attention.py:203-289 in reverse):
+ * out[b, t, :] = sum_s w[s, b, t] * x[s, b, :];  w fp32 [S, B, Tk] (dscore -> d(W k), probs -> d values), x [S, B, D]
+ * (decoder outputs / context gradients), out [B, Tk, D] in `dtype`.  Replaces two batched thin-K GEMMs (+ two casts). */
+int b200st_las_stack_grad(int dtype, const float* w, const void* x, void* out, int64_t S, int64_t B, int64_t Tk, int64_t D,
+                          b200st_stream_t stream);
 /* argmax over the last dim (Dec.py:331 topk(1), Seq2seq.py:255 topk(1)); first index wins ties. */
 int b200st_argmax_rows(int dtype, const void* x, int64_t ld, int64_t rows, int64_t cols,
                        int64_t* idx, int64_t idx_stride, b200st_stream_t stream);

@@ -922,10 +922,8 @@ class _LASDecoder(Function):
             dec_out_stack = XD[n_layers - 1]
         # keys / values first -- d_enc is what the BLSTM backward is waiting for:
         # d wk[b] = dscore[:, b]^T dec_out[:, b];  d vals[b] = probs[:, b]^T dctx[:, b]
-        dsc = k.cast(DSC, dt).permute(1, 0, 2)                                   # [B][S,Tk]
-        prb = k.cast(PROBS, dt).permute(1, 0, 2)
-        d_wk = k.gemm(dsc, dec_out_stack.permute(1, 0, 2), trans_a=True)         # [B,Tk,D]
-        d_enc = k.gemm(prb, DCTX.permute(1, 0, 2), trans_a=True)                 # [B,Tk,2H]
+        d_wk = k.las_stack_grad(DSC, dec_out_stack.contiguous())                 # [B,Tk,D]   (one launch each: the fp32
+        d_enc = k.las_stack_grad(PROBS, DCTX)                                    # [B,Tk,2H]   weights are read as they are)
         k.gemm(d_wk.view(B * Tk, D), rt.operand(w_att), residual=d_enc.view(B * Tk, H2),
                out=d_enc.view(B * Tk, H2))
         # every weight gradient of the loop is ONE GEMM over S*B rows; none of them is read again in backward: side

@@ -420,6 +420,16 @@ class CudaKernels:
         return dgates
 
     # -- LAS attention / decode helpers -------------------------------------------------------------
+    def las_stack_grad(self, w, x):
+        """out[b, t, :] = sum_s w[s, b, t] * x[s, b, :]  (w fp32 [S, B, Tk], x [S, B, D]) -> [B, Tk, D] in x.dtype."""
+        self._need_cuda(w, x)
+        assert w.dtype == torch.float32 and w.is_contiguous() and x.is_contiguous() and w.shape[:2] == x.shape[:2]
+        S, B, Tk = w.shape
+        D = x.size(2)
+        out = torch.empty((B, Tk, D), dtype=x.dtype, device=x.device)
+        _lib.check(self.lib.b200st_las_stack_grad(_dt(x), _p(w), _p(x), _p(out), S, B, Tk, D, self._stream()), 'las_stack_grad')
+        return out
+
     def las_attn_fwd(self, q, wk, vals, klens, ctx_out=None, probs_out=None):
         self._need_cuda(q, wk, vals, klens)
         B, Tk, D = wk.shape

@@ -987,6 +987,51 @@ __global__ void las_update_lengths_kernel(const int64_t* __restrict__ sym, int64
   if ((s == 3 /*EOS*/ || s == 0 /*PAD*/) && lengths[b] > step) lengths[b] = step + 1;  // Dec.py:334-340
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Key / value gradients of the LAS attention over ALL decode steps at once (attention.py:203-289 in reverse):
+//   out[b, t, :] = sum_s w[s, b, t] * x[s, b, :]        w fp32 [S, B, Tk] (dscore or probs), x [S, B, D], out [B, Tk, D]
+// i.e. per sequence a [Tk x S] . [S x D] product with S ~ 31: far too thin for a tensor-core tile, and as a batched GEMM on
+// the CUDA-core fallback it took 36 us per call on the backward critical path (the BLSTM backward waits for it).  Here a
+// CTA owns (sequence, 16 keys): the weights sit in shared memory, a thread owns two adjacent columns, x is streamed once per
+// CTA with 4-byte loads.  Writes dominate: B * Tk * D * sizeof.
+template <typename T>
+__global__ void __launch_bounds__(256) las_stack_grad_kernel(const float* __restrict__ w, const T* __restrict__ x,
+                                                             T* __restrict__ out, int S, int B, int Tk, int D) {
+  pdl_wait();
+  pdl_launch_dependents();
+  constexpr int TT = 16, SMAX = 64;
+  __shared__ float ws[SMAX][TT];
+  const int b = blockIdx.x, t0 = blockIdx.y * TT;
+  for (int s0 = 0; s0 < S; s0 += SMAX) {
+    const int sn = min(SMAX, S - s0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < sn * TT; i += blockDim.x) {
+      const int s = i / TT, tt = i % TT;
+      ws[s][tt] = (t0 + tt < Tk) ? w[((int64_t)(s0 + s) * B + b) * Tk + t0 + tt] : 0.f;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x * 2; c < D; c += blockDim.x * 2) {
+      float a0[TT], a1[TT];
+#pragma unroll
+      for (int tt = 0; tt < TT; ++tt) { a0[tt] = 0.f; a1[tt] = 0.f; }
+      const bool pair = c + 1 < D;
+      for (int s = 0; s < sn; ++s) {
+        const T* xp = x + ((int64_t)(s0 + s) * B + b) * D + c;
+        const float x0 = to_f(xp[0]), x1 = pair ? to_f(xp[1]) : 0.f;
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) { a0[tt] = fmaf(ws[s][tt], x0, a0[tt]); a1[tt] = fmaf(ws[s][tt], x1, a1[tt]); }
+      }
+#pragma unroll
+      for (int tt = 0; tt < TT; ++tt) {
+        if (t0 + tt >= Tk) break;
+        T* op = out + ((int64_t)b * Tk + t0 + tt) * D + c;
+        if (s0 == 0) { op[0] = from_f<T>(a0[tt]); if (pair) op[1] = from_f<T>(a1[tt]); }
+        else { op[0] = from_f<T>(to_f(op[0]) + a0[tt]); if (pair) op[1] = from_f<T>(to_f(op[1]) + a1[tt]); }
+      }
+    }
+  }
+}
+
 }  // namespace b200st
 
 using namespace b200st;
@@ -1267,6 +1312,18 @@ int b200st_las_update_lengths(const int64_t* sym, int64_t sym_stride, int32_t* l
   las_update_lengths_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(
       sym, sym_stride, lengths, step, B);
   B200ST_LAUNCH_CHECK("las_update_lengths");
+  return 0;
+}
+
+int b200st_las_stack_grad(int dtype, const float* w, const void* x, void* out, int64_t S, int64_t B, int64_t Tk, int64_t D,
+                          b200st_stream_t stream) {
+  if (S <= 0 || B <= 0 || Tk <= 0 || D <= 0) return 0;
+  dim3 grid((unsigned)B, (unsigned)ceil_div(Tk, 16));
+  B200ST_DISPATCH(dtype, T, {
+    B200ST_CUDA(launch_pdl(las_stack_grad_kernel<T>, grid, dim3(256), 0, (cudaStream_t)stream, w, (const T*)x, (T*)out, (int)S,
+                           (int)B, (int)Tk, (int)D));
+  });
+  B200ST_LAUNCH_CHECK("las_stack_grad");
   return 0;
 }
 

@@ -64,14 +64,18 @@ __global__ void add_posenc_kernel(const T* __restrict__ x, const float* __restri
     out[i] = from_f<T>(to_f(x[i]) + pe[i % LD]);
 }
 
+constexpr int TR_RPB = 32;      // (a, b) rows per CTA: one CTA per row meant 64 512 tiny CTAs for the acoustic input (36 us of block scheduling)
 template <typename TI, typename TO>
 __global__ void transpose01_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t A,
                                    int64_t Bd, int64_t C) {
-  // one CTA per (a, b) row of C contiguous elements
-  const int64_t a = blockIdx.x / Bd, b = blockIdx.x % Bd;
-  const TI* src = in + (a * Bd + b) * C;
-  TO* dst = out + (b * A + a) * C;
-  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) dst[c] = from_f<TO>(to_f(src[c]));
+  // rows (a, b) of C contiguous elements move to (b, a); a CTA owns TR_RPB consecutive source rows
+  const int64_t r0 = (int64_t)blockIdx.x * TR_RPB, rows = A * Bd;
+  const int64_t n = min((int64_t)TR_RPB, rows - r0) * C;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t r = r0 + i / C, c = i % C;
+    const int64_t a = r / Bd, b = r % Bd;
+    out[(b * A + a) * C + c] = from_f<TO>(to_f(in[r * C + c]));
+  }
 }
 
 template <typename TI, typename TO>
@@ -249,8 +253,8 @@ int b200st_add_posenc(int dtype, const void* x, const float* pe, void* out, int6
 int b200st_transpose01(int dtype_in, int dtype_out, const void* in, void* out, int64_t A, int64_t Bd,
                        int64_t C, b200st_stream_t stream) {
   if (A * Bd * C <= 0) return 0;
-  const unsigned grid = (unsigned)(A * Bd);
-  const int block = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
+  const unsigned grid = (unsigned)ceil_div(A * Bd, TR_RPB);
+  const int block = 256;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype_in == B200ST_F32 && dtype_out == B200ST_F32)
     transpose01_kernel<float, float><<<grid, block, 0, st>>>((const float*)in, (float*)out, A, Bd, C);

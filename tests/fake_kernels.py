@@ -425,6 +425,9 @@ class FakeKernels:
         return dg_all
 
     # -- LAS attention / decode helpers -------------------------------------------------------------
+    def las_stack_grad(self, w, x):
+        return torch.einsum('sbt,sbd->btd', w.float(), x.float()).to(x.dtype)
+
     def las_attn_fwd(self, q, wk, vals, klens, ctx_out=None, probs_out=None):
         B, Tk, D = wk.shape
         s = torch.bmm(q.float().unsqueeze(1), wk.float().transpose(1, 2)).squeeze(1)

@@ -599,3 +599,12 @@ def test_gemm_lnbwd_fused_epilogue(ks, M, K, with_add):
     dln = torch.zeros(2, 512, device='cuda')
     dx0 = c.layernorm_bwd(dy, x, gamma, mean, rstd, dln[0], dln[1], add=add)
     assert rel_err(dx, dx0) < 2e-2 and rel_err(part.sum(0), dln.reshape(-1)) < 1e-2
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('S,B,Tk,D', [(31, 64, 126, 512), (5, 3, 13, 48), (70, 2, 17, 33), (1, 1, 1, 8)])
+def test_las_stack_grad(ks, dtype, S, B, Tk, D):
+    c, f = ks
+    w = rnd(S, B, Tk, seed=1)
+    x = rnd(S, B, D, dtype=dtype, seed=2)
+    assert rel_err(c.las_stack_grad(w, x), f.las_stack_grad(w, x)) < TOL[dtype]
