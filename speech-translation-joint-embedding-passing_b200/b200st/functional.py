@@ -553,13 +553,13 @@ class _BLSTMLayer(Function):
         need_grad = any(ctx.needs_input_grad)
         hs, acts, cs = k.blstm_fwd(xproj, w_hh_f, w_hh_r, lens, out, ld_t, ld_b, pair, save=need_grad)
         ctx.geom = (T, B, I, H, pair, ld_t, ld_b)
-        ctx.save_for_backward(x2, lens, hs, acts, cs, w_ih_f, w_hh_f, w_ih_r, w_hh_r)
+        ctx.save_for_backward(x2, lens, hs, acts, cs, w_ih_f, w_hh_f, w_ih_r, w_hh_r, b_ih_f, b_hh_f, b_ih_r, b_hh_r)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         k = K()
-        x2, lens, hs, acts, cs, w_ih_f, w_hh_f, w_ih_r, w_hh_r = ctx.saved_tensors
+        x2, lens, hs, acts, cs, w_ih_f, w_hh_f, w_ih_r, w_hh_r, b_ih_f, b_hh_f, b_ih_r, b_hh_r = ctx.saved_tensors
         T, B, I, H, pair, ld_t, ld_b = ctx.geom
         dg = k.blstm_bwd(_c(dout), ld_t, ld_b, pair, acts, cs, w_hh_f, w_hh_r, lens, x2.dtype)
         dgf, dgr = dg[0].view(T * B, 4 * H), dg[1].view(T * B, 4 * H)
@@ -569,24 +569,25 @@ class _BLSTMLayer(Function):
         dw_hh_f, dw_hh_r = torch.empty_like(w_hh_f), torch.empty_like(w_hh_r)
         db_f = torch.empty(4 * H, dtype=f32, device=dev)
         db_r = torch.empty(4 * H, dtype=f32, device=dev)
-        # bias gradients: b_ih and b_hh get the same values but need two tensors (autograd adopts a returned gradient
-        # only if nothing else references it)
-        db_f2 = torch.empty(4 * H, dtype=f32, device=dev)
-        db_r2 = torch.empty(4 * H, dtype=f32, device=dev)
-        side = rt.side_streams(dev, 2, pool='dw') if rt.can_defer(w_ih_f, w_hh_f, w_ih_r, w_hh_r) else [None, None]
-        with rt.fork(side[0]):          # recurrent-weight gradients are split-K GEMMs over T*B rows: they leave SMs idle
+        side = (rt.side_streams(dev, 2, pool='dw')
+                if rt.can_defer(w_ih_f, w_hh_f, w_ih_r, w_hh_r, b_ih_f, b_hh_f, b_ih_r, b_hh_r) else [None, None])
+        # Weight AND bias gradients leave the dependent chain (nothing in backward reads them): split-K GEMMs and column sums
+        # over T*B rows on the side streams, under the next layer's recurrence.  b_ih and b_hh get the same values -- ONE pass
+        # over the gate gradients (132 MB at the bottom layer) and a 4 KB copy, because autograd adopts a returned gradient only
+        # if nothing else references it.
+        with rt.fork(side[0]):
             k.gemm(dgf, hs[0, :T].reshape(T * B, H), trans_a=True, out=dw_hh_f)
             k.gemm(dgr, hs[1, 1:].reshape(T * B, H), trans_a=True, out=dw_hh_r)
+            k.colsum(dgf, out=db_f)
+            db_f2 = k.cast(db_f, f32, out=torch.empty_like(db_f))
         with rt.fork(side[1]):
             k.gemm(dgf, x2, trans_a=True, out=dw_ih_f)
             k.gemm(dgr, x2, trans_a=True, out=dw_ih_r)
-        # no join here: the weight gradients keep running under the NEXT layer's recurrence (rt.defer)
-        rt.defer(side[0], (dg, hs), [(w_hh_f, dw_hh_f), (w_hh_r, dw_hh_r)])
-        rt.defer(side[1], (dg, x2), [(w_ih_f, dw_ih_f), (w_ih_r, dw_ih_r)])
-        k.colsum(dgf, out=db_f)
-        k.colsum(dgr, out=db_r)
-        k.colsum(dgf, out=db_f2)
-        k.colsum(dgr, out=db_r2)
+            k.colsum(dgr, out=db_r)
+            db_r2 = k.cast(db_r, f32, out=torch.empty_like(db_r))
+        # no join here: the gradients keep running under the NEXT layer's recurrence (rt.defer)
+        rt.defer(side[0], (dg, hs), [(w_hh_f, dw_hh_f), (w_hh_r, dw_hh_r), (b_ih_f, db_f), (b_hh_f, db_f2)])
+        rt.defer(side[1], (dg, x2), [(w_ih_f, dw_ih_f), (w_ih_r, dw_ih_r), (b_ih_r, db_r), (b_hh_r, db_r2)])
         dx = None
         if ctx.needs_input_grad[0]:
             # both directions' contributions in ONE launch (two-segment K loop into the same accumulator)
@@ -943,7 +944,8 @@ class _LASDecoder(Function):
                     below = XD[i - 1] if XD is not None else (RES[i - 1] if RES[i - 1] is not None else Hst[i - 1][1:])
                     dw_ih = k.gemm(dg2, below.reshape(SB, D), trans_a=True, out_dtype=f32)
                 dw_hh = k.gemm(dg2, Hst[i][:S].reshape(SB, D), trans_a=True, out_dtype=f32)
-                db_i, db_h = k.colsum(dg2), k.colsum(dg2)
+                db_i = k.colsum(dg2)
+                db_h = k.cast(db_i, f32, out=torch.empty_like(db_i))     # b_ih and b_hh share the values; autograd wants two tensors
                 grads_lstm += [dw_ih, dw_hh, db_i, db_h]
                 expect += list(zip(lp[i], (dw_ih, dw_hh, db_i, db_h)))
             dcv2 = DCV.view(SB, D)

@@ -59,7 +59,9 @@ class GraphedTrainStep:
             rt.clear_cache()                  # weight copies get re-cast inside the captured region on every replay
         rt.reset_deferred()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # captured on a high-priority stream: the kernel nodes of the dependent chain inherit it, the deferred
+        # weight-gradient branches (runtime.side_streams pool 'dw', default priority) fill the SMs the chain leaves idle
+        with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(priority=rt.CHAIN_PRIORITY)):
             self.loss = trainer._train_batch_device(model, self.static)
             if with_optimizer:
                 trainer.optimizer.step()

@@ -174,6 +174,9 @@ def clear_cache():
 # capture they become parallel branches, in eager mode they overlap through the hardware queues.
 # ------------------------------------------------------------------------------------------------
 _side = {}
+_rot = [0]
+DW_STREAMS = 4            # streams the deferred weight-gradient work rotates over
+CHAIN_PRIORITY = -1       # CUDA stream priority of the dependent chain (capture stream + its forked branches); deferred work: 0
 
 
 def side_streams(device, n, pool='main'):
@@ -184,8 +187,20 @@ def side_streams(device, n, pool='main'):
         return [None] * n
     key = (device.index if device.index is not None else torch.cuda.current_device(), pool)
     streams = _side.setdefault(key, [])
+    if pool == 'dw' and DW_STREAMS > n:
+        # Deferred weight-gradient work (joined only at the end of backward): the callers' requests rotate over DW_STREAMS
+        # default-priority streams.  With two, the ~250 deferred GEMMs / column sums of a step queued up behind each other
+        # and the optimizer ended up waiting for that backlog (4 streams: -0.10 ms; 8: no further change).
+        while len(streams) < DW_STREAMS:
+            streams.append(torch.cuda.Stream(device=device, priority=0))
+        off = _rot[0] % DW_STREAMS
+        _rot[0] += n
+        return [streams[(off + i) % DW_STREAMS] for i in range(n)]
     while len(streams) < n:
-        streams.append(torch.cuda.Stream(device=device))
+        # branches of the step's dependent chain share the capture stream's HIGH priority (b200st/graph.py): a chain
+        # kernel that is ready takes free SMs before deferred work does (-0.10 ms once the backlog above is gone; with
+        # the backlog it made the step slower)
+        streams.append(torch.cuda.Stream(device=device, priority=0 if pool == 'dw' else CHAIN_PRIORITY))
     return streams[:n]
 
 
