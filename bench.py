@@ -552,6 +552,8 @@ def run_b200(args):
             model.zero_grad(set_to_none=True)
             graphed = GraphedTrainStep(model, trainer, dev_items, with_optimizer=True)
         except Exception as ex:            # e.g. a collective that cannot be captured: stay eager, say so
+            import traceback
+            traceback.print_exc()
             print(f'[bench] CUDA graph capture failed ({type(ex).__name__}: {ex}); timing the eager step', file=sys.stderr)
             graphed = None
             model.zero_grad(set_to_none=True)
