@@ -133,6 +133,7 @@ class KernelTimer:
         self.backend, self.names = backend, list(names)
         self.records = {n: [] for n in names}
         self.meta = {n: [] for n in names}
+        self.calls = {}            # family -> [(bound method, args, kwargs)] of the roofline kernel's launches, for re-timing
         self.big = {}              # (family, shape key) -> (bound method, args, kwargs, flops) of the >= 5e10 FLOP GEMMs
         self._orig = {}
 
@@ -166,9 +167,11 @@ class KernelTimer:
                 elif __n in ('blstm_fwd',):
                     _, T, B, H4 = a[0].shape
                     self.meta[__n].append(2 * 2 * T * B * (H4 // 4) * H4)
+                    self.calls.setdefault(__n, []).append((__orig, a, dict(kw)))
                 elif __n in ('blstm_bwd',):
                     _, T, B, H = a[5].shape
                     self.meta[__n].append(2 * 2 * T * B * H * 4 * H)
+                    self.calls.setdefault(__n, []).append((__orig, a, dict(kw)))
                 return r
             setattr(self.backend, n, wrapped)
         return self
@@ -514,7 +517,29 @@ def run_b200(args):
     # list, profiles/r01_launches_summary.txt; the eager per-family sums above overstate the many tiny GEMM launches
     # because each bracket then also contains host launch gaps).
     roof_names = ['blstm_fwd', 'blstm_bwd']
-    roof = {n: fam[n] for n in roof_names}
+    roof = {n: dict(fam[n]) for n in roof_names}
+    # The bracket of the eager pass also contains whatever the host did between the two event records -- for the recurrence
+    # wrappers that is the allocation of ~0.7 GB of saved state, and a cudaMalloc there shows up as tens of ms of "kernel
+    # time" in some runs.  Every recorded launch is therefore re-issued on its own operands three times (the allocator has
+    # the blocks cached from the second time on) and the MINIMUM bracket is what enters `roofline`.
+    for n in roof_names:
+        total = 0.0
+        for fn, a, kw in kt.calls.get(n, []):
+            best = None
+            for _ in range(3):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out_ = fn(*a, **kw)
+                e1.record()
+                torch.cuda.synchronize()
+                del out_
+                t = e0.elapsed_time(e1)
+                best = t if best is None else min(best, t)
+            total += best
+        if kt.calls.get(n):
+            roof[n]['ms'] = total
+            fam[n] = dict(fam[n], ms=total)
     # secondary roofline: the tensor-bound GEMMs proper (BLSTM input projections and their input-gradient GEMMs =
     # gemm_tc_pair_kernel, cta_group::2): each distinct call of the step re-issued back to back on its own operands
     b_ms = b_fl = 0.0
@@ -661,8 +686,10 @@ def run_b200(args):
                          'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': peak_src,
                          'us_per_time_step': 1e3 * r_ms / (2 * sum((args.frames + 8 - args.frames % 8) // 2 ** l for l in range(4))),
                          'launches': r_calls, 'avg_launch_ms': r_ms / max(r_calls, 1),
-                         'timed': 'CUDA events around every launch of this kernel family on its stream, eager pass of the '
-                                  'same step in this run (the timed region replays the step as one CUDA graph)',
+                         'timed': 'every launch of this kernel family in an eager pass of the same step is re-issued alone on its '
+                                  'own operands three times, CUDA events around the call on its stream, minimum taken (a first '
+                                  'bracket can contain the allocation of the saved state); the timed region itself replays the '
+                                  'step as one CUDA graph',
                          'note': 'recurrent-GEMM FLOPs 2*2dirs*T*B*H*4H per launch; this kernel is bound by the '
                                  'serial time-step chain (latency), not by tensor throughput'},
         }
