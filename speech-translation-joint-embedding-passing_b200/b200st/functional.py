@@ -252,7 +252,7 @@ class _MHABlock(Function):
         dfc = k.dropout(dout2, p_fc, rng, s_fc) if p_fc > 0 else dout2      # gradient of the fc output
         do = k.gemm(dfc, rt.operand(w_fc))
         # weight gradients: off the dX chain on side streams, joined at the end of backward (rt.defer).  Every returned
-        # gradient is a whole fresh tensor so that autograd adopts it instead of copying it (hence two GEMMs for K | V)
+        # gradient is a fresh dense tensor (or a row block of one) so that autograd adopts it instead of copying it
         side = rt.side_streams(q2.device, 2, pool='dw') if rt.can_defer(w_fc, w_q, w_k, w_v) else [None, None]
         with rt.fork(side[0]):
             dw_fc = k.gemm(dfc, o2, trans_a=True, out_dtype=torch.float32)
@@ -265,8 +265,10 @@ class _MHABlock(Function):
                   dropout=(p_attn, rng, s_attn))
         with rt.fork(side[1]):
             dw_q = k.gemm(dqp, qn, trans_a=True, out_dtype=torch.float32)
-            dw_k = k.gemm(dkvp[:, :HD], kv2, trans_a=True, out_dtype=torch.float32)
-            dw_v = k.gemm(dkvp[:, HD:], kv2, trans_a=True, out_dtype=torch.float32)
+            # K | V weight gradients from ONE GEMM on the concatenated gate gradients: the two halves are contiguous ROW
+            # blocks of its output, which autograd adopts as they are (a row-slice view is dense; column slices are not)
+            dw_kv = k.gemm(dkvp, kv2, trans_a=True, out_dtype=torch.float32)
+            dw_k, dw_v = dw_kv[:HD], dw_kv[HD:]
         rt.defer(side[1], (dqp, qn, dkvp, kv2), [(w_q, dw_q), (w_k, dw_k), (w_v, dw_v)])
         # dX of the K | V projections runs on a parallel branch beside the dQ GEMM; for self-attention its epilogue also
         # adds the skip-connection gradient, and the LayerNorm-backward kernel adds that sum to its own dx: the chain is
