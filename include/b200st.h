@@ -67,6 +67,10 @@ int b200st_gemm2(int dtype_ab, int dtype_c, int trans_a, int trans_b, int64_t M,
  * two SMs) kernel for the largest shapes; default 3, 0 = always one tile per CTA.  Returns the previous mask (test /
  * bench hook). */
 int b200st_set_gemm_persistent(int on);
+/* SM budget of the PERSISTENT GEMM kernels launched from now on (0 = all SMs; returns the previous value).  Deferred
+ * weight-gradient GEMMs that run on side streams under a latency-bound recurrence kernel are launched with a budget that
+ * leaves that kernel's SMs free: a persistent CTA holds its SM for the whole GEMM. */
+int b200st_set_gemm_sm_budget(int n);
 
 /* GEMM kernel selection: 0 = auto (bf16 operands that TMA can address -> tcgen05 tensor-core kernel, everything
  * else -> exact CUDA-core kernel), 1 = CUDA cores only, 2 = tensor cores required (error if not eligible).

@@ -532,6 +532,10 @@ def fused_softmax_nll(logits, target, mask, scale, eps=0.0):
 # ------------------------------------------------------------------------------------------------
 # One bidirectional packed LSTM layer of the pyramidal encoder: Enc.py:150-167 (x4)
 # ------------------------------------------------------------------------------------------------
+import os as _os
+DEFERRED_SM_BUDGET = int(_os.environ.get('B200ST_DEFERRED_SM_BUDGET', '84'))     # 148 - the 64 SMs of a recurrence kernel
+
+
 class _BLSTMLayer(Function):
     @staticmethod
     def forward(ctx, x, lens, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, pair,
@@ -577,16 +581,24 @@ class _BLSTMLayer(Function):
         # over T*B rows on the side streams, under the next layer's recurrence.  b_ih and b_hh get the same values -- ONE pass
         # over the gate gradients (132 MB at the bottom layer) and a 4 KB copy, because autograd adopts a returned gradient only
         # if nothing else references it.
-        with rt.fork(side[0]):
-            k.gemm(dgf, hs[0, :T].reshape(T * B, H), trans_a=True, out=dw_hh_f)
-            k.gemm(dgr, hs[1, 1:].reshape(T * B, H), trans_a=True, out=dw_hh_r)
-            k.colsum(dgf, out=db_f)
-            db_f2 = k.cast(db_f, f32, out=torch.empty_like(db_f))
-        with rt.fork(side[1]):
-            k.gemm(dgf, x2, trans_a=True, out=dw_ih_f)
-            k.gemm(dgr, x2, trans_a=True, out=dw_ih_r)
-            k.colsum(dgr, out=db_r)
-            db_r2 = k.cast(db_r, f32, out=torch.empty_like(db_r))
+        # A layer above the bottom one is followed by the next recurrence kernel (64 SMs in clusters of 8): its deferred
+        # persistent GEMMs are launched with an SM budget that leaves those SMs free (a persistent CTA holds its SM for the
+        # whole GEMM; recurrence clusters that find no room wait for it to end).
+        budget = DEFERRED_SM_BUDGET if (side[0] is not None and ctx.needs_input_grad[0]) else 0
+        old_budget = k.set_gemm_sm_budget(budget)
+        try:
+            with rt.fork(side[0]):
+                k.gemm(dgf, hs[0, :T].reshape(T * B, H), trans_a=True, out=dw_hh_f)
+                k.gemm(dgr, hs[1, 1:].reshape(T * B, H), trans_a=True, out=dw_hh_r)
+                k.colsum(dgf, out=db_f)
+                db_f2 = k.cast(db_f, f32, out=torch.empty_like(db_f))
+            with rt.fork(side[1]):
+                k.gemm(dgf, x2, trans_a=True, out=dw_ih_f)
+                k.gemm(dgr, x2, trans_a=True, out=dw_ih_r)
+                k.colsum(dgr, out=db_r)
+                db_r2 = k.cast(db_r, f32, out=torch.empty_like(db_r))
+        finally:
+            k.set_gemm_sm_budget(old_budget)
         # no join here: the gradients keep running under the NEXT layer's recurrence (rt.defer)
         rt.defer(side[0], (dg, hs), [(w_hh_f, dw_hh_f), (w_hh_r, dw_hh_r), (b_ih_f, db_f), (b_hh_f, db_f2)])
         rt.defer(side[1], (dg, x2), [(w_ih_f, dw_ih_f), (w_ih_r, dw_ih_r), (b_ih_r, db_r), (b_hh_r, db_r2)])

@@ -69,6 +69,9 @@ class CudaKernels:
         """1 = persistent tcgen05 GEMM for the many-tile shapes (default), 0 = one tile per CTA.  Returns the old value."""
         return int(self.lib.b200st_set_gemm_persistent(int(on)))
 
+    def set_gemm_sm_budget(self, n: int) -> int:
+        return int(self.lib.b200st_set_gemm_sm_budget(int(n)))
+
     def set_blstm_backend(self, mode: int) -> int:
         """0 auto (tcgen05 recurrence for bf16/H=256), 1 CUDA cores only.  Returns the previous mode."""
         return int(self.lib.b200st_set_blstm_backend(int(mode)))

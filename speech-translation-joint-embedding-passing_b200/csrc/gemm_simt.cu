@@ -170,7 +170,9 @@ int gemm_tc(int dtype_c, int ta, int tb, int64_t M, int64_t N, int64_t K, float 
 static int g_gemm_backend = 0;   // 0 auto, 1 CUDA cores only, 2 tensor cores required
 }  // namespace b200st
 
-namespace b200st { int gemm_tc_set_persistent(int on); int gemm_tc_set_pair(int on); int gemm_tc_set_pair_dbg(int v); }
+namespace b200st { int gemm_tc_set_persistent(int on); int gemm_tc_set_pair(int on); int gemm_tc_set_pair_dbg(int v); int gemm_tc_set_sm_budget(int n); }
+
+extern "C" int b200st_set_gemm_sm_budget(int n) { return b200st::gemm_tc_set_sm_budget(n); }
 // bit 0: persistent kernels, bit 1: CTA-pair (cta_group::2) kernel for the largest shapes; returns the previous mask
 extern "C" int b200st_set_gemm_persistent(int on) {
   const int old = b200st::gemm_tc_set_persistent(-1) | (b200st::gemm_tc_set_pair(-1) << 1);

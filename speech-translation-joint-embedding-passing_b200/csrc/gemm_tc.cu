@@ -1175,6 +1175,12 @@ static int launch_tc_clk(int64_t M, int64_t N, int64_t K, float alpha, const CUt
 static int g_persist_enabled = 1;
 int gemm_tc_set_persistent(int on) { const int old = g_persist_enabled; if (on == 0 || on == 1) g_persist_enabled = on; return old; }
 static int g_sm_count = 0;
+// SM budget of the persistent kernels (0 = all SMs): deferred weight-gradient GEMMs that run on side streams UNDER a
+// latency-bound recurrence are launched with a budget that leaves the recurrence's SMs free -- a persistent CTA holds its
+// SM for the whole GEMM, and thread-block clusters of the recurrence that find no free SMs wait for it to end.
+static int g_sm_budget = 0;
+int gemm_tc_set_sm_budget(int n) { const int old = g_sm_budget; g_sm_budget = n < 0 ? 0 : n; return old; }
+static inline int sm_budget() { return g_sm_budget > 0 && g_sm_budget < g_sm_count ? g_sm_budget : g_sm_count; }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, typename TC>
 static int launch_tc_persist(int64_t M, int64_t N, int64_t K, float alpha, const CUtensorMap& ma, const CUtensorMap& mb,
@@ -1191,7 +1197,7 @@ static int launch_tc_persist(int64_t M, int64_t N, int64_t K, float alpha, const
   const int n_tiles = (int)(ceil_div(M, TC_BM) * n_tiles_n);
   auto kern = gemm_tc_persist_kernel<BN, STAGES, A_MN, B_MN, TC>;
   B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-  dim3 grid((unsigned)min(n_tiles, g_sm_count));
+  dim3 grid((unsigned)min(n_tiles, sm_budget()));
   B200ST_CUDA(launch_pdl(kern, grid, dim3(TCP_THREADS), S::TOTAL, st, ma, mb, ma2, mb2, kb_seg1, (TC*)C, ldc, (const TC*)R,
                          ldr, bias, relu, alpha, (int)M, (int)N, (int)K, n_tiles_n, n_tiles));
   B200ST_LAUNCH_CHECK("gemm_tc_persist");
@@ -1240,7 +1246,7 @@ static int launch_tc_pair(int64_t M, int64_t N, int64_t K, float alpha, const CU
   const int n_tiles = (int)(ceil_div(M, 256) * n_tiles_n);
   auto kern = gemm_tc_pair_kernel<STAGES, A_MN, B_MN, TC>;
   B200ST_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-  dim3 grid((unsigned)(2 * min(n_tiles * splits, g_sm_count / 2)));
+  dim3 grid((unsigned)(2 * min(n_tiles * splits, sm_budget() / 2)));
   B200ST_CUDA(launch_pdl_pair(kern, grid, dim3(TCP_THREADS), S::TOTAL, st, ma, mb, ma2, mb2, kb_seg1, (TC*)C, ldc,
                               (const TC*)R, ldr, bias, relu, alpha, (int)M, (int)N, (int)K, n_tiles_n, n_tiles, g_pair_dbg, splits, kb_per_split));
   B200ST_LAUNCH_CHECK("gemm_tc_pair");
