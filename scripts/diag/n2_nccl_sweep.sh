@@ -1,4 +1,4 @@
-# N = 2 sweep of NCCL settings for the data-parallel step (bench.py under torchrun): which knob moves the +0.4 ms?
+# N = 2 sweep of NCCL settings (results: profiles/r02_dp_timeline_n2.txt).  # N = 2 sweep of NCCL settings for the data-parallel step (bench.py under torchrun): which knob moves the +0.4 ms?
 mkdir -p gpurun_out
 run() {  # label, env...
   label=$1; shift

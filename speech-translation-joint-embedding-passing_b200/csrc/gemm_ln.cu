@@ -33,7 +33,6 @@ __device__ __forceinline__ uint32_t gl_mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ float gl_round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 __global__ void __cluster_dims__(GL_CL, 1, 1) __launch_bounds__(GL_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
