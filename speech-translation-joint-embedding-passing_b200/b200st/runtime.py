@@ -357,6 +357,7 @@ def new_step():
     when no dropout is active."""
     _site[0] = 0
     _pending[0] = True
+    _prenorm[0] = None        # an offer nobody took (a forward pass that ended early) must not outlive its pass
 
 
 def next_site(tag: str = '', p: float = 0.0) -> int:
