@@ -85,14 +85,15 @@ int b200st_set_gemm_backend(int mode);
  * replaces b200st_gemm(+residual) followed by b200st_layernorm_fwd.  Four CTAs (a cluster) cover a 128-row block; row
  * statistics are exchanged through distributed shared memory.  b200st_gemm_ln_eligible returns 1 when the shapes /
  * alignments are served (bf16, N == 512, K % 8 == 0, 16-byte aligned rows; Y / YN rows 32-byte aligned); callers use
- * the two separate kernels otherwise.  bias and R may be NULL. */
+ * the two separate kernels otherwise.  bias and R may be NULL.  drop_p > 0: dropout on the projection's output before the
+ * skip connection (layers.py:194-195, 248-250) with the mask b200st_dropout(site, rng) draws for the dense [M, N] tensor. */
 int b200st_gemm_ln_eligible(int dtype, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* W,
                             int64_t ldw, const void* R, int64_t ldr, const void* Y, int64_t ldy, const void* YN,
                             int64_t ldyn, const float* bias, const float* gamma, const float* beta);
 int b200st_gemm_ln(int dtype, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* W, int64_t ldw,
                    const float* bias, const void* R, int64_t ldr, void* Y, int64_t ldy, const float* gamma,
-                   const float* beta, float eps, void* YN, int64_t ldyn, float* mean, float* rstd,
-                   b200st_stream_t stream);
+                   const float* beta, float eps, void* YN, int64_t ldyn, float* mean, float* rstd, float drop_p,
+                   const int64_t* rng, int64_t site, b200st_stream_t stream);
 
 /* The backward twin (csrc/gemm_ln.cu): the input-gradient GEMM that feeds a LayerNorm backward, with that backward as
  * its epilogue (replaces b200st_gemm followed by b200st_layernorm_bwd_partial):

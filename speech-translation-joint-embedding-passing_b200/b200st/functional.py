@@ -225,12 +225,13 @@ class _MHABlock(Function):
                          dropout=(p_attn, rng, s_attn))
         o2 = o.view(-1, HD)
         wfc = rt.operand(w_fc)
-        if p_fc > 0:
-            out = k.dropout(k.gemm(o2, wfc, trans_b=True), p_fc, rng, s_fc, residual=q2)
-        elif next_ln is not None and k.gemm_ln_ok(o2, wfc, q2):
-            # fc + skip connection + the NEXT sub-layer's LayerNorm in one launch; the result is handed over through rt
-            out, yn, mean_n, rstd_n = k.gemm_ln(o2, wfc, None, q2, next_ln[0], next_ln[1], next_ln[2])
+        if next_ln is not None and k.gemm_ln_ok(o2, wfc, q2):
+            # fc (+ dropout) + skip connection + the NEXT sub-layer's LayerNorm in one launch; handed over through rt
+            out, yn, mean_n, rstd_n = k.gemm_ln(o2, wfc, None, q2, next_ln[0], next_ln[1], next_ln[2],
+                                                dropout=(p_fc, rng, s_fc) if p_fc > 0 else None)
             rt.offer_prenorm(out, next_ln[0], next_ln[1], next_ln[2], yn, mean_n, rstd_n)
+        elif p_fc > 0:
+            out = k.dropout(k.gemm(o2, wfc, trans_b=True), p_fc, rng, s_fc, residual=q2)
         else:
             out = k.gemm(o2, wfc, trans_b=True, residual=q2)
         ctx.self_attn, ctx.n_head, ctx.temperature, ctx.dims = self_attn, n_head, temperature, (B, Lq, Lk, D, HD)
@@ -315,7 +316,12 @@ class _FFNBlock(Function):
         rng = None
         if p > 0:            # x + dropout(w_2(.)) (layers.py:248-250)
             rng = rt.current_rng(x.device)
-            out = k.dropout(k.gemm(h, rt.operand(w2), trans_b=True, bias=b2), p, rng, site, residual=x2)
+            if next_ln is not None and k.gemm_ln_ok(h, rt.operand(w2), x2):
+                out, yn, mean_n, rstd_n = k.gemm_ln(h, rt.operand(w2), b2, x2, next_ln[0], next_ln[1], next_ln[2],
+                                                    dropout=(p, rng, site))
+                rt.offer_prenorm(out, next_ln[0], next_ln[1], next_ln[2], yn, mean_n, rstd_n)
+            else:
+                out = k.dropout(k.gemm(h, rt.operand(w2), trans_b=True, bias=b2), p, rng, site, residual=x2)
         elif next_ln is not None and k.gemm_ln_ok(h, rt.operand(w2), x2):
             out, yn, mean_n, rstd_n = k.gemm_ln(h, rt.operand(w2), b2, x2, next_ln[0], next_ln[1], next_ln[2])
             rt.offer_prenorm(out, next_ln[0], next_ln[1], next_ln[2], yn, mean_n, rstd_n)

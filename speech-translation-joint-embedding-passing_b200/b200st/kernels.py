@@ -162,10 +162,11 @@ class CudaKernels:
             return False
         return residual is None or (residual.dtype == torch.bfloat16 and tuple(residual.shape) == (a.size(0), 512))
 
-    def gemm_ln(self, a, w, bias, residual, gamma, beta, eps):
-        """y = a @ w^T (+ bias) + residual;  yn, mean, rstd = LayerNorm(y; gamma, beta, eps)  in ONE launch
-        (csrc/gemm_ln.cu).  a [M, K], w [512, K] bf16.  Returns (y, yn, mean, rstd)."""
+    def gemm_ln(self, a, w, bias, residual, gamma, beta, eps, dropout=None):
+        """y = dropout?(a @ w^T (+ bias)) + residual;  yn, mean, rstd = LayerNorm(y; gamma, beta, eps)  in ONE launch
+        (csrc/gemm_ln.cu).  a [M, K], w [512, K] bf16; dropout = None or (p, rng_state, site).  Returns (y, yn, mean, rstd)."""
         self._need_cuda(a, w, bias, residual, gamma, beta)
+        dp, rng, site = dropout if dropout is not None and dropout[0] > 0 else (0.0, None, 0)
         M, K = a.shape
         N = w.size(0)
         y = torch.empty((M, N), dtype=a.dtype, device=a.device)
@@ -174,7 +175,8 @@ class CudaKernels:
         rstd = torch.empty(M, dtype=torch.float32, device=a.device)
         _lib.check(self.lib.b200st_gemm_ln(_dt(a), M, N, K, _p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(residual),
                                            residual.stride(0) if residual is not None else 0, _p(y), N, _p(gamma), _p(beta),
-                                           float(eps), _p(yn), N, _p(mean), _p(rstd), self._stream()), 'gemm_ln')
+                                           float(eps), _p(yn), N, _p(mean), _p(rstd), float(dp), _p(rng), int(site),
+                                           self._stream()), 'gemm_ln')
         return y, yn, mean, rstd
 
     def gemm_lnbwd_ok(self, a, w, x, add=None) -> bool:

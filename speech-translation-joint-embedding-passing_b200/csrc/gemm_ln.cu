@@ -18,6 +18,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "philox.cuh"
 #include "umma.cuh"
 
 namespace b200st {
@@ -34,12 +35,15 @@ __device__ __forceinline__ uint32_t gl_mapa(uint32_t addr, uint32_t rank) {
   return r;
 }
 
+__device__ __forceinline__ float gl_round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
 __global__ void __cluster_dims__(GL_CL, 1, 1) __launch_bounds__(GL_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __nv_bfloat16* __restrict__ R, int64_t ldr, const float* __restrict__ bias,
                __nv_bfloat16* __restrict__ Y, int64_t ldy, const float* __restrict__ gamma,
                const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ YN, int64_t ldyn,
-               float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int K) {
+               float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int K, float drop_p,
+               const int64_t* __restrict__ rng, int64_t site) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + GL_BAR_OFF);
@@ -128,6 +132,20 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int q = 0; q < 32; q += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + ch * 32 + q);
           v[q] += b4.x; v[q + 1] += b4.y; v[q + 2] += b4.z; v[q + 3] += b4.w;
+        }
+      }
+      if (drop_p > 0.f) {
+        // dropout on the projection's output before the skip connection (layers.py:194-195, 248-250): the same counter-based
+        // mask b200st_dropout draws for a dense [M, 512] tensor (element index row * 512 + column, one Philox call per four
+        // columns), applied to the bf16-rounded value the separate GEMM would have stored; backward re-draws it
+        DropRng dr;
+        dr.init(rng, site, drop_p);
+        const uint64_t g0 = ((uint64_t)row * GL_N + (uint64_t)(n0 + ch * 32)) >> 2;
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          const Philox4 rr = dr.group(g0 + (q >> 2));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[q + e] = rr.v[e] >= dr.thresh ? gl_round_bf16(v[q + e]) * dr.scale : 0.f;
         }
       }
 #pragma unroll
@@ -470,8 +488,11 @@ int b200st_gemm_ln_eligible(int dtype, int64_t M, int64_t N, int64_t K, const vo
 
 int b200st_gemm_ln(int dtype, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* W, int64_t ldw,
                    const float* bias, const void* R, int64_t ldr, void* Y, int64_t ldy, const float* gamma,
-                   const float* beta, float eps, void* YN, int64_t ldyn, float* mean, float* rstd,
-                   b200st_stream_t stream) {
+                   const float* beta, float eps, void* YN, int64_t ldyn, float* mean, float* rstd, float drop_p,
+                   const int64_t* rng, int64_t site, b200st_stream_t stream) {
+  if (!(drop_p >= 0.f && drop_p < 1.f) || (drop_p > 0.f && rng == nullptr))
+    return set_error("gemm_ln: dropout p=%f outside [0, 1) or no rng state", (double)drop_p);
+  if (drop_p > 0.f && ldy != GL_N) return set_error("gemm_ln: the fused dropout mask is defined for a dense [M, 512] output");
   if (!b200st_gemm_ln_eligible(dtype, M, N, K, A, lda, W, ldw, R, ldr, Y, ldy, YN, ldyn, bias, gamma, beta))
     return set_error("gemm_ln: needs bf16, N = 512, K %% 8 == 0, 16-byte aligned operands (got M=%lld N=%lld K=%lld)",
                      (long long)M, (long long)N, (long long)K);
@@ -491,7 +512,7 @@ int b200st_gemm_ln(int dtype, int64_t M, int64_t N, int64_t K, const void* A, in
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   B200ST_CUDA(cudaLaunchKernelEx(&cfg, gemm_ln_kernel, ma, mb, (const __nv_bfloat16*)R, ldr, bias, (__nv_bfloat16*)Y, ldy,
-                                 gamma, beta, eps, (__nv_bfloat16*)YN, ldyn, mean, rstd, (int)M, (int)K));
+                                 gamma, beta, eps, (__nv_bfloat16*)YN, ldyn, mean, rstd, (int)M, (int)K, drop_p, rng, site));
   B200ST_LAUNCH_CHECK("gemm_ln");
   return 0;
 }

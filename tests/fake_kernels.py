@@ -180,11 +180,13 @@ class FakeKernels:
     def gemm_ln_ok(self, a, w, residual=None, bias=None):
         return a.dim() == 2 and w.dim() == 2 and w.size(0) == 512 and a.dtype == torch.bfloat16
 
-    def gemm_ln(self, a, w, bias, residual, gamma, beta, eps):
+    def gemm_ln(self, a, w, bias, residual, gamma, beta, eps, dropout=None):
         y = a.float() @ w.float().t()
         if bias is not None:
             y = y + bias
-        if residual is not None:
+        if dropout is not None and dropout[0] > 0:
+            y = self.dropout(y.to(a.dtype), dropout[0], dropout[1], dropout[2], residual=residual).float()
+        elif residual is not None:
             y = y + residual.float()
         y = y.to(a.dtype)
         yn, mean, rstd = self.layernorm_fwd(y, gamma, beta, eps)

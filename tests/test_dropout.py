@@ -281,3 +281,48 @@ def test_dropout_train_step_bf16_graph_replays_draw_new_masks():
         assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
     finally:
         rt.set_compute_dtype('fp32')
+
+
+@pytest.mark.gpu
+def test_dropout_fused_gemm_ln_path_matches_separate_kernels_bf16():
+    """d_model = 512, bf16, the reference's default dropouts: with the sub-layer-closing GEMMs running dropout + skip +
+    the next LayerNorm in their epilogue (csrc/gemm_ln.cu) the step gives the same loss and gradients as with the separate
+    GEMM -> dropout(+residual) -> LayerNorm kernels, mask for mask (same seed, same sites)."""
+    cfg = O.STConfig(enc_vocab_size=304, dec_vocab_size=304, enc_embedding_size=24, dec_embedding_size=24, max_seq_len_src=8,
+                     max_seq_len_tgt=11, num_heads=8, dim_model=512, dim_feedforward=128, enc_layers=2, dec_layers=2,
+                     acous_dim=16, acous_hidden_size=256)
+    P = O.init_params(cfg, seed=3)
+    data = O.synthetic_batch(cfg, batch=8, frames=64, seed=4, ragged=True)
+    k = kernels.K()
+    rt.set_compute_dtype('bf16')
+    try:
+        results = []
+        for fused in (True, False):
+            model = build_model(cfg, P, device='cuda')
+            _set_dropout(model)
+            model.train()
+            rt.manual_seed(123)
+            calls = {'n': 0}
+            ok0 = k.gemm_ln_ok
+            if fused:
+                k.gemm_ln_ok = lambda *a, **kw: (calls.__setitem__('n', calls['n'] + 1), ok0(*a, **kw))[1]
+            else:
+                k.gemm_ln_ok = lambda *a, **kw: False
+            try:
+                loss, out = train_step(model, data, 'cuda')
+                loss.backward()
+            finally:
+                del k.gemm_ln_ok
+            torch.cuda.synchronize()
+            assert (calls['n'] > 0) == fused
+            results.append((loss.get_loss(), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None}))
+    finally:
+        rt.set_compute_dtype('fp32')
+    (l1, g1), (l0, g0) = results
+    assert abs(l1 - l0) < 5e-3 * abs(l0), (l1, l0)
+    gn = sum(float(v.double().norm() ** 2) for v in g0.values()) ** 0.5
+    for n, v in g0.items():
+        if n.startswith('las.'):
+            continue          # (the LAS forward is identical in both runs; its gradients are the Transformer's passed through BPTT)
+        err = float((g1[n].double() - v.double()).norm())
+        assert err <= 3e-2 * max(float(v.double().norm()), 1e-3 * gn), (n, err, float(v.norm()))

@@ -608,3 +608,28 @@ def test_las_stack_grad(ks, dtype, S, B, Tk, D):
     w = rnd(S, B, Tk, seed=1)
     x = rnd(S, B, D, dtype=dtype, seed=2)
     assert rel_err(c.las_stack_grad(w, x), f.las_stack_grad(w, x)) < TOL[dtype]
+
+
+@pytest.mark.parametrize('M,K,with_bias', [(3200, 512, False), (2048, 1024, True), (77, 512, True)])
+def test_gemm_ln_fused_dropout(ks, M, K, with_bias):
+    """Dropout on the projection output inside the fused epilogue draws the SAME mask as b200st_dropout (layers.py:194-195,248-250)."""
+    c, f = ks
+    a = rnd(M, K, dtype=torch.bfloat16, seed=1)
+    w = rnd(512, K, dtype=torch.bfloat16, seed=2, scale=K ** -0.5)
+    bias = rnd(512, seed=3) if with_bias else None
+    res = rnd(M, 512, dtype=torch.bfloat16, seed=4, scale=2.0)
+    gamma, beta = 1 + 0.2 * rnd(512, seed=5), 0.1 * rnd(512, seed=6)
+    rng = torch.tensor([0x1234567, 9], dtype=torch.int64, device='cuda')
+    p, site = 0.2, 17
+    y, yn, mean, rstd = c.gemm_ln(a, w, bias, res, gamma, beta, 1e-6, dropout=(p, rng, site))
+    g0 = c.gemm(a, w, trans_b=True, bias=bias)
+    y0 = c.dropout(g0, p, rng, site, residual=res)
+    keep = c.dropout(torch.ones_like(g0), p, rng, site) != 0
+    # the same elements are dropped (y == residual exactly there) and the kept ones agree to bf16 rounding
+    assert torch.equal(y[~keep], res[~keep])
+    assert 0.15 < float((~keep).float().mean()) < 0.25
+    assert rel_err(y, y0) < 1e-2
+    yn1, mean1, rstd1 = c.layernorm_fwd(y, gamma, beta, 1e-6)
+    assert rel_err(yn, yn1) < 4e-3 and rel_err(mean, mean1) < 1e-5 and rel_err(rstd, rstd1) < 1e-5
+    yr, ynr, _, _ = f.gemm_ln(a, w, bias, res, gamma, beta, 1e-6, dropout=(p, rng, site))
+    assert rel_err(y, yr) < 1e-2 and rel_err(yn, ynr) < 2e-2
