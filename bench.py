@@ -192,7 +192,7 @@ class KernelTimer:
         return out
 
 
-ALL_FAMILIES = ['gemm', 'gemm2', 'layernorm_fwd', 'layernorm_bwd', 'mha_fwd', 'mha_bwd', 'lstm_cell_fwd', 'lstm_cell_bwd',
+ALL_FAMILIES = ['gemm', 'gemm2', 'gemm_ln', 'gemm_lnbwd', 'las_decoder_fwd', 'las_stack_grad', 'layernorm_fwd', 'layernorm_bwd', 'mha_fwd', 'mha_bwd', 'lstm_cell_fwd', 'lstm_cell_bwd',
                 'blstm_fwd', 'blstm_bwd', 'las_attn_fwd', 'las_attn_bwd', 'argmax_rows', 'las_update_lengths',
                 'embedding_fwd', 'embedding_bwd', 'mix_gather_concat', 'log_softmax_fwd', 'log_softmax_bwd',
                 'masked_nll_fwd', 'masked_nll_bwd', 'add', 'add_posenc', 'transpose01', 'cast', 'colsum',
