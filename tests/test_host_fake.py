@@ -204,3 +204,26 @@ def test_prenorm_handover_between_sublayers_fake():
         assert rel_err(o1, o0) < 1e-2 and rel_err(g1, g0) < 2e-2
     finally:
         kernels.set_backend(old)
+
+
+def test_blstm_blocked_saved_state_layout_roundtrip():
+    """The register-resident recurrence kernels keep their saved gates / cell states in a per-thread blocked layout
+    (include/b200st.h: b200st_blstm_saved_layout); the documented index formula and the pack / unpack helpers agree."""
+    from b200st.kernels import CudaKernels as CK
+    T, B, H = 3, 21, 256
+    g = torch.Generator().manual_seed(0)
+    acts, cs = torch.randn(2, T, B, 4 * H, generator=g), torch.randn(2, T, B, H, generator=g)
+    ab, cb = CK.blstm_block(acts, cs)
+    assert ab.shape == (2, T, 32, 4 * H) and cb.shape == (2, T, 32, H)
+    a2, c2 = CK.blstm_unblock(ab, cb, B)
+    assert torch.equal(a2, acts) and torch.equal(c2, cs)
+    fa, fc, G = ab.reshape(-1), cb.reshape(-1), 2
+    rnd = torch.randint(0, 10 ** 9, (200, 5), generator=g).tolist()
+    for r0, r1, r2, r3, r4 in rnd:
+        d, t, b, gate, u = r0 % 2, r1 % T, r2 % B, r3 % 4, r4 % H
+        grp, nt, c, j = b // 16, (b % 16) // 8, (b % 8) // 2, b % 2
+        rank, ub, r = u // 32, (u % 32) // 8, u % 8
+        tid = (nt * 4 + ub) * 32 + r * 4 + c
+        slot = (((d * T + t) * G + grp) * 8 + rank) * 256 + tid
+        assert fa[slot * 8 + gate * 2 + j] == acts[d, t, b, gate * H + u]
+        assert fc[slot * 2 + j] == cs[d, t, b, u]
