@@ -58,6 +58,7 @@ class GraphedTrainStep:
         else:
             rt.clear_cache()                  # weight copies get re-cast inside the captured region on every replay
         rt.reset_deferred()
+        rt.unit_grad_probes.clear()
         self.graph = torch.cuda.CUDAGraph()
         # captured on a high-priority stream: the kernel nodes of the dependent chain inherit it, the deferred
         # weight-gradient branches (runtime.side_streams pool 'dw', default priority) fill the SMs the chain leaves idle
@@ -66,6 +67,12 @@ class GraphedTrainStep:
             if with_optimizer:
                 trainer.optimizer.step()
         self._epoch = rt.cache_epoch()
+        self._probes_pending = bool(rt.unit_grad_probes)
+
+    def _after_replay(self):
+        if self._probes_pending:          # first replay only: one host sync
+            self._probes_pending = False
+            rt.check_unit_grad_probes()
 
     def _check_epoch(self):
         if rt.cache_epoch() != self._epoch:
@@ -125,6 +132,7 @@ class GraphedTrainStep:
         self._pending = None
         self._check_epoch()
         self.graph.replay()
+        self._after_replay()
         if self.with_optimizer:
             rt.after_raw_update()             # copies the captured kernel does not maintain are stale now
         return self.loss
@@ -134,6 +142,7 @@ class GraphedTrainStep:
             self.load(items)
         self._check_epoch()
         self.graph.replay()
+        self._after_replay()
         if self.with_optimizer:
             rt.after_raw_update()             # copies the captured kernel does not maintain are stale now
         return self.loss

@@ -300,6 +300,24 @@ def join_deferred():
 # ------------------------------------------------------------------------------------------------
 _prenorm = [None]
 
+# Upstream gradients of the fused loss that a capture ASSUMED to be exactly 1 (functional._FusedSoftmaxNLL.backward skips a
+# full pass over [rows, V] then): device copies taken inside the capture, checked on the host after the first replay.
+unit_grad_probes = []
+
+
+def check_unit_grad_probes():
+    """Raise if a captured graph skipped the `dlogits * g` pass although its upstream gradient is not 1."""
+    probes, bad = list(unit_grad_probes), []
+    unit_grad_probes.clear()
+    for t in probes:
+        v = float(t)
+        if v != 1.0:
+            bad.append(v)
+    if bad:
+        raise RuntimeError(f'b200st: a CUDA graph was captured assuming the fused loss receives an upstream gradient of 1 '
+                           f'(as its eager warm-up did), but the replay saw {bad}: capture with the same loss scaling as the '
+                           f'warm-up passes')
+
 
 def offer_prenorm(out, ln_w, ln_b, eps, yn, mean, rstd):
     _prenorm[0] = (out.data_ptr(), out.numel(), out.dtype, ln_w.data_ptr(), ln_b.data_ptr(), float(eps), yn, mean, rstd)
