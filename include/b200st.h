@@ -211,6 +211,9 @@ int b200st_blstm_fwd(int dtype, const void* xproj, const float* w_hh_f, const fl
 /* Debug aid: register (or clear with NULL) a device buffer of >= 128 int64; the tensor-core recurrence kernels then
  * record clock64() at fixed points of time steps 64..71 (16 slots per step) for the first CTA. */
 int b200st_debug_timeline(void* buf);
+/* Debug aid: a one-thread kernel that writes the device's %globaltimer (ns) to *slot at this point of `stream` -- captured into a
+ * CUDA graph it time-stamps section boundaries of the replayed step (scripts/graph_timeline.py). */
+int b200st_debug_stamp(int64_t* slot, b200st_stream_t stream);
 /* Recurrence kernel selection: 0 = auto (bf16 activations with H = 256 -> tcgen05 kernels, lstm_tc.cu), 1 = CUDA cores
  * only, 2 = same as 0, 3 = register-resident warp-MMA kernels (lstm_rg.cu: measured on a par with the tcgen05 kernels,
  * profiles/r02_blstm_experiments.txt; kept selectable, not the default).  Returns the previous mode (test / profiling hook). */

@@ -541,7 +541,14 @@ def fused_softmax_nll(logits, target, mask, scale, eps=0.0):
 # One bidirectional packed LSTM layer of the pyramidal encoder: Enc.py:150-167 (x4)
 # ------------------------------------------------------------------------------------------------
 import os as _os
-DEFERRED_SM_BUDGET = int(_os.environ.get('B200ST_DEFERRED_SM_BUDGET', '84'))     # 148 - the 64 SMs of a recurrence kernel
+# SM budget of the PERSISTENT weight-gradient GEMMs that are deferred onto side streams and end up running under a BLSTM
+# backward recurrence (the upper BLSTM layers' own, and the LAS decoder's): measured inside the replayed step graph
+# (scripts/graph_timeline.py, profiles/r02_graph_timeline.txt) those GEMMs, streaming 130-260 MB each at full speed, slowed
+# every backward recurrence by ~25 % (1444 instead of 1160 us for the bottom layer) -- the recurrence's per-step loads of the
+# saved state are prefetched two steps ahead and a saturated memory system pushes their latency past that.  On <= 24 SMs the
+# GEMMs still finish inside the recurrence they run under and the recurrence keeps its stand-alone speed: -0.4 ms per step.
+DEFERRED_SM_BUDGET = int(_os.environ.get('B200ST_DEFERRED_SM_BUDGET', '16'))
+LAS_DEFERRED_SM_BUDGET = int(_os.environ.get('B200ST_LAS_DEFERRED_SM_BUDGET', '16'))
 
 
 class _BLSTMLayer(Function):
@@ -589,9 +596,9 @@ class _BLSTMLayer(Function):
         # over T*B rows on the side streams, under the next layer's recurrence.  b_ih and b_hh get the same values -- ONE pass
         # over the gate gradients (132 MB at the bottom layer) and a 4 KB copy, because autograd adopts a returned gradient only
         # if nothing else references it.
-        # A layer above the bottom one is followed by the next recurrence kernel (64 SMs in clusters of 8): its deferred
-        # persistent GEMMs are launched with an SM budget that leaves those SMs free (a persistent CTA holds its SM for the
-        # whole GEMM; recurrence clusters that find no room wait for it to end).
+        # A layer above the bottom one is followed by the next recurrence kernel: its deferred persistent GEMMs are launched
+        # with a small SM budget (see DEFERRED_SM_BUDGET) so that they neither hold the SMs the recurrence's clusters need nor
+        # saturate the memory system under it.
         budget = DEFERRED_SM_BUDGET if (side[0] is not None and ctx.needs_input_grad[0]) else 0
         old_budget = k.set_gemm_sm_budget(budget)
         try:
@@ -954,6 +961,7 @@ class _LASDecoder(Function):
         flat_params = [q for layer in lp for q in layer]
         side = rt.side_streams(dev, 1, pool='dw') if rt.can_defer(emb_table, w_att, w_ffn, *flat_params) else [None]
         expect = []
+        old_budget = k.set_gemm_sm_budget(LAS_DEFERRED_SM_BUDGET if side[0] is not None else 0)
         with rt.fork(side[0]):
             grads_lstm = []
             for i in range(n_layers):
@@ -981,6 +989,7 @@ class _LASDecoder(Function):
             k.embedding_bwd(ids_in.reshape(-1), DEMB.view(SB, E), d_table, PAD)  # Dec.py:80-81 padding_idx
             dw_att = k.gemm(d_wk.view(B * Tk, D), enc.view(B * Tk, H2), trans_a=True, out_dtype=f32)
             expect += [(w_ffn, dw_ffn), (emb_table, d_table), (w_att, dw_att)]
+        k.set_gemm_sm_budget(old_budget)
         rt.defer(side[0], (DG, EMB, CV, Hst, RES, XD, DCV, CTX, CTXD, DEMB, ids_in, d_wk, enc, dec_out_stack), expect)
         return (d_enc, None, None, None, None, None, d_table, dw_att, dw_ffn, dw_out, db_out, *grads_lstm)
 

@@ -69,6 +69,10 @@ class CudaKernels:
         """1 = persistent tcgen05 GEMM for the many-tile shapes (default), 0 = one tile per CTA.  Returns the old value."""
         return int(self.lib.b200st_set_gemm_persistent(int(on)))
 
+    def debug_stamp(self, slot):
+        """slot: 1-element int64 CUDA tensor (view); receives the device nanosecond timer at this point of the stream."""
+        _lib.check(self.lib.b200st_debug_stamp(_p(slot), self._stream()), 'debug_stamp')
+
     def set_gemm_sm_budget(self, n: int) -> int:
         return int(self.lib.b200st_set_gemm_sm_budget(int(n)))
 

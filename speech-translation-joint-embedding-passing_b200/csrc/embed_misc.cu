@@ -388,6 +388,13 @@ dropout_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ res, 
 
 __global__ void rng_advance_kernel(int64_t* rng) { rng[1] += 1; }
 
+// debug aid: the device's nanosecond timer at the point of the stream where this one-thread kernel runs
+__global__ void stamp_kernel(long long* slot) {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+
 }  // namespace b200st
 
 extern "C" {
@@ -407,6 +414,12 @@ int b200st_dropout(int dtype, const void* x, int64_t ldx, const void* residual, 
                            site, vec));
   });
   B200ST_LAUNCH_CHECK("dropout");
+  return 0;
+}
+
+int b200st_debug_stamp(int64_t* slot, b200st_stream_t stream) {
+  stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)slot);
+  B200ST_LAUNCH_CHECK("debug_stamp");
   return 0;
 }
 
