@@ -962,34 +962,37 @@ class _LASDecoder(Function):
         side = rt.side_streams(dev, 1, pool='dw') if rt.can_defer(emb_table, w_att, w_ffn, *flat_params) else [None]
         expect = []
         old_budget = k.set_gemm_sm_budget(LAS_DEFERRED_SM_BUDGET if side[0] is not None else 0)
-        with rt.fork(side[0]):
-            grads_lstm = []
-            for i in range(n_layers):
-                dg2 = DG[i].view(SB, 4 * D)
-                if i == 0:
-                    dw_ih = torch.empty_like(lp[0][0])
-                    k.gemm(dg2, EMB.view(SB, E), trans_a=True, out=dw_ih[:, :E])
-                    k.gemm(dg2, CV[:S].reshape(SB, D), trans_a=True, out=dw_ih[:, E:])
-                else:
-                    below = XD[i - 1] if XD is not None else (RES[i - 1] if RES[i - 1] is not None else Hst[i - 1][1:])
-                    dw_ih = k.gemm(dg2, below.reshape(SB, D), trans_a=True, out_dtype=f32)
-                dw_hh = k.gemm(dg2, Hst[i][:S].reshape(SB, D), trans_a=True, out_dtype=f32)
-                db_i = k.colsum(dg2)
-                db_h = k.cast(db_i, f32, out=torch.empty_like(db_i))     # b_ih and b_hh share the values; autograd wants two tensors
-                grads_lstm += [dw_ih, dw_hh, db_i, db_h]
-                expect += list(zip(lp[i], (dw_ih, dw_hh, db_i, db_h)))
-            dcv2 = DCV.view(SB, D)
-            dw_ffn = torch.empty_like(w_ffn)
-            k.gemm(dcv2, (CTXD if CTXD is not None else CTX).view(SB, H2), trans_a=True, out=dw_ffn[:, :H2])
-            k.gemm(dcv2, dec_out_stack.reshape(SB, D), trans_a=True, out=dw_ffn[:, H2:])
-            if p_emb > 0:
-                d_e = DEMB[0] if fused_feed else DEMB.view(SB, E)
-                k.dropout(d_e, p_emb, rng, site_emb, out=d_e)
-            d_table = torch.zeros_like(emb_table)
-            k.embedding_bwd(ids_in.reshape(-1), DEMB.view(SB, E), d_table, PAD)  # Dec.py:80-81 padding_idx
-            dw_att = k.gemm(d_wk.view(B * Tk, D), enc.view(B * Tk, H2), trans_a=True, out_dtype=f32)
-            expect += [(w_ffn, dw_ffn), (emb_table, d_table), (w_att, dw_att)]
-        k.set_gemm_sm_budget(old_budget)
+        # (under the top BLSTM layer's backward recurrence: see DEFERRED_SM_BUDGET)
+        try:
+            with rt.fork(side[0]):
+                grads_lstm = []
+                for i in range(n_layers):
+                    dg2 = DG[i].view(SB, 4 * D)
+                    if i == 0:
+                        dw_ih = torch.empty_like(lp[0][0])
+                        k.gemm(dg2, EMB.view(SB, E), trans_a=True, out=dw_ih[:, :E])
+                        k.gemm(dg2, CV[:S].reshape(SB, D), trans_a=True, out=dw_ih[:, E:])
+                    else:
+                        below = XD[i - 1] if XD is not None else (RES[i - 1] if RES[i - 1] is not None else Hst[i - 1][1:])
+                        dw_ih = k.gemm(dg2, below.reshape(SB, D), trans_a=True, out_dtype=f32)
+                    dw_hh = k.gemm(dg2, Hst[i][:S].reshape(SB, D), trans_a=True, out_dtype=f32)
+                    db_i = k.colsum(dg2)
+                    db_h = k.cast(db_i, f32, out=torch.empty_like(db_i))     # b_ih and b_hh share the values; autograd wants two tensors
+                    grads_lstm += [dw_ih, dw_hh, db_i, db_h]
+                    expect += list(zip(lp[i], (dw_ih, dw_hh, db_i, db_h)))
+                dcv2 = DCV.view(SB, D)
+                dw_ffn = torch.empty_like(w_ffn)
+                k.gemm(dcv2, (CTXD if CTXD is not None else CTX).view(SB, H2), trans_a=True, out=dw_ffn[:, :H2])
+                k.gemm(dcv2, dec_out_stack.reshape(SB, D), trans_a=True, out=dw_ffn[:, H2:])
+                if p_emb > 0:
+                    d_e = DEMB[0] if fused_feed else DEMB.view(SB, E)
+                    k.dropout(d_e, p_emb, rng, site_emb, out=d_e)
+                d_table = torch.zeros_like(emb_table)
+                k.embedding_bwd(ids_in.reshape(-1), DEMB.view(SB, E), d_table, PAD)  # Dec.py:80-81 padding_idx
+                dw_att = k.gemm(d_wk.view(B * Tk, D), enc.view(B * Tk, H2), trans_a=True, out_dtype=f32)
+                expect += [(w_ffn, dw_ffn), (emb_table, d_table), (w_att, dw_att)]
+        finally:
+            k.set_gemm_sm_budget(old_budget)
         rt.defer(side[0], (DG, EMB, CV, Hst, RES, XD, DCV, CTX, CTXD, DEMB, ids_in, d_wk, enc, dec_out_stack), expect)
         return (d_enc, None, None, None, None, None, d_table, dw_att, dw_ffn, dw_out, db_out, *grads_lstm)
 
