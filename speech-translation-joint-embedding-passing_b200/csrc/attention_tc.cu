@@ -161,18 +161,22 @@ mha_fwd_tc_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_b
     if (lane < 16) {
       if (row < Lq) {
         const uint8_t* mr = mask ? mask + b * mask_sb + row * mask_sq : nullptr;
+        // scores are kept in units of log2(e): softmax(x) = 2^(x' - max x') with x' = x * log2e / temperature, one FMUL in front
+        // and FADD + MUFU.EX2 per element (a true division and __expf's extra multiply per element were a third of the
+        // instructions of this phase, which only half of the lanes of a warp can execute: M = 64 rows sit in lanes 0..15)
+        const float sc = kLog2e / temperature;                        // layers.py:216
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
-          float sv = s[j] / temperature;                              // layers.py:216
-          if (j < Lk && mr && mr[j] == 0) sv = -1e9f;                 // layers.py:224
+          float sv = s[j] * sc;
+          if (j < Lk && mr && mr[j] == 0) sv = -1e9f * kLog2e;        // layers.py:224
           if (j >= Lk) sv = -INFINITY;
           s[j] = sv;
           mx = fmaxf(mx, sv);
         }
         float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) { s[j] = __expf(s[j] - mx); sum += s[j]; }
+        for (int j = 0; j < 64; ++j) { s[j] = ex2_approx(s[j] - mx); sum += s[j]; }
         const float inv = 1.f / sum;
 #pragma unroll
         for (int j = 0; j < 64; ++j) s[j] *= inv;

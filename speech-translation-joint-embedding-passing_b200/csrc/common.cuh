@@ -95,6 +95,15 @@ static inline cudaError_t launch_pdl_cluster_z(void (*kernel)(KArgs...), dim3 gr
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// 2^v on the SFU (MUFU.EX2, relative error 2^-22): for bf16-output kernels, exp(x - m) = ex2_approx(x * log2e - m * log2e) is one
+// FFMA + one MUFU where expf() is ~10 instructions
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_approx(float v) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);

@@ -423,12 +423,15 @@ softmax_nll_fused_vec_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, co
     }
   }
   mx = block_max(mx, scratch);
+  // exp(x - mx) as one FFMA + one MUFU.EX2 (relative error 2^-22, far inside the bf16 gradient this kernel writes): with expf the
+  // kernel was bound by instruction issue, not by HBM
+  const float nmx = -mx * kLog2e;
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     if (k * 512 + (int)threadIdx.x < nvec) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { v[k][e] = expf(v[k][e] - mx); s += v[k][e]; }
+      for (int e = 0; e < 8; ++e) { v[k][e] = ex2_approx(fmaf(v[k][e], kLog2e, nmx)); s += v[k][e]; }
     }
   }
   s = block_sum(s, scratch);
@@ -440,17 +443,17 @@ softmax_nll_fused_vec_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, co
     if (eps != 0.f) l -= u * sx;
     atomicAdd(loss_sum, l);
   }
-  const float sc = scale[0], inv = 1.f / s;
+  const float sc = scale[0], sci = sc / s;
+  const float qo = -sc * u, qt = -sc * ((1.f - eps) + u);   // dx = sc * (p - q): q = u off the target, (1 - eps) + u on it
+  const int ti = (int)t;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int i = k * 512 + threadIdx.x;
     if (i < nvec) {
       float o[8];
+      const int te = ti - 8 * i;                    // position of the target inside this thread's 8 columns (or outside 0..7)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float q = ((int64_t)(8 * i + e) == t ? 1.f - eps : 0.f) + u;
-        o[e] = sc * (v[k][e] * inv - q);
-      }
+      for (int e = 0; e < 8; ++e) o[e] = fmaf(v[k][e], sci, e == te ? qt : qo);
       uint4 w;
       __nv_bfloat162* ww = reinterpret_cast<__nv_bfloat162*>(&w);
 #pragma unroll
