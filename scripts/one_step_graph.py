@@ -1,6 +1,7 @@
 """One replay of the whole-step CUDA graph (the thing bench.py times) after warm-up, for an ncu launch list of the GRAPH's
 kernel nodes:  ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv python scripts/one_step_graph.py
-(ncu profiles the kernel nodes of a replayed graph one by one).  A 7-element fill marks the start of the measured replay."""
+(ncu profiles the kernel nodes of a replayed graph one by one).  One `stamp_kernel` launch (b200st_debug_stamp) marks the start of the measured
+replay; scripts/summarize_graph_launches.py aggregates what follows it."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -25,7 +26,9 @@ for _ in range(2):
     g()
 torch.cuda.synchronize()
 print('MARK replay begins', flush=True)
-marker = torch.zeros(7, device=dev)
+from b200st.kernels import K
+marker = torch.zeros(1, dtype=torch.int64, device=dev)
+K().debug_stamp(marker)
 loss = g()
 torch.cuda.synchronize()
 print('loss', float(loss) if loss is not None else None)
