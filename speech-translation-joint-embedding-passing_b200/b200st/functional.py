@@ -898,10 +898,15 @@ class _LASDecoder(Function):
 
         DG = [e(S, B, 4 * D) for _ in range(n_layers)]
         DCTX = e(S, B, H2)
+        # Without context dropout the context's projection is folded into the attention values once, in front of the loop:
+        # dP = (dcv W_fa) V^T = dcv (V W_fa^T)^T, so the attention backward reads dcv directly and the GEMM dcv W_fa leaves every
+        # step's dependent chain (8 -> 7 kernels per step); DCTX (needed for d_enc only) is ONE GEMM over all steps after the loop.
+        fold_ctx = p_drop == 0
+        VW = k.gemm(enc.reshape(B * Tk, H2), wf[:, :H2], trans_b=True).view(B, Tk, D) if fold_ctx else None
         DSC = e(S, B, Tk, dtype=f32)
         DEMB = e(S, B, E)
-        # Per-step critical path (4 GEMMs): dcv W_fa -> attention bwd -> cell2 bwd -> dG2 W_ih2 -> cell1 bwd -> dG1 W_ih1
-        # -> cell0 bwd -> dG0 W_ih0[:, E:] (into DCV[s-1]).  The recurrent products dG_i W_hh_i (needed one step later),
+        # Per-step critical path (4 GEMMs, 3 with fold_ctx): dcv W_fa -> attention bwd -> cell2 bwd -> dG2 W_ih2 -> cell1 bwd
+        # -> dG1 W_ih1 -> cell0 bwd -> dG0 W_ih0[:, E:] (into DCV[s-1]).  The recurrent products dG_i W_hh_i (needed one step later),
         # dcv W_fb (needed after the attention backward) and dG0 W_ih0[:, :E] (needed after the loop) run on side streams.
         side = rt.side_streams(dev, n_layers + 1)
         DHN = [e(B, D) for _ in range(n_layers)]             # dh flowing to the previous step, per layer
@@ -913,10 +918,13 @@ class _LASDecoder(Function):
             # cell_value = ctx Wf[:, :2H]^T + dec_out Wf[:, 2H:]^T
             with rt.fork(side[n_layers]):
                 k.gemm(dcv, wf[:, H2:], out=D_OUT)
-            k.gemm(dcv, wf[:, :H2], out=DCTX[s])
-            if p_drop > 0:                       # gradient of the dropped context -> gradient of the context
+            if fold_ctx:
+                _, dq_att = k.las_attn_bwd(dcv, wk, VW, PROBS[s], dscore_out=DSC[s])
+            else:
+                k.gemm(dcv, wf[:, :H2], out=DCTX[s])
+                # gradient of the dropped context -> gradient of the context
                 k.dropout(DCTX[s], p_drop, rng, site_att[s], out=DCTX[s])
-            _, dq_att = k.las_attn_bwd(DCTX[s], wk, enc, PROBS[s], dscore_out=DSC[s])
+                _, dq_att = k.las_attn_bwd(DCTX[s], wk, enc, PROBS[s], dscore_out=DSC[s])
             rt.join(side[n_layers])
             # dec_out = y_{n-1};  y_i = h_i (+ y_{i-1} on residual layers, Dec.py:417-418)
             dy_parts = [D_OUT, dq_att]
@@ -945,6 +953,8 @@ class _LASDecoder(Function):
                     k.gemm(dgi, wih[0][:, E:], residual=DCV[s - 1], out=DCV[s - 1])
         for st in side:
             rt.join(st)
+        if fold_ctx:
+            k.gemm(DCV.view(S * B, D), wf[:, :H2], out=DCTX.view(S * B, H2))
 
         SB = S * B
         dec_out_stack = RES[n_layers - 1] if RES[n_layers - 1] is not None else Hst[n_layers - 1][1:]
